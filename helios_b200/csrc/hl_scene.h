@@ -1,0 +1,92 @@
+// hl_scene.h — device-side view of the scene: the reference's shader ABI tables (descriptor sets 0-4,
+// path_trace_rgen.glsl:8-60) plus the acceleration structures that replace the driver's TLAS/BLAS.
+#pragma once
+#include "../../include/helios_b200.h"
+#include "hl_hd.h"
+
+namespace hl
+{
+// 8-wide compressed BVH node, 80 bytes = five 16-byte vector loads.
+//   n0: origin p.xyz (fp32), exponents e.xyz (u8), imask (u8: slot holds an internal child)
+//   n1: child_base (u32), leaf_base (u32), meta[8] (u8: 0 empty | 001sssss internal, slot 24+i |
+//       cccooooo leaf, c = unary count, o = offset from leaf_base)
+//   n2: qlo.x[8], qlo.y[8]   n3: qlo.z[8], qhi.x[8]   n4: qhi.y[8], qhi.z[8]    (u8 grid coordinates)
+// child box = p + q * 2^(e-127...) — see wide_node_decode_scale().
+struct WideNode
+{
+    float    px, py, pz;
+    uint8_t  ex, ey, ez, imask;
+    uint32_t child_base, leaf_base;
+    uint8_t  meta[8];
+    uint8_t  qlox[8], qloy[8];
+    uint8_t  qloz[8], qhix[8];
+    uint8_t  qhiy[8], qhiz[8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+
+// 48-byte leaf triangle: p0, e1 = p1 - p0, e2 = p2 - p0 (fp32, computed once exactly as the traversal
+// would) + identity: primitive index inside its geometry, geometry (submesh) index, opaque flag.
+struct LeafTri
+{
+    float    p0x, p0y, p0z;
+    uint32_t prim;
+    float    e1x, e1y, e1z;
+    uint32_t geom_flags; // bit 31 = VK_GEOMETRY_OPAQUE_BIT, bits 0..30 geometry index
+    float    e2x, e2y, e2z;
+    uint32_t pad;
+};
+static_assert(sizeof(LeafTri) == 48, "LeafTri must be 48 bytes");
+
+struct MeshView
+{
+    const hl_vertex* vertices;
+    const uint32_t*  indices;
+    const WideNode*  nodes; // BLAS, root = node 0
+    const LeafTri*   tris;
+    uint32_t         n_tris;
+    uint32_t         n_submeshes;
+};
+
+struct TexView
+{
+    const void* texels;
+    uint32_t    w, h;
+    int32_t     format;
+    uint32_t    pad;
+};
+
+struct EnvView
+{
+    const f4* faces; // 6 * size * size
+    uint32_t  size;  // 0 = black default cube map
+};
+
+struct SceneView
+{
+    const hl_material* materials;
+    const hl_instance* instances;
+    const float*       inst_inv;       // 12 floats per instance: world->object 3x4, row-major
+    const uint32_t*    submesh_info;   // flattened (prim offset, material) pairs
+    const uint32_t*    submesh_offset; // per instance: first pair index in submesh_info
+    const hl_light*    lights;
+    const MeshView*    meshes;
+    const TexView*     textures;
+    const float*       lut8; // 3 x 256: unorm, srgb, snorm decode tables
+    EnvView            env;
+    const WideNode*    tlas_nodes; // leaves reference tlas_leaf[]
+    const uint32_t*    tlas_leaf;  // instance index per TLAS leaf slot
+    uint32_t           n_instances;
+    uint32_t           n_lights;
+    uint32_t           single_identity; // 1: one instance with an identity transform -> BLAS traversed directly
+};
+
+struct Hit
+{
+    float    t, u, v;
+    uint32_t instance, geometry, primitive; // 0xFFFFFFFF = miss
+};
+
+#define HL_MISS 0xFFFFFFFFu
+#define HL_RAY_OPAQUE 1u    /* gl_RayFlagsOpaqueEXT: the any-hit stage never runs */
+#define HL_RAY_TERMINATE 2u /* gl_RayFlagsTerminateOnFirstHitEXT */
+} // namespace hl

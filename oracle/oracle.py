@@ -1,0 +1,143 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (ctypes wrapper around oracle/_build/libhelios_oracle.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+The product package (helios_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "_build" / "libhelios_oracle.so"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    src = [_HERE / "helios_oracle.cpp", _HERE / "glsl_math.h"]
+    if force or not _LIB_PATH.exists() or any(s.stat().st_mtime > _LIB_PATH.stat().st_mtime for s in src):
+        subprocess.check_call(["make", "-C", str(_HERE), "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.or_scene_new.restype = C.c_void_p
+        _lib.or_scene_add_mesh.restype = C.c_int
+        _lib.or_scene_add_texture.restype = C.c_int
+        _lib.or_rng_hash.restype = C.c_uint32
+        _lib.or_tri_test.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def hosek_dataset():
+    d = np.fromfile(_HERE.parent / "helios_b200" / "data" / "hosek_rgb_v1_4a.f64", dtype="<f8")
+    assert d.size == 3600
+    return np.ascontiguousarray(d[:3240]), np.ascontiguousarray(d[3240:])
+
+
+def sky_coeffs(sun_direction, turbidity=4.0, albedo=0.1, normalized_sun_y=1.15) -> np.ndarray:
+    rgb, rad = hosek_dataset()
+    out = np.zeros(40, np.float32)
+    d = np.asarray(sun_direction, np.float32)
+    lib().or_sky_coeffs(_p(rgb), _p(rad), _p(d), C.c_float(turbidity), C.c_float(albedo), C.c_float(normalized_sun_y), _p(out))
+    return out
+
+
+def sky_bake(coeffs, sun_direction, size=512) -> np.ndarray:
+    out = np.zeros((6, size, size, 4), np.float32)
+    cf = np.ascontiguousarray(coeffs, np.float32)
+    d = np.ascontiguousarray(sun_direction, np.float32)
+    lib().or_sky_bake(_p(cf), _p(d), C.c_uint32(size), _p(out))
+    return out
+
+
+class OracleScene:
+    """CPU scene built from a helios_b200.scenes.SceneData."""
+
+    def __init__(self, scene, brute_force: bool = False, sky_size: int = 512):
+        L = lib()
+        self.scene = scene
+        self.h = C.c_void_p(L.or_scene_new())
+        self._keep = []
+        for m in scene.meshes:
+            v, i, s = np.ascontiguousarray(m.vertices), np.ascontiguousarray(m.indices), np.ascontiguousarray(m.submeshes)
+            L.or_scene_add_mesh(self.h, _p(v), C.c_uint32(len(v)), _p(i), C.c_uint32(len(i)), _p(s), C.c_uint32(len(s)))
+        for fmt, w, h, data in scene.textures:
+            d = np.ascontiguousarray(data)
+            L.or_scene_add_texture(self.h, C.c_int(fmt), C.c_uint32(w), C.c_uint32(h), _p(d))
+        if scene.env_cube is not None:
+            size, faces = scene.env_cube
+            f = np.ascontiguousarray(faces, np.float32)
+            L.or_scene_set_envmap(self.h, C.c_uint32(size), _p(f))
+        elif scene.sun_direction is not None:
+            cf = sky_coeffs(scene.sun_direction)
+            faces = sky_bake(cf, scene.sun_direction, sky_size)
+            L.or_scene_set_envmap(self.h, C.c_uint32(sky_size), _p(faces))
+        mats = np.ascontiguousarray(scene.materials)
+        inst = np.ascontiguousarray(scene.instances)
+        lights = np.ascontiguousarray(scene.lights)
+        tabs = [np.ascontiguousarray(t, np.uint32) for t in scene.submesh_info]
+        ptrs = (C.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+        self._keep += tabs
+        L.or_scene_set_tables(self.h, _p(mats), C.c_uint32(len(mats)), _p(inst), ptrs, C.c_uint32(len(inst)), _p(lights), C.c_uint32(len(lights)))
+        L.or_scene_set_brute_force(self.h, C.c_int(1 if brute_force else 0))
+        self.counters = np.zeros(2, np.uint64)
+
+    def __del__(self):
+        try:
+            lib().or_scene_free(self.h)
+        except Exception:
+            pass
+
+    def set_brute_force(self, on: bool):
+        lib().or_scene_set_brute_force(self.h, C.c_int(1 if on else 0))
+
+    def render_frame(self, pc, accum: np.ndarray, launch=(0, 0), raw_L: np.ndarray | None = None):
+        """one launch; accum (H,W,4 float32) is updated in place (prev == cur, pixels are independent)"""
+        pcb = np.ascontiguousarray(pc)
+        lib().or_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), _p(accum), _p(accum), _p(self.counters), _p(raw_L))
+
+    def render(self, n_launches: int, **kw) -> np.ndarray:
+        """Renderer::render loop: clear, then launches num_frames = 0 .. n_launches-1 (frame 0 is discarded
+        by the reference blend)."""
+        s = self.scene
+        accum = np.zeros((s.height, s.width, 4), np.float32)
+        accum[..., 3] = 1.0
+        for f in range(n_launches):
+            self.render_frame(s.push_constants(f, **kw), accum)
+        return accum
+
+    def trace_primary_ids(self, pc):
+        s = self.scene
+        n = s.width * s.height
+        inst, geom, prim = (np.zeros(n, np.uint32) for _ in range(3))
+        t, u, v = (np.zeros(n, np.float32) for _ in range(3))
+        pcb = np.ascontiguousarray(pc)
+        lib().or_trace_primary_ids(self.h, _p(pcb), _p(inst), _p(geom), _p(prim), _p(t), _p(u), _p(v))
+        return inst, geom, prim, t, u, v
+
+    def trace_rays(self, rays: np.ndarray, flags: int = 0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros((len(rays), 6), np.float32)
+        lib().or_trace_rays(self.h, _p(rays), C.c_uint32(len(rays)), C.c_uint32(flags), _p(hits))
+        return hits
+
+
+def tonemap(accum: np.ndarray, exposure=1.0, op=0, sample_scale=1.0) -> np.ndarray:
+    H, W = accum.shape[:2]
+    out = np.zeros((H, W, 4), np.uint8)
+    a = np.ascontiguousarray(accum, np.float32)
+    lib().or_tonemap(_p(a), C.c_uint32(W), C.c_uint32(H), C.c_float(exposure), C.c_int(op), C.c_float(sample_scale), _p(out))
+    return out
