@@ -1,0 +1,177 @@
+"""Thin Python driver over the C ABI — test / bench orchestration only (the host layer proper is the C++
+shim in helios_b200/host, mirroring the reference's Scene / Renderer / PathIntegrator classes)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from ._lib import HeliosError, load
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """hl_context: one GPU, one stream, one W x H accumulation image."""
+
+    def __init__(self, width: int, height: int, device: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        st = self.lib.hl_context_create(C.c_int(device), C.c_uint32(width), C.c_uint32(height), C.byref(self.h))
+        if st != 0:
+            raise HeliosError(st, self.lib.hl_last_error(None).decode())
+        self.width, self.height = width, height
+        self.meshes = []
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.hl_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st):
+        if st != 0:
+            raise HeliosError(st, self.lib.hl_last_error(self.h).decode())
+
+    # ---- resources
+    def create_mesh(self, vertices, indices, submeshes):
+        v = np.ascontiguousarray(vertices, abi.VERTEX)
+        i = np.ascontiguousarray(indices, np.uint32)
+        s = np.ascontiguousarray(submeshes, abi.SUBMESH)
+        m = C.c_void_p()
+        self._chk(self.lib.hl_mesh_create(self.h, _p(v), C.c_uint32(len(v)), _p(i), C.c_uint32(len(i)), _p(s), C.c_uint32(len(s)), C.byref(m)))
+        self.meshes.append(m)
+        return m
+
+    def mesh_build_stats(self, mesh) -> np.ndarray:
+        out = np.zeros((), abi.BUILD_STATS)
+        self._chk(self.lib.hl_mesh_build_stats(self.h, mesh, _p(out)))
+        return out
+
+    def create_texture(self, fmt, w, h, data) -> int:
+        d = np.ascontiguousarray(data)
+        idx = C.c_int32()
+        self._chk(self.lib.hl_texture2d_create(self.h, C.c_int(fmt), C.c_uint32(w), C.c_uint32(h), _p(d), C.byref(idx)))
+        return idx.value
+
+    def set_envmap(self, size, faces):
+        f = np.ascontiguousarray(faces, np.float32) if size else None
+        self._chk(self.lib.hl_envmap_set(self.h, C.c_uint32(size), _p(f)))
+
+    def sky_update(self, coeffs40, sun_direction):
+        cf = np.ascontiguousarray(coeffs40, np.float32)
+        d = np.ascontiguousarray(sun_direction, np.float32)
+        self._chk(self.lib.hl_sky_update(self.h, _p(cf), _p(d)))
+
+    def read_envmap(self):
+        size = C.c_uint32()
+        self._chk(self.lib.hl_envmap_read(self.h, None, C.byref(size)))
+        out = np.zeros((6, size.value, size.value, 4), np.float32)
+        if size.value:
+            self._chk(self.lib.hl_envmap_read(self.h, _p(out), C.byref(size)))
+        return out
+
+    def set_tables(self, materials, instances, meshes, submesh_info, lights):
+        mats = np.ascontiguousarray(materials, abi.MATERIAL)
+        inst = np.ascontiguousarray(instances, abi.INSTANCE)
+        lts = np.ascontiguousarray(lights, abi.LIGHT)
+        tabs = [np.ascontiguousarray(t, np.uint32) for t in submesh_info]
+        ptrs = (C.c_void_p * max(len(tabs), 1))(*[t.ctypes.data for t in tabs])
+        mh = (C.c_void_p * max(len(meshes), 1))(*[m.value for m in meshes])
+        self._chk(self.lib.hl_scene_set_tables(self.h, _p(mats), C.c_uint32(len(mats)), _p(inst), mh, ptrs, C.c_uint32(len(inst)), _p(lts), C.c_uint32(len(lts))))
+
+    def load_scene(self, scene, sky_coeffs=None):
+        """uploads a helios_b200.scenes.SceneData: meshes (+BLAS build), textures, environment, tables (+TLAS)"""
+        handles = [self.create_mesh(m.vertices, m.indices, m.submeshes) for m in scene.meshes]
+        for fmt, w, h, data in scene.textures:
+            self.create_texture(fmt, w, h, data)
+        if scene.env_cube is not None:
+            self.set_envmap(scene.env_cube[0], scene.env_cube[1])
+        elif scene.sun_direction is not None:
+            if sky_coeffs is None:
+                from .sky import sky_coefficients
+
+                sky_coeffs = sky_coefficients(scene.sun_direction)
+            self.sky_update(sky_coeffs, scene.sun_direction)
+        self.set_tables(scene.materials, scene.instances, [handles[int(i["mesh_index"])] for i in scene.instances], scene.submesh_info, scene.lights)
+        return handles
+
+    # ---- hot path
+    def render_frame(self, pc, launch=(0, 0)):
+        pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
+        self._chk(self.lib.hl_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1])))
+
+    def accum_clear(self):
+        self._chk(self.lib.hl_accum_clear(self.h))
+
+    def set_accum_mode(self, mode):
+        self._chk(self.lib.hl_set_accum_mode(self.h, C.c_int(mode)))
+
+    def trace_primary_ids(self, pc):
+        n = self.width * self.height
+        inst, geom, prim = (np.zeros(n, np.uint32) for _ in range(3))
+        t, u, v = (np.zeros(n, np.float32) for _ in range(3))
+        pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
+        self._chk(self.lib.hl_trace_primary_ids(self.h, _p(pcb), _p(inst), _p(geom), _p(prim), _p(t), _p(u), _p(v)))
+        return inst, geom, prim, t, u, v
+
+    def trace_rays(self, rays, flags=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros((len(rays), 6), np.float32)
+        self._chk(self.lib.hl_trace_rays(self.h, _p(rays), C.c_uint32(len(rays)), C.c_uint32(flags), _p(hits)))
+        return hits
+
+    def tonemap(self, exposure=1.0, op=abi.TONE_MAP_ACES, sample_scale=1.0, download=True):
+        out = np.zeros((self.height, self.width, 4), np.uint8) if download else None
+        self._chk(self.lib.hl_tonemap(self.h, C.c_float(exposure), C.c_int(op), C.c_float(sample_scale), _p(out)))
+        return out
+
+    def read_accum(self):
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        self._chk(self.lib.hl_read_accum(self.h, _p(out)))
+        return out
+
+    def write_accum(self, a):
+        a = np.ascontiguousarray(a, np.float32)
+        assert a.shape == (self.height, self.width, 4)
+        self._chk(self.lib.hl_write_accum(self.h, _p(a)))
+
+    def accum_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._chk(self.lib.hl_accum_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def synchronize(self):
+        self._chk(self.lib.hl_synchronize(self.h))
+
+    def counters(self) -> np.ndarray:
+        out = np.zeros((), abi.COUNTERS)
+        self._chk(self.lib.hl_get_counters(self.h, _p(out)))
+        return out
+
+    def reset_counters(self):
+        self._chk(self.lib.hl_reset_counters(self.h))
+
+    def set_profiling(self, on: bool):
+        self._chk(self.lib.hl_set_profiling(self.h, C.c_int(1 if on else 0)))
+
+    def kernel_launches(self) -> int:
+        n = C.c_uint64()
+        self._chk(self.lib.hl_kernel_launches(self.h, C.byref(n)))
+        return n.value
+
+    def render(self, scene, n_launches, **kw):
+        """Renderer::render loop: clear, then launches with num_frames = 0 .. n_launches-1"""
+        self.accum_clear()
+        for f in range(n_launches):
+            self.render_frame(scene.push_constants(f, **kw))
+        return self.read_accum()

@@ -1,0 +1,498 @@
+// hl_api.cu — the extern "C" boundary declared in include/helios_b200.h.  No exception crosses it: every entry
+// point catches, stores the message in the context and returns an hl_status.  There is no CPU path: without
+// a CUDA device hl_context_create fails with HL_ERR_NO_DEVICE.
+#include "hl_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace hl;
+
+static thread_local std::string g_create_error;
+
+#define HL_TRY(ctx_)                                      \
+    hl_context_t* c_ = (ctx_);                            \
+    if (!c_) return HL_ERR_INVALID_ARGUMENT;              \
+    try                                                   \
+    {                                                     \
+        HL_CUDA(cudaSetDevice(c_->device));
+#define HL_CATCH                                          \
+    }                                                     \
+    catch (const hl::CudaError& e)                        \
+    {                                                     \
+        c_->err = e.what();                               \
+        return e.status;                                  \
+    }                                                     \
+    catch (const std::bad_alloc&)                         \
+    {                                                     \
+        c_->err = "host out of memory";                   \
+        return HL_ERR_OUT_OF_MEMORY;                      \
+    }                                                     \
+    catch (const std::exception& e)                       \
+    {                                                     \
+        c_->err = e.what();                               \
+        return HL_ERR_CUDA;                               \
+    }                                                     \
+    return HL_OK;
+#define HL_FAIL(code, msg)       \
+    do                           \
+    {                            \
+        c_->err = (msg);         \
+        return (code);           \
+    } while (0)
+
+extern "C" {
+
+const char* hl_version(void) { return "helios_b200 0.1 (sm_100a)"; }
+
+const char* hl_last_error(hl_context ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+hl_status hl_context_create(int device_ordinal, uint32_t width, uint32_t height, hl_context* out_ctx)
+{
+    if (!out_ctx || width == 0 || height == 0)
+    {
+        g_create_error = "hl_context_create: invalid argument";
+        return HL_ERR_INVALID_ARGUMENT;
+    }
+    *out_ctx  = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device_ordinal < 0 || device_ordinal >= count)
+    {
+        cudaGetLastError();
+        g_create_error = "hl_context_create: no CUDA device (this library has no CPU path)";
+        return HL_ERR_NO_DEVICE;
+    }
+    hl_context_t* c = new hl_context_t();
+    try
+    {
+        c->device = device_ordinal;
+        HL_CUDA(cudaSetDevice(device_ordinal));
+        HL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        HL_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal));
+        c->W = width, c->H = height;
+        // 8-bit decode tables (unorm, srgb, snorm), computed in double like the oracle's
+        float lut[768];
+        for (int i = 0; i < 256; i++)
+        {
+            const double v = i / 255.0;
+            lut[i]         = (float)v;
+            lut[256 + i]   = (float)(v <= 0.04045 ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4));
+            const int sn   = (int8_t)(uint8_t)i;
+            lut[512 + i]   = (float)std::max(-1.0, sn / 127.0);
+        }
+        c->lut8.upload(lut, sizeof(lut), c->stream);
+        wavefront_alloc(c);
+        HL_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    catch (const std::exception& e)
+    {
+        g_create_error = e.what();
+        delete c;
+        return HL_ERR_CUDA;
+    }
+    *out_ctx = c;
+    return HL_OK;
+}
+
+hl_status hl_context_destroy(hl_context ctx)
+{
+    if (!ctx) return HL_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto m : ctx->meshes) delete m;
+    for (auto t : ctx->textures) delete t;
+    if (ctx->ev_ready)
+        for (auto& e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return HL_OK;
+}
+
+hl_status hl_context_resize(hl_context ctx, uint32_t width, uint32_t height)
+{
+    HL_TRY(ctx)
+    if (width == 0 || height == 0) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_context_resize: zero extent");
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    c_->W = width, c_->H = height;
+    c_->accum.release(), c_->rgba8.release(), c_->state_a.release(), c_->state_b.release();
+    for (int k = 0; k < 2; k++) c_->ext_o[k].release(), c_->ext_d[k].release();
+    c_->hit_a.release(), c_->hit_b.release(), c_->sh_o.release(), c_->sh_d.release(), c_->sh_c.release();
+    wavefront_alloc(c_);
+    HL_CATCH
+}
+
+hl_status hl_mesh_create(hl_context ctx, const hl_vertex* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, const hl_submesh* submeshes, uint32_t n_submeshes,
+                         hl_mesh* out_mesh)
+{
+    HL_TRY(ctx)
+    if (!out_mesh || (!vertices && n_vertices) || (!indices && n_indices) || (!submeshes && n_submeshes)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_mesh_create: null argument");
+    *out_mesh = nullptr;
+    uint64_t tris = 0;
+    for (uint32_t g = 0; g < n_submeshes; g++)
+    {
+        if ((uint64_t)submeshes[g].base_index + submeshes[g].index_count > n_indices) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_mesh_create: submesh index range exceeds the index buffer");
+        tris += submeshes[g].index_count / 3;
+    }
+    if (tris > 0x7FFFFFFFull) HL_FAIL(HL_ERR_LIMIT, "hl_mesh_create: more than 2^31 triangles");
+    for (uint32_t i = 0; i < n_indices; i++)
+        if (indices[i] >= n_vertices) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_mesh_create: index out of range");
+    hl_mesh_t* m = new hl_mesh_t();
+    try
+    {
+        m->subs.assign(submeshes, submeshes + n_submeshes);
+        m->n_vertices = n_vertices, m->n_indices = n_indices;
+        m->vertices.upload(vertices, sizeof(hl_vertex) * (size_t)n_vertices, c_->stream);
+        m->indices.upload(indices, 4ull * n_indices, c_->stream);
+        build_mesh_bvh(c_, m);
+    }
+    catch (...)
+    {
+        delete m;
+        throw;
+    }
+    c_->meshes.push_back(m);
+    c_->scene_ready = false;
+    *out_mesh       = m;
+    HL_CATCH
+}
+
+hl_status hl_mesh_destroy(hl_context ctx, hl_mesh mesh)
+{
+    HL_TRY(ctx)
+    auto it = std::find(c_->meshes.begin(), c_->meshes.end(), mesh);
+    if (it == c_->meshes.end()) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_mesh_destroy: unknown mesh");
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    delete *it;
+    c_->meshes.erase(it);
+    c_->scene_ready = false;
+    HL_CATCH
+}
+
+hl_status hl_mesh_build_stats(hl_context ctx, hl_mesh mesh, hl_build_stats* out)
+{
+    HL_TRY(ctx)
+    if (!mesh || !out) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_mesh_build_stats: null argument");
+    *out = mesh->stats;
+    HL_CATCH
+}
+
+hl_status hl_texture2d_create(hl_context ctx, int format, uint32_t width, uint32_t height, const void* texels, int32_t* out_index)
+{
+    HL_TRY(ctx)
+    if (!texels || !out_index || width == 0 || height == 0 || format < 0 || format > 3) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_texture2d_create: invalid argument");
+    if (c_->textures.size() >= HL_MAX_SCENE_MATERIAL_TEXTURE_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_texture2d_create: MAX_SCENE_MATERIAL_TEXTURE_COUNT exceeded");
+    DevBuf* b = new DevBuf();
+    c_->textures.push_back(b);
+    b->upload(texels, (size_t)width * height * (format == HL_TEX_RGBA32F ? 16 : 4), c_->stream);
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    TexView v;
+    v.texels = b->p, v.w = width, v.h = height, v.format = format, v.pad = 0;
+    c_->tex_views.push_back(v);
+    *out_index      = (int32_t)c_->tex_views.size() - 1;
+    c_->scene_ready = false;
+    HL_CATCH
+}
+
+hl_status hl_textures_clear(hl_context ctx)
+{
+    HL_TRY(ctx)
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    for (auto t : c_->textures) delete t;
+    c_->textures.clear(), c_->tex_views.clear();
+    c_->scene_ready = false;
+    HL_CATCH
+}
+
+hl_status hl_envmap_set(hl_context ctx, uint32_t size, const float* faces)
+{
+    HL_TRY(ctx)
+    if (size && !faces) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_envmap_set: null faces");
+    c_->env_size = size;
+    if (size)
+    {
+        c_->env_faces.upload(faces, (size_t)6 * size * size * 16, c_->stream);
+        HL_CUDA(cudaStreamSynchronize(c_->stream));
+    }
+    c_->view.env.faces = c_->env_faces.as<f4>(), c_->view.env.size = size;
+    HL_CATCH
+}
+
+hl_status hl_sky_update(hl_context ctx, const float coeffs[40], const float sun_direction[3])
+{
+    HL_TRY(ctx)
+    if (!coeffs || !sun_direction) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_sky_update: null argument");
+    sky_bake(c_, coeffs, sun_direction, 512); // SKY_CUBEMAP_SIZE, hosek_wilkie_sky_model.cpp:17
+    c_->view.env.faces = c_->env_faces.as<f4>(), c_->view.env.size = c_->env_size;
+    HL_CATCH
+}
+
+hl_status hl_envmap_read(hl_context ctx, float* faces, uint32_t* out_size)
+{
+    HL_TRY(ctx)
+    if (out_size) *out_size = c_->env_size;
+    if (faces && c_->env_size)
+    {
+        HL_CUDA(cudaMemcpyAsync(faces, c_->env_faces.p, (size_t)6 * c_->env_size * c_->env_size * 16, cudaMemcpyDeviceToHost, c_->stream));
+        HL_CUDA(cudaStreamSynchronize(c_->stream));
+    }
+    HL_CATCH
+}
+
+// world -> object 3x4 (row-major) from the column-major model matrix: double precision, rounded once
+static void affine_inverse(const float* m, float* out)
+{
+    double a00 = m[0], a01 = m[4], a02 = m[8], t0 = m[12];
+    double a10 = m[1], a11 = m[5], a12 = m[9], t1 = m[13];
+    double a20 = m[2], a21 = m[6], a22 = m[10], t2 = m[14];
+    double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    double det = a00 * c00 + a01 * c01 + a02 * c02;
+    double id  = 1.0 / det;
+    double i00 = c00 * id, i01 = (a02 * a21 - a01 * a22) * id, i02 = (a01 * a12 - a02 * a11) * id;
+    double i10 = c01 * id, i11 = (a00 * a22 - a02 * a20) * id, i12 = (a02 * a10 - a00 * a12) * id;
+    double i20 = c02 * id, i21 = (a01 * a20 - a00 * a21) * id, i22 = (a00 * a11 - a01 * a10) * id;
+    out[0] = (float)i00, out[1] = (float)i01, out[2] = (float)i02, out[3] = (float)(-(i00 * t0 + i01 * t1 + i02 * t2));
+    out[4] = (float)i10, out[5] = (float)i11, out[6] = (float)i12, out[7] = (float)(-(i10 * t0 + i11 * t1 + i12 * t2));
+    out[8] = (float)i20, out[9] = (float)i21, out[10] = (float)i22, out[11] = (float)(-(i20 * t0 + i21 * t1 + i22 * t2));
+}
+
+hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint32_t n_materials, const hl_instance* instances, const hl_mesh* meshes,
+                              const uint32_t* const* submesh_info, uint32_t n_instances, const hl_light* lights, uint32_t n_lights)
+{
+    HL_TRY(ctx)
+    if ((!materials && n_materials) || (n_instances && (!instances || !meshes || !submesh_info)) || (!lights && n_lights)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: null argument");
+    if (n_instances > HL_MAX_SCENE_MESH_INSTANCE_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_scene_set_tables: MAX_SCENE_MESH_INSTANCE_COUNT (1024) exceeded");
+    if (n_materials > HL_MAX_SCENE_MATERIAL_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_scene_set_tables: MAX_SCENE_MATERIAL_COUNT (4096) exceeded");
+    if (n_lights > HL_MAX_SCENE_LIGHT_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_scene_set_tables: MAX_SCENE_LIGHT_COUNT (100000) exceeded");
+    cudaStream_t st = c_->stream;
+    HL_CUDA(cudaStreamSynchronize(st)); // Scene::create_gpu_resources calls wait_idle (scene.cpp:929)
+    // mesh table in context order; instance.mesh_index is rewritten to that order
+    std::vector<MeshView> views(c_->meshes.size());
+    for (size_t k = 0; k < c_->meshes.size(); k++)
+    {
+        hl_mesh_t* m = c_->meshes[k];
+        MeshView&  v = views[k];
+        v.vertices = m->vertices.as<hl_vertex>(), v.indices = m->indices.as<uint32_t>();
+        v.nodes = m->bvh.nodes.as<WideNode>(), v.tris = m->bvh.leaves.as<LeafTri>();
+        v.n_tris = m->bvh.n_leaves, v.n_submeshes = (uint32_t)m->subs.size();
+    }
+    std::vector<hl_instance> inst(instances, instances + n_instances);
+    std::vector<float>       inv((size_t)n_instances * 12);
+    std::vector<uint32_t>    info, offset(n_instances);
+    std::vector<Box>         boxes(n_instances);
+    bool                     identity = n_instances == 1;
+    static const float       I16[16]  = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    for (uint32_t i = 0; i < n_instances; i++)
+    {
+        auto it = std::find(c_->meshes.begin(), c_->meshes.end(), meshes[i]);
+        if (it == c_->meshes.end()) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: instance refers to an unknown mesh");
+        hl_mesh_t* m       = *it;
+        inst[i].mesh_index = (uint32_t)(it - c_->meshes.begin());
+        offset[i]          = (uint32_t)(info.size() / 2);
+        for (size_t g = 0; g < m->subs.size(); g++)
+        {
+            if (submesh_info[i][2 * g + 1] >= n_materials) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: material index out of range");
+            info.push_back(submesh_info[i][2 * g]), info.push_back(submesh_info[i][2 * g + 1]);
+        }
+        affine_inverse(inst[i].model_matrix, &inv[(size_t)i * 12]);
+        if (memcmp(inst[i].model_matrix, I16, 64) != 0) identity = false;
+        // world box of the transformed object-space root box (8 corners in double, padded)
+        double       lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+        const float* M     = inst[i].model_matrix;
+        const Box&   rb    = m->bvh.root;
+        for (int cidx = 0; cidx < 8; cidx++)
+        {
+            const double x = (cidx & 1) ? rb.hi[0] : rb.lo[0], y = (cidx & 2) ? rb.hi[1] : rb.lo[1], z = (cidx & 4) ? rb.hi[2] : rb.lo[2];
+            for (int a = 0; a < 3; a++)
+            {
+                const double w = (double)M[a] * x + (double)M[4 + a] * y + (double)M[8 + a] * z + (double)M[12 + a];
+                lo[a] = std::min(lo[a], w), hi[a] = std::max(hi[a], w);
+            }
+        }
+        for (int a = 0; a < 3; a++)
+        {
+            const double pad = 1e-5 * (std::fabs(lo[a]) + std::fabs(hi[a]) + (hi[a] - lo[a]));
+            boxes[i].lo[a] = (float)(lo[a] - pad), boxes[i].hi[a] = (float)(hi[a] + pad);
+        }
+    }
+    c_->materials.upload(materials, sizeof(hl_material) * (size_t)n_materials, st);
+    c_->instances.upload(inst.data(), sizeof(hl_instance) * (size_t)n_instances, st);
+    c_->inst_inv.upload(inv.data(), 4 * inv.size(), st);
+    c_->submesh_info.upload(info.data(), 4 * info.size(), st);
+    c_->submesh_offset.upload(offset.data(), 4 * offset.size(), st);
+    c_->lights.upload(lights, sizeof(hl_light) * (size_t)n_lights, st);
+    c_->mesh_views.upload(views.data(), sizeof(MeshView) * views.size(), st);
+    c_->tex_views_dev.upload(c_->tex_views.data(), sizeof(TexView) * c_->tex_views.size(), st);
+    HL_CUDA(cudaStreamSynchronize(st));
+    build_tlas(c_, boxes);
+    SceneView& v = c_->view;
+    v.materials = c_->materials.as<hl_material>(), v.instances = c_->instances.as<hl_instance>(), v.inst_inv = c_->inst_inv.as<float>();
+    v.submesh_info = c_->submesh_info.as<uint32_t>(), v.submesh_offset = c_->submesh_offset.as<uint32_t>(), v.lights = c_->lights.as<hl_light>();
+    v.meshes = c_->mesh_views.as<MeshView>(), v.textures = c_->tex_views_dev.as<TexView>(), v.lut8 = c_->lut8.as<float>();
+    v.env.faces = c_->env_faces.as<f4>(), v.env.size = c_->env_size;
+    v.tlas_nodes = c_->tlas.nodes.as<WideNode>(), v.tlas_leaf = c_->tlas.leaves.as<uint32_t>();
+    v.n_instances = n_instances, v.n_lights = n_lights, v.single_identity = identity ? 1u : 0u;
+    c_->scene_ready = true;
+    HL_CATCH
+}
+
+static bool clip_launch(hl_context_t* c, const hl_push_constants* pc, uint32_t& lw, uint32_t& lh)
+{
+    const uint32_t W = pc->launch_id_size[2], H = pc->launch_id_size[3];
+    if (W != c->W || H != c->H) return false;
+    const uint32_t tx = pc->launch_id_size[0], ty = pc->launch_id_size[1];
+    if (lw == 0) lw = W;
+    if (lh == 0) lh = H;
+    lw = tx >= W ? 0 : std::min(lw, W - tx); // pixels with launch_id >= (W,H) do nothing (rgen:185)
+    lh = ty >= H ? 0 : std::min(lh, H - ty);
+    return true;
+}
+
+hl_status hl_render_frame(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h)
+{
+    HL_TRY(ctx)
+    if (!pc) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame: null push constants");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_frame: hl_scene_set_tables has not been called since the last resource change");
+    if (!clip_launch(c_, pc, launch_w, launch_h)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame: launch_id_size.zw differs from the context extent");
+    if (pc->max_ray_bounces > HL_MAX_BOUNCES) HL_FAIL(HL_ERR_LIMIT, "hl_render_frame: max_ray_bounces > 64");
+    wavefront_render_frame(c_, *pc, launch_w, launch_h);
+    HL_CUDA(cudaGetLastError());
+    HL_CATCH
+}
+
+hl_status hl_accum_clear(hl_context ctx)
+{
+    HL_TRY(ctx)
+    film_clear(c_);
+    HL_CATCH
+}
+
+hl_status hl_set_accum_mode(hl_context ctx, int mode)
+{
+    HL_TRY(ctx)
+    if (mode != HL_ACCUM_RUNNING_MEAN && mode != HL_ACCUM_SUM) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_set_accum_mode: unknown mode");
+    c_->accum_mode = mode;
+    HL_CATCH
+}
+
+hl_status hl_trace_primary_ids(hl_context ctx, const hl_push_constants* pc, uint32_t* instance, uint32_t* geometry, uint32_t* primitive, float* t, float* u, float* v)
+{
+    HL_TRY(ctx)
+    if (!pc) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_trace_primary_ids: null push constants");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_trace_primary_ids: scene tables not set");
+    if (pc->launch_id_size[2] != c_->W || pc->launch_id_size[3] != c_->H) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_trace_primary_ids: extent mismatch");
+    wavefront_primary_hits(c_, *pc);
+    const size_t       n = (size_t)c_->W * c_->H;
+    std::vector<float> ha(n * 4);
+    std::vector<uint32_t> hb(n * 2);
+    HL_CUDA(cudaMemcpyAsync(ha.data(), c_->hit_a.p, n * 16, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaMemcpyAsync(hb.data(), c_->hit_b.p, n * 8, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    for (size_t i = 0; i < n; i++)
+    {
+        const bool hit = hb[2 * i] != HL_MISS;
+        if (instance) instance[i] = hb[2 * i];
+        if (geometry) geometry[i] = hb[2 * i + 1];
+        if (primitive) memcpy(&primitive[i], &ha[4 * i + 3], 4);
+        if (t) t[i] = hit ? ha[4 * i] : INFINITY;
+        if (u) u[i] = hit ? ha[4 * i + 1] : 0.0f;
+        if (v) v[i] = hit ? ha[4 * i + 2] : 0.0f;
+    }
+    HL_CATCH
+}
+
+hl_status hl_trace_rays(hl_context ctx, const float* rays, uint32_t n_rays, uint32_t flags, void* hits)
+{
+    HL_TRY(ctx)
+    if ((!rays || !hits) && n_rays) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_trace_rays: null argument");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_trace_rays: scene tables not set");
+    DevBuf dr, dh;
+    dr.upload(rays, (size_t)n_rays * 32, c_->stream);
+    dh.alloc((size_t)n_rays * 24);
+    wavefront_trace_rays(c_, dr.as<float>(), n_rays, flags, dh.p);
+    if (n_rays) HL_CUDA(cudaMemcpyAsync(hits, dh.p, (size_t)n_rays * 24, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    HL_CATCH
+}
+
+hl_status hl_tonemap(hl_context ctx, float exposure, int op, float sample_scale, uint8_t* rgba8_host)
+{
+    HL_TRY(ctx)
+    film_tonemap(c_, exposure, op, sample_scale);
+    if (rgba8_host)
+    {
+        HL_CUDA(cudaMemcpyAsync(rgba8_host, c_->rgba8.p, (size_t)c_->W * c_->H * 4, cudaMemcpyDeviceToHost, c_->stream));
+        HL_CUDA(cudaStreamSynchronize(c_->stream));
+    }
+    HL_CATCH
+}
+
+hl_status hl_read_accum(hl_context ctx, float* out)
+{
+    HL_TRY(ctx)
+    if (!out) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_read_accum: null pointer");
+    HL_CUDA(cudaMemcpyAsync(out, c_->accum.p, (size_t)c_->W * c_->H * 16, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    HL_CATCH
+}
+
+hl_status hl_write_accum(hl_context ctx, const float* in)
+{
+    HL_TRY(ctx)
+    if (!in) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_write_accum: null pointer");
+    HL_CUDA(cudaMemcpyAsync(c_->accum.p, in, (size_t)c_->W * c_->H * 16, cudaMemcpyHostToDevice, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    HL_CATCH
+}
+
+hl_status hl_accum_device_ptr(hl_context ctx, void** out_ptr)
+{
+    HL_TRY(ctx)
+    if (!out_ptr) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_accum_device_ptr: null pointer");
+    *out_ptr = c_->accum.p;
+    HL_CATCH
+}
+
+hl_status hl_synchronize(hl_context ctx)
+{
+    HL_TRY(ctx)
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    HL_CUDA(cudaGetLastError());
+    HL_CATCH
+}
+
+hl_status hl_get_counters(hl_context ctx, hl_counters* out)
+{
+    HL_TRY(ctx)
+    if (!out) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_get_counters: null pointer");
+    uint64_t totals[2];
+    HL_CUDA(cudaMemcpyAsync(totals, (char*)c_->counters.p + ((257 * 4 + 7) / 8 * 8), 16, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    *out                = c_->last;
+    out->extension_rays = totals[0], out->shadow_rays = totals[1], out->frames = c_->frames;
+    HL_CATCH
+}
+
+hl_status hl_reset_counters(hl_context ctx)
+{
+    HL_TRY(ctx)
+    HL_CUDA(cudaMemsetAsync((char*)c_->counters.p + ((257 * 4 + 7) / 8 * 8), 0, 16, c_->stream));
+    c_->frames = 0;
+    HL_CATCH
+}
+
+hl_status hl_set_profiling(hl_context ctx, int enabled)
+{
+    HL_TRY(ctx)
+    c_->profiling = enabled != 0;
+    HL_CATCH
+}
+
+hl_status hl_kernel_launches(hl_context ctx, uint64_t* out)
+{
+    HL_TRY(ctx)
+    if (!out) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_kernel_launches: null pointer");
+    *out = c_->launches;
+    HL_CATCH
+}
+
+} // extern "C"

@@ -1,0 +1,238 @@
+// hl_builder.cu — GPU BVH builder (replaces vkCmdBuildAccelerationStructuresKHR: per-mesh BLAS build
+// src/engine/gfx/vk.cpp:3207-3226, TLAS build src/engine/gfx/renderer.cpp:147-168 in the reference).
+// Kernels are thin per-thread loops around the element functions in hl_build.h.
+//
+// Pass list and algorithmic bytes per triangle (N triangles, fp32 boxes of 24 B, 64-bit Morton keys):
+//   tri_boxes      12 idx + 36 pos read, 24 written                      72
+//   box_reduce     24 read                                               24
+//   morton         24 read, 8 + 4 written                                36
+//   radix sort     8 passes x (12 read + 12 written)  (CUB, 63 key bits) 192
+//   radix_tree     ~2 x 8 key reads (cached), 24 written                 40
+//   fit            24 read (sorted box) + 2 x 24 written + 48 read       120
+//   collapse       ~48 read (boxes) + 0.2 x 80 node + 48 leaf + 48 src   160
+//   total                                                              ~ 640 B / triangle
+#include "hl_internal.h"
+#include <cub/cub.cuh>
+
+namespace hl
+{
+__global__ void k_tri_boxes(const hl_vertex* v, const uint32_t* idx, const hl_submesh* subs, const uint32_t* tri_start, uint32_t n_geom, uint32_t n, Box* out)
+{
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) out[f] = triangle_box(v, idx, subs, tri_start, n_geom, f);
+}
+
+__global__ void k_box_reduce(const Box* in, uint32_t n, Box* out)
+{
+    __shared__ Box sm[256];
+    Box            acc;
+    for (int k = 0; k < 3; k++) acc.lo[k] = 3.0e38f, acc.hi[k] = -3.0e38f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc = box_union(acc, in[i]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1)
+    {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] = box_union(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+
+__global__ void k_morton(const Box* boxes, const Box* scene, uint32_t n, uint64_t* keys, uint32_t* vals)
+{
+    const Box sb = *scene;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        keys[i] = morton_key(boxes[i], sb);
+        vals[i] = i;
+    }
+}
+
+__global__ void k_radix_tree(const uint64_t* keys, BinaryTree t)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < t.n; i += gridDim.x * blockDim.x) radix_tree_node(keys, t, (int)i);
+}
+
+struct DeviceFence
+{
+    __device__ void operator()() const { __threadfence(); }
+};
+__global__ void k_fit(BinaryTree t, const Box* prim_boxes, const uint32_t* sorted)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < t.n; j += gridDim.x * blockDim.x)
+    {
+        t.box[(t.n - 1) + j] = prim_boxes[sorted[j]];
+        fit_from_leaf(t, j, DeviceFence());
+    }
+}
+
+template <class LeafWriter>
+__global__ void k_collapse(BinaryTree t, const CollapseTask* tasks, uint32_t n_tasks, WideOut out, CollapseTask* next, uint32_t* next_count, LeafWriter writer)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tasks) collapse_one(t, tasks[i], out, next, next_count, writer);
+}
+
+static inline int grid_for(uint32_t n, int block, int cap) { return (int)std::min<uint64_t>(((uint64_t)n + block - 1) / block, (uint64_t)cap); }
+
+// Generic build over `n` primitive boxes already on the device.  make_writer(sorted_prim, leaf_buffer) returns the
+// leaf-record writer; leaf_bytes = size of one leaf record.
+template <class MakeWriter>
+static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n, size_t leaf_bytes, WideBVHDev& out, MakeWriter make_writer)
+{
+    cudaStream_t st = ctx->stream;
+    out.n_nodes = out.n_leaves = out.n_binary = 0;
+    out.ms_build = 0.0f;
+    for (int k = 0; k < 3; k++) out.root.lo[k] = out.root.hi[k] = 0.0f;
+    if (n == 0)
+    {
+        out.nodes.alloc(sizeof(WideNode));
+        out.leaves.alloc(leaf_bytes);
+        return;
+    }
+    cudaEvent_t e0, e1;
+    HL_CUDA(cudaEventCreate(&e0));
+    HL_CUDA(cudaEventCreate(&e1));
+    HL_CUDA(cudaEventRecord(e0, st));
+
+    const int cap = ctx->sm_count * 8;
+    // scene box
+    DevBuf partial, scene;
+    const int rb = grid_for(n, 256, 1024);
+    partial.alloc(sizeof(Box) * rb);
+    scene.alloc(sizeof(Box));
+    k_box_reduce<<<rb, 256, 0, st>>>(d_boxes, n, partial.as<Box>());
+    k_box_reduce<<<1, 256, 0, st>>>(partial.as<Box>(), (uint32_t)rb, scene.as<Box>());
+    ctx->launches += 2;
+    // Morton keys + sort
+    DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp;
+    keys_a.alloc(8ull * n), keys_b.alloc(8ull * n), vals_a.alloc(4ull * n), vals_b.alloc(4ull * n);
+    k_morton<<<grid_for(n, 256, cap), 256, 0, st>>>(d_boxes, scene.as<Box>(), n, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+    ctx->launches++;
+    cub::DoubleBuffer<uint64_t> dk(keys_a.as<uint64_t>(), keys_b.as<uint64_t>());
+    cub::DoubleBuffer<uint32_t> dv(vals_a.as<uint32_t>(), vals_b.as<uint32_t>());
+    size_t                      tmp_bytes = 0;
+    HL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, 63, st));
+    cub_tmp.alloc(tmp_bytes);
+    HL_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, dk, dv, (int)n, 0, 63, st));
+    ctx->launches += 8;
+    const uint64_t* keys   = dk.Current();
+    const uint32_t* sorted = dv.Current();
+    // binary radix tree
+    DevBuf     tree_u32, tree_box;
+    const size_t ni = n > 1 ? n - 1 : 1;
+    tree_u32.alloc(4ull * (ni * 5 + 2ull * n));
+    tree_box.alloc(sizeof(Box) * (2ull * n));
+    BinaryTree t;
+    t.n      = n;
+    t.left   = tree_u32.as<uint32_t>();
+    t.right  = t.left + ni;
+    t.first  = t.right + ni;
+    t.last   = t.first + ni;
+    t.visits = t.last + ni;
+    t.parent = t.visits + ni;
+    t.box    = tree_box.as<Box>();
+    HL_CUDA(cudaMemsetAsync(t.visits, 0, 4ull * ni, st));
+    HL_CUDA(cudaMemsetAsync(t.parent, 0xFF, 4ull * 2 * n, st));
+    if (n > 1)
+    {
+        k_radix_tree<<<grid_for(n - 1, 256, cap), 256, 0, st>>>(keys, t);
+        ctx->launches++;
+    }
+    k_fit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted);
+    ctx->launches++;
+    // collapse, level by level
+    DevBuf big_nodes, tasks_a, tasks_b, ctr;
+    big_nodes.alloc(sizeof(WideNode) * (size_t)n);
+    out.leaves.alloc(leaf_bytes * (size_t)n);
+    tasks_a.alloc(sizeof(CollapseTask) * (size_t)n);
+    tasks_b.alloc(sizeof(CollapseTask) * (size_t)n);
+    ctr.alloc(16);
+    uint32_t h_ctr[4] = { 1u, 0u, 0u, 0u }; // node counter, leaf counter, next count
+    HL_CUDA(cudaMemcpyAsync(ctr.p, h_ctr, 16, cudaMemcpyHostToDevice, st));
+    CollapseTask root_task;
+    root_task.wide = 0, root_task.bnode = 0;
+    HL_CUDA(cudaMemcpyAsync(tasks_a.p, &root_task, sizeof(root_task), cudaMemcpyHostToDevice, st));
+    WideOut wo;
+    wo.nodes = big_nodes.as<WideNode>(), wo.node_counter = ctr.as<uint32_t>(), wo.leaf_counter = ctr.as<uint32_t>() + 1;
+    auto          writer  = make_writer(sorted, out.leaves.p);
+    uint32_t      n_tasks = 1;
+    CollapseTask *cur = tasks_a.as<CollapseTask>(), *nxt = tasks_b.as<CollapseTask>();
+    int           levels = 0;
+    while (n_tasks)
+    {
+        HL_CUDA(cudaMemsetAsync(ctr.as<uint32_t>() + 2, 0, 4, st));
+        k_collapse<<<(n_tasks + 127) / 128, 128, 0, st>>>(t, cur, n_tasks, wo, nxt, ctr.as<uint32_t>() + 2, writer);
+        ctx->launches++;
+        HL_CUDA(cudaMemcpyAsync(&n_tasks, ctr.as<uint32_t>() + 2, 4, cudaMemcpyDeviceToHost, st));
+        HL_CUDA(cudaStreamSynchronize(st));
+        std::swap(cur, nxt);
+        if (++levels > 256) throw CudaError(HL_ERR_CUDA, "BVH collapse did not terminate");
+    }
+    HL_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, 8, cudaMemcpyDeviceToHost, st));
+    HL_CUDA(cudaMemcpyAsync(&out.root, t.box, sizeof(Box), cudaMemcpyDeviceToHost, st));
+    HL_CUDA(cudaStreamSynchronize(st));
+    out.n_nodes = h_ctr[0], out.n_leaves = h_ctr[1], out.n_binary = 2 * n - 1;
+    out.nodes.alloc(sizeof(WideNode) * (size_t)out.n_nodes);
+    HL_CUDA(cudaMemcpyAsync(out.nodes.p, big_nodes.p, sizeof(WideNode) * (size_t)out.n_nodes, cudaMemcpyDeviceToDevice, st));
+    HL_CUDA(cudaEventRecord(e1, st));
+    HL_CUDA(cudaEventSynchronize(e1));
+    HL_CUDA(cudaEventElapsedTime(&out.ms_build, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+}
+
+void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
+{
+    cudaStream_t          st = ctx->stream;
+    const uint32_t        ng = (uint32_t)mesh->subs.size();
+    std::vector<uint32_t> tri_start(ng + 1, 0);
+    for (uint32_t g = 0; g < ng; g++) tri_start[g + 1] = tri_start[g] + mesh->subs[g].index_count / 3;
+    const uint32_t n = tri_start[ng];
+    mesh->tri_start.upload(tri_start.data(), 4ull * (ng + 1), st);
+    mesh->submeshes.upload(mesh->subs.data(), sizeof(hl_submesh) * (size_t)ng, st);
+    DevBuf boxes;
+    boxes.alloc(sizeof(Box) * (size_t)std::max(n, 1u));
+    cudaEvent_t e0, e1;
+    HL_CUDA(cudaEventCreate(&e0));
+    HL_CUDA(cudaEventCreate(&e1));
+    HL_CUDA(cudaEventRecord(e0, st));
+    if (n)
+    {
+        k_tri_boxes<<<grid_for(n, 256, ctx->sm_count * 8), 256, 0, st>>>(mesh->vertices.as<hl_vertex>(), mesh->indices.as<uint32_t>(), mesh->submeshes.as<hl_submesh>(), mesh->tri_start.as<uint32_t>(), ng, n, boxes.as<Box>());
+        ctx->launches++;
+    }
+    HL_CUDA(cudaEventRecord(e1, st));
+    const hl_vertex*  dv  = mesh->vertices.as<hl_vertex>();
+    const uint32_t*   di  = mesh->indices.as<uint32_t>();
+    const hl_submesh* dsm = mesh->submeshes.as<hl_submesh>();
+    const uint32_t*   dts = mesh->tri_start.as<uint32_t>();
+    build_wide_device(ctx, boxes.as<Box>(), n, sizeof(LeafTri), mesh->bvh, [=](const uint32_t* sorted, void* leaves) {
+        TriLeafWriter w;
+        w.vertices = dv, w.indices = di, w.submeshes = dsm, w.tri_start = dts, w.n_geom = ng, w.sorted_prim = sorted, w.tris = (LeafTri*)leaves;
+        return w;
+    });
+    float ms0 = 0.0f;
+    HL_CUDA(cudaEventSynchronize(e1));
+    HL_CUDA(cudaEventElapsedTime(&ms0, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    mesh->stats.triangles       = n;
+    mesh->stats.wide_nodes      = mesh->bvh.n_nodes;
+    mesh->stats.binary_nodes    = mesh->bvh.n_binary;
+    mesh->stats.ms_build        = mesh->bvh.ms_build + ms0;
+    mesh->stats.sah_cost        = 0.0f;
+    mesh->stats.bytes_nodes     = sizeof(WideNode) * (uint64_t)mesh->bvh.n_nodes;
+    mesh->stats.bytes_triangles = sizeof(LeafTri) * (uint64_t)mesh->bvh.n_leaves;
+}
+
+void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes)
+{
+    DevBuf boxes;
+    boxes.upload(instance_boxes.data(), sizeof(Box) * instance_boxes.size(), ctx->stream);
+    build_wide_device(ctx, boxes.as<Box>(), (uint32_t)instance_boxes.size(), sizeof(uint32_t), ctx->tlas, [](const uint32_t* sorted, void* leaves) {
+        InstLeafWriter w;
+        w.sorted_prim = sorted, w.leaf = (uint32_t*)leaves;
+        return w;
+    });
+}
+} // namespace hl

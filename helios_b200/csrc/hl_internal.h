@@ -1,0 +1,127 @@
+// hl_internal.h — host-side internals of libhelios_b200.so (context, device buffers, launch prototypes).
+#pragma once
+#include "hl_build.h"
+#include "hl_scene.h"
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace hl
+{
+struct CudaError : std::runtime_error
+{
+    int status;
+    CudaError(int st, const std::string& m) : std::runtime_error(m), status(st) {}
+};
+#define HL_CUDA(call)                                                                                                              \
+    do                                                                                                                             \
+    {                                                                                                                              \
+        cudaError_t e_ = (call);                                                                                                   \
+        if (e_ != cudaSuccess)                                                                                                     \
+            throw hl::CudaError(e_ == cudaErrorMemoryAllocation ? HL_ERR_OUT_OF_MEMORY : HL_ERR_CUDA,                              \
+                                std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+struct DevBuf
+{
+    void*  p     = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&)            = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr, bytes = 0;
+    }
+    void alloc(size_t n)
+    {
+        if (n <= bytes && p) return;
+        release();
+        if (n == 0) n = 16;
+        HL_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void upload(const void* src, size_t n, cudaStream_t s)
+    {
+        alloc(n);
+        if (n) HL_CUDA(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, s));
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+struct WideBVHDev
+{
+    DevBuf   nodes, leaves;
+    uint32_t n_nodes = 0, n_leaves = 0, n_binary = 0;
+    Box      root;
+    float    ms_build = 0.0f;
+};
+
+#define HL_MAX_BOUNCES 64
+
+} // namespace hl
+
+struct hl_mesh_t
+{
+    hl::DevBuf              vertices, indices, submeshes, tri_start;
+    std::vector<hl_submesh> subs;
+    uint32_t                n_vertices = 0, n_indices = 0;
+    hl::WideBVHDev          bvh;
+    hl_build_stats          stats {};
+};
+
+struct hl_context_t
+{
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t     W = 0, H = 0;
+    int          sm_count = 148;
+    std::string  err;
+    uint64_t     launches = 0;
+    bool         profiling = false;
+    int          accum_mode = HL_ACCUM_RUNNING_MEAN;
+
+    // resources
+    std::vector<hl_mesh_t*>  meshes;
+    std::vector<hl::DevBuf*> textures;
+    std::vector<hl::TexView> tex_views;
+    hl::DevBuf               env_faces;
+    uint32_t                 env_size = 0;
+    // scene tables
+    hl::DevBuf      materials, instances, inst_inv, submesh_info, submesh_offset, lights, mesh_views, tex_views_dev, lut8;
+    hl::WideBVHDev  tlas;
+    hl::SceneView   view {};
+    bool            scene_ready = false;
+    // film + wavefront state
+    hl::DevBuf accum, rgba8;
+    hl::DevBuf state_a, state_b;         // per path: (T.xyz, rng.x), (L.xyz, rng.y)
+    hl::DevBuf ext_o[2], ext_d[2];       // extension queue: (o.xyz, path), (d.xyz, -)
+    hl::DevBuf hit_a, hit_b;             // (t,u,v,prim), (instance, geometry)
+    hl::DevBuf sh_o, sh_d, sh_c;         // shadow queue: (o.xyz, path), (d.xyz, tmax), (contribution.xyz, -)
+    hl::DevBuf counters;                 // uint32: ext_count[65], sh_count[64], fetch_ext[64], fetch_sh[64]; then uint64 totals[2]
+    size_t     queue_capacity = 0;
+    // profiling
+    cudaEvent_t ev[2 + 4 * HL_MAX_BOUNCES + 4] {};
+    bool        ev_ready = false;
+    hl_counters last {};
+    uint64_t    frames = 0;
+};
+
+namespace hl
+{
+// hl_builder.cu
+void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh);
+void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes);
+// hl_wavefront.cu
+void wavefront_alloc(hl_context_t* ctx);
+void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh);
+void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc);
+void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits);
+void film_clear(hl_context_t* ctx);
+void film_tonemap(hl_context_t* ctx, float exposure, int op, float scale);
+void sky_bake(hl_context_t* ctx, const float* coeffs40, const float* sun3, uint32_t size);
+} // namespace hl

@@ -1,0 +1,416 @@
+// hl_wavefront.cu — the wavefront path integrator that replaces vkCmdTraceRaysKHR on the reference's
+// recursive RT pipeline (PathIntegrator::launch_rays, src/engine/gfx/path_integrator.cpp:125-200).
+//
+// One frame = generate, then per bounce { extend, shade, connect }, then resolve:
+//   generate  path_trace_rgen.glsl:180-215   RNG seed, thin-lens primary ray, payload init
+//   extend    traceRayEXT (rgen:205, rchit:523) + path_trace_rahit.glsl   closest hit per extension ray
+//   shade     path_trace_rchit.glsl:542-580 / path_trace_rmiss.glsl:60-65  NEE sample, BRDF sample, RR,
+//             queue compaction with warp ballot + one atomic per warp
+//   connect   traceRayEXT (rchit:438) + path_trace_shadow.{rchit,rmiss}     visibility, L += direct term
+//   resolve   rgen:217-248 (+ tone_map.frag when fused)                      clamp, progressive blend
+// No host synchronisation inside a frame: queue sizes live in device memory, extend/connect are persistent
+// kernels that pull 32 rays per warp from an atomic cursor, shade is a grid-stride loop.
+#include "hl_bvh.h"
+#include "hl_camera.h"
+#include "hl_film.h"
+#include "hl_internal.h"
+#include "hl_shade.h"
+
+namespace hl
+{
+#define HL_TRACE_BLOCK 128
+#define HL_SHADE_BLOCK 128
+
+// device counter block layout (uint32 indices)
+#define CTR_EXT_COUNT 0                    /* [HL_MAX_BOUNCES + 1] */
+#define CTR_SH_COUNT (CTR_EXT_COUNT + 65)  /* [HL_MAX_BOUNCES] */
+#define CTR_EXT_FETCH (CTR_SH_COUNT + 64)  /* [HL_MAX_BOUNCES] */
+#define CTR_SH_FETCH (CTR_EXT_FETCH + 64)  /* [HL_MAX_BOUNCES] */
+#define CTR_U32_TOTAL (CTR_SH_FETCH + 64)  /* = 257 */
+#define CTR_BYTES (CTR_U32_TOTAL * 4 + 12 + 16) /* + padding to 8, then uint64 totals[2] */
+#define CTR_TOTALS_OFFSET ((CTR_U32_TOTAL * 4 + 7) / 8 * 8)
+
+struct FrameParams
+{
+    hl_push_constants pc;
+    uint32_t          lw, lh; // launch rectangle (already clipped to the image)
+};
+
+__device__ __forceinline__ float4 ld4(const float4* p) { return *p; }
+
+// ---- generate --------------------------------------------------------------------------------------
+__global__ void k_generate(FrameParams fp, float4* state_a, float4* state_b, float4* ext_o, float4* ext_d, uint32_t* counters)
+{
+    const uint32_t n = fp.lw * fp.lh;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) counters[CTR_EXT_COUNT] = n;
+    if (i >= n) return;
+    const uint32_t px = fp.pc.launch_id_size[0] + i % fp.lw, py = fp.pc.launch_id_size[1] + i / fp.lw;
+    Rng            rng = rng_seed(px, py, fp.pc.num_frames);
+    f3             o, d;
+    primary_ray(fp.pc, px, py, rng, o, d);
+    state_a[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng.x));
+    state_b[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(rng.y));
+    ext_o[i]   = make_float4(o.x, o.y, o.z, __uint_as_float(i));
+    ext_d[i]   = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+// ---- extend ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HL_TRACE_BLOCK) k_extend(SceneView s, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
+                                                           uint32_t* fetch, float tmin, float tmax, uint32_t flags, float4* __restrict__ hit_a, uint2* __restrict__ hit_b)
+{
+    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
+    TravStack     st;
+    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    const uint32_t count = *count_ptr;
+    const uint32_t lane  = threadIdx.x & 31u;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) break;
+        const uint32_t i = base + lane;
+        if (i < count)
+        {
+            const float4 o = ld4(ray_o + i), d = ld4(ray_d + i);
+            Hit          h;
+            trace_ray(s, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), tmax, flags, h, st);
+            hit_a[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.primitive));
+            hit_b[i] = make_uint2(h.instance, h.geometry);
+        }
+    }
+}
+
+// ---- shade -----------------------------------------------------------------------------------------
+// warp-aggregated queue append: one atomicAdd per warp, slots handed out by ballot prefix
+__device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* counter, uint32_t lane)
+{
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred);
+    uint32_t       base = 0;
+    if (lane == 0 && mask) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(HL_SHADE_BLOCK) k_shade(SceneView s, ShadeParams prm, uint32_t depth, const uint32_t* __restrict__ count_ptr, const float4* __restrict__ ray_o,
+                                                          const float4* __restrict__ ray_d, const float4* __restrict__ hit_a, const uint2* __restrict__ hit_b, float4* state_a,
+                                                          float4* state_b, float4* next_o, float4* next_d, uint32_t* next_count, float4* sh_o, float4* sh_d, float4* sh_c,
+                                                          uint32_t* sh_count)
+{
+    const uint32_t count  = *count_ptr;
+    const uint32_t lane   = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < count; base += stride)
+    {
+        const uint32_t i      = base + lane;
+        const bool     active = i < count;
+        bool           want_shadow = false, want_next = false;
+        ShadeResult    r;
+        uint32_t       path = 0;
+        if (active)
+        {
+            const float4 ha = hit_a[i];
+            const uint2  hb = hit_b[i];
+            const float4 d4 = ray_d[i];
+            path            = __float_as_uint(ray_o[i].w);
+            float4 sa = state_a[path], sb = state_b[path];
+            const f3 T = mk3(sa.x, sa.y, sa.z);
+            const f3 dir = mk3(d4.x, d4.y, d4.z);
+            if (hb.x == HL_MISS)
+            {
+                const f3 e = shade_miss(s, depth, dir, T);
+                sb.x += e.x, sb.y += e.y, sb.z += e.z;
+                state_b[path] = sb;
+            }
+            else
+            {
+                Hit h;
+                h.t = ha.x, h.u = ha.y, h.v = ha.z, h.primitive = __float_as_uint(ha.w), h.instance = hb.x, h.geometry = hb.y;
+                Rng rng;
+                rng.x = __float_as_uint(sa.w), rng.y = __float_as_uint(sb.w);
+                shade_hit(s, prm, depth, dir, h, T, rng, r);
+                want_shadow = r.has_shadow, want_next = r.continues;
+                sb.x += r.emitted.x, sb.y += r.emitted.y, sb.z += r.emitted.z;
+                sb.w = __uint_as_float(rng.y);
+                if (want_next) sa.x = r.T.x, sa.y = r.T.y, sa.z = r.T.z;
+                sa.w          = __uint_as_float(rng.x);
+                state_a[path] = sa, state_b[path] = sb;
+            }
+        }
+        const uint32_t si = warp_append(want_shadow, sh_count, lane);
+        if (want_shadow)
+        {
+            sh_o[si] = make_float4(r.shadow_o.x, r.shadow_o.y, r.shadow_o.z, __uint_as_float(path));
+            sh_d[si] = make_float4(r.shadow_d.x, r.shadow_d.y, r.shadow_d.z, r.shadow_tmax);
+            sh_c[si] = make_float4(r.direct.x, r.direct.y, r.direct.z, 0.0f);
+        }
+        const uint32_t ni = warp_append(want_next, next_count, lane);
+        if (want_next)
+        {
+            next_o[ni] = make_float4(r.next_o.x, r.next_o.y, r.next_o.z, __uint_as_float(path));
+            next_d[ni] = make_float4(r.next_d.x, r.next_d.y, r.next_d.z, 0.0f);
+        }
+    }
+}
+
+// ---- connect ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HL_TRACE_BLOCK) k_connect(SceneView s, const float4* __restrict__ sh_o, const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
+                                                            const uint32_t* __restrict__ count_ptr, uint32_t* fetch, float tmin, uint32_t flags, float4* state_b)
+{
+    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
+    TravStack     st;
+    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    const uint32_t count = *count_ptr;
+    const uint32_t lane  = threadIdx.x & 31u;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) break;
+        const uint32_t i = base + lane;
+        if (i < count)
+        {
+            const float4 o = ld4(sh_o + i), d = ld4(sh_d + i);
+            Hit          h;
+            trace_ray(s, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), d.w, flags, h, st);
+            if (h.instance == HL_MISS) // the shadow miss shader ran: p_Visibility = true
+            {
+                const float4   c    = ld4(sh_c + i);
+                const uint32_t path = __float_as_uint(o.w);
+                float4         sb   = state_b[path];
+                sb.x += c.x, sb.y += c.y, sb.z += c.z;
+                state_b[path] = sb;
+            }
+        }
+    }
+}
+
+// ---- resolve ---------------------------------------------------------------------------------------
+__global__ void k_resolve(FrameParams fp, const float4* __restrict__ state_b, float4* accum, int accum_mode, uint32_t* rgba8, int fused, float exposure, int op)
+{
+    const uint32_t n = fp.lw * fp.lh;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t W = fp.pc.launch_id_size[2], H = fp.pc.launch_id_size[3];
+    const uint32_t px = fp.pc.launch_id_size[0] + i % fp.lw, py = fp.pc.launch_id_size[1] + i / fp.lw;
+    const size_t   pix = (size_t)py * W + px;
+    const float4   sb  = state_b[i];
+    const float4   pv  = accum[pix];
+    const f3       L = mk3(sb.x, sb.y, sb.z), prev = mk3(pv.x, pv.y, pv.z);
+    const f3       c = accum_mode == HL_ACCUM_SUM ? accumulate_sum(L, prev) : accumulate_running_mean(L, prev, fp.pc.num_frames);
+    accum[pix]       = make_float4(c.x, c.y, c.z, 1.0f);
+    if (fused) rgba8[(size_t)(H - 1 - py) * W + px] = tone_map_rgba8(c, exposure, op);
+}
+
+__global__ void k_totals(uint32_t* counters, unsigned long long* totals, uint32_t bounces)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+    {
+        unsigned long long e = 0, s = 0;
+        for (uint32_t b = 0; b < bounces; b++) e += counters[CTR_EXT_COUNT + b], s += counters[CTR_SH_COUNT + b];
+        totals[0] += e, totals[1] += s;
+    }
+}
+
+// ---- film ------------------------------------------------------------------------------------------
+__global__ void k_clear(float4* accum, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) accum[i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f); // renderer.cpp:212-223 clear colour
+}
+__global__ void k_tonemap(const float4* __restrict__ accum, uint32_t W, uint32_t H, float exposure, int op, float scale, uint32_t* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)W * H) return;
+    const uint32_t r = (uint32_t)(i / W), x = (uint32_t)(i % W);
+    const float4   a = accum[(size_t)(H - 1 - r) * W + x];
+    out[i]           = tone_map_rgba8(mk3(a.x * scale, a.y * scale, a.z * scale), exposure, op);
+}
+struct SkyCoeffs
+{
+    float cf[40];
+    float sun[3];
+};
+__global__ void k_sky(SkyCoeffs c, uint32_t size, float4* out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)6 * size * size;
+    if (i >= n) return;
+    const int      face = (int)(i / ((size_t)size * size));
+    const uint32_t j = (uint32_t)((i / size) % size), x = (uint32_t)(i % size);
+    const f3       v = hosek_wilkie_radiance(c.cf, cube_texel_direction(face, x, j, size), mk3(c.sun));
+    out[i]           = make_float4(v.x, v.y, v.z, 1.0f);
+}
+__global__ void __launch_bounds__(HL_TRACE_BLOCK) k_trace_generic(SceneView s, const float* __restrict__ rays, uint32_t n, uint32_t flags, float* __restrict__ hits)
+{
+    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
+    TravStack     st;
+    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float* r = rays + (size_t)i * 8;
+        Hit          h;
+        trace_ray(s, mk3(r[0], r[1], r[2]), r[3], mk3(r[4], r[5], r[6]), r[7], flags, h, st);
+        float*     o   = hits + (size_t)i * 6;
+        const bool hit = h.instance != HL_MISS;
+        o[0] = hit ? h.t : hl_inf(), o[1] = hit ? h.u : 0.0f, o[2] = hit ? h.v : 0.0f;
+        o[3] = __uint_as_float(h.instance), o[4] = __uint_as_float(h.geometry), o[5] = __uint_as_float(h.primitive);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+void wavefront_alloc(hl_context_t* ctx)
+{
+    const size_t n = (size_t)ctx->W * ctx->H;
+    ctx->accum.alloc(n * 16), ctx->rgba8.alloc(n * 4);
+    ctx->state_a.alloc(n * 16), ctx->state_b.alloc(n * 16);
+    for (int k = 0; k < 2; k++) ctx->ext_o[k].alloc(n * 16), ctx->ext_d[k].alloc(n * 16);
+    ctx->hit_a.alloc(n * 16), ctx->hit_b.alloc(n * 8);
+    ctx->sh_o.alloc(n * 16), ctx->sh_d.alloc(n * 16), ctx->sh_c.alloc(n * 16);
+    ctx->counters.alloc(CTR_BYTES);
+    HL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, CTR_BYTES, ctx->stream));
+    ctx->queue_capacity = n;
+    film_clear(ctx);
+}
+
+void film_clear(hl_context_t* ctx)
+{
+    const size_t n = (size_t)ctx->W * ctx->H;
+    k_clear<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->accum.as<float4>(), n);
+    ctx->launches++;
+    HL_CUDA(cudaMemsetAsync(ctx->rgba8.p, 0, n * 4, ctx->stream));
+}
+
+void film_tonemap(hl_context_t* ctx, float exposure, int op, float scale)
+{
+    const size_t n = (size_t)ctx->W * ctx->H;
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->accum.as<float4>(), ctx->W, ctx->H, exposure, op, scale, ctx->rgba8.as<uint32_t>());
+    ctx->launches++;
+}
+
+void sky_bake(hl_context_t* ctx, const float* coeffs40, const float* sun3, uint32_t size)
+{
+    SkyCoeffs c;
+    memcpy(c.cf, coeffs40, sizeof(c.cf));
+    memcpy(c.sun, sun3, sizeof(c.sun));
+    const size_t n = (size_t)6 * size * size;
+    ctx->env_faces.alloc(n * 16);
+    ctx->env_size = size;
+    k_sky<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(c, size, ctx->env_faces.as<float4>());
+    ctx->launches++;
+}
+
+static void ensure_events(hl_context_t* ctx)
+{
+    if (ctx->ev_ready) return;
+    for (auto& e : ctx->ev) HL_CUDA(cudaEventCreate(&e));
+    ctx->ev_ready = true;
+}
+
+static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounces, bool shade)
+{
+    cudaStream_t st   = ctx->stream;
+    uint32_t*    ctr  = ctx->counters.as<uint32_t>();
+    const int    tgrid = ctx->sm_count * 8; // persistent: 8 blocks of 128 threads per SM
+    const int    sgrid = ctx->sm_count * 8;
+    ShadeParams  prm;
+    prm.num_lights = fp.pc.num_lights, prm.max_ray_bounces = fp.pc.max_ray_bounces, prm.shadow_ray_bias = fp.pc.shadow_ray_bias;
+    const bool prof = ctx->profiling;
+    for (uint32_t b = 0; b < bounces; b++)
+    {
+        const int cur = b & 1, nxt = cur ^ 1;
+        // ray parameters per SURVEY A.5: primary tmin 0.001 flags 0; indirect tmin 0.0001 Opaque
+        const float    ext_tmin  = b == 0 ? 0.001f : 0.0001f;
+        const uint32_t ext_flags = b == 0 ? 0u : HL_RAY_OPAQUE;
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 0], st));
+        k_extend<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, ctx->ext_o[cur].as<float4>(), ctx->ext_d[cur].as<float4>(), ctr + CTR_EXT_COUNT + b, ctr + CTR_EXT_FETCH + b, ext_tmin,
+                                                   10000.0f, ext_flags, ctx->hit_a.as<float4>(), ctx->hit_b.as<uint2>());
+        ctx->launches++;
+        if (!shade) break;
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 1], st));
+        k_shade<<<sgrid, HL_SHADE_BLOCK, 0, st>>>(ctx->view, prm, b, ctr + CTR_EXT_COUNT + b, ctx->ext_o[cur].as<float4>(), ctx->ext_d[cur].as<float4>(), ctx->hit_a.as<float4>(),
+                                                  ctx->hit_b.as<uint2>(), ctx->state_a.as<float4>(), ctx->state_b.as<float4>(), ctx->ext_o[nxt].as<float4>(), ctx->ext_d[nxt].as<float4>(),
+                                                  ctr + CTR_EXT_COUNT + b + 1, ctx->sh_o.as<float4>(), ctx->sh_d.as<float4>(), ctx->sh_c.as<float4>(), ctr + CTR_SH_COUNT + b);
+        ctx->launches++;
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 2], st));
+        // shadow rays: depth 0 -> flags 0 (any-hit runs); deeper -> Opaque | TerminateOnFirstHit (rchit:286-290)
+        const uint32_t sh_flags = b == 0 ? 0u : (HL_RAY_OPAQUE | HL_RAY_TERMINATE);
+        k_connect<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, ctx->sh_o.as<float4>(), ctx->sh_d.as<float4>(), ctx->sh_c.as<float4>(), ctr + CTR_SH_COUNT + b, ctr + CTR_SH_FETCH + b, 0.0001f,
+                                                    sh_flags, ctx->state_b.as<float4>());
+        ctx->launches++;
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 3], st));
+    }
+}
+
+void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh)
+{
+    cudaStream_t st = ctx->stream;
+    FrameParams  fp;
+    fp.pc = pc;
+    fp.lw = lw, fp.lh = lh;
+    const uint32_t n = lw * lh;
+    if (n == 0) return;
+    const uint32_t bounces = std::min<uint32_t>(pc.max_ray_bounces, HL_MAX_BOUNCES);
+    const bool     prof    = ctx->profiling;
+    if (prof) ensure_events(ctx);
+    uint32_t* ctr = ctx->counters.as<uint32_t>();
+    HL_CUDA(cudaMemsetAsync(ctr, 0, CTR_U32_TOTAL * 4, st));
+    if (prof) HL_CUDA(cudaEventRecord(ctx->ev[0], st));
+    k_generate<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_a.as<float4>(), ctx->state_b.as<float4>(), ctx->ext_o[0].as<float4>(), ctx->ext_d[0].as<float4>(), ctr);
+    ctx->launches++;
+    run_bounces(ctx, fp, bounces, true);
+    const size_t last = 2 + 4 * (size_t)bounces;
+    if (prof) HL_CUDA(cudaEventRecord(ctx->ev[last], st));
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, ctx->rgba8.as<uint32_t>(), 0, 1.0f, 0);
+    k_totals<<<1, 32, 0, st>>>(ctr, (unsigned long long*)((char*)ctx->counters.p + CTR_TOTALS_OFFSET), bounces);
+    ctx->launches += 2;
+    if (prof)
+    {
+        HL_CUDA(cudaEventRecord(ctx->ev[1], st));
+        HL_CUDA(cudaEventSynchronize(ctx->ev[1]));
+        hl_counters& c = ctx->last;
+        c.ms_generate = c.ms_extend = c.ms_shade = c.ms_connect = c.ms_resolve = 0.0f;
+        float ms;
+        HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]));
+        c.ms_generate = ms;
+        for (uint32_t b = 0; b < bounces; b++)
+        {
+            HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 + 4 * b], ctx->ev[2 + 4 * b + 1]));
+            c.ms_extend += ms;
+            HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 + 4 * b + 1], ctx->ev[2 + 4 * b + 2]));
+            c.ms_shade += ms;
+            HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 + 4 * b + 2], ctx->ev[2 + 4 * b + 3]));
+            c.ms_connect += ms;
+        }
+        HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[last], ctx->ev[1]));
+        c.ms_resolve = ms;
+        HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        c.ms_frame = ms;
+    }
+    ctx->frames++;
+}
+
+void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc)
+{
+    cudaStream_t st = ctx->stream;
+    FrameParams  fp;
+    fp.pc = pc;
+    fp.pc.launch_id_size[0] = fp.pc.launch_id_size[1] = 0;
+    fp.lw = ctx->W, fp.lh = ctx->H;
+    const uint32_t n   = fp.lw * fp.lh;
+    uint32_t*      ctr = ctx->counters.as<uint32_t>();
+    HL_CUDA(cudaMemsetAsync(ctr, 0, CTR_U32_TOTAL * 4, st));
+    k_generate<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_a.as<float4>(), ctx->state_b.as<float4>(), ctx->ext_o[0].as<float4>(), ctx->ext_d[0].as<float4>(), ctr);
+    ctx->launches++;
+    run_bounces(ctx, fp, 1, false);
+}
+
+void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits)
+{
+    if (!n) return;
+    k_trace_generic<<<ctx->sm_count * 8, HL_TRACE_BLOCK, 0, ctx->stream>>>(ctx->view, d_rays, n, flags, (float*)d_hits);
+    ctx->launches++;
+}
+} // namespace hl

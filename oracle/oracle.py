@@ -66,7 +66,7 @@ def sky_bake(coeffs, sun_direction, size=512) -> np.ndarray:
 class OracleScene:
     """CPU scene built from a helios_b200.scenes.SceneData."""
 
-    def __init__(self, scene, brute_force: bool = False, sky_size: int = 512):
+    def __init__(self, scene, brute_force: bool = False, sky_size: int = 512, sky_coeffs_override=None):
         L = lib()
         self.scene = scene
         self.h = C.c_void_p(L.or_scene_new())
@@ -82,7 +82,7 @@ class OracleScene:
             f = np.ascontiguousarray(faces, np.float32)
             L.or_scene_set_envmap(self.h, C.c_uint32(size), _p(f))
         elif scene.sun_direction is not None:
-            cf = sky_coeffs(scene.sun_direction)
+            cf = sky_coeffs(scene.sun_direction) if sky_coeffs_override is None else sky_coeffs_override
             faces = sky_bake(cf, scene.sun_direction, sky_size)
             L.or_scene_set_envmap(self.h, C.c_uint32(sky_size), _p(faces))
         mats = np.ascontiguousarray(scene.materials)

@@ -1,0 +1,152 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): primary-ray hit IDs (instance, geometry, primitive) bit-exact and hit
+parameters (t, u, v) bit-exact — the triangle test is pure IEEE fp32 add/mul/div in a fixed order on both
+sides; radiance within a stated relative MSE at equal spp with the same RNG seeding (transcendentals differ
+by ulps between glibc and CUDA, which can flip rare discrete decisions).
+"""
+import numpy as np
+import pytest
+
+from helios_b200 import abi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from helios_b200 import api as _api
+
+    return _api
+
+
+def rel_mse(a, b):
+    a, b = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    return float(np.mean((a - b) ** 2) / max(np.mean(b**2), 1e-12))
+
+
+def check_ids(gpu, ref, max_mismatch_frac=0.0, ids_only=False):
+    names = ["instance", "geometry", "primitive", "t", "u", "v"]
+    n = gpu[0].size
+    bad_any = np.zeros(n, bool)
+    for name, g, r in list(zip(names, gpu, ref))[: 3 if ids_only else 6]:
+        if g.dtype == np.float32:
+            bad = g.view(np.uint32) != r.view(np.uint32)
+        else:
+            bad = g != r
+        bad_any |= bad
+    frac = bad_any.sum() / n
+    assert frac <= max_mismatch_frac, f"{bad_any.sum()} of {n} primary hits differ"
+    return frac
+
+
+def test_cornell_primary_ids_bit_exact(api, oracle_mod):
+    s = scenes.cornell_box(256, 256, aperture_radius=0.0)
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    for frame in (0, 1, 7):
+        pc = s.push_constants(frame)
+        check_ids(ctx.trace_primary_ids(pc), o.trace_primary_ids(pc))
+    ctx.close()
+
+
+def test_cornell_thin_lens_ids(api, oracle_mod):
+    s = scenes.cornell_box(128, 128, aperture_radius=0.1)
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    pc = s.push_constants(3)
+    # cosf/sinf of the lens angle differ by ulps between CUDA and glibc: origins may differ in the last bit,
+    # so IDs must agree everywhere but t/u/v only to fp32 rounding
+    g, r = ctx.trace_primary_ids(pc), o.trace_primary_ids(pc)
+    for k in range(3):
+        assert (g[k] != r[k]).mean() < 1e-3
+    ok = g[0] == r[0]
+    assert np.allclose(g[3][ok & np.isfinite(r[3])], r[3][ok & np.isfinite(r[3])], rtol=1e-4)
+    ctx.close()
+
+
+def test_cornell_radiance(api, oracle_mod):
+    s = scenes.cornell_box(128, 128)
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s)
+    n = 9
+    a = ctx.render(s, n)
+    b = o.render(n)
+    d = np.abs(a - b)[..., :3].max(-1)
+    assert (d > 1e-4).mean() < 0.01, f"{(d > 1e-4).sum()} pixels differ by more than 1e-4"
+    assert rel_mse(a, b) < 1e-3
+    assert np.all(a[..., 3] == 1.0)
+    c = ctx.counters()
+    assert c["extension_rays"] == o.counters[0], (c["extension_rays"], o.counters)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_tris", [1000, 100_000])
+def test_soup_primary_ids_bit_exact(api, oracle_mod, n_tris):
+    s = scenes.triangle_soup(n_tris, 480, 270)
+    ctx = api.Context(s.width, s.height)
+    handles = ctx.load_scene(s)
+    st = ctx.mesh_build_stats(handles[0])
+    assert st["triangles"] == n_tris and st["wide_nodes"] > 0
+    o = oracle_mod.OracleScene(s)
+    pc = s.push_constants(1)
+    check_ids(ctx.trace_primary_ids(pc), o.trace_primary_ids(pc))
+    ctx.close()
+
+
+def test_terrain_sky_scene(api, oracle_mod):
+    from helios_b200.sky import sky_coefficients
+
+    s = scenes.terrain_scene(grid=96, n_spheres=8, sphere_level=2, width=320, height=180)
+    cf = sky_coefficients(s.sun_direction)
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s, sky_coeffs=cf)
+    o = oracle_mod.OracleScene(s, sky_coeffs_override=cf)
+    pc = s.push_constants(1)
+    # thin lens (aperture 0.05): cosf/sinf of the lens angle differ by ulps between CUDA and glibc, so ray origins
+    # differ in the last bit; the ID triple must still agree on >= 99.99 % of the rays (north_star bar)
+    g, r = ctx.trace_primary_ids(pc), o.trace_primary_ids(pc)
+    check_ids(g, r, max_mismatch_frac=1e-4, ids_only=True)
+    ok = (g[0] == r[0]) & np.isfinite(r[3])
+    assert np.allclose(g[3][ok], r[3][ok], rtol=1e-4)
+    # sky cube map: CUDA expf/powf/acosf vs glibc
+    sky_gpu = ctx.read_envmap()
+    sky_ref = oracle_mod.sky_bake(cf, s.sun_direction, 512)
+    assert np.allclose(sky_gpu, sky_ref, rtol=2e-5, atol=1e-6)
+    a = ctx.render(s, 5)
+    b = o.render(5)
+    assert rel_mse(a, b) < 2e-3
+    ctx.close()
+
+
+def test_tonemap_matches_oracle(api, oracle_mod):
+    s = scenes.cornell_box(64, 48)
+    ctx = api.Context(s.width, s.height)
+    rng = np.random.default_rng(0)
+    acc = (rng.random((s.height, s.width, 4), dtype=np.float32) * 1.5).astype(np.float32)
+    acc[0, 0, :3] = [0.0, 0.18, 4.0]
+    ctx.write_accum(acc)
+    for op in (abi.TONE_MAP_ACES, abi.TONE_MAP_REINHARD):
+        for exposure in (1.0, 2.0):
+            g = ctx.tonemap(exposure, op)
+            r = oracle_mod.tonemap(acc, exposure, op)
+            assert np.abs(g.astype(int) - r.astype(int)).max() <= 1  # powf ulp at a rounding boundary
+            assert (g != r).mean() < 0.01
+    ctx.close()
+
+
+def test_errors_are_reported(api):
+    from helios_b200._lib import HeliosError
+
+    ctx = api.Context(32, 32)
+    s = scenes.cornell_box(32, 32)
+    with pytest.raises(HeliosError):
+        ctx.render_frame(s.push_constants(0))  # no scene tables yet -> HL_ERR_STATE
+    with pytest.raises(HeliosError):
+        bad = s.meshes[0].indices.copy()
+        bad[0] = 10_000_000
+        ctx.create_mesh(s.meshes[0].vertices, bad, s.meshes[0].submeshes)
+    ctx.close()
