@@ -169,6 +169,14 @@ class Context:
         self._chk(self.lib.hl_kernel_launches(self.h, C.byref(n)))
         return n.value
 
+    def event_record(self, slot: int):
+        self._chk(self.lib.hl_event_record(self.h, C.c_int(slot)))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.hl_event_elapsed_ms(self.h, C.c_int(a), C.c_int(b), C.byref(ms)))
+        return ms.value
+
     def render(self, scene, n_launches, **kw):
         """Renderer::render loop: clear, then launches with num_frames = 0 .. n_launches-1"""
         self.accum_clear()

@@ -103,6 +103,8 @@ hl_status hl_context_destroy(hl_context ctx)
     for (auto t : ctx->textures) delete t;
     if (ctx->ev_ready)
         for (auto& e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->user_ev_ready)
+        for (auto& e : ctx->user_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HL_OK;
@@ -484,6 +486,28 @@ hl_status hl_set_profiling(hl_context ctx, int enabled)
 {
     HL_TRY(ctx)
     c_->profiling = enabled != 0;
+    HL_CATCH
+}
+
+hl_status hl_event_record(hl_context ctx, int slot)
+{
+    HL_TRY(ctx)
+    if (slot < 0 || slot >= 8) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_event_record: slot out of range");
+    if (!c_->user_ev_ready)
+    {
+        for (auto& e : c_->user_ev) HL_CUDA(cudaEventCreate(&e));
+        c_->user_ev_ready = true;
+    }
+    HL_CUDA(cudaEventRecord(c_->user_ev[slot], c_->stream));
+    HL_CATCH
+}
+
+hl_status hl_event_elapsed_ms(hl_context ctx, int a, int b, float* out_ms)
+{
+    HL_TRY(ctx)
+    if (a < 0 || a >= 8 || b < 0 || b >= 8 || !out_ms || !c_->user_ev_ready) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_event_elapsed_ms: invalid argument");
+    HL_CUDA(cudaEventSynchronize(c_->user_ev[b]));
+    HL_CUDA(cudaEventElapsedTime(out_ms, c_->user_ev[a], c_->user_ev[b]));
     HL_CATCH
 }
 

@@ -108,6 +108,8 @@ struct hl_context_t
     cudaEvent_t ev[2 + 4 * HL_MAX_BOUNCES + 4] {};
     bool        ev_ready = false;
     hl_counters last {};
+    cudaEvent_t user_ev[8] {};
+    bool        user_ev_ready = false;
     uint64_t    frames = 0;
 };
 

@@ -239,6 +239,10 @@ HL_API hl_status hl_get_counters(hl_context ctx, hl_counters* out);
 HL_API hl_status hl_reset_counters(hl_context ctx);
 /* per-stage CUDA-event timing on/off (off by default: no events inside the frame) */
 HL_API hl_status hl_set_profiling(hl_context ctx, int enabled);
+/* CUDA-event stopwatch on the context's stream (slots 0..7): the library launches on its own stream, which
+ * torch.cuda.Event does not observe */
+HL_API hl_status hl_event_record(hl_context ctx, int slot);
+HL_API hl_status hl_event_elapsed_ms(hl_context ctx, int slot_begin, int slot_end, float* out_ms); /* synchronises on slot_end */
 /* number of kernels launched by this library on this context since creation */
 HL_API hl_status hl_kernel_launches(hl_context ctx, uint64_t* out);
 
