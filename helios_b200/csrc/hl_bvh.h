@@ -9,12 +9,41 @@
 //   * node tests are conservative (never cull a triangle the fp32 triangle test would accept).
 // Node layout and the octant-ordered traversal follow the 8-wide compressed BVH of Ylitie, Karras and
 // Laine (HPG 2017); the code is written from the paper's description.
+//
+// Execution shape: ONE loop per ray for both levels (an instance entry pushes a sentinel and switches the
+// ray to object space; popping the sentinel switches back), and the loop condition is a warp vote, so the
+// 32 rays of a warp re-converge at the top of every iteration: lanes that finished idle until the warp's
+// last ray is done instead of drifting into private instruction streams.
 #pragma once
 #include "hl_scene.h"
 #include "hl_tex.h"
 
 namespace hl
 {
+#if defined(HL_TRAVERSAL_STATS) && !defined(__CUDA_ARCH__)
+// emulator-only instrumentation (tests/emul): nodes visited / leaf primitives tested per query
+struct TraversalStats
+{
+    uint64_t nodes = 0, leaves = 0;
+};
+inline TraversalStats& traversal_stats()
+{
+    static thread_local TraversalStats s;
+    return s;
+}
+#define HL_STAT_NODE() (traversal_stats().nodes++)
+#define HL_STAT_LEAF() (traversal_stats().leaves++)
+#else
+#define HL_STAT_NODE() ((void)0)
+#define HL_STAT_LEAF() ((void)0)
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define HL_WARP_ANY(p) __any_sync(0xFFFFFFFFu, (p))
+#else
+#define HL_WARP_ANY(p) (p)
+#endif
+
 #ifndef HL_STACK_FAST
 #define HL_STACK_FAST 12 /* entries kept in fast (shared) memory per ray */
 #endif
@@ -51,7 +80,6 @@ struct RayCtx
 {
     f3       o, d, idir;
     uint32_t octinv; // 3 bits: bit2 = x, bit1 = y, bit0 = z; set when the direction component is >= 0
-    float    tmin;
 };
 
 HL_HD float safe_rcp_dir(float d)
@@ -61,98 +89,95 @@ HL_HD float safe_rcp_dir(float d)
     if (fabsf(d) < lim) return (f2u(d) >> 31) ? -1e20f : 1e20f;
     return 1.0f / d;
 }
-HL_HD RayCtx make_ray_ctx(f3 o, f3 d, float tmin)
+HL_HD RayCtx make_ray_ctx(f3 o, f3 d)
 {
     RayCtx r;
-    r.o = o, r.d = d, r.tmin = tmin;
+    r.o = o, r.d = d;
     r.idir   = mk3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
     r.octinv = (r.idir.x < 0.0f ? 0u : 4u) | (r.idir.y < 0.0f ? 0u : 2u) | (r.idir.z < 0.0f ? 0u : 1u);
     return r;
 }
 
-// Tests the 8 quantised child boxes of one node; returns the hit mask: bits 24..31 = internal children in
-// octant-permuted order (highest bit = visit first), bits 0..23 = leaf primitives (offset from leaf_base).
-HL_HD uint32_t intersect_children(const WideNode& n, const RayCtx& r, float tbest)
+struct U4
 {
-    const float adjx = u2f((uint32_t)n.ex << 23) * r.idir.x;
-    const float adjy = u2f((uint32_t)n.ey << 23) * r.idir.y;
-    const float adjz = u2f((uint32_t)n.ez << 23) * r.idir.z;
-    const float orgx = (n.px - r.o.x) * r.idir.x;
-    const float orgy = (n.py - r.o.y) * r.idir.y;
-    const float orgz = (n.pz - r.o.z) * r.idir.z;
-    // conservative slack (absolute, in t): covers the rounding of org/adj/fma and the fact that the fp32
-    // triangle test can accept rays that miss the exact box by a few ulp of the ray-box distance
-    const float slack = 1.9073486e-6f /* 2^-19 */ *
-                        (fmaxf(fabsf(orgx), fmaxf(fabsf(orgy), fabsf(orgz))) + 255.0f * fmaxf(fabsf(adjx), fmaxf(fabsf(adjy), fabsf(adjz))));
-    const float tlo_bound = r.tmin - slack;
-    const float thi_bound = tbest + slack;
+    uint32_t x, y, z, w;
+};
+HL_HD U4 load_u4(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg((const uint4*)p);
+    U4          r;
+    r.x = v.x, r.y = v.y, r.z = v.z, r.w = v.w;
+    return r;
+#else
+    U4 r;
+    memcpy(&r, p, 16);
+    return r;
+#endif
+}
+// u8 -> float without the conversion pipe: 0x4B000000 | b is the float 2^23 + b
+HL_HD float byte_to_float(uint32_t word, int i) { return u2f(0x4B000000u | ((word >> (8 * i)) & 0xFFu)) - 8388608.0f; }
+
+// Tests the 8 quantised child boxes of one node (five 16-byte loads); returns the hit mask: bits 24..31 =
+// internal children in octant-permuted order (highest bit = visit first), bits 0..23 = leaf primitives.
+HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float tmin, float tbest, uint32_t& child_base, uint32_t& leaf_base, uint32_t& imask)
+{
+    const U4 n0 = load_u4((const char*)node + 0);
+    const U4 n1 = load_u4((const char*)node + 16);
+    const U4 n2 = load_u4((const char*)node + 32);
+    const U4 n3 = load_u4((const char*)node + 48);
+    const U4 n4 = load_u4((const char*)node + 64);
+    child_base  = n1.x, leaf_base = n1.y, imask = n0.w >> 24;
+    const float adjx = u2f((n0.w & 0xFFu) << 23) * r.idir.x;
+    const float adjy = u2f(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
+    const float adjz = u2f(((n0.w >> 16) & 0xFFu) << 23) * r.idir.z;
+    const float orgx = (u2f(n0.x) - r.o.x) * r.idir.x;
+    const float orgy = (u2f(n0.y) - r.o.y) * r.idir.y;
+    const float orgz = (u2f(n0.z) - r.o.z) * r.idir.z;
+    // conservative per-axis slack (in t): covers the rounding of org/adj/fma and the fact that the fp32
+    // triangle test can accept rays that miss the exact box by a few ulp of the ray-box distance.  It is
+    // folded into the fma addend: near planes use org - s, far planes org + s.  (Per axis, not a common
+    // maximum: an axis with a near-zero direction component has a huge |idir| and would otherwise open
+    // every box of the tree.)
+    const float C  = 1.9073486e-6f; /* 2^-19 */
+    const float sx = C * (fabsf(orgx) + 255.0f * fabsf(adjx));
+    const float sy = C * (fabsf(orgy) + 255.0f * fabsf(adjy));
+    const float sz = C * (fabsf(orgz) + 255.0f * fabsf(adjz));
+    const float onx = orgx - sx, ofx = orgx + sx;
+    const float ony = orgy - sy, ofy = orgy + sy;
+    const float onz = orgz - sz, ofz = orgz + sz;
     const bool  nx = r.idir.x < 0.0f, ny = r.idir.y < 0.0f, nz = r.idir.z < 0.0f;
     uint32_t    hitmask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < 8; j++)
+    for (int h = 0; h < 2; h++)
     {
-        const uint32_t meta = n.meta[j];
-        if (meta == 0) continue;
-        const float qnx = (float)(nx ? n.qhix[j] : n.qlox[j]), qfx = (float)(nx ? n.qlox[j] : n.qhix[j]);
-        const float qny = (float)(ny ? n.qhiy[j] : n.qloy[j]), qfy = (float)(ny ? n.qloy[j] : n.qhiy[j]);
-        const float qnz = (float)(nz ? n.qhiz[j] : n.qloz[j]), qfz = (float)(nz ? n.qloz[j] : n.qhiz[j]);
-        const float tnear = fmaxf(fmaxf(hl_fma(qnx, adjx, orgx), hl_fma(qny, adjy, orgy)), fmaxf(hl_fma(qnz, adjz, orgz), tlo_bound));
-        const float tfar  = fminf(fminf(hl_fma(qfx, adjx, orgx), hl_fma(qfy, adjy, orgy)), fminf(hl_fma(qfz, adjz, orgz), thi_bound));
-        if (tnear <= tfar + slack)
+        // words holding children 4h..4h+3 of each plane set
+        const uint32_t meta4 = h ? n1.w : n1.z;
+        const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z;
+        const uint32_t loz = h ? n3.y : n3.x, hix = h ? n3.w : n3.z;
+        const uint32_t hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
+        const uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+        const uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+        const uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; j++)
         {
-            const bool     inner = (meta & 0x18u) == 0x18u;
-            const uint32_t bit   = inner ? ((meta ^ r.octinv) & 0x1Fu) : (meta & 0x1Fu);
-            hitmask |= (meta >> 5) << bit;
+            const uint32_t meta = (meta4 >> (8 * j)) & 0xFFu;
+            const float tnear = fmaxf(fmaxf(hl_fma(byte_to_float(nearx, j), adjx, onx), hl_fma(byte_to_float(neary, j), adjy, ony)), fmaxf(hl_fma(byte_to_float(nearz, j), adjz, onz), tmin));
+            const float tfar  = fminf(fminf(hl_fma(byte_to_float(farx, j), adjx, ofx), hl_fma(byte_to_float(fary, j), adjy, ofy)), fminf(hl_fma(byte_to_float(farz, j), adjz, ofz), tbest));
+            if (meta != 0 && tnear <= tfar)
+            {
+                const bool     inner = (meta & 0x18u) == 0x18u;
+                const uint32_t bit   = inner ? ((meta ^ r.octinv) & 0x1Fu) : (meta & 0x1Fu);
+                hitmask |= (meta >> 5) << bit;
+            }
         }
     }
     return hitmask;
-}
-
-// Generic octant-ordered traversal of one wide BVH.  leaf(index, tbest) handles one leaf primitive,
-// may shrink tbest, and returns true to terminate the whole query (TerminateOnFirstHit).
-template <class Leaf>
-HL_HD bool traverse_wide(const WideNode* nodes, const RayCtx& r, float& tbest, TravStack& st, Leaf& leaf)
-{
-    const int sp0 = st.sp;
-    u2        ngroup;
-    ngroup.x = 0, ngroup.y = 0x80000000u;
-    for (;;)
-    {
-        u2 tgroup;
-        tgroup.x = 0, tgroup.y = 0;
-        if (ngroup.y > 0x00FFFFFFu)
-        {
-            const uint32_t hits = ngroup.y;
-            const int      bit  = hl_bfind(hits);
-            const uint32_t base = ngroup.x;
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
-            const uint32_t  slot = (uint32_t)(bit - 24) ^ r.octinv;
-            const uint32_t  rel  = (uint32_t)hl_popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
-            const WideNode& n    = nodes[base + rel];
-            const uint32_t  mask = intersect_children(n, r, tbest);
-            ngroup.x = n.child_base, ngroup.y = (mask & 0xFF000000u) | n.imask;
-            tgroup.x = n.leaf_base, tgroup.y = mask & 0x00FFFFFFu;
-        }
-        while (tgroup.y)
-        {
-            const int i = hl_bfind(tgroup.y);
-            tgroup.y &= ~(1u << i);
-            if (leaf(tgroup.x + (uint32_t)i, tbest))
-            {
-                st.sp = sp0;
-                return true;
-            }
-        }
-        if (ngroup.y <= 0x00FFFFFFu)
-        {
-            if (st.sp == sp0) break;
-            ngroup = st.pop();
-        }
-    }
-    return false;
 }
 
 // path_trace_rahit.glsl:174-188: true when the candidate intersection is ignored (albedo alpha < 0.1)
@@ -173,103 +198,153 @@ HL_HD bool any_hit_ignores(const SceneView& s, uint32_t inst, uint32_t geom, uin
     return sample_texture_lod0(s, mat.texture_indices0[0], tu, tv).w < 0.1f;
 }
 
-struct TriLeaf
+// Moeller-Trumbore against one 48-byte leaf record; updates `best` per the closest-hit / tie rule.
+// Returns true when the candidate was accepted.
+HL_HD bool test_leaf_triangle(const SceneView& s, const LeafTri* tri, f3 o, f3 d, float tmin, float tmax, uint32_t inst, uint32_t flags, Hit& b)
 {
-    const SceneView* s;
-    const LeafTri*   tris;
-    f3               o, d; // object space
-    float            tmin, tmax;
-    uint32_t         inst, flags;
-    Hit*             best;
-    HL_HD bool       operator()(uint32_t index, float& tbest)
+    const U4    a = load_u4((const char*)tri + 0), e1w = load_u4((const char*)tri + 16), e2w = load_u4((const char*)tri + 32);
+    const f3    e1   = mk3(u2f(e1w.x), u2f(e1w.y), u2f(e1w.z));
+    const f3    e2   = mk3(u2f(e2w.x), u2f(e2w.y), u2f(e2w.z));
+    const f3    pvec = cross(d, e2);
+    const float det  = dot(e1, pvec);
+    if (det == 0.0f || det != det) return false;
+    const float inv  = 1.0f / det;
+    const f3    tvec = o - mk3(u2f(a.x), u2f(a.y), u2f(a.z));
+    const float u    = dot(tvec, pvec) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const f3    qvec = cross(tvec, e1);
+    const float v    = dot(d, qvec) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    const float t = dot(e2, qvec) * inv;
+    if (!(t > tmin && t < tmax)) return false;
+    const uint32_t prim = a.w, geom = e1w.w & 0x7FFFFFFFu;
+    if (!(t < b.t))
     {
-        const LeafTri tr   = tris[index];
-        const f3      e1   = mk3(tr.e1x, tr.e1y, tr.e1z);
-        const f3      e2   = mk3(tr.e2x, tr.e2y, tr.e2z);
-        const f3      pvec = cross(d, e2);
-        const float   det  = dot(e1, pvec);
-        if (det == 0.0f || det != det) return false;
-        const float inv  = 1.0f / det;
-        const f3    tvec = o - mk3(tr.p0x, tr.p0y, tr.p0z);
-        const float u    = dot(tvec, pvec) * inv;
-        if (!(u >= 0.0f && u <= 1.0f)) return false;
-        const f3    qvec = cross(tvec, e1);
-        const float v    = dot(d, qvec) * inv;
-        if (!(v >= 0.0f && u + v <= 1.0f)) return false;
-        const float t = dot(e2, qvec) * inv;
-        if (!(t > tmin && t < tmax)) return false;
-        const uint32_t geom = tr.geom_flags & 0x7FFFFFFFu;
-        Hit&           b    = *best;
-        if (!(t < b.t))
+        if (t > b.t) return false;
+        // equal t: lexicographic (instance, geometry, primitive)
+        if (inst != b.instance)
         {
-            if (t > b.t) return false;
-            // equal t: lexicographic (instance, geometry, primitive)
-            if (inst != b.instance)
-            {
-                if (inst > b.instance) return false;
-            }
-            else if (geom != b.geometry)
-            {
-                if (geom > b.geometry) return false;
-            }
-            else if (tr.prim >= b.primitive)
-                return false;
+            if (inst > b.instance) return false;
         }
-        if (!(flags & HL_RAY_OPAQUE) && !(tr.geom_flags >> 31) && any_hit_ignores(*s, inst, geom, tr.prim, u, v)) return false;
-        b.t = t, b.u = u, b.v = v, b.instance = inst, b.geometry = geom, b.primitive = tr.prim;
-        tbest = t;
-        return (flags & HL_RAY_TERMINATE) != 0;
+        else if (geom != b.geometry)
+        {
+            if (geom > b.geometry) return false;
+        }
+        else if (prim >= b.primitive)
+            return false;
     }
-};
+    if (!(flags & HL_RAY_OPAQUE) && !(e1w.w >> 31) && any_hit_ignores(s, inst, geom, prim, u, v)) return false;
+    b.t = t, b.u = u, b.v = v, b.instance = inst, b.geometry = geom, b.primitive = prim;
+    return true;
+}
 
-struct InstLeaf
-{
-    const SceneView* s;
-    f3               o, d; // world space
-    float            tmin, tmax;
-    uint32_t         flags;
-    Hit*             best;
-    TravStack*       st;
-    HL_HD bool       operator()(uint32_t index, float& tbest)
-    {
-        const uint32_t inst = s->tlas_leaf[index];
-        const float*   m    = s->inst_inv + 12 * (size_t)inst;
-        TriLeaf        leaf;
-        leaf.o.x = (m[0] * o.x + m[1] * o.y + m[2] * o.z) + m[3];
-        leaf.o.y = (m[4] * o.x + m[5] * o.y + m[6] * o.z) + m[7];
-        leaf.o.z = (m[8] * o.x + m[9] * o.y + m[10] * o.z) + m[11];
-        leaf.d.x = m[0] * d.x + m[1] * d.y + m[2] * d.z;
-        leaf.d.y = m[4] * d.x + m[5] * d.y + m[6] * d.z;
-        leaf.d.z = m[8] * d.x + m[9] * d.y + m[10] * d.z;
-        const MeshView& mesh = s->meshes[s->instances[inst].mesh_index];
-        if (mesh.n_tris == 0) return false;
-        leaf.s = s, leaf.tris = mesh.tris, leaf.tmin = tmin, leaf.tmax = tmax, leaf.inst = inst, leaf.flags = flags, leaf.best = best;
-        const RayCtx r = make_ray_ctx(leaf.o, leaf.d, tmin);
-        return traverse_wide(mesh.nodes, r, tbest, *st, leaf);
-    }
-};
-
-// traceRayEXT: fills `best` (instance == HL_MISS when nothing was hit)
-HL_HD void trace_ray(const SceneView& s, f3 o, float tmin, f3 d, float tmax, uint32_t flags, Hit& best, TravStack& st)
+// traceRayEXT: fills `best` (instance == HL_MISS when nothing was hit).  `active` = false runs an empty query
+// (GPU lanes without a ray still take part in the warp votes).
+HL_HD void trace_ray(const SceneView& s, bool active, f3 o, float tmin, f3 d, float tmax, uint32_t flags, Hit& best, TravStack& st)
 {
     best.t = tmax, best.u = 0.0f, best.v = 0.0f;
     best.instance = best.geometry = best.primitive = HL_MISS;
-    float tbest   = tmax;
-    st.sp         = 0;
-    if (s.n_instances == 0) return;
-    if (s.single_identity)
+    st.sp = 0;
+    u2 ngroup, tgroup;
+    ngroup.x = 0, ngroup.y = 0, tgroup.x = 0, tgroup.y = 0;
+    RayCtx          r      = make_ray_ctx(o, d);
+    const WideNode* nodes  = s.tlas_nodes;
+    const LeafTri*  tris   = nullptr;
+    uint32_t        inst   = HL_MISS; // HL_MISS = top level
+    if (active && s.n_instances != 0)
     {
-        const MeshView& mesh = s.meshes[s.instances[0].mesh_index];
-        if (mesh.n_tris == 0) return;
-        TriLeaf leaf;
-        leaf.s = &s, leaf.tris = mesh.tris, leaf.o = o, leaf.d = d, leaf.tmin = tmin, leaf.tmax = tmax, leaf.inst = 0, leaf.flags = flags, leaf.best = &best;
-        const RayCtx r = make_ray_ctx(o, d, tmin);
-        traverse_wide(mesh.nodes, r, tbest, st, leaf);
-        return;
+        if (s.single_identity)
+        {
+            const MeshView& mesh = s.meshes[s.instances[0].mesh_index];
+            if (mesh.n_tris != 0) nodes = mesh.nodes, tris = mesh.tris, inst = 0, ngroup.y = 0x80000000u;
+        }
+        else
+            ngroup.y = 0x80000000u;
     }
-    InstLeaf leaf;
-    leaf.s = &s, leaf.o = o, leaf.d = d, leaf.tmin = tmin, leaf.tmax = tmax, leaf.flags = flags, leaf.best = &best, leaf.st = &st;
-    const RayCtx r = make_ray_ctx(o, d, tmin);
-    traverse_wide(s.tlas_nodes, r, tbest, st, leaf);
+    for (;;)
+    {
+        const bool busy = ngroup.y > 0x00FFFFFFu || tgroup.y != 0 || st.sp > 0;
+        if (!HL_WARP_ANY(busy)) break;
+        if (!busy) continue;
+        if (tgroup.y == 0)
+        {
+            if (ngroup.y > 0x00FFFFFFu)
+            {
+                // visit the nearest pending child of the current node group
+                const uint32_t hits = ngroup.y;
+                const int      bit  = hl_bfind(hits);
+                const uint32_t base = ngroup.x;
+                ngroup.y &= ~(1u << bit);
+                if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
+                const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+                const uint32_t rel  = (uint32_t)hl_popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
+                HL_STAT_NODE();
+                uint32_t       cb, lb, im;
+                const uint32_t mask = intersect_children(nodes + (base + rel), r, tmin, best.t, cb, lb, im);
+                ngroup.x = cb, ngroup.y = (mask & 0xFF000000u) | im;
+                tgroup.x = lb, tgroup.y = mask & 0x00FFFFFFu;
+            }
+            else
+            {
+                const u2 e = st.pop();
+                if (e.y == 0)
+                {
+                    // sentinel: leave the instance, back to world space and the top-level tree
+                    r = make_ray_ctx(o, d), nodes = s.tlas_nodes, tris = nullptr, inst = HL_MISS;
+                }
+                else if (e.y > 0x00FFFFFFu)
+                    ngroup = e;
+                else
+                    tgroup = e;
+            }
+        }
+        if (tgroup.y != 0)
+        {
+            if (inst != HL_MISS)
+            {
+                // bottom level: test every pending triangle of this leaf group
+                bool done = false;
+                while (tgroup.y)
+                {
+                    const int i = hl_bfind(tgroup.y);
+                    tgroup.y &= ~(1u << i);
+                    HL_STAT_LEAF();
+                    if (test_leaf_triangle(s, tris + (tgroup.x + (uint32_t)i), r.o, r.d, tmin, tmax, inst, flags, best) && (flags & HL_RAY_TERMINATE))
+                    {
+                        done = true;
+                        break;
+                    }
+                }
+                if (done) ngroup.y = 0, tgroup.y = 0, st.sp = 0;
+            }
+            else
+            {
+                // top level: enter ONE instance; the rest of the leaf group and the node group wait on the stack
+                const int i = hl_bfind(tgroup.y);
+                tgroup.y &= ~(1u << i);
+                HL_STAT_LEAF();
+                const uint32_t  id   = s.tlas_leaf[tgroup.x + (uint32_t)i];
+                const MeshView& mesh = s.meshes[s.instances[id].mesh_index];
+                if (mesh.n_tris != 0)
+                {
+                    if (tgroup.y) st.push(tgroup);
+                    if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
+                    u2 sentinel;
+                    sentinel.x = 0xFFFFFFFFu, sentinel.y = 0;
+                    st.push(sentinel);
+                    const float* m = s.inst_inv + 12 * (size_t)id;
+                    f3           oo, od;
+                    oo.x = (m[0] * o.x + m[1] * o.y + m[2] * o.z) + m[3];
+                    oo.y = (m[4] * o.x + m[5] * o.y + m[6] * o.z) + m[7];
+                    oo.z = (m[8] * o.x + m[9] * o.y + m[10] * o.z) + m[11];
+                    od.x = m[0] * d.x + m[1] * d.y + m[2] * d.z;
+                    od.y = m[4] * d.x + m[5] * d.y + m[6] * d.z;
+                    od.z = m[8] * d.x + m[9] * d.y + m[10] * d.z;
+                    r = make_ray_ctx(oo, od), nodes = mesh.nodes, tris = mesh.tris, inst = id;
+                    ngroup.x = 0, ngroup.y = 0x80000000u, tgroup.y = 0;
+                }
+            }
+        }
+    }
 }
 } // namespace hl

@@ -70,12 +70,14 @@ __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_extend(SceneView s, const fl
         if (lane == 0) base = atomicAdd(fetch, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= count) break;
-        const uint32_t i = base + lane;
-        if (i < count)
+        const uint32_t i   = base + lane;
+        const bool     act = i < count;
+        float4         o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
+        if (act) o = ld4(ray_o + i), d = ld4(ray_d + i);
+        Hit h;
+        trace_ray(s, act, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), tmax, flags, h, st); // warp-convergent call
+        if (act)
         {
-            const float4 o = ld4(ray_o + i), d = ld4(ray_d + i);
-            Hit          h;
-            trace_ray(s, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), tmax, flags, h, st);
             hit_a[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.primitive));
             hit_b[i] = make_uint2(h.instance, h.geometry);
         }
@@ -169,20 +171,19 @@ __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_connect(SceneView s, const f
         if (lane == 0) base = atomicAdd(fetch, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= count) break;
-        const uint32_t i = base + lane;
-        if (i < count)
+        const uint32_t i   = base + lane;
+        const bool     act = i < count;
+        float4         o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
+        if (act) o = ld4(sh_o + i), d = ld4(sh_d + i);
+        Hit h;
+        trace_ray(s, act, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), d.w, flags, h, st);
+        if (act && h.instance == HL_MISS) // the shadow miss shader ran: p_Visibility = true
         {
-            const float4 o = ld4(sh_o + i), d = ld4(sh_d + i);
-            Hit          h;
-            trace_ray(s, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), d.w, flags, h, st);
-            if (h.instance == HL_MISS) // the shadow miss shader ran: p_Visibility = true
-            {
-                const float4   c    = ld4(sh_c + i);
-                const uint32_t path = __float_as_uint(o.w);
-                float4         sb   = state_b[path];
-                sb.x += c.x, sb.y += c.y, sb.z += c.z;
-                state_b[path] = sb;
-            }
+            const float4   c    = ld4(sh_c + i);
+            const uint32_t path = __float_as_uint(o.w);
+            float4         sb   = state_b[path];
+            sb.x += c.x, sb.y += c.y, sb.z += c.z;
+            state_b[path] = sb;
         }
     }
 }
@@ -248,11 +249,15 @@ __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_trace_generic(SceneView s, c
     __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
     TravStack     st;
     st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x)
     {
-        const float* r = rays + (size_t)i * 8;
-        Hit          h;
-        trace_ray(s, mk3(r[0], r[1], r[2]), r[3], mk3(r[4], r[5], r[6]), r[7], flags, h, st);
+        const uint32_t i   = base + lane;
+        const bool     act = i < n;
+        const float*   r   = rays + (size_t)(act ? i : 0) * 8;
+        Hit            h;
+        trace_ray(s, act, mk3(r[0], r[1], r[2]), r[3], mk3(r[4], r[5], r[6]), r[7], flags, h, st);
+        if (!act) continue;
         float*     o   = hits + (size_t)i * 6;
         const bool hit = h.instance != HL_MISS;
         o[0] = hit ? h.t : hl_inf(), o[1] = hit ? h.u : 0.0f, o[2] = hit ? h.v : 0.0f;

@@ -6,6 +6,7 @@
 // with plain loops in wavefront order (generate -> extend -> shade -> connect -> resolve), so that the builder,
 // the traversal and the shading can be checked against the oracle before GPU time is spent.  It is never
 // loaded by the helios_b200 package and is not a fallback: the product path is the CUDA library only.
+#define HL_TRAVERSAL_STATS 1
 #include "../../helios_b200/csrc/hl_build.h"
 #include "../../helios_b200/csrc/hl_bvh.h"
 #include "../../helios_b200/csrc/hl_camera.h"
@@ -258,7 +259,7 @@ static void trace_one(const SceneView& s, f3 o, float tmin, f3 d, float tmax, ui
     u2        fast[HL_STACK_FAST];
     TravStack st;
     st.fast = fast, st.stride = 1, st.sp = 0;
-    trace_ray(s, o, tmin, d, tmax, flags, h, st);
+    trace_ray(s, true, o, tmin, d, tmax, flags, h, st);
 }
 
 EM_API void em_trace_primary_ids(const EmScene* s, const hl_push_constants* pc, uint32_t* inst, uint32_t* geom, uint32_t* prim, float* t, float* u, float* v)
@@ -294,6 +295,11 @@ EM_API void em_trace_rays(const EmScene* s, const float* rays, uint32_t n, uint3
         ou[3] = h.instance, ou[4] = h.geometry, ou[5] = h.primitive;
     }
 }
+
+// optional per-ray traversal log for em_render_frame: [16 bounces][cap] = nodes | leaves << 16
+static uint32_t* g_node_log     = nullptr;
+static size_t    g_node_log_cap = 0;
+EM_API void      em_set_node_log(uint32_t* buf, size_t cap) { g_node_log = buf, g_node_log_cap = cap; }
 
 // one launch in wavefront order; accum is updated in place
 EM_API void em_render_frame(const EmScene* sc, const hl_push_constants* pcp, uint32_t lw, uint32_t lh, float* accum, uint64_t* counters, int accum_mode)
@@ -347,7 +353,13 @@ EM_API void em_render_frame(const EmScene* sc, const hl_push_constants* pcp, uin
         const float    ext_tmin  = depth == 0 ? 0.001f : 0.0001f;
         hits.resize(q.size());
 #pragma omp parallel for schedule(dynamic, 256)
-        for (int64_t i = 0; i < (int64_t)q.size(); i++) trace_one(s, q[i].o, ext_tmin, q[i].d, 10000.0f, ext_flags, hits[i]); // extend
+        for (int64_t i = 0; i < (int64_t)q.size(); i++) // extend
+        {
+            TraversalStats& ts = traversal_stats();
+            ts.nodes = ts.leaves = 0;
+            trace_one(s, q[i].o, ext_tmin, q[i].d, 10000.0f, ext_flags, hits[i]);
+            if (g_node_log && depth < 16 && (size_t)i < g_node_log_cap) g_node_log[depth * g_node_log_cap + i] = (uint32_t)ts.nodes | ((uint32_t)ts.leaves << 16);
+        }
         if (counters) counters[0] += q.size();
         std::vector<ShadeResult> res(q.size());
         std::vector<uint8_t>     is_hit(q.size());
@@ -403,6 +415,24 @@ EM_API void em_render_frame(const EmScene* sc, const hl_push_constants* pcp, uin
         const f3 c    = accum_mode == HL_ACCUM_SUM ? accumulate_sum(p.L, prev) : accumulate_running_mean(p.L, prev, pc.num_frames);
         a[0] = c.x, a[1] = c.y, a[2] = c.z, a[3] = 1.0f;
     }
+}
+// per-query traversal statistics over a ray batch: out[0] = node visits, out[1] = leaf primitive tests,
+// out[2] = max node visits of a single ray
+EM_API void em_traversal_stats(const EmScene* s, const float* rays, uint32_t n, uint32_t flags, uint64_t* out)
+{
+    uint64_t nodes = 0, leaves = 0, worst = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, leaves) reduction(max : worst)
+    for (int64_t i = 0; i < (int64_t)n; i++)
+    {
+        const float* r = rays + i * 8;
+        Hit          h;
+        TraversalStats& st = traversal_stats();
+        st.nodes = st.leaves = 0;
+        trace_one(s->view, mk3(r[0], r[1], r[2]), r[3], mk3(r[4], r[5], r[6]), r[7], flags, h);
+        nodes += st.nodes, leaves += st.leaves;
+        worst = std::max<uint64_t>(worst, st.nodes);
+    }
+    out[0] = nodes, out[1] = leaves, out[2] = worst;
 }
 EM_API void em_tonemap(const float* accum, uint32_t W, uint32_t H, float exposure, int op, float scale, uint8_t* out)
 {

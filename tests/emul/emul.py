@@ -101,6 +101,12 @@ class EmulScene:
         lib().em_trace_rays(self.h, _p(rays), C.c_uint32(len(rays)), C.c_uint32(flags), _p(hits))
         return hits
 
+    def traversal_stats(self, rays, flags=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        out = np.zeros(3, np.uint64)
+        lib().em_traversal_stats(self.h, _p(rays), C.c_uint32(len(rays)), C.c_uint32(flags), _p(out))
+        return {"nodes_per_ray": out[0] / len(rays), "leaf_tests_per_ray": out[1] / len(rays), "max_nodes": int(out[2])}
+
     def mesh_stats(self, mesh=0):
         out = np.zeros(3, np.uint32)
         lib().em_mesh_stats(self.h, C.c_int(mesh), _p(out))
