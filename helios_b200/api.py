@@ -169,6 +169,9 @@ class Context:
         self._chk(self.lib.hl_kernel_launches(self.h, C.byref(n)))
         return n.value
 
+    def set_option(self, option: int, value: int):
+        self._chk(self.lib.hl_set_option(self.h, C.c_int(option), C.c_int64(value)))
+
     def event_record(self, slot: int):
         self._chk(self.lib.hl_event_record(self.h, C.c_int(slot)))
 

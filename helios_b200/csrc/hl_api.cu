@@ -467,7 +467,7 @@ hl_status hl_get_counters(hl_context ctx, hl_counters* out)
     HL_TRY(ctx)
     if (!out) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_get_counters: null pointer");
     uint64_t totals[2];
-    HL_CUDA(cudaMemcpyAsync(totals, (char*)c_->counters.p + ((257 * 4 + 7) / 8 * 8), 16, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaMemcpyAsync(totals, (char*)c_->counters.p + CTR_TOTALS_OFFSET, 16, cudaMemcpyDeviceToHost, c_->stream));
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     *out                = c_->last;
     out->extension_rays = totals[0], out->shadow_rays = totals[1], out->frames = c_->frames;
@@ -477,7 +477,7 @@ hl_status hl_get_counters(hl_context ctx, hl_counters* out)
 hl_status hl_reset_counters(hl_context ctx)
 {
     HL_TRY(ctx)
-    HL_CUDA(cudaMemsetAsync((char*)c_->counters.p + ((257 * 4 + 7) / 8 * 8), 0, 16, c_->stream));
+    HL_CUDA(cudaMemsetAsync((char*)c_->counters.p + CTR_TOTALS_OFFSET, 0, 16, c_->stream));
     c_->frames = 0;
     HL_CATCH
 }
@@ -508,6 +508,18 @@ hl_status hl_event_elapsed_ms(hl_context ctx, int a, int b, float* out_ms)
     if (a < 0 || a >= 8 || b < 0 || b >= 8 || !out_ms || !c_->user_ev_ready) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_event_elapsed_ms: invalid argument");
     HL_CUDA(cudaEventSynchronize(c_->user_ev[b]));
     HL_CUDA(cudaEventElapsedTime(out_ms, c_->user_ev[a], c_->user_ev[b]));
+    HL_CATCH
+}
+
+hl_status hl_set_option(hl_context ctx, int option, int64_t value)
+{
+    HL_TRY(ctx)
+    if (option == HL_OPT_TAIL_THRESHOLD)
+        c_->tail_threshold = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 0x7FFFFFFF));
+    else if (option == HL_OPT_TAIL_START)
+        c_->tail_start = (uint32_t)std::max<int64_t>(1, value);
+    else
+        HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_set_option: unknown option");
     HL_CATCH
 }
 

@@ -63,6 +63,19 @@ struct WideBVHDev
 
 #define HL_MAX_BOUNCES 64
 
+// device counter block layout (uint32 indices), zeroed at the start of every frame; uint64 totals[2] follow
+#define CTR_EXT_COUNT 0                    /* [HL_MAX_BOUNCES + 1] extension-queue sizes per bounce */
+#define CTR_SH_COUNT (CTR_EXT_COUNT + 65)  /* [HL_MAX_BOUNCES] shadow-queue sizes per bounce */
+#define CTR_EXT_FETCH (CTR_SH_COUNT + 64)  /* [HL_MAX_BOUNCES] work cursors of the persistent extend launches */
+#define CTR_SH_FETCH (CTR_EXT_FETCH + 64)  /* [HL_MAX_BOUNCES] work cursors of the persistent connect launches */
+#define CTR_TAIL_FETCH (CTR_SH_FETCH + 64)
+#define CTR_TAIL_EXT (CTR_TAIL_FETCH + 1)
+#define CTR_TAIL_SH (CTR_TAIL_FETCH + 2)
+#define CTR_TAIL_DONE (CTR_TAIL_FETCH + 3)
+#define CTR_U32_TOTAL (CTR_TAIL_FETCH + 4)
+#define CTR_TOTALS_OFFSET ((CTR_U32_TOTAL * 4 + 7) / 8 * 8)
+#define CTR_BYTES (CTR_TOTALS_OFFSET + 16)
+
 } // namespace hl
 
 struct hl_mesh_t
@@ -84,6 +97,7 @@ struct hl_context_t
     uint64_t     launches = 0;
     bool         profiling = false;
     int          accum_mode = HL_ACCUM_RUNNING_MEAN;
+    uint32_t     tail_start = 2, tail_threshold = 98304; // see k_tail (hl_wavefront.cu)
 
     // resources
     std::vector<hl_mesh_t*>  meshes;

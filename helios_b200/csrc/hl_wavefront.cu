@@ -21,15 +21,6 @@ namespace hl
 #define HL_TRACE_BLOCK 128
 #define HL_SHADE_BLOCK 128
 
-// device counter block layout (uint32 indices)
-#define CTR_EXT_COUNT 0                    /* [HL_MAX_BOUNCES + 1] */
-#define CTR_SH_COUNT (CTR_EXT_COUNT + 65)  /* [HL_MAX_BOUNCES] */
-#define CTR_EXT_FETCH (CTR_SH_COUNT + 64)  /* [HL_MAX_BOUNCES] */
-#define CTR_SH_FETCH (CTR_EXT_FETCH + 64)  /* [HL_MAX_BOUNCES] */
-#define CTR_U32_TOTAL (CTR_SH_FETCH + 64)  /* = 257 */
-#define CTR_BYTES (CTR_U32_TOTAL * 4 + 12 + 16) /* + padding to 8, then uint64 totals[2] */
-#define CTR_TOTALS_OFFSET ((CTR_U32_TOTAL * 4 + 7) / 8 * 8)
-
 struct FrameParams
 {
     hl_push_constants pc;
@@ -188,6 +179,86 @@ __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_connect(SceneView s, const f
     }
 }
 
+// ---- tail ------------------------------------------------------------------------------------------
+// Russian roulette thins the queues quickly: past the first bounces a launch carries a few thousand rays and
+// its duration is the latency of its slowest ray, not throughput.  When the extension queue of bounce
+// `depth0` holds at most `threshold` rays, this kernel finishes those paths in one launch — extend, shade and
+// connect in a per-path loop over the remaining bounces, same arithmetic and same accumulation order as the
+// wavefront stages — and zeroes the queue so that the wavefront launches enqueued behind it are no-ops.
+__global__ void __launch_bounds__(HL_TRACE_BLOCK) k_tail(SceneView s, ShadeParams prm, uint32_t depth0, uint32_t threshold, uint32_t* counters, const float4* __restrict__ ray_o,
+                                                         const float4* __restrict__ ray_d, const float4* __restrict__ state_a, float4* state_b)
+{
+    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
+    TravStack     st;
+    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    const uint32_t count = counters[CTR_EXT_COUNT + depth0];
+    if (count == 0 || count > threshold) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t       n_ext = 0, n_sh = 0;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counters + CTR_TAIL_FETCH, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) break;
+        const uint32_t i     = base + lane;
+        bool           alive = i < count;
+        f3             o = mk3(0.0f), d = mk3(0.0f), T = mk3(0.0f), L = mk3(0.0f);
+        Rng            rng;
+        rng.x = rng.y = 0;
+        uint32_t path = 0, depth = depth0;
+        float    lw = 0.0f;
+        if (alive)
+        {
+            const float4 o4 = ray_o[i], d4 = ray_d[i];
+            path            = __float_as_uint(o4.w);
+            const float4 sa = state_a[path], sb = state_b[path];
+            o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
+            T = mk3(sa.x, sa.y, sa.z), L = mk3(sb.x, sb.y, sb.z);
+            rng.x = __float_as_uint(sa.w), rng.y = __float_as_uint(sb.w), lw = sb.w;
+        }
+        const bool mine = alive;
+        while (__any_sync(0xFFFFFFFFu, alive))
+        {
+            Hit h;
+            trace_ray(s, alive, o, depth == 0 ? 0.001f : 0.0001f, d, 10000.0f, depth == 0 ? 0u : HL_RAY_OPAQUE, h, st);
+            ShadeResult r;
+            r.has_shadow = false, r.continues = false;
+            if (alive)
+            {
+                n_ext++;
+                if (h.instance == HL_MISS)
+                    L = L + shade_miss(s, depth, d, T);
+                else
+                {
+                    shade_hit(s, prm, depth, d, h, T, rng, r);
+                    L = L + r.emitted;
+                }
+            }
+            Hit hs;
+            trace_ray(s, r.has_shadow, r.shadow_o, 0.0001f, r.shadow_d, r.shadow_tmax, depth == 0 ? HL_RAY_TERMINATE : (HL_RAY_OPAQUE | HL_RAY_TERMINATE), hs, st);
+            if (r.has_shadow)
+            {
+                n_sh++;
+                if (hs.instance == HL_MISS) L = L + r.direct;
+            }
+            alive = alive && r.continues;
+            if (alive) o = r.next_o, d = r.next_d, T = r.T, depth++;
+        }
+        if (mine) state_b[path] = make_float4(L.x, L.y, L.z, lw);
+    }
+    // ray counters: one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) n_ext += __shfl_down_sync(0xFFFFFFFFu, n_ext, off), n_sh += __shfl_down_sync(0xFFFFFFFFu, n_sh, off);
+    if (lane == 0 && (n_ext | n_sh)) atomicAdd(counters + CTR_TAIL_EXT, n_ext), atomicAdd(counters + CTR_TAIL_SH, n_sh);
+    // last block out closes the queue: the wavefront launches behind this kernel see an empty bounce
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        if (atomicAdd(counters + CTR_TAIL_DONE, 1u) == gridDim.x - 1) counters[CTR_EXT_COUNT + depth0] = 0, counters[CTR_TAIL_DONE] = 0, counters[CTR_TAIL_FETCH] = 0;
+    }
+}
+
 // ---- resolve ---------------------------------------------------------------------------------------
 __global__ void k_resolve(FrameParams fp, const float4* __restrict__ state_b, float4* accum, int accum_mode, uint32_t* rgba8, int fused, float exposure, int op)
 {
@@ -211,6 +282,7 @@ __global__ void k_totals(uint32_t* counters, unsigned long long* totals, uint32_
     {
         unsigned long long e = 0, s = 0;
         for (uint32_t b = 0; b < bounces; b++) e += counters[CTR_EXT_COUNT + b], s += counters[CTR_SH_COUNT + b];
+        e += counters[CTR_TAIL_EXT], s += counters[CTR_TAIL_SH];
         totals[0] += e, totals[1] += s;
     }
 }
@@ -330,6 +402,13 @@ static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounc
         const float    ext_tmin  = b == 0 ? 0.001f : 0.0001f;
         const uint32_t ext_flags = b == 0 ? 0u : HL_RAY_OPAQUE;
         if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 0], st));
+        if (shade && b >= ctx->tail_start && ctx->tail_threshold > 0)
+        {
+            // sparse late bounces: finish the surviving paths in one launch when the queue is small (see k_tail)
+            k_tail<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, prm, b, ctx->tail_threshold, ctr, ctx->ext_o[cur].as<float4>(), ctx->ext_d[cur].as<float4>(), ctx->state_a.as<float4>(),
+                                                     ctx->state_b.as<float4>());
+            ctx->launches++;
+        }
         k_extend<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, ctx->ext_o[cur].as<float4>(), ctx->ext_d[cur].as<float4>(), ctr + CTR_EXT_COUNT + b, ctr + CTR_EXT_FETCH + b, ext_tmin,
                                                    10000.0f, ext_flags, ctx->hit_a.as<float4>(), ctx->hit_b.as<uint2>());
         ctx->launches++;
@@ -340,8 +419,11 @@ static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounc
                                                   ctr + CTR_EXT_COUNT + b + 1, ctx->sh_o.as<float4>(), ctx->sh_d.as<float4>(), ctx->sh_c.as<float4>(), ctr + CTR_SH_COUNT + b);
         ctx->launches++;
         if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 2], st));
-        // shadow rays: depth 0 -> flags 0 (any-hit runs); deeper -> Opaque | TerminateOnFirstHit (rchit:286-290)
-        const uint32_t sh_flags = b == 0 ? 0u : (HL_RAY_OPAQUE | HL_RAY_TERMINATE);
+        // shadow rays: depth 0 -> flags 0 (any-hit runs); deeper -> Opaque | TerminateOnFirstHit (rchit:286-290).
+        // Visibility only asks whether ANY accepted intersection exists in (tmin, tmax) — acceptance is a
+        // per-candidate test (alpha), independent of order — so the depth-0 query may also stop at its first
+        // accepted hit: the result is identical to the reference's closest-hit + shadow.rchit sequence.
+        const uint32_t sh_flags = b == 0 ? HL_RAY_TERMINATE : (HL_RAY_OPAQUE | HL_RAY_TERMINATE);
         k_connect<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, ctx->sh_o.as<float4>(), ctx->sh_d.as<float4>(), ctx->sh_c.as<float4>(), ctr + CTR_SH_COUNT + b, ctr + CTR_SH_FETCH + b, 0.0001f,
                                                     sh_flags, ctx->state_b.as<float4>());
         ctx->launches++;
