@@ -205,8 +205,12 @@ def main():
         ctx.set_accum_mode(abi.ACCUM_SUM)
     W, K = args.warmup, args.steps
 
-    def frame_index(step):  # spp sharding: rank g renders frames g+1, g+1+G, ... (frame 0 is discarded upstream)
-        return 1 + rank + step * world
+    from helios_b200 import multi_gpu
+
+    _frames = multi_gpu.frame_indices(rank, world, W + K)  # spp sharding: rank g renders frames g+1, g+1+G, ...
+
+    def frame_index(step):
+        return _frames[step]
 
     def barrier():
         ctx.synchronize()
@@ -230,8 +234,8 @@ def main():
         ctx.render_frame(pcs[s])
     if dist is not None:
         ctx.synchronize()
-        acc = torch.as_tensor(_DevArray(ctx.accum_device_ptr(), scene.width * scene.height * 4), device=f"cuda:{local_rank}")
-        dist.all_reduce(acc)
+        acc = torch.as_tensor(multi_gpu.DeviceArray(ctx.accum_device_ptr(), scene.width * scene.height * 4), device=f"cuda:{local_rank}")
+        multi_gpu.all_reduce_sum(acc, dist)
         torch.cuda.synchronize()
     ctx.event_record(1)
     ms_total = ctx.event_elapsed_ms(0, 1)
@@ -323,13 +327,6 @@ def main():
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
-
-
-class _DevArray:
-    """__cuda_array_interface__ view of the library's accumulation image for torch.distributed"""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
 
 
 if __name__ == "__main__":

@@ -527,7 +527,8 @@ def checker_texture(size, seed, base_rgb, alpha_disc=False):
     """procedural RGBA8 sRGB texture: noisy checker in the base colour; alpha_disc -> alpha in {0,255} disc mask"""
     rng = np.random.default_rng(seed)
     y, x = np.mgrid[0:size, 0:size]
-    chk = (((x // (size // 16)) + (y // (size // 16))) & 1).astype(np.float32)
+    cell = max(size // 16, 1)
+    chk = (((x // cell) + (y // cell)) & 1).astype(np.float32)
     noise = rng.random((size, size), dtype=np.float32) * 0.15
     lum = 0.6 + 0.4 * chk - noise
     rgb = np.clip(lum[..., None] * np.asarray(base_rgb, np.float32)[None, None, :] * 255.0, 0, 255).astype(np.uint8)
@@ -536,3 +537,161 @@ def checker_texture(size, seed, base_rgb, alpha_disc=False):
         r2 = (x - size / 2 + 0.5) ** 2 + (y - size / 2 + 0.5) ** 2
         a[..., 0] = np.where(r2 < (0.45 * size) ** 2, 255, 0)
     return (abi.TEX_RGBA8_SRGB, size, size, np.ascontiguousarray(np.concatenate([rgb, a], -1)))
+
+
+# ----------------------------------------------------------------------------------------------
+# config 3: alpha-tested foliage, 64 area + 16 punctual lights
+# ----------------------------------------------------------------------------------------------
+def foliage_scene(n_clusters=50_000, cards_per_cluster=50, width=1920, height=1080, seed=2, ground_grid=64, tex_size=256) -> SceneData:
+    """config 3: leaf-card clusters (alpha-masked albedo texture, geometry NOT opaque -> any-hit) over a ground mesh;
+    64 area lights = ONE untranslated mesh node with 64 emissive 2-triangle submeshes (lights are registered per emissive
+    submesh; only triangle 0 of each quad is sampled, A.8-2) + 8 point + 8 spot lights; no directional
+    light and no IBL -> no environment light: num_lights = 80.  Defaults give 2*64^2 + 50,000*50*2 + 128 = 5,008,320 tris."""
+    rng = np.random.default_rng(seed)
+    extent = 60.0
+    textures = [checker_texture(tex_size, seed, (0.25, 0.6, 0.2), alpha_disc=True)]
+    GROUND, LEAF, EMIT = 0, 1, 2
+    mats = _stack(
+        [
+            make_material((0.45, 0.38, 0.3, 1.0), roughness=0.9),
+            make_material((0.0, 0.0, 0.0, 0.0), roughness=0.6, albedo_tex=0),
+            make_material((0.0, 0.0, 0.0, 1.0), emissive=(40.0, 36.0, 30.0)),
+        ],
+        abi.MATERIAL,
+    )
+    # ground
+    n = ground_grid + 1
+    gx, gz = np.meshgrid(np.linspace(-extent / 2, extent / 2, n), np.linspace(-extent / 2, extent / 2, n), indexing="xy")
+    gy = 1.5 * (_fbm(gx * 0.1 + 50.0, gz * 0.1 + 50.0, seed) - 0.5)
+    pos = np.stack([gx, gy, gz], -1).reshape(-1, 3)
+    qi, qj = np.meshgrid(np.arange(ground_grid), np.arange(ground_grid), indexing="xy")
+    v00 = (qj * n + qi).reshape(-1)
+    tris = np.stack([v00, v00 + n, v00 + n + 1, v00, v00 + n + 1, v00 + 1], -1).astype(np.uint32).reshape(-1)
+    nrm = np.zeros_like(pos)
+    nrm[:, 1] = 1.0
+    gv = make_vertices(pos, np.stack([gx / 4, gz / 4], -1).reshape(-1, 2), nrm, submesh_index=np.zeros(len(pos), np.float32))
+    gs = np.zeros(1, abi.SUBMESH)
+    gs[0] = (0, tris.size, len(pos), 1)
+    ground = MeshData(gv, tris, gs, [GROUND])
+    # foliage: clusters of randomly oriented quads ("leaf cards")
+    ncards = n_clusters * cards_per_cluster
+    cc = (rng.random((n_clusters, 3)) - 0.5) * np.array([extent * 0.9, 0.0, extent * 0.9]) + np.array([0.0, 2.5, 0.0])
+    cc[:, 1] += rng.random(n_clusters) * 3.0
+    centre = np.repeat(cc, cards_per_cluster, axis=0) + rng.normal(scale=0.6, size=(ncards, 3))
+    a = rng.normal(size=(ncards, 3))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b = np.cross(a, rng.normal(size=(ncards, 3)))
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    size = 0.12 + rng.random((ncards, 1)) * 0.1
+    a *= size
+    b *= size
+    quad = np.stack([centre - a - b, centre + a - b, centre + a + b, centre - a + b], 1).reshape(-1, 3)
+    fn = np.repeat(np.cross(a, b) / np.linalg.norm(np.cross(a, b), axis=1, keepdims=True), 4, axis=0)
+    fuv = np.tile(np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float64), (ncards, 1))
+    base = (np.arange(ncards, dtype=np.uint32) * 4)[:, None]
+    fidx = (base + np.array([0, 1, 2, 0, 2, 3], np.uint32)[None, :]).reshape(-1).astype(np.uint32)
+    fv = make_vertices(quad, fuv, fn, submesh_index=np.zeros(len(quad), np.float32))
+    fs = np.zeros(1, abi.SUBMESH)
+    fs[0] = (0, fidx.size, len(quad), 0)  # alpha tested -> no VK_GEOMETRY_OPAQUE_BIT (mesh.cpp:73-76)
+    foliage = MeshData(fv, fidx, fs, [LEAF])
+    # 64 emissive quads (8 x 8 grid above the canopy), one submesh each, facing down
+    lb = _MeshBuilder()
+    for k in range(64):
+        lx, lz = ((k % 8) - 3.5) * extent / 9.0, ((k // 8) - 3.5) * extent / 9.0
+        h, y = 0.4, 9.0
+        lb.begin_submesh(EMIT)
+        p, i, nn = _quad((lx - h, y, lz - h), (lx + h, y, lz - h), (lx + h, y, lz + h), (lx - h, y, lz + h))
+        lb.add(p, i, nn, uv=[[0, 0], [1, 0], [1, 1], [0, 1]])
+        lb.end_submesh()
+    lights_mesh = lb.build()
+    meshes = [ground, foliage, lights_mesh]
+    instances = _stack([make_instance(mesh_index=k) for k in range(3)], abi.INSTANCE)
+    light_rows = area_lights_for(lights_mesh, 2, mats)
+    for k in range(8):
+        ang = 2 * math.pi * k / 8
+        light_rows.append(point_light((18 * math.cos(ang), 6.0, 18 * math.sin(ang)), color=(1.0, 0.9, 0.8), intensity=60.0, radius=0.2))
+    for k in range(8):
+        ang = 2 * math.pi * (k + 0.5) / 8
+        light_rows.append(spot_light((8 * math.cos(ang), 8.0, 8 * math.sin(ang)), forward=(0.0, 1.0, 0.0), color=(0.8, 0.9, 1.0), intensity=120.0, radius=0.1, inner_deg=25.0, outer_deg=25.0))
+    cam = Camera.look_at((0.0, 5.0, 26.0), (0.0, 2.5, 0.0), fov=60.0, near=1.0, far=1000.0, focal_length=24.0, aperture_radius=0.0)
+    return SceneData(f"foliage{n_clusters}x{cards_per_cluster}", width, height, meshes, mats, instances, [submesh_table(m) for m in meshes], _stack(light_rows, abi.LIGHT), cam, textures=textures)
+
+
+# ----------------------------------------------------------------------------------------------
+# config 4: instanced city
+# ----------------------------------------------------------------------------------------------
+def _building_mesh(rng, floors, detail, materials):
+    """a box tower with `detail` x `detail` window-ledge quads per floor and side: 12 + floors*4*detail*2*... triangles"""
+    b = _MeshBuilder()
+    w, d, fh = 1.0, 1.0, 0.35
+    h = floors * fh
+
+    def add_quad(p0, p1, p2, p3):
+        p, i, nn = _quad(p0, p1, p2, p3)
+        b.add(p, i, nn, uv=[[0, 0], [1, 0], [1, 1], [0, 1]])
+
+    b.begin_submesh(materials[0])
+    # walls as a grid of quads (floors x detail per side) so triangle counts scale
+    for side in range(4):
+        for f in range(floors):
+            for k in range(detail):
+                u0, u1 = -w + 2 * w * k / detail, -w + 2 * w * (k + 1) / detail
+                y0, y1 = f * fh, (f + 1) * fh
+                if side == 0:
+                    add_quad((u0, y0, d), (u1, y0, d), (u1, y1, d), (u0, y1, d))
+                elif side == 1:
+                    add_quad((u1, y0, -d), (u0, y0, -d), (u0, y1, -d), (u1, y1, -d))
+                elif side == 2:
+                    add_quad((w, y0, -u0), (w, y0, -u1), (w, y1, -u1), (w, y1, -u0))
+                else:
+                    add_quad((-w, y0, u0), (-w, y0, u1), (-w, y1, u1), (-w, y1, u0))
+    b.end_submesh()
+    b.begin_submesh(materials[1])
+    add_quad((-w, h, d), (w, h, d), (w, h, -d), (-w, h, -d))  # roof
+    # ledges: small protruding boxes' top faces per floor
+    for f in range(floors):
+        y = f * fh + 0.02
+        add_quad((-w * 1.05, y, d * 1.05), (w * 1.05, y, d * 1.05), (w * 1.05, y, d), (-w * 1.05, y, d))
+    b.end_submesh()
+    return b.build()
+
+
+def city_scene(n_instances=1023, n_meshes=32, width=3840, height=2160, seed=4, floors=(8, 40), detail=(8, 60)) -> SceneData:
+    """config 4: <= 1024 instances (reference limit include/resource/scene.h:14) of <= 32 unique building meshes on a
+    grid + a ground instance; directional light -> Hosek-Wilkie sky + environment light.  Defaults: ~20M instanced triangles."""
+    rng = np.random.default_rng(seed)
+    palette = [(0.6, 0.6, 0.62), (0.5, 0.45, 0.4), (0.7, 0.68, 0.6), (0.35, 0.4, 0.5), (0.8, 0.8, 0.85), (0.3, 0.3, 0.32)]
+    mats = [make_material((*c, 1.0), roughness=0.4 + 0.1 * i, metallic=1.0 if i == 4 else 0.0) for i, c in enumerate(palette)]
+    mats.append(make_material((0.25, 0.25, 0.25, 1.0), roughness=0.95))  # ground
+    mats = _stack(mats, abi.MATERIAL)
+    GROUND = len(palette)
+    meshes = []
+    for m in range(n_meshes):
+        fl = int(rng.integers(floors[0], floors[1] + 1))
+        dt = int(rng.integers(detail[0], detail[1] + 1))
+        meshes.append(_building_mesh(rng, fl, dt, [int(rng.integers(0, 4)), int(4 + rng.integers(0, 2))]))
+    side = int(math.ceil(math.sqrt(n_instances)))
+    spacing = 3.2
+    half = side * spacing / 2
+    gb = _MeshBuilder()
+    gb.begin_submesh(GROUND)
+    p, i, nn = _quad((-half - 5, 0.0, half + 5), (half + 5, 0.0, half + 5), (half + 5, 0.0, -half - 5), (-half - 5, 0.0, -half - 5))
+    gb.add(p, i, nn, uv=[[0, 0], [8, 0], [8, 8], [0, 8]])
+    gb.end_submesh()
+    meshes.append(gb.build())
+    inst_rows, tables = [], []
+    for k in range(n_instances):
+        mi = int(rng.integers(0, n_meshes))
+        gx, gz = k % side, k // side
+        sc = 0.8 + 0.6 * rng.random()
+        M = trs(((gx + 0.5) * spacing - half, 0.0, (gz + 0.5) * spacing - half), (sc, 0.7 + 0.8 * rng.random(), sc), rot_y_deg=float(rng.integers(0, 4)) * 90.0 + rng.normal() * 3.0)
+        inst_rows.append(make_instance(M, mesh_index=mi))
+        tables.append(submesh_table(meshes[mi]))
+    inst_rows.append(make_instance(mesh_index=n_meshes))
+    tables.append(submesh_table(meshes[n_meshes]))
+    el = math.radians(35.0)
+    sun = np.array([math.cos(el) * 0.5, math.sin(el), math.cos(el) * 0.866], np.float64)
+    sun /= np.linalg.norm(sun)
+    lights = _stack([env_light(), directional_light(-sun, color=(1.0, 0.95, 0.9), intensity=3.0, radius=0.02)], abi.LIGHT)
+    cam = Camera.look_at((half * 0.9, half * 0.55, half * 1.1), (0.0, 2.0, 0.0), fov=55.0, near=1.0, far=2000.0, focal_length=half, aperture_radius=0.0)
+    return SceneData(f"city{n_instances}", width, height, meshes, mats, _stack(inst_rows, abi.INSTANCE), tables, lights, cam, sun_direction=sun.astype(np.float32))
