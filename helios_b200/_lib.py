@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libhelios_b200.so"
+import os
+
+# HELIOS_B200_LIB selects another build of the same library (tools/tune_trace.py compiles tuning variants)
+LIB_PATH = Path(os.environ.get("HELIOS_B200_LIB") or Path(__file__).resolve().parent / "libhelios_b200.so")
 
 # every symbol include/helios_b200.h declares
 SYMBOLS = [

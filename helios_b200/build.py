@@ -31,14 +31,17 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
-        return LIB
+def build_library(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: Path | None = None) -> Path:
+    """`defines` / `out` build a tuning variant (e.g. ["-DHL_REFILL_MIN=4"]) next to the product library."""
+    lib = Path(out) if out else LIB
+    if not defines and not force and not needs_build():
+        return lib
+    lib.parent.mkdir(parents=True, exist_ok=True)
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, *( ["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    cmd = [nvcc, *NVCC_FLAGS, *(defines or []), *( ["-Xptxas", "-v"] if verbose else []), "-o", str(lib), *[str(CSRC / s) for s in SOURCES]]
     print("[helios_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -10,10 +10,10 @@
 // Node layout and the octant-ordered traversal follow the 8-wide compressed BVH of Ylitie, Karras and
 // Laine (HPG 2017); the code is written from the paper's description.
 //
-// Execution shape: ONE loop per ray for both levels (an instance entry pushes a sentinel and switches the
-// ray to object space; popping the sentinel switches back), and the loop condition is a warp vote, so the
-// 32 rays of a warp re-converge at the top of every iteration: lanes that finished idle until the warp's
-// last ray is done instead of drifting into private instruction streams.
+// Execution shape: ONE step function per ray for both levels (an instance entry pushes a sentinel and
+// switches the ray to object space; popping the sentinel switches back).  The callers loop on a warp vote, so
+// the 32 rays of a warp re-converge at the top of every step instead of drifting into private instruction
+// streams, and the persistent trace kernels refill finished lanes with new rays between steps.
 #pragma once
 #include "hl_scene.h"
 #include "hl_tex.h"
@@ -115,8 +115,11 @@ HL_HD U4 load_u4(const void* p)
     return r;
 #endif
 }
-// u8 -> float without the conversion pipe: 0x4B000000 | b is the float 2^23 + b
-HL_HD float byte_to_float(uint32_t word, int i) { return u2f(0x4B000000u | ((word >> (8 * i)) & 0xFFu)) - 8388608.0f; }
+// Quantised plane byte -> t in two instructions: one PRMT drops byte i of `word` into mantissa bits 8..15
+// of 1.0f, giving F = 1 + b * 2^-15 exactly, and one FMA evaluates F * A + B with A = adj * 2^15 and
+// B = (org -+ slack) - A, i.e. b * adj + org -+ slack.  The only new error is the rounding of B
+// (<= 2^-24 |org| + 2^-9 |adj|), which the slack below absorbs.
+HL_HD float plane_t(uint32_t word, int i, float A, float B) { return hl_fma(u2f(hl_prmt(word, 0x3F800000u, 0x7604u | ((uint32_t)i << 4))), A, B); }
 
 // Tests the 8 quantised child boxes of one node (five 16-byte loads); returns the hit mask: bits 24..31 =
 // internal children in octant-permuted order (highest bit = visit first), bits 0..23 = leaf primitives.
@@ -134,20 +137,23 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
     const float orgx = (u2f(n0.x) - r.o.x) * r.idir.x;
     const float orgy = (u2f(n0.y) - r.o.y) * r.idir.y;
     const float orgz = (u2f(n0.z) - r.o.z) * r.idir.z;
-    // conservative per-axis slack (in t): covers the rounding of org/adj/fma and the fact that the fp32
+    // conservative per-axis slack (in t): covers the rounding of org/adj/B/fma and the fact that the fp32
     // triangle test can accept rays that miss the exact box by a few ulp of the ray-box distance.  It is
     // folded into the fma addend: near planes use org - s, far planes org + s.  (Per axis, not a common
     // maximum: an axis with a near-zero direction component has a huge |idir| and would otherwise open
-    // every box of the tree.)
+    // every box of the tree.)  2^-19 * 1536 |adj| = 2^-8.4 |adj| > 2^-9 |adj| (rounding of B) + the
+    // 2^-19 * 255 |adj| of the exact-byte formulation.
     const float C  = 1.9073486e-6f; /* 2^-19 */
-    const float sx = C * (fabsf(orgx) + 255.0f * fabsf(adjx));
-    const float sy = C * (fabsf(orgy) + 255.0f * fabsf(adjy));
-    const float sz = C * (fabsf(orgz) + 255.0f * fabsf(adjz));
-    const float onx = orgx - sx, ofx = orgx + sx;
-    const float ony = orgy - sy, ofy = orgy + sy;
-    const float onz = orgz - sz, ofz = orgz + sz;
+    const float sx = C * (fabsf(orgx) + 1536.0f * fabsf(adjx));
+    const float sy = C * (fabsf(orgy) + 1536.0f * fabsf(adjy));
+    const float sz = C * (fabsf(orgz) + 1536.0f * fabsf(adjz));
+    const float Ax = adjx * 32768.0f, Ay = adjy * 32768.0f, Az = adjz * 32768.0f;
+    const float Bnx = (orgx - sx) - Ax, Bfx = (orgx + sx) - Ax;
+    const float Bny = (orgy - sy) - Ay, Bfy = (orgy + sy) - Ay;
+    const float Bnz = (orgz - sz) - Az, Bfz = (orgz + sz) - Az;
     const bool  nx = r.idir.x < 0.0f, ny = r.idir.y < 0.0f, nz = r.idir.z < 0.0f;
-    uint32_t    hitmask = 0;
+    const uint32_t oct4 = r.octinv * 0x01010101u;
+    uint32_t       hitmask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -161,20 +167,18 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
         const uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
         const uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
         const uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+        // four children at a time: inner children (meta & 0x18 == 0x18) take the octant-permuted bit index
+        const uint32_t inner4 = ((meta4 & (meta4 << 1)) & 0x10101010u) >> 4; // 0x01 per inner child
+        const uint32_t bit4   = (meta4 ^ (oct4 & (inner4 * 0xFFu))) & 0x1F1F1F1Fu;
+        const uint32_t cnt4   = (meta4 >> 5) & 0x07070707u; // 0 for an empty slot: contributes nothing
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int j = 0; j < 4; j++)
         {
-            const uint32_t meta = (meta4 >> (8 * j)) & 0xFFu;
-            const float tnear = fmaxf(fmaxf(hl_fma(byte_to_float(nearx, j), adjx, onx), hl_fma(byte_to_float(neary, j), adjy, ony)), fmaxf(hl_fma(byte_to_float(nearz, j), adjz, onz), tmin));
-            const float tfar  = fminf(fminf(hl_fma(byte_to_float(farx, j), adjx, ofx), hl_fma(byte_to_float(fary, j), adjy, ofy)), fminf(hl_fma(byte_to_float(farz, j), adjz, ofz), tbest));
-            if (meta != 0 && tnear <= tfar)
-            {
-                const bool     inner = (meta & 0x18u) == 0x18u;
-                const uint32_t bit   = inner ? ((meta ^ r.octinv) & 0x1Fu) : (meta & 0x1Fu);
-                hitmask |= (meta >> 5) << bit;
-            }
+            const float tnear = fmaxf(fmaxf(plane_t(nearx, j, Ax, Bnx), plane_t(neary, j, Ay, Bny)), fmaxf(plane_t(nearz, j, Az, Bnz), tmin));
+            const float tfar  = fminf(fminf(plane_t(farx, j, Ax, Bfx), plane_t(fary, j, Ay, Bfy)), fminf(plane_t(farz, j, Az, Bfz), tbest));
+            if (tnear <= tfar) hitmask |= hl_prmt(cnt4, 0u, 0x4440u | (uint32_t)j) << hl_prmt(bit4, 0u, 0x4440u | (uint32_t)j);
         }
     }
     return hitmask;
@@ -238,113 +242,150 @@ HL_HD bool test_leaf_triangle(const SceneView& s, const LeafTri* tri, f3 o, f3 d
     return true;
 }
 
-// traceRayEXT: fills `best` (instance == HL_MISS when nothing was hit).  `active` = false runs an empty query
-// (GPU lanes without a ray still take part in the warp votes).
-HL_HD void trace_ray(const SceneView& s, bool active, f3 o, float tmin, f3 d, float tmax, uint32_t flags, Hit& best, TravStack& st)
+// ---- traceRayEXT as a resumable state machine ---------------------------------------------------------
+// trav_begin / trav_busy / trav_step: one step = (visit one node OR pop one stack entry) followed by up to
+// HL_TRI_PER_STEP triangle tests (or one instance entry at the top level).  The persistent trace kernels
+// call trav_step in a warp-convergent loop and hand finished lanes a new ray between steps; trace_ray()
+// below runs one query per lane to completion (tail kernel, generic trace entry point, emulator).
+#ifndef HL_TRI_PER_STEP
+#define HL_TRI_PER_STEP 2
+#endif
+struct Trav
 {
-    best.t = tmax, best.u = 0.0f, best.v = 0.0f;
-    best.instance = best.geometry = best.primitive = HL_MISS;
+    RayCtx          r;    // ray in the space of the tree being traversed
+    f3              o, d; // world-space ray
+    float           tmin, tmax;
+    uint32_t        flags;
+    const WideNode* nodes;
+    const LeafTri*  tris;
+    uint32_t        inst; // HL_MISS = top level
+    u2              ngroup, tgroup;
+    Hit             best; // instance == HL_MISS when nothing was hit
+};
+
+HL_HD void trav_begin(const SceneView& s, Trav& t, TravStack& st, bool active, f3 o, float tmin, f3 d, float tmax, uint32_t flags)
+{
+    t.best.t = tmax, t.best.u = 0.0f, t.best.v = 0.0f;
+    t.best.instance = t.best.geometry = t.best.primitive = HL_MISS;
     st.sp = 0;
-    u2 ngroup, tgroup;
-    ngroup.x = 0, ngroup.y = 0, tgroup.x = 0, tgroup.y = 0;
-    RayCtx          r      = make_ray_ctx(o, d);
-    const WideNode* nodes  = s.tlas_nodes;
-    const LeafTri*  tris   = nullptr;
-    uint32_t        inst   = HL_MISS; // HL_MISS = top level
+    t.ngroup.x = 0, t.ngroup.y = 0, t.tgroup.x = 0, t.tgroup.y = 0;
+    t.o = o, t.d = d, t.tmin = tmin, t.tmax = tmax, t.flags = flags;
+    t.r     = make_ray_ctx(o, d);
+    t.nodes = s.tlas_nodes, t.tris = nullptr, t.inst = HL_MISS;
     if (active && s.n_instances != 0)
     {
         if (s.single_identity)
         {
             const MeshView& mesh = s.meshes[s.instances[0].mesh_index];
-            if (mesh.n_tris != 0) nodes = mesh.nodes, tris = mesh.tris, inst = 0, ngroup.y = 0x80000000u;
+            if (mesh.n_tris != 0) t.nodes = mesh.nodes, t.tris = mesh.tris, t.inst = 0, t.ngroup.y = 0x80000000u;
         }
         else
-            ngroup.y = 0x80000000u;
+            t.ngroup.y = 0x80000000u;
     }
+}
+HL_HD bool trav_busy(const Trav& t, const TravStack& st) { return t.ngroup.y > 0x00FFFFFFu || t.tgroup.y != 0 || st.sp > 0; }
+
+HL_HD void trav_step(const SceneView& s, Trav& t, TravStack& st)
+{
+    if (t.tgroup.y == 0)
+    {
+        if (t.ngroup.y > 0x00FFFFFFu)
+        {
+            // visit the nearest pending child of the current node group
+            const uint32_t hits = t.ngroup.y;
+            const int      bit  = hl_bfind(hits);
+            const uint32_t base = t.ngroup.x;
+            t.ngroup.y &= ~(1u << bit);
+            if (t.ngroup.y > 0x00FFFFFFu) st.push(t.ngroup);
+            const uint32_t slot = (uint32_t)(bit - 24) ^ t.r.octinv;
+            const uint32_t rel  = (uint32_t)hl_popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
+            HL_STAT_NODE();
+            uint32_t       cb, lb, im;
+            const uint32_t mask = intersect_children(t.nodes + (base + rel), t.r, t.tmin, t.best.t, cb, lb, im);
+            t.ngroup.x = cb, t.ngroup.y = (mask & 0xFF000000u) | im;
+            t.tgroup.x = lb, t.tgroup.y = mask & 0x00FFFFFFu;
+        }
+        else
+        {
+            const u2 e = st.pop();
+            if (e.y == 0)
+            {
+                // sentinel: leave the instance, back to world space and the top-level tree
+                t.r = make_ray_ctx(t.o, t.d), t.nodes = s.tlas_nodes, t.tris = nullptr, t.inst = HL_MISS;
+            }
+            else if (e.y > 0x00FFFFFFu)
+                t.ngroup = e;
+            else
+                t.tgroup = e;
+        }
+    }
+    if (t.tgroup.y != 0)
+    {
+        if (t.inst != HL_MISS)
+        {
+            // bottom level: test pending triangles of this leaf group
+            bool done = false;
+#if HL_TRI_PER_STEP < 24
+            for (int k = 0; k < HL_TRI_PER_STEP && t.tgroup.y; k++)
+#else
+            while (t.tgroup.y)
+#endif
+            {
+                const int i = hl_bfind(t.tgroup.y);
+                t.tgroup.y &= ~(1u << i);
+                HL_STAT_LEAF();
+                if (test_leaf_triangle(s, t.tris + (t.tgroup.x + (uint32_t)i), t.r.o, t.r.d, t.tmin, t.tmax, t.inst, t.flags, t.best) && (t.flags & HL_RAY_TERMINATE))
+                {
+                    done = true;
+                    break;
+                }
+            }
+            if (done) t.ngroup.y = 0, t.tgroup.y = 0, st.sp = 0;
+        }
+        else
+        {
+            // top level: enter ONE instance; the rest of the leaf group and the node group wait on the stack
+            const int i = hl_bfind(t.tgroup.y);
+            t.tgroup.y &= ~(1u << i);
+            HL_STAT_LEAF();
+            const uint32_t  id   = s.tlas_leaf[t.tgroup.x + (uint32_t)i];
+            const MeshView& mesh = s.meshes[s.instances[id].mesh_index];
+            if (mesh.n_tris != 0)
+            {
+                if (t.tgroup.y) st.push(t.tgroup);
+                if (t.ngroup.y > 0x00FFFFFFu) st.push(t.ngroup);
+                u2 sentinel;
+                sentinel.x = 0xFFFFFFFFu, sentinel.y = 0;
+                st.push(sentinel);
+                const float* m = s.inst_inv + 12 * (size_t)id;
+                const f3     o = t.o, d = t.d;
+                f3           oo, od;
+                oo.x = (m[0] * o.x + m[1] * o.y + m[2] * o.z) + m[3];
+                oo.y = (m[4] * o.x + m[5] * o.y + m[6] * o.z) + m[7];
+                oo.z = (m[8] * o.x + m[9] * o.y + m[10] * o.z) + m[11];
+                od.x = m[0] * d.x + m[1] * d.y + m[2] * d.z;
+                od.y = m[4] * d.x + m[5] * d.y + m[6] * d.z;
+                od.z = m[8] * d.x + m[9] * d.y + m[10] * d.z;
+                t.r = make_ray_ctx(oo, od), t.nodes = mesh.nodes, t.tris = mesh.tris, t.inst = id;
+                t.ngroup.x = 0, t.ngroup.y = 0x80000000u, t.tgroup.y = 0;
+            }
+        }
+    }
+}
+
+// traceRayEXT, one query per lane to completion: fills `best` (instance == HL_MISS when nothing was hit).
+// `active` = false runs an empty query (GPU lanes without a ray still take part in the warp votes: the loop
+// condition is a warp vote, so the 32 rays of a warp re-converge at the top of every step).
+HL_HD void trace_ray(const SceneView& s, bool active, f3 o, float tmin, f3 d, float tmax, uint32_t flags, Hit& best, TravStack& st)
+{
+    Trav t;
+    trav_begin(s, t, st, active, o, tmin, d, tmax, flags);
     for (;;)
     {
-        const bool busy = ngroup.y > 0x00FFFFFFu || tgroup.y != 0 || st.sp > 0;
+        const bool busy = trav_busy(t, st);
         if (!HL_WARP_ANY(busy)) break;
-        if (!busy) continue;
-        if (tgroup.y == 0)
-        {
-            if (ngroup.y > 0x00FFFFFFu)
-            {
-                // visit the nearest pending child of the current node group
-                const uint32_t hits = ngroup.y;
-                const int      bit  = hl_bfind(hits);
-                const uint32_t base = ngroup.x;
-                ngroup.y &= ~(1u << bit);
-                if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
-                const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
-                const uint32_t rel  = (uint32_t)hl_popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
-                HL_STAT_NODE();
-                uint32_t       cb, lb, im;
-                const uint32_t mask = intersect_children(nodes + (base + rel), r, tmin, best.t, cb, lb, im);
-                ngroup.x = cb, ngroup.y = (mask & 0xFF000000u) | im;
-                tgroup.x = lb, tgroup.y = mask & 0x00FFFFFFu;
-            }
-            else
-            {
-                const u2 e = st.pop();
-                if (e.y == 0)
-                {
-                    // sentinel: leave the instance, back to world space and the top-level tree
-                    r = make_ray_ctx(o, d), nodes = s.tlas_nodes, tris = nullptr, inst = HL_MISS;
-                }
-                else if (e.y > 0x00FFFFFFu)
-                    ngroup = e;
-                else
-                    tgroup = e;
-            }
-        }
-        if (tgroup.y != 0)
-        {
-            if (inst != HL_MISS)
-            {
-                // bottom level: test every pending triangle of this leaf group
-                bool done = false;
-                while (tgroup.y)
-                {
-                    const int i = hl_bfind(tgroup.y);
-                    tgroup.y &= ~(1u << i);
-                    HL_STAT_LEAF();
-                    if (test_leaf_triangle(s, tris + (tgroup.x + (uint32_t)i), r.o, r.d, tmin, tmax, inst, flags, best) && (flags & HL_RAY_TERMINATE))
-                    {
-                        done = true;
-                        break;
-                    }
-                }
-                if (done) ngroup.y = 0, tgroup.y = 0, st.sp = 0;
-            }
-            else
-            {
-                // top level: enter ONE instance; the rest of the leaf group and the node group wait on the stack
-                const int i = hl_bfind(tgroup.y);
-                tgroup.y &= ~(1u << i);
-                HL_STAT_LEAF();
-                const uint32_t  id   = s.tlas_leaf[tgroup.x + (uint32_t)i];
-                const MeshView& mesh = s.meshes[s.instances[id].mesh_index];
-                if (mesh.n_tris != 0)
-                {
-                    if (tgroup.y) st.push(tgroup);
-                    if (ngroup.y > 0x00FFFFFFu) st.push(ngroup);
-                    u2 sentinel;
-                    sentinel.x = 0xFFFFFFFFu, sentinel.y = 0;
-                    st.push(sentinel);
-                    const float* m = s.inst_inv + 12 * (size_t)id;
-                    f3           oo, od;
-                    oo.x = (m[0] * o.x + m[1] * o.y + m[2] * o.z) + m[3];
-                    oo.y = (m[4] * o.x + m[5] * o.y + m[6] * o.z) + m[7];
-                    oo.z = (m[8] * o.x + m[9] * o.y + m[10] * o.z) + m[11];
-                    od.x = m[0] * d.x + m[1] * d.y + m[2] * d.z;
-                    od.y = m[4] * d.x + m[5] * d.y + m[6] * d.z;
-                    od.z = m[8] * d.x + m[9] * d.y + m[10] * d.z;
-                    r = make_ray_ctx(oo, od), nodes = mesh.nodes, tris = mesh.tris, inst = id;
-                    ngroup.x = 0, ngroup.y = 0x80000000u, tgroup.y = 0;
-                }
-            }
-        }
+        if (busy) trav_step(s, t, st);
     }
+    best = t.best;
 }
 } // namespace hl

@@ -167,5 +167,18 @@ HL_HD int hl_clz64(uint64_t x)
 #endif
 }
 HL_HD uint32_t hl_byte(uint32_t v, int i) { return (v >> (8 * i)) & 0xFFu; }
+// PRMT: result byte k = byte number (sel >> 4k) & 7 of the 8-byte pool {a.b0..a.b3, b.b0..b.b3}
+// (selector nibbles are always < 8 here, so the sign-replication mode of the instruction is never used)
+HL_HD uint32_t hl_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t       r    = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
+    return r;
+#endif
+}
 HL_HD float    hl_inf() { return u2f(0x7f800000u); }
 } // namespace hl

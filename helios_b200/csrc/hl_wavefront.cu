@@ -46,33 +46,84 @@ __global__ void k_generate(FrameParams fp, float4* state_a, float4* state_b, flo
     ext_d[i]   = make_float4(d.x, d.y, d.z, 0.0f);
 }
 
+// ---- persistent trace loop -------------------------------------------------------------------------
+// Shared by extend and connect.  Every lane owns one traversal (hl_bvh.h Trav); the loop condition is a warp
+// vote, and whenever at least HL_REFILL_MIN lanes have finished their ray the warp takes that many new rays
+// from the queue's atomic cursor in one transaction (ballot + popc prefix), so lanes do not idle until the
+// warp's slowest ray is done.  Results are stored by ray index: the output does not depend on which lane
+// traced which ray.  Q supplies load(i, ...) and done(i, hit).
+#ifndef HL_REFILL_MIN
+#define HL_REFILL_MIN 8
+#endif
+template <class Q>
+__device__ __forceinline__ void trace_queue(const SceneView& s, const Q& q, uint32_t count, uint32_t* fetch, uint32_t flags, TravStack& st)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    Trav           t;
+    trav_begin(s, t, st, false, mk3(0.0f), 0.0f, mk3(0.0f), 0.0f, flags);
+    uint32_t mine      = 0xFFFFFFFFu; // index of the ray this lane is tracing
+    bool     exhausted = false;       // warp-uniform: the cursor ran past the end of the queue
+    for (;;)
+    {
+        bool busy = trav_busy(t, st);
+        if (!busy && mine != 0xFFFFFFFFu) q.done(mine, t.best), mine = 0xFFFFFFFFu;
+        uint32_t bm = __ballot_sync(0xFFFFFFFFu, busy);
+        if (!exhausted && 32 - __popc(bm) >= HL_REFILL_MIN)
+        {
+            const uint32_t idle = ~bm;
+            const uint32_t want = (uint32_t)__popc(idle);
+            uint32_t       base = 0;
+            if (lane == 0) base = atomicAdd(fetch, want);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            exhausted = base + want >= count;
+            const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+            if (!busy && i < count)
+            {
+                f3    o, d;
+                float tmin, tmax;
+                q.load(i, o, tmin, d, tmax);
+                trav_begin(s, t, st, true, o, tmin, d, tmax, flags);
+                mine = i, busy = true; // (a query that starts with nothing to do is retired on the next pass)
+            }
+            bm = __ballot_sync(0xFFFFFFFFu, busy);
+        }
+        if (bm == 0)
+        {
+            if (exhausted) break;
+            continue; // fewer than HL_REFILL_MIN idle lanes cannot happen with bm == 0; kept for clarity
+        }
+        if (trav_busy(t, st)) trav_step(s, t, st);
+    }
+}
+
 // ---- extend ----------------------------------------------------------------------------------------
+struct ExtendQueue
+{
+    const float4* __restrict__ ray_o;
+    const float4* __restrict__ ray_d;
+    float4* __restrict__ hit_a;
+    uint2* __restrict__ hit_b;
+    float tmin, tmax;
+    __device__ __forceinline__ void load(uint32_t i, f3& o, float& t0, f3& d, float& t1) const
+    {
+        const float4 o4 = ld4(ray_o + i), d4 = ld4(ray_d + i);
+        o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z), t0 = tmin, t1 = tmax;
+    }
+    __device__ __forceinline__ void done(uint32_t i, const Hit& h) const
+    {
+        hit_a[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.primitive));
+        hit_b[i] = make_uint2(h.instance, h.geometry);
+    }
+};
 __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_extend(SceneView s, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
                                                            uint32_t* fetch, float tmin, float tmax, uint32_t flags, float4* __restrict__ hit_a, uint2* __restrict__ hit_b)
 {
     __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
     TravStack     st;
     st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
-    const uint32_t count = *count_ptr;
-    const uint32_t lane  = threadIdx.x & 31u;
-    for (;;)
-    {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= count) break;
-        const uint32_t i   = base + lane;
-        const bool     act = i < count;
-        float4         o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
-        if (act) o = ld4(ray_o + i), d = ld4(ray_d + i);
-        Hit h;
-        trace_ray(s, act, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), tmax, flags, h, st); // warp-convergent call
-        if (act)
-        {
-            hit_a[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.primitive));
-            hit_b[i] = make_uint2(h.instance, h.geometry);
-        }
-    }
+    ExtendQueue q;
+    q.ray_o = ray_o, q.ray_d = ray_d, q.hit_a = hit_a, q.hit_b = hit_b, q.tmin = tmin, q.tmax = tmax;
+    trace_queue(s, q, *count_ptr, fetch, flags, st);
 }
 
 // ---- shade -----------------------------------------------------------------------------------------
@@ -148,35 +199,39 @@ __global__ void __launch_bounds__(HL_SHADE_BLOCK) k_shade(SceneView s, ShadePara
 }
 
 // ---- connect ---------------------------------------------------------------------------------------
+struct ConnectQueue
+{
+    const float4* __restrict__ sh_o;
+    const float4* __restrict__ sh_d;
+    const float4* __restrict__ sh_c;
+    float4* state_b;
+    float   tmin;
+    __device__ __forceinline__ void load(uint32_t i, f3& o, float& t0, f3& d, float& t1) const
+    {
+        const float4 o4 = ld4(sh_o + i), d4 = ld4(sh_d + i);
+        o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z), t0 = tmin, t1 = d4.w;
+    }
+    __device__ __forceinline__ void done(uint32_t i, const Hit& h) const
+    {
+        if (h.instance != HL_MISS) return; // occluded
+        // the shadow miss shader ran: p_Visibility = true.  One shadow ray per path and bounce: no other
+        // thread touches this path's radiance while the connect stage runs.
+        const float4   c    = ld4(sh_c + i);
+        const uint32_t path = __float_as_uint(ld4(sh_o + i).w);
+        float4         sb   = state_b[path];
+        sb.x += c.x, sb.y += c.y, sb.z += c.z;
+        state_b[path] = sb;
+    }
+};
 __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_connect(SceneView s, const float4* __restrict__ sh_o, const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                             const uint32_t* __restrict__ count_ptr, uint32_t* fetch, float tmin, uint32_t flags, float4* state_b)
 {
     __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
     TravStack     st;
     st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
-    const uint32_t count = *count_ptr;
-    const uint32_t lane  = threadIdx.x & 31u;
-    for (;;)
-    {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= count) break;
-        const uint32_t i   = base + lane;
-        const bool     act = i < count;
-        float4         o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
-        if (act) o = ld4(sh_o + i), d = ld4(sh_d + i);
-        Hit h;
-        trace_ray(s, act, mk3(o.x, o.y, o.z), tmin, mk3(d.x, d.y, d.z), d.w, flags, h, st);
-        if (act && h.instance == HL_MISS) // the shadow miss shader ran: p_Visibility = true
-        {
-            const float4   c    = ld4(sh_c + i);
-            const uint32_t path = __float_as_uint(o.w);
-            float4         sb   = state_b[path];
-            sb.x += c.x, sb.y += c.y, sb.z += c.z;
-            state_b[path] = sb;
-        }
-    }
+    ConnectQueue q;
+    q.sh_o = sh_o, q.sh_d = sh_d, q.sh_c = sh_c, q.state_b = state_b, q.tmin = tmin;
+    trace_queue(s, q, *count_ptr, fetch, flags, st);
 }
 
 // ---- tail ------------------------------------------------------------------------------------------
