@@ -1,8 +1,8 @@
 // hl_build.h — per-element logic of the GPU BVH builder that replaces vkCmdBuildAccelerationStructuresKHR
 // (reference call sites: src/engine/gfx/vk.cpp:3207-3226 for the per-mesh BLAS, src/engine/gfx/renderer.cpp:147-168
 // for the TLAS).  Pipeline: primitive boxes -> 63-bit Morton keys -> radix sort -> binary radix tree (Karras 2012)
-// -> bottom-up box fit -> SAH-guided collapse into 8-wide nodes with octant-ordered child slots and 8-bit
-// quantised child boxes (Ylitie et al. 2017).  Each function handles ONE element so that the CUDA kernels are
+// -> bottom-up box fit + SAH cost tables -> SAH-optimal collapse (dynamic programme) into 8-wide nodes with
+// octant-ordered child slots and 8-bit quantised child boxes (Ylitie et al. 2017).  Each function handles ONE element so that the CUDA kernels are
 // thin loops over thread ids (and the tests/emul harness can run the same logic sequentially).
 #pragma once
 #include "hl_scene.h"
@@ -64,6 +64,9 @@ struct BinaryTree
     uint32_t* parent; // [2n-1]
     Box*      box;    // [2n-1]
     uint32_t* visits; // [n-1] arrival counters for the bottom-up pass
+    float*    cost;   // [(2n-1) * 7] SAH cost table of the collapse DP (see sah_node_costs)
+    uint32_t* dec;    // [n-1] packed decisions of the collapse DP
+    float     c_prim; // SAH cost of one leaf primitive test relative to one wide-node visit
 };
 HL_HD int key_delta(const uint64_t* keys, int n, int i, int j)
 {
@@ -118,34 +121,99 @@ HL_HD Box box_union(const Box& a, const Box& b)
     for (int k = 0; k < 3; k++) r.lo[k] = fminf(a.lo[k], b.lo[k]), r.hi[k] = fmaxf(a.hi[k], b.hi[k]);
     return r;
 }
-// bottom-up fit: called once per leaf (after its box is written); the second arrival at a node continues.
-// On the GPU the caller issues __threadfence() between the box write and the counter increment.
-template <class Fence>
-HL_HD void fit_from_leaf(BinaryTree& t, uint32_t leaf, Fence fence)
-{
-    uint32_t node = t.parent[(t.n - 1) + leaf];
-    while (node != 0xFFFFFFFFu)
-    {
-        fence();
-        if (hl_atomic_add(&t.visits[node], 1u) == 0u) return;
-        fence();
-        t.box[node] = box_union(load_box_coherent(&t.box[t.left[node]]), load_box_coherent(&t.box[t.right[node]]));
-        node        = t.parent[node];
-    }
-}
 HL_HD float box_half_area(const Box& b)
 {
     const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
     return dx * dy + dy * dz + dz * dx;
 }
-
-// ---- collapse to 8-wide ----------------------------------------------------------------------------
 #define HL_MAX_LEAF_PRIMS 3u
 HL_HD uint32_t subtree_prims(const BinaryTree& t, uint32_t node)
 {
     return node >= t.n - 1 ? 1u : t.last[node] - t.first[node] + 1u;
 }
 HL_HD uint32_t subtree_first(const BinaryTree& t, uint32_t node) { return node >= t.n - 1 ? node - (t.n - 1) : t.first[node]; }
+
+// ---- SAH-optimal collapse, bottom-up half (dynamic programme of Ylitie, Karras, Laine, HPG 2017 §4, written
+// from the paper's recurrences).  C(n, i), i = 1..7 = cheapest SAH cost of representing binary subtree n with
+// at most i child slots of one wide node:
+//   C(n, 1) = min( leaf:  A_n * P_n * c_prim           (P_n <= 3 primitives),
+//                  inner: A_n * c_node + D(n, 8) )      n becomes a wide node of its own
+//   C(n, i) = min( D(n, i), C(n, i-1) )                 i = 2..7
+//   D(n, j) = min over 0 < k < j of C(left, k) + C(right, j - k)
+// dec[n] packs what achieved each minimum, 4 bits per i (0 = leaf, 15 = inner, k = split giving the left
+// child k slots) and the k of D(n, 8) in bits 28..30; collapse_one() replays it top-down.
+#define HL_SAH_C_NODE 1.0f
+#ifndef HL_SAH_C_PRIM_TRIANGLE
+#define HL_SAH_C_PRIM_TRIANGLE 0.35f /* measured: ~90 SASS instructions per triangle test vs ~250 per node visit */
+#endif
+#define HL_SAH_C_PRIM_INSTANCE 16.0f /* an instance entry costs a whole bottom-level traversal */
+HL_HD float load_f32_coherent(const float* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+HL_HD void sah_leaf_costs(BinaryTree& t, uint32_t node, float area)
+{
+    for (int i = 0; i < 7; i++) t.cost[(size_t)node * 7 + i] = area * t.c_prim;
+}
+HL_HD void sah_node_costs(BinaryTree& t, uint32_t node, float area)
+{
+    float cl[8], cr[8];
+    const float inf = hl_inf();
+    cl[0] = cr[0] = inf;
+    for (int i = 0; i < 7; i++) cl[i + 1] = load_f32_coherent(t.cost + (size_t)t.left[node] * 7 + i), cr[i + 1] = load_f32_coherent(t.cost + (size_t)t.right[node] * 7 + i);
+    float    D[9];
+    uint32_t K[9];
+    for (int j = 2; j <= 8; j++)
+    {
+        float    best = inf;
+        uint32_t kb   = 1;
+        for (int k = (j - 7 > 1 ? j - 7 : 1); k < j && k <= 7; k++)
+        {
+            const float c = cl[k] + cr[j - k];
+            if (c < best) best = c, kb = (uint32_t)k;
+        }
+        D[j] = best, K[j] = kb;
+    }
+    const uint32_t P       = subtree_prims(t, node);
+    const float    c_leaf  = P <= HL_MAX_LEAF_PRIMS ? area * (float)P * t.c_prim : inf;
+    const float    c_inner = area * HL_SAH_C_NODE + D[8];
+    float          c       = c_leaf <= c_inner ? c_leaf : c_inner;
+    uint32_t       d       = c_leaf <= c_inner ? 0u : 15u;
+    uint32_t       packed  = d | (K[8] << 28);
+    t.cost[(size_t)node * 7] = c;
+    for (int i = 2; i <= 7; i++)
+    {
+        if (D[i] < c) c = D[i], d = K[i];
+        packed |= d << (4 * (i - 1));
+        t.cost[(size_t)node * 7 + (i - 1)] = c;
+    }
+    t.dec[node] = packed;
+}
+
+// bottom-up fit: called once per leaf (after its box is written); the second arrival at a node continues.
+// On the GPU the caller issues __threadfence() between the writes and the counter increment.
+template <class Fence>
+HL_HD void fit_from_leaf(BinaryTree& t, uint32_t leaf, Fence fence)
+{
+    sah_leaf_costs(t, (t.n - 1) + leaf, box_half_area(t.box[(t.n - 1) + leaf]));
+    uint32_t node = t.parent[(t.n - 1) + leaf];
+    while (node != 0xFFFFFFFFu)
+    {
+        fence();
+        if (hl_atomic_add(&t.visits[node], 1u) == 0u) return;
+        fence();
+        const Box b = box_union(load_box_coherent(&t.box[t.left[node]]), load_box_coherent(&t.box[t.right[node]]));
+        t.box[node] = b;
+        sah_node_costs(t, node, box_half_area(b));
+        node = t.parent[node];
+    }
+}
+
+// ---- collapse to 8-wide, top-down half -------------------------------------------------------------
 
 // smallest biased exponent e with 255 * 2^(e-127) >= extent (0 for a flat axis)
 HL_HD uint32_t quant_exponent(float extent)
@@ -192,28 +260,34 @@ template <class LeafWriter>
 HL_HD void collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, CollapseTask* next, uint32_t* next_count, LeafWriter& leaf_writer)
 {
     uint32_t ch[8];
+    uint32_t ch_inner = 0; // bit k: child k becomes a wide node of its own
     int      nch = 0;
     const uint32_t leaf0 = t.n - 1;
     if (task.bnode >= leaf0 || subtree_prims(t, task.bnode) <= HL_MAX_LEAF_PRIMS)
         ch[nch++] = task.bnode; // tiny tree: the root's only child is one leaf
     else
     {
-        ch[nch++] = t.left[task.bnode];
-        ch[nch++] = t.right[task.bnode];
-        while (nch < 8)
+        // replay the DP: (node, slots) pairs; at most 8 are ever pending
+        uint32_t sn[8], ss[8];
+        int      sp = 0;
+        const uint32_t k8 = (t.dec[task.bnode] >> 28) & 7u;
+        sn[sp] = t.right[task.bnode], ss[sp++] = 8u - k8;
+        sn[sp] = t.left[task.bnode], ss[sp++] = k8;
+        while (sp > 0 && nch < 8)
         {
-            int   best = -1;
-            float barea = -1.0f;
-            for (int k = 0; k < nch; k++)
+            sp--;
+            const uint32_t m = sn[sp], i = ss[sp];
+            uint32_t       d = 0;
+            if (m < leaf0) d = (t.dec[m] >> (4 * ((i < 1 ? 1 : i) - 1))) & 15u;
+            if (m >= leaf0 || d == 0u)
+                ch[nch++] = m;
+            else if (d == 15u)
+                ch_inner |= 1u << nch, ch[nch++] = m;
+            else
             {
-                if (ch[k] >= leaf0 || subtree_prims(t, ch[k]) <= HL_MAX_LEAF_PRIMS) continue;
-                const float a = box_half_area(t.box[ch[k]]);
-                if (a > barea) barea = a, best = k;
+                sn[sp] = t.right[m], ss[sp++] = i - d;
+                sn[sp] = t.left[m], ss[sp++] = d;
             }
-            if (best < 0) break;
-            const uint32_t b = ch[best];
-            ch[best]         = t.left[b];
-            ch[nch++]        = t.right[b];
         }
     }
     const Box nb = t.box[task.bnode];
@@ -262,7 +336,7 @@ HL_HD void collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, Col
     {
         if (slot_child[s] < 0) continue;
         const uint32_t c = ch[slot_child[s]];
-        if (c < leaf0 && subtree_prims(t, c) > HL_MAX_LEAF_PRIMS)
+        if (ch_inner & (1u << slot_child[s]))
             n_inner++, imask |= 1u << s;
         else
             n_leafprims += subtree_prims(t, c);

@@ -122,7 +122,12 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     const size_t ni = n > 1 ? n - 1 : 1;
     tree_u32.alloc(4ull * (ni * 5 + 2ull * n));
     tree_box.alloc(sizeof(Box) * (2ull * n));
+    DevBuf tree_cost;
+    tree_cost.alloc(4ull * (7ull * 2 * n + ni));
     BinaryTree t;
+    t.cost   = tree_cost.as<float>();
+    t.dec    = (uint32_t*)(t.cost + 7ull * 2 * n);
+    t.c_prim = leaf_bytes == sizeof(LeafTri) ? HL_SAH_C_PRIM_TRIANGLE : HL_SAH_C_PRIM_INSTANCE;
     t.n      = n;
     t.left   = tree_u32.as<uint32_t>();
     t.right  = t.left + ni;

@@ -31,6 +31,11 @@ inline TraversalStats& traversal_stats()
     static thread_local TraversalStats s;
     return s;
 }
+inline bool& emul_force_postpone()
+{
+    static bool f = false;
+    return f;
+}
 #define HL_STAT_NODE() (traversal_stats().nodes++)
 #define HL_STAT_LEAF() (traversal_stats().leaves++)
 #else
@@ -39,9 +44,9 @@ inline TraversalStats& traversal_stats()
 #endif
 
 #if defined(__CUDA_ARCH__)
-#define HL_WARP_ANY(p) __any_sync(0xFFFFFFFFu, (p))
+#define HL_WARP_BALLOT(p) __ballot_sync(0xFFFFFFFFu, (p))
 #else
-#define HL_WARP_ANY(p) (p)
+#define HL_WARP_BALLOT(p) ((p) ? 1u : 0u)
 #endif
 
 #ifndef HL_STACK_FAST
@@ -243,10 +248,11 @@ HL_HD bool test_leaf_triangle(const SceneView& s, const LeafTri* tri, f3 o, f3 d
 }
 
 // ---- traceRayEXT as a resumable state machine ---------------------------------------------------------
-// trav_begin / trav_busy / trav_step: one step = (visit one node OR pop one stack entry) followed by up to
-// HL_TRI_PER_STEP triangle tests (or one instance entry at the top level).  The persistent trace kernels
-// call trav_step in a warp-convergent loop and hand finished lanes a new ray between steps; trace_ray()
-// below runs one query per lane to completion (tail kernel, generic trace entry point, emulator).
+// trav_begin / trav_busy / trav_step_warp: one step = (pop a stack entry if nothing is current, visit one
+// node) followed by up to HL_TRI_PER_STEP triangle tests (or one instance entry at the top level).  The
+// persistent trace kernels call trav_step_warp in a warp-convergent loop and hand finished lanes a new ray
+// between steps; trace_ray() below runs one query per lane to completion (tail kernel, generic trace entry
+// point, emulator).
 #ifndef HL_TRI_PER_STEP
 #define HL_TRI_PER_STEP 2
 #endif
@@ -285,92 +291,140 @@ HL_HD void trav_begin(const SceneView& s, Trav& t, TravStack& st, bool active, f
 }
 HL_HD bool trav_busy(const Trav& t, const TravStack& st) { return t.ngroup.y > 0x00FFFFFFu || t.tgroup.y != 0 || st.sp > 0; }
 
-HL_HD void trav_step(const SceneView& s, Trav& t, TravStack& st)
+// phase 1 of a step: nothing current -> pop one stack entry; then, if a node group is current, visit its
+// nearest pending child.  (Pop and visit share a step so that a lane never sits out the other lanes' node
+// test just to fetch its next entry.)
+HL_HD void trav_step_nodes(const SceneView& s, Trav& t, TravStack& st)
 {
-    if (t.tgroup.y == 0)
+    if (t.tgroup.y != 0) return;
+    if (t.ngroup.y <= 0x00FFFFFFu)
     {
-        if (t.ngroup.y > 0x00FFFFFFu)
+        if (st.sp <= 0) return;
+        const u2 e = st.pop();
+        if (e.y == 0)
         {
-            // visit the nearest pending child of the current node group
-            const uint32_t hits = t.ngroup.y;
-            const int      bit  = hl_bfind(hits);
-            const uint32_t base = t.ngroup.x;
-            t.ngroup.y &= ~(1u << bit);
-            if (t.ngroup.y > 0x00FFFFFFu) st.push(t.ngroup);
-            const uint32_t slot = (uint32_t)(bit - 24) ^ t.r.octinv;
-            const uint32_t rel  = (uint32_t)hl_popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
-            HL_STAT_NODE();
-            uint32_t       cb, lb, im;
-            const uint32_t mask = intersect_children(t.nodes + (base + rel), t.r, t.tmin, t.best.t, cb, lb, im);
-            t.ngroup.x = cb, t.ngroup.y = (mask & 0xFF000000u) | im;
-            t.tgroup.x = lb, t.tgroup.y = mask & 0x00FFFFFFu;
+            // sentinel: leave the instance, back to world space and the top-level tree
+            t.r = make_ray_ctx(t.o, t.d), t.nodes = s.tlas_nodes, t.tris = nullptr, t.inst = HL_MISS;
+            return;
         }
-        else
+        if (e.y <= 0x00FFFFFFu)
         {
-            const u2 e = st.pop();
-            if (e.y == 0)
-            {
-                // sentinel: leave the instance, back to world space and the top-level tree
-                t.r = make_ray_ctx(t.o, t.d), t.nodes = s.tlas_nodes, t.tris = nullptr, t.inst = HL_MISS;
-            }
-            else if (e.y > 0x00FFFFFFu)
-                t.ngroup = e;
-            else
-                t.tgroup = e;
+            t.tgroup = e;
+            return;
         }
+        t.ngroup = e;
     }
-    if (t.tgroup.y != 0)
+    // visit the nearest pending child of the current node group
+    const uint32_t hits = t.ngroup.y;
+    const int      bit  = hl_bfind(hits);
+    const uint32_t base = t.ngroup.x;
+    t.ngroup.y &= ~(1u << bit);
+    if (t.ngroup.y > 0x00FFFFFFu) st.push(t.ngroup);
+    const uint32_t slot = (uint32_t)(bit - 24) ^ t.r.octinv;
+    const uint32_t rel  = (uint32_t)hl_popc((hits & 0xFFu) & ~(0xFFFFFFFFu << slot));
+    HL_STAT_NODE();
+    uint32_t       cb, lb, im;
+    const uint32_t mask = intersect_children(t.nodes + (base + rel), t.r, t.tmin, t.best.t, cb, lb, im);
+    t.ngroup.x = cb, t.ngroup.y = (mask & 0xFF000000u) | im;
+    t.tgroup.x = lb, t.tgroup.y = mask & 0x00FFFFFFu;
+}
+// triangle postponing (after Ylitie et al.): a lane that has a leaf group AND inner children pending may
+// put the leaf group on the stack and keep descending, so that triangle tests run when many lanes have one
+HL_HD bool trav_can_postpone(const Trav& t) { return t.inst != HL_MISS && t.ngroup.y > 0x00FFFFFFu; }
+HL_HD void trav_postpone(Trav& t, TravStack& st)
+{
+    // below the node group: the nearer inner children are visited first, then these triangles
+    st.push(t.tgroup);
+    t.tgroup.y = 0;
+}
+// phase 2 of a step: up to HL_TRI_PER_STEP triangle tests of the current leaf group (bottom level), or one
+// instance entry (top level)
+HL_HD void trav_step_leaves(const SceneView& s, Trav& t, TravStack& st)
+{
+    if (t.tgroup.y == 0) return;
+    if (t.inst != HL_MISS)
     {
-        if (t.inst != HL_MISS)
-        {
-            // bottom level: test pending triangles of this leaf group
-            bool done = false;
+        bool done = false;
 #if HL_TRI_PER_STEP < 24
-            for (int k = 0; k < HL_TRI_PER_STEP && t.tgroup.y; k++)
+        for (int k = 0; k < HL_TRI_PER_STEP && t.tgroup.y; k++)
 #else
-            while (t.tgroup.y)
+        while (t.tgroup.y)
 #endif
-            {
-                const int i = hl_bfind(t.tgroup.y);
-                t.tgroup.y &= ~(1u << i);
-                HL_STAT_LEAF();
-                if (test_leaf_triangle(s, t.tris + (t.tgroup.x + (uint32_t)i), t.r.o, t.r.d, t.tmin, t.tmax, t.inst, t.flags, t.best) && (t.flags & HL_RAY_TERMINATE))
-                {
-                    done = true;
-                    break;
-                }
-            }
-            if (done) t.ngroup.y = 0, t.tgroup.y = 0, st.sp = 0;
-        }
-        else
         {
-            // top level: enter ONE instance; the rest of the leaf group and the node group wait on the stack
             const int i = hl_bfind(t.tgroup.y);
             t.tgroup.y &= ~(1u << i);
             HL_STAT_LEAF();
-            const uint32_t  id   = s.tlas_leaf[t.tgroup.x + (uint32_t)i];
-            const MeshView& mesh = s.meshes[s.instances[id].mesh_index];
-            if (mesh.n_tris != 0)
+            if (test_leaf_triangle(s, t.tris + (t.tgroup.x + (uint32_t)i), t.r.o, t.r.d, t.tmin, t.tmax, t.inst, t.flags, t.best) && (t.flags & HL_RAY_TERMINATE))
             {
-                if (t.tgroup.y) st.push(t.tgroup);
-                if (t.ngroup.y > 0x00FFFFFFu) st.push(t.ngroup);
-                u2 sentinel;
-                sentinel.x = 0xFFFFFFFFu, sentinel.y = 0;
-                st.push(sentinel);
-                const float* m = s.inst_inv + 12 * (size_t)id;
-                const f3     o = t.o, d = t.d;
-                f3           oo, od;
-                oo.x = (m[0] * o.x + m[1] * o.y + m[2] * o.z) + m[3];
-                oo.y = (m[4] * o.x + m[5] * o.y + m[6] * o.z) + m[7];
-                oo.z = (m[8] * o.x + m[9] * o.y + m[10] * o.z) + m[11];
-                od.x = m[0] * d.x + m[1] * d.y + m[2] * d.z;
-                od.y = m[4] * d.x + m[5] * d.y + m[6] * d.z;
-                od.z = m[8] * d.x + m[9] * d.y + m[10] * d.z;
-                t.r = make_ray_ctx(oo, od), t.nodes = mesh.nodes, t.tris = mesh.tris, t.inst = id;
-                t.ngroup.x = 0, t.ngroup.y = 0x80000000u, t.tgroup.y = 0;
+                done = true;
+                break;
             }
         }
+        if (done) t.ngroup.y = 0, t.tgroup.y = 0, st.sp = 0;
     }
+    else
+    {
+        // top level: enter ONE instance; the rest of the leaf group and the node group wait on the stack
+        const int i = hl_bfind(t.tgroup.y);
+        t.tgroup.y &= ~(1u << i);
+        HL_STAT_LEAF();
+        const uint32_t  id   = s.tlas_leaf[t.tgroup.x + (uint32_t)i];
+        const MeshView& mesh = s.meshes[s.instances[id].mesh_index];
+        if (mesh.n_tris != 0)
+        {
+            if (t.tgroup.y) st.push(t.tgroup);
+            if (t.ngroup.y > 0x00FFFFFFu) st.push(t.ngroup);
+            u2 sentinel;
+            sentinel.x = 0xFFFFFFFFu, sentinel.y = 0;
+            st.push(sentinel);
+            const float* m = s.inst_inv + 12 * (size_t)id;
+            const f3     o = t.o, d = t.d;
+            f3           oo, od;
+            oo.x = (m[0] * o.x + m[1] * o.y + m[2] * o.z) + m[3];
+            oo.y = (m[4] * o.x + m[5] * o.y + m[6] * o.z) + m[7];
+            oo.z = (m[8] * o.x + m[9] * o.y + m[10] * o.z) + m[11];
+            od.x = m[0] * d.x + m[1] * d.y + m[2] * d.z;
+            od.y = m[4] * d.x + m[5] * d.y + m[6] * d.z;
+            od.z = m[8] * d.x + m[9] * d.y + m[10] * d.z;
+            t.r = make_ray_ctx(oo, od), t.nodes = mesh.nodes, t.tris = mesh.tris, t.inst = id;
+            t.ngroup.x = 0, t.ngroup.y = 0x80000000u, t.tgroup.y = 0;
+        }
+    }
+}
+
+// One step of every lane of the warp; `busy_mask` = ballot of the lanes that hold an unfinished query (all
+// 32 lanes must call this).  The leaf phase runs when at least HL_TRI_MIN_LANES lanes (or every busy lane)
+// have a leaf group; otherwise lanes that can postpone do so and the others keep theirs for the next step
+// (their count only grows, so the phase is eventually taken).  Scheduling only: which step tests which
+// triangle never changes the result (closest hit + tie rule are order independent).
+#ifndef HL_TRI_MIN_LANES
+#define HL_TRI_MIN_LANES 1
+#endif
+HL_HD void trav_step_warp(const SceneView& s, Trav& t, TravStack& st, bool busy, uint32_t busy_mask)
+{
+    if (busy) trav_step_nodes(s, t, st);
+    const bool want = busy && t.tgroup.y != 0;
+#if defined(__CUDA_ARCH__)
+    const uint32_t wm = __ballot_sync(0xFFFFFFFFu, want);
+    if (wm == 0) return;
+    const int  need = min((int)HL_TRI_MIN_LANES, __popc(busy_mask));
+    const bool run  = __popc(wm) >= need;
+#elif defined(HL_TRAVERSAL_STATS)
+    const bool run = !emul_force_postpone(); // emulator: can exercise the postponing path on every opportunity
+    (void)busy_mask;
+#else
+    const bool run = true;
+    (void)busy_mask;
+#endif
+    if (!want) return;
+    if (run)
+        trav_step_leaves(s, t, st);
+    else if (trav_can_postpone(t))
+        trav_postpone(t, st);
+#if !defined(__CUDA_ARCH__)
+    else
+        trav_step_leaves(s, t, st); // a single host lane cannot wait for company
+#endif
 }
 
 // traceRayEXT, one query per lane to completion: fills `best` (instance == HL_MISS when nothing was hit).
@@ -382,9 +436,10 @@ HL_HD void trace_ray(const SceneView& s, bool active, f3 o, float tmin, f3 d, fl
     trav_begin(s, t, st, active, o, tmin, d, tmax, flags);
     for (;;)
     {
-        const bool busy = trav_busy(t, st);
-        if (!HL_WARP_ANY(busy)) break;
-        if (busy) trav_step(s, t, st);
+        const bool     busy = trav_busy(t, st);
+        const uint32_t bm   = HL_WARP_BALLOT(busy);
+        if (bm == 0) break;
+        trav_step_warp(s, t, st, busy, bm);
     }
     best = t.best;
 }

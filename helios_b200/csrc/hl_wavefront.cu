@@ -92,7 +92,7 @@ __device__ __forceinline__ void trace_queue(const SceneView& s, const Q& q, uint
             if (exhausted) break;
             continue; // fewer than HL_REFILL_MIN idle lanes cannot happen with bm == 0; kept for clarity
         }
-        if (trav_busy(t, st)) trav_step(s, t, st);
+        trav_step_warp(s, t, st, busy, bm);
     }
 }
 

@@ -631,20 +631,31 @@ def _building_mesh(rng, floors, detail, materials):
         b.add(p, i, nn, uv=[[0, 0], [1, 0], [1, 1], [0, 1]])
 
     b.begin_submesh(materials[0])
-    # walls as a grid of quads (floors x detail per side) so triangle counts scale
+    # walls as a grid of quads (floors x detail per side) so triangle counts scale; vectorised, quad order
+    # side -> floor -> column, vertices (u0,y0) (u1,y0) (u1,y1) (u0,y1)
+    kk = np.arange(detail, dtype=np.float64)
+    u0, u1 = -w + 2 * w * kk / detail, -w + 2 * w * (kk + 1) / detail
+    ff = np.arange(floors, dtype=np.float64)
+    y0, y1 = ff * fh, (ff + 1) * fh
+    U0, Y0 = np.meshgrid(u0, y0, indexing="xy")  # [floors, detail]
+    U1, Y1 = np.meshgrid(u1, y1, indexing="xy")
+    ua = np.stack([U0, U1, U1, U0], -1).reshape(-1)  # per-vertex u, 4 per quad
+    ya = np.stack([Y0, Y0, Y1, Y1], -1).reshape(-1)
+    nq = floors * detail
+    qidx = (np.arange(nq, dtype=np.uint32)[:, None] * 4 + np.array([0, 1, 2, 0, 2, 3], np.uint32)[None, :]).reshape(-1)
+    quv = np.tile(np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float64), (nq, 1))
+    ub = np.stack([U1, U0, U0, U1], -1).reshape(-1)  # side 1 runs the other way
+    one = np.ones_like(ua)
     for side in range(4):
-        for f in range(floors):
-            for k in range(detail):
-                u0, u1 = -w + 2 * w * k / detail, -w + 2 * w * (k + 1) / detail
-                y0, y1 = f * fh, (f + 1) * fh
-                if side == 0:
-                    add_quad((u0, y0, d), (u1, y0, d), (u1, y1, d), (u0, y1, d))
-                elif side == 1:
-                    add_quad((u1, y0, -d), (u0, y0, -d), (u0, y1, -d), (u1, y1, -d))
-                elif side == 2:
-                    add_quad((w, y0, -u0), (w, y0, -u1), (w, y1, -u1), (w, y1, -u0))
-                else:
-                    add_quad((-w, y0, u0), (-w, y0, u1), (-w, y1, u1), (-w, y1, u0))
+        if side == 0:
+            pos, nrm = np.stack([ua, ya, d * one], -1), (0.0, 0.0, 1.0)
+        elif side == 1:
+            pos, nrm = np.stack([ub, ya, -d * one], -1), (0.0, 0.0, -1.0)
+        elif side == 2:
+            pos, nrm = np.stack([w * one, ya, -ua], -1), (1.0, 0.0, 0.0)
+        else:
+            pos, nrm = np.stack([-w * one, ya, ua], -1), (-1.0, 0.0, 0.0)
+        b.add(pos, qidx, nrm, uv=quv)
     b.end_submesh()
     b.begin_submesh(materials[1])
     add_quad((-w, h, d), (w, h, d), (w, h, -d), (-w, h, -d))  # roof
@@ -656,7 +667,7 @@ def _building_mesh(rng, floors, detail, materials):
     return b.build()
 
 
-def city_scene(n_instances=1023, n_meshes=32, width=3840, height=2160, seed=4, floors=(8, 40), detail=(8, 60)) -> SceneData:
+def city_scene(n_instances=1023, n_meshes=32, width=3840, height=2160, seed=4, floors=(8, 40), detail=(40, 125)) -> SceneData:
     """config 4: <= 1024 instances (reference limit include/resource/scene.h:14) of <= 32 unique building meshes on a
     grid + a ground instance; directional light -> Hosek-Wilkie sky + environment light.  Defaults: ~20M instanced triangles."""
     rng = np.random.default_rng(seed)

@@ -47,7 +47,10 @@ static void build_wide(const std::vector<Box>& prim, WideBVH& out, MakeWriter ma
     for (uint32_t i = 0; i < n; i++) skeys[i] = keys[order[i]];
     std::vector<uint32_t> left(n), right(n), first(n), last(n), parent(2 * n, 0xFFFFFFFFu), visits(n, 0);
     std::vector<Box>      box(2 * n);
+    std::vector<float>    cost((size_t)2 * n * 7);
+    std::vector<uint32_t> dec(n, 0);
     BinaryTree            t;
+    t.cost = cost.data(), t.dec = dec.data(), t.c_prim = tri_leaves ? HL_SAH_C_PRIM_TRIANGLE : HL_SAH_C_PRIM_INSTANCE;
     t.n = n, t.left = left.data(), t.right = right.data(), t.first = first.data(), t.last = last.data();
     t.parent = parent.data(), t.box = box.data(), t.visits = visits.data();
     for (int i = 0; i + 1 < (int)n; i++) radix_tree_node(skeys.data(), t, i);
@@ -299,6 +302,7 @@ EM_API void em_trace_rays(const EmScene* s, const float* rays, uint32_t n, uint3
 // optional per-ray traversal log for em_render_frame: [16 bounces][cap] = nodes | leaves << 16
 static uint32_t* g_node_log     = nullptr;
 static size_t    g_node_log_cap = 0;
+EM_API void      em_set_force_postpone(int on) { emul_force_postpone() = on != 0; }
 EM_API void      em_set_node_log(uint32_t* buf, size_t cap) { g_node_log = buf, g_node_log_cap = cap; }
 
 // one launch in wavefront order; accum is updated in place

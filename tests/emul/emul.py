@@ -3,13 +3,15 @@ build container; never imported by the helios_b200 package."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-_SO = _HERE / "_build" / "libhl_emul.so"
+_EXTRA = os.environ.get("HL_EMUL_CXXFLAGS", "").split()  # tuning experiments (tools/bvh_stats.py)
+_SO = _HERE / "_build" / ("libhl_emul.so" if not _EXTRA else "libhl_emul_" + "_".join(x.strip("-").replace("=", "") for x in _EXTRA) + ".so")
 _lib = None
 
 
@@ -19,7 +21,7 @@ def build(force=False):
         _SO.parent.mkdir(exist_ok=True)
         cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
         subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-fvisibility=hidden",
-                               "-Wno-unknown-pragmas", "-o", str(_SO), str(_HERE / "emul.cpp")])
+                               "-Wno-unknown-pragmas", *_EXTRA, "-o", str(_SO), str(_HERE / "emul.cpp")])
     return _SO
 
 

@@ -89,6 +89,22 @@ def test_random_rays_and_flags(flags, oracle_mod, emul):
     assert np.isfinite(a[:, 0]).mean() > 0.05
 
 
+def test_triangle_postponing_does_not_change_hits(oracle_mod, emul):
+    """the GPU step scheduler may put a leaf group on the stack and keep descending (hl_bvh.h trav_postpone);
+    forced on every opportunity here, single- and two-level, the hits stay bit-identical to the oracle"""
+    s = scenes.triangle_soup(20000, 96, 54)
+    o, e1 = pair(s, oracle_mod, emul)
+    _, e2 = pair(s, oracle_mod, emul, force_two_level=True)
+    pc = s.push_constants(3)
+    ref = o.trace_primary_ids(pc)
+    emul.lib().em_set_force_postpone(1)
+    try:
+        assert_ids_equal(ref, e1.trace_primary_ids(pc))
+        assert_ids_equal(ref, e2.trace_primary_ids(pc))
+    finally:
+        emul.lib().em_set_force_postpone(0)
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 9, 33])
 def test_tiny_meshes(n, oracle_mod, emul):
     s = scenes.triangle_soup(max(n, 1), 48, 27, seed=100 + n)

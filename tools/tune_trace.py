@@ -6,10 +6,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 VARIANTS = {
-    "refill1": ["-DHL_REFILL_MIN=1"], "refill4": ["-DHL_REFILL_MIN=4"], "refill8": ["-DHL_REFILL_MIN=8"], "refill16": ["-DHL_REFILL_MIN=16"],
-    "refill32": ["-DHL_REFILL_MIN=32"],
-    "refill8_tri1": ["-DHL_REFILL_MIN=8", "-DHL_TRI_PER_STEP=1"], "refill8_tri2": ["-DHL_REFILL_MIN=8", "-DHL_TRI_PER_STEP=2"],
-    "refill4_tri2": ["-DHL_REFILL_MIN=4", "-DHL_TRI_PER_STEP=2"],
+    "tmin1": ["-DHL_TRI_MIN_LANES=1"], "tmin4": ["-DHL_TRI_MIN_LANES=4"], "tmin8": ["-DHL_TRI_MIN_LANES=8"], "tmin12": ["-DHL_TRI_MIN_LANES=12"],
+    "tmin16": ["-DHL_TRI_MIN_LANES=16"], "tmin8_tri24": ["-DHL_TRI_MIN_LANES=8", "-DHL_TRI_PER_STEP=24"], "tmin12_tri24": ["-DHL_TRI_MIN_LANES=12", "-DHL_TRI_PER_STEP=24"],
+    "tmin8_tri3": ["-DHL_TRI_MIN_LANES=8", "-DHL_TRI_PER_STEP=3"], "tmin8_refill4": ["-DHL_TRI_MIN_LANES=8", "-DHL_REFILL_MIN=4"],
+    "tmin8_refill12": ["-DHL_TRI_MIN_LANES=8", "-DHL_REFILL_MIN=12"],
 }
 OUT = ROOT / "build" / "variants"
 if sys.argv[1] == "build":
