@@ -44,5 +44,32 @@ def build_library(force: bool = False, verbose: bool = False, defines: list[str]
     return lib
 
 
+SHIM = ROOT / "shim"
+ENGINE_LIB = ROOT / "libhelios_engine.so"
+HEADLESS = ROOT / "helios_headless"
+
+
+def build_shim(force: bool = False) -> Path:
+    """C++ host layer with the reference's class surface (helios_b200/shim) + the headless driver.  Plain g++:
+    it only talks to the C ABI, so it links against libhelios_b200.so and needs no CUDA headers."""
+    srcs = sorted((SHIM / "src").glob("*.cpp"))
+    hdrs = list((SHIM / "include").rglob("*.h")) + list((SHIM / "include").rglob("*.hpp")) + [ROOT.parent / "include" / "helios_b200.h"]
+    tool = SHIM / "tools" / "helios_headless.cpp"
+    newest = max(f.stat().st_mtime for f in [*srcs, *hdrs, tool])
+    if not force and ENGINE_LIB.exists() and HEADLESS.exists() and min(ENGINE_LIB.stat().st_mtime, HEADLESS.stat().st_mtime) > newest and ENGINE_LIB.stat().st_mtime > LIB.stat().st_mtime:
+        return HEADLESS
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    common = [cxx, "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-unused-function", f"-I{SHIM / 'include'}", f"-I{ROOT.parent / 'include'}"]
+    link = [f"-L{ROOT}", "-lhelios_b200", "-ldl", "-Wl,-rpath,$ORIGIN"]
+    cmd = [*common, "-shared", "-o", str(ENGINE_LIB), *map(str, srcs), *link]
+    print("[helios_b200] " + " ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    cmd = [*common, "-o", str(HEADLESS), str(tool), "-lhelios_engine", *link]
+    print("[helios_b200] " + " ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return HEADLESS
+
+
 if __name__ == "__main__":
     build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_shim(force="--force" in sys.argv)

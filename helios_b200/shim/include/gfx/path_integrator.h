@@ -1,0 +1,61 @@
+// gfx/path_integrator.h — PathIntegrator (reference: include/gfx/path_integrator.h:9-60,
+// src/engine/gfx/path_integrator.cpp:48-84 render, :125-200 launch_rays, :312-336 compute_tile_coords).
+// Same public surface and the same sample / tile counters; launch_rays fills the 192-byte PushConstants block
+// exactly as the reference does and calls hl_render_frame where the reference records vkCmdTraceRaysKHR.
+#pragma once
+#include <gfx/vk.h>
+#include <resource/scene.h>
+#include <vector>
+
+namespace helios
+{
+class PathIntegrator
+{
+public:
+    using Ptr = std::shared_ptr<PathIntegrator>;
+
+    PathIntegrator(vk::Backend::Ptr backend);
+    ~PathIntegrator();
+
+    inline uint32_t max_ray_bounces() { return m_max_ray_bounces; }
+    inline uint32_t max_samples() { return m_max_samples; }
+    inline uint32_t num_accumulated_samples() { return m_max_samples * m_tile_idx + m_num_accumulated_samples; }
+    inline uint32_t num_target_samples() { return m_max_samples * (uint32_t)m_tile_coords.size(); }
+    inline uint32_t tile_idx() { return m_tile_idx; }
+    inline bool     is_tiled() { return m_tiled; }
+    inline float    shadow_ray_bias() { return m_shadow_ray_bias; }
+    inline void     restart_bake()
+    {
+        m_num_accumulated_samples = 0;
+        m_tile_idx                = 0;
+    }
+    inline void set_max_ray_bounces(const uint32_t& n) { m_max_ray_bounces = n; }
+    inline void set_max_samples(const uint32_t& n) { m_max_samples = n; }
+    inline void set_shadow_ray_bias(const float& bias) { m_shadow_ray_bias = bias; }
+
+    void render(RenderState& render_state);
+    void on_window_resize();
+    void set_tiled(bool tiled);
+
+    // the block the last launch used (tests compare it with the Python host's restatement)
+    inline const hl_push_constants& last_push_constants() const { return m_last_push_constants; }
+    // fills a PushConstants block for (camera, counters) without launching
+    hl_push_constants make_push_constants(RenderState& render_state, const glm::mat4& view, const glm::mat4& projection, const glm::ivec2& tile_coord, const glm::ivec2& pixel_coord);
+
+private:
+    void launch_rays(RenderState& render_state, const uint32_t& x, const uint32_t& y, const uint32_t& z, const glm::mat4& view, const glm::mat4& projection, const glm::ivec2& tile_coord,
+                     const glm::ivec2& pixel_coord);
+    void compute_tile_coords();
+
+    bool                       m_tiled                   = false;
+    uint32_t                   m_max_ray_bounces         = 7;
+    uint32_t                   m_max_samples             = 5000;
+    uint32_t                   m_num_accumulated_samples = 0;
+    uint32_t                   m_tile_idx                = 0;
+    float                      m_shadow_ray_bias         = 0.0f;
+    glm::uvec2                 m_tile_size;
+    std::vector<glm::uvec2>    m_tile_coords;
+    std::weak_ptr<vk::Backend> m_backend;
+    hl_push_constants          m_last_push_constants {};
+};
+} // namespace helios

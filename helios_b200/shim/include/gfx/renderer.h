@@ -1,0 +1,65 @@
+// gfx/renderer.h — Renderer (reference: include/gfx/renderer.h:35-120, src/engine/gfx/renderer.cpp:106-330
+// render, :369-428 tone_map, :637-711 save path).  render(RenderState&) = (re)build the top level when the
+// hierarchy changed, clear the accumulation when the bake restarts, one PathIntegrator iteration, tone map.
+// The swap-chain copy, ImGui, ray-debug and G-buffer debug views of the reference are outside the path.
+#pragma once
+#include <gfx/path_integrator.h>
+#include <resource/scene.h>
+#include <string>
+#include <vector>
+
+namespace helios
+{
+enum ToneMapOperator
+{
+    TONE_MAP_OPERATOR_ACES,
+    TONE_MAP_OPERATOR_REINHARD
+};
+
+enum OutputBuffer
+{
+    OUTPUT_BUFFER_ALBEDO,
+    OUTPUT_BUFFER_NORMALS,
+    OUTPUT_BUFFER_ROUGHNESS,
+    OUTPUT_BUFFER_METALLIC,
+    OUTPUT_BUFFER_EMISSIVE,
+    OUTPUT_BUFFER_FINAL
+};
+
+class Renderer
+{
+public:
+    Renderer(vk::Backend::Ptr backend);
+    ~Renderer();
+
+    inline void                set_tone_map_operator(const ToneMapOperator& tone_map) { m_tone_map_operator = tone_map; }
+    inline void                set_exposure(const float& exposure) { m_exposure = exposure; }
+    inline void                set_current_output_buffer(OutputBuffer buffer) { m_current_output_buffer = buffer; }
+    inline PathIntegrator::Ptr path_integrator() { return m_path_integrator; }
+    inline ToneMapOperator     tone_map_operator() { return m_tone_map_operator; }
+    inline OutputBuffer        current_output_buffer() { return m_current_output_buffer; }
+    inline float               exposure() { return m_exposure; }
+
+    void render(RenderState& render_state);
+    void on_window_resize();
+    // queues a save of the tone-mapped image; it is written at the end of the next render(), as in the reference
+    // (.ppm / .pfm here: the reference's stb_image_write PNG encoder is not part of this path)
+    void save_image_to_disk(const std::string& path);
+
+    // headless read-backs (the reference presents to a swap chain instead)
+    std::vector<uint8_t> read_tone_mapped_image(); // RGBA8, row 0 = top
+    std::vector<float>   read_accumulation();      // RGBA32F, row 0 = v 0
+
+private:
+    void tone_map(uint8_t* rgba8_host);
+
+    std::weak_ptr<vk::Backend> m_backend;
+    PathIntegrator::Ptr        m_path_integrator;
+    bool                       m_output_image_recreated = true;
+    bool                       m_save_image_to_disk     = false;
+    std::string                m_image_save_path        = "";
+    ToneMapOperator            m_tone_map_operator      = TONE_MAP_OPERATOR_ACES;
+    float                      m_exposure               = 1.0f;
+    OutputBuffer               m_current_output_buffer  = OUTPUT_BUFFER_FINAL;
+};
+} // namespace helios

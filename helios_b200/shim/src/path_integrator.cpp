@@ -1,0 +1,116 @@
+// path_integrator.cpp — PathIntegrator (reference: src/engine/gfx/path_integrator.cpp).
+#include <gfx/path_integrator.h>
+#include <cmath>
+#include <cstring>
+
+namespace helios
+{
+#define TILE_SIZE 128
+
+static_assert(sizeof(hl_push_constants) == 192, "PushConstants must match the 192-byte block of path_trace_rgen.glsl:93-110");
+
+PathIntegrator::PathIntegrator(vk::Backend::Ptr backend) : m_backend(backend) { compute_tile_coords(); }
+PathIntegrator::~PathIntegrator() {}
+
+// :48-84 — restart on any scene change; one launch per call; max_samples per tile, then the next tile
+void PathIntegrator::render(RenderState& render_state)
+{
+    if (render_state.scene_state() != SCENE_STATE_READY)
+    {
+        m_tile_idx                = 0;
+        m_num_accumulated_samples = 0;
+    }
+    if (m_tile_idx < m_tile_coords.size())
+    {
+        if (!render_state.camera())
+        {
+            HELIOS_LOG_ERROR("PathIntegrator::render: the scene has no enabled camera");
+            return;
+        }
+        const glm::uvec2 tile = m_tile_coords[m_tile_idx];
+        launch_rays(render_state, m_tile_size.x, m_tile_size.y, 1, render_state.camera()->view_matrix(), render_state.camera()->projection_matrix(), glm::ivec2((int)tile.x, (int)tile.y),
+                    glm::ivec2(0, 0));
+        m_num_accumulated_samples++;
+    }
+    if (m_num_accumulated_samples == m_max_samples)
+    {
+        m_num_accumulated_samples = 0;
+        m_tile_idx++;
+    }
+}
+
+void PathIntegrator::on_window_resize()
+{
+    restart_bake();
+    compute_tile_coords();
+}
+
+void PathIntegrator::set_tiled(bool tiled)
+{
+    m_tiled = tiled;
+    compute_tile_coords();
+}
+
+// :136-161
+hl_push_constants PathIntegrator::make_push_constants(RenderState& render_state, const glm::mat4& view, const glm::mat4& projection, const glm::ivec2& tile_coord, const glm::ivec2& pixel_coord)
+{
+    auto           backend = m_backend.lock();
+    const auto     extents = backend->swap_chain_extents();
+    CameraNode*    cam     = render_state.camera();
+    const glm::vec3 right = cam->left(), up = cam->up(), forward = -cam->forward(), camera_pos = cam->global_position();
+    const glm::vec3 focal_point = camera_pos + forward * cam->focal_length();
+    glm::vec4       focal_plane = glm::vec4(-forward, 0.0f);
+    focal_plane.w               = -(focal_plane.x * focal_point.x + focal_plane.y * focal_point.y + focal_plane.z * focal_point.z);
+
+    hl_push_constants pc;
+    std::memset(&pc, 0, sizeof(pc));
+    const glm::mat4 vpi = glm::inverse(projection * view);
+    std::memcpy(pc.view_proj_inverse, glm::value_ptr(vpi), 64);
+    pc.camera_pos[0] = camera_pos.x, pc.camera_pos[1] = camera_pos.y, pc.camera_pos[2] = camera_pos.z, pc.camera_pos[3] = 0.0f;
+    pc.up_direction[0] = up.x, pc.up_direction[1] = up.y, pc.up_direction[2] = up.z;
+    pc.right_direction[0] = right.x, pc.right_direction[1] = right.y, pc.right_direction[2] = right.z;
+    pc.focal_plane[0] = focal_plane.x, pc.focal_plane[1] = focal_plane.y, pc.focal_plane[2] = focal_plane.z, pc.focal_plane[3] = focal_plane.w;
+    pc.ray_debug_pixel_coord[0] = pixel_coord.x, pc.ray_debug_pixel_coord[1] = (int32_t)extents.height - pixel_coord.y;
+    pc.ray_debug_pixel_coord[2] = (int32_t)extents.width, pc.ray_debug_pixel_coord[3] = (int32_t)extents.height;
+    pc.launch_id_size[0] = (uint32_t)tile_coord.x, pc.launch_id_size[1] = (uint32_t)tile_coord.y, pc.launch_id_size[2] = extents.width, pc.launch_id_size[3] = extents.height;
+    pc.num_lights      = render_state.num_lights();
+    pc.num_frames      = m_num_accumulated_samples;
+    pc.accumulation    = float(pc.num_frames) / float(pc.num_frames + 1);
+    pc.debug_vis       = 0;
+    pc.max_ray_bounces = m_max_ray_bounces;
+    pc.shadow_ray_bias = m_shadow_ray_bias;
+    pc.focal_length    = cam->focal_length();
+    pc.aperture_radius = cam->aperture_radius();
+    return pc;
+}
+
+// :125-200 — vkCmdTraceRaysKHR(x, y, z) becomes hl_render_frame over the same launch rectangle
+void PathIntegrator::launch_rays(RenderState& render_state, const uint32_t& x, const uint32_t& y, const uint32_t& z, const glm::mat4& view, const glm::mat4& projection, const glm::ivec2& tile_coord,
+                                 const glm::ivec2& pixel_coord)
+{
+    (void)z;
+    auto backend          = m_backend.lock();
+    m_last_push_constants = make_push_constants(render_state, view, projection, tile_coord, pixel_coord);
+    backend->check(hl_render_frame(backend->require_device("PathIntegrator::launch_rays"), &m_last_push_constants, x, y), "hl_render_frame");
+}
+
+// :312-336
+void PathIntegrator::compute_tile_coords()
+{
+    auto       backend = m_backend.lock();
+    const auto extents = backend->swap_chain_extents();
+    m_tile_coords.clear();
+    if (m_tiled)
+    {
+        const uint32_t nx = (uint32_t)ceilf(float(extents.width) / float(TILE_SIZE)), ny = (uint32_t)ceilf(float(extents.height) / float(TILE_SIZE));
+        for (uint32_t x = 0; x < nx; x++)
+            for (uint32_t y = 0; y < ny; y++) m_tile_coords.push_back(glm::uvec2(x * TILE_SIZE, y * TILE_SIZE));
+        m_tile_size = glm::uvec2(TILE_SIZE, TILE_SIZE);
+    }
+    else
+    {
+        m_tile_coords.push_back(glm::uvec2(0, 0));
+        m_tile_size = glm::uvec2(extents.width, extents.height);
+    }
+}
+} // namespace helios

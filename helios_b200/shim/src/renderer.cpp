@@ -1,0 +1,97 @@
+// renderer.cpp — Renderer (reference: src/engine/gfx/renderer.cpp:106-330 render, :369-428 tone_map,
+// :637-711 copy_and_save_tone_mapped_image, :715-726 on_window_resize).
+#include <gfx/renderer.h>
+#include <cstdio>
+
+namespace helios
+{
+Renderer::Renderer(vk::Backend::Ptr backend) : m_backend(backend) { m_path_integrator = std::shared_ptr<PathIntegrator>(new PathIntegrator(backend)); }
+Renderer::~Renderer() {}
+
+void Renderer::render(RenderState& render_state)
+{
+    auto backend = m_backend.lock();
+    if (!backend)
+    {
+        HELIOS_LOG_FATAL("Renderer::render: the backend was destroyed before the renderer");
+        throw std::runtime_error("Renderer::render: the backend was destroyed before the renderer");
+    }
+    hl_context ctx = backend->require_device("Renderer::render");
+    // (the top-level rebuild of :111-181 happened inside Scene::update -> hl_scene_set_tables)
+    // restart branch, :205-223: any scene change, or a bake that is about to take its first sample
+    if (m_output_image_recreated || render_state.m_scene_state != SCENE_STATE_READY || (m_path_integrator->num_accumulated_samples() == 0 && m_path_integrator->tile_idx() == 0))
+    {
+        backend->check(hl_accum_clear(ctx), "hl_accum_clear");
+        m_output_image_recreated = false;
+    }
+    if (render_state.m_scene) m_path_integrator->render(render_state);
+    // tone map into the RGBA8 target (device only unless a save is pending)
+    if (m_save_image_to_disk)
+    {
+        const auto           ext = backend->swap_chain_extents();
+        std::vector<uint8_t> img((size_t)ext.width * ext.height * 4);
+        tone_map(img.data());
+        bool              ok  = false;
+        const std::string& p  = m_image_save_path;
+        const bool        pfm = p.size() > 4 && p.substr(p.size() - 4) == ".pfm";
+        if (FILE* f = std::fopen(p.c_str(), "wb"))
+        {
+            if (pfm)
+            {
+                const std::vector<float> acc = read_accumulation();
+                std::fprintf(f, "PF\n%u %u\n-1.0\n", ext.width, ext.height);
+                // PFM rows run bottom-up, and so does the accumulation image (launch row 0 is the bottom of the view:
+                // the tone-map pass flips it, tone_map.frag + the negative-height viewport)
+                for (size_t i = 0; i < (size_t)ext.width * ext.height; i++) std::fwrite(&acc[i * 4], 4, 3, f);
+            }
+            else
+            {
+                std::fprintf(f, "P6\n%u %u\n255\n", ext.width, ext.height);
+                for (size_t i = 0; i < (size_t)ext.width * ext.height; i++) std::fwrite(&img[i * 4], 1, 3, f);
+            }
+            ok = std::fclose(f) == 0;
+        }
+        if (!ok) HELIOS_LOG_ERROR("Renderer::save_image_to_disk: cannot write " + p);
+        m_save_image_to_disk = false;
+    }
+    else
+        tone_map(nullptr);
+}
+
+void Renderer::tone_map(uint8_t* rgba8_host)
+{
+    auto backend = m_backend.lock();
+    backend->check(hl_tonemap(backend->require_device("Renderer::tone_map"), m_exposure, m_tone_map_operator == TONE_MAP_OPERATOR_ACES ? HL_TONE_MAP_ACES : HL_TONE_MAP_REINHARD, 1.0f, rgba8_host),
+                   "hl_tonemap");
+}
+
+void Renderer::on_window_resize()
+{
+    m_output_image_recreated = true;
+    m_path_integrator->on_window_resize();
+}
+
+void Renderer::save_image_to_disk(const std::string& path)
+{
+    m_save_image_to_disk = true;
+    m_image_save_path    = path;
+}
+
+std::vector<uint8_t> Renderer::read_tone_mapped_image()
+{
+    auto                 backend = m_backend.lock();
+    const auto           ext     = backend->swap_chain_extents();
+    std::vector<uint8_t> img((size_t)ext.width * ext.height * 4);
+    tone_map(img.data());
+    return img;
+}
+
+std::vector<float> Renderer::read_accumulation()
+{
+    auto               backend = m_backend.lock();
+    const auto         ext     = backend->swap_chain_extents();
+    std::vector<float> acc((size_t)ext.width * ext.height * 4);
+    backend->check(hl_read_accum(backend->require_device("Renderer::read_accumulation"), acc.data()), "hl_read_accum");
+    return acc;
+}
+} // namespace helios

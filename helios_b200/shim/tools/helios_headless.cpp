@@ -1,0 +1,320 @@
+// helios_headless — headless driver of the path-trace pass through the engine's own interfaces
+// (SURVEY.md §7 step 3).  It loads a scene description (helios_b200/scene_io.py), rebuilds it with
+// Texture2D / Material / Mesh / MeshNode / ...LightNode / CameraNode / IBLNode, and runs the reference's frame
+// loop (src/viewer/main.cpp:66-76):  render_state.setup(w, h, cmd) -> scene->update(render_state) ->
+// renderer->render(render_state), once per sample.
+//
+//   helios_headless --scene file.hlsc [--spp N] [--device D] [--tiled] [--bounces B] [--exposure E]
+//                   [--out image.ppm|.pfm] [--dump-accum raw.f32] [--dump-tables tables.bin] [--no-device]
+//
+// --no-device builds the scene graph and the tables on the host only (for inspection); rendering needs a GPU.
+#include <gfx/renderer.h>
+#include <resource/material.h>
+#include <resource/mesh.h>
+#include <resource/scene.h>
+#include <resource/texture.h>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+using namespace helios;
+
+namespace
+{
+struct Reader
+{
+    std::vector<char> buf;
+    size_t            pos = 0;
+    explicit Reader(const std::string& path)
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw std::runtime_error("cannot open " + path);
+        buf.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    }
+    void raw(void* dst, size_t n)
+    {
+        if (pos + n > buf.size()) throw std::runtime_error("scene file is truncated");
+        std::memcpy(dst, buf.data() + pos, n);
+        pos += n;
+    }
+    template <class T>
+    T get()
+    {
+        T v;
+        raw(&v, sizeof(T));
+        return v;
+    }
+};
+glm::vec3 read_vec3(Reader& r)
+{
+    const float x = r.get<float>(), y = r.get<float>(), z = r.get<float>();
+    return glm::vec3(x, y, z);
+}
+glm::quat read_quat(Reader& r)
+{
+    const float w = r.get<float>(), x = r.get<float>(), y = r.get<float>(), z = r.get<float>();
+    return glm::quat(w, x, y, z);
+}
+template <class T>
+void write_vec(FILE* f, const std::vector<T>& v)
+{
+    const uint32_t n = (uint32_t)v.size();
+    std::fwrite(&n, 4, 1, f);
+    if (n) std::fwrite(v.data(), sizeof(T), n, f);
+}
+} // namespace
+
+int main(int argc, char** argv)
+{
+    std::string scene_path, out_path, accum_path, tables_path;
+    uint32_t    spp = 16, bounces = 0;
+    int         device = 0;
+    bool        tiled = false, no_device = false;
+    float       exposure = 1.0f;
+    for (int i = 1; i < argc; i++)
+    {
+        const std::string a = argv[i];
+        auto              next = [&]() -> std::string {
+            if (i + 1 >= argc) throw std::runtime_error("missing value for " + a);
+            return argv[++i];
+        };
+        try
+        {
+            if (a == "--scene") scene_path = next();
+            else if (a == "--spp") spp = (uint32_t)std::stoul(next());
+            else if (a == "--device") device = std::stoi(next());
+            else if (a == "--bounces") bounces = (uint32_t)std::stoul(next());
+            else if (a == "--exposure") exposure = std::stof(next());
+            else if (a == "--out") out_path = next();
+            else if (a == "--dump-accum") accum_path = next();
+            else if (a == "--dump-tables") tables_path = next();
+            else if (a == "--tiled") tiled = true;
+            else if (a == "--no-device") no_device = true;
+            else
+            {
+                std::fprintf(stderr, "unknown argument %s\n", a.c_str());
+                return 2;
+            }
+        }
+        catch (const std::exception& e)
+        {
+            std::fprintf(stderr, "%s\n", e.what());
+            return 2;
+        }
+    }
+    if (scene_path.empty())
+    {
+        std::fprintf(stderr, "usage: helios_headless --scene file.hlsc [--spp N] [--out image.ppm] ...\n");
+        return 2;
+    }
+    try
+    {
+        Reader r(scene_path);
+        char   magic[8];
+        r.raw(magic, 8);
+        if (std::memcmp(magic, "HLSC0001", 8) != 0) throw std::runtime_error("not a HLSC0001 scene file");
+        const uint32_t width = r.get<uint32_t>(), height = r.get<uint32_t>(), file_bounces = r.get<uint32_t>();
+        const float    bias = r.get<float>();
+
+        vk::Backend::Ptr  backend = no_device ? vk::Backend::create_without_device(width, height) : vk::Backend::create(device, width, height);
+        vk::BatchUploader uploader(backend);
+
+        std::vector<Texture2D::Ptr> textures(r.get<uint32_t>());
+        for (auto& t : textures)
+        {
+            const int32_t        fmt = r.get<int32_t>();
+            const uint32_t       w = r.get<uint32_t>(), h = r.get<uint32_t>();
+            std::vector<uint8_t> texels((size_t)w * h * (fmt == HL_TEX_RGBA32F ? 16 : 4));
+            r.raw(texels.data(), texels.size());
+            t = Texture2D::create(backend, fmt, w, h, texels.data(), "texture");
+        }
+        std::vector<Material::Ptr> materials(r.get<uint32_t>());
+        for (size_t k = 0; k < materials.size(); k++)
+        {
+            const uint32_t type = r.get<uint32_t>(), alpha_test = r.get<uint32_t>();
+            glm::vec4      albedo, emissive;
+            r.raw(&albedo, 16), r.raw(&emissive, 16);
+            const float   metallic = r.get<float>(), roughness = r.get<float>();
+            int32_t       tex[5];
+            r.raw(tex, sizeof(tex));
+            const int32_t rough_ch = r.get<int32_t>(), metal_ch = r.get<int32_t>();
+            // each Material owns a local texture list; TextureInfo::array_index points into it
+            std::vector<Texture2D::Ptr> local;
+            TextureInfo                 info[5];
+            for (int s = 0; s < 5; s++)
+                if (tex[s] >= 0)
+                {
+                    info[s].array_index = (int32_t)local.size();
+                    local.push_back(textures.at((size_t)tex[s]));
+                }
+            info[2].channel_index = metal_ch, info[3].channel_index = rough_ch;
+            materials[k] = Material::create(backend, type == 0 ? MATERIAL_OPAQUE : MATERIAL_TRANSPARENT, local, info[0], info[1], info[2], info[3], info[4], albedo, emissive, metallic, roughness,
+                                            alpha_test != 0, "material" + std::to_string(k));
+        }
+        std::vector<Mesh::Ptr> meshes(r.get<uint32_t>());
+        for (size_t k = 0; k < meshes.size(); k++)
+        {
+            const uint32_t        nv = r.get<uint32_t>(), ni = r.get<uint32_t>(), nsub = r.get<uint32_t>();
+            std::vector<Vertex>   vertices(nv);
+            std::vector<uint32_t> indices(ni);
+            r.raw(vertices.data(), sizeof(Vertex) * (size_t)nv);
+            r.raw(indices.data(), 4 * (size_t)ni);
+            std::vector<SubMesh> subs(nsub);
+            for (auto& s : subs)
+            {
+                s.mat_idx = r.get<uint32_t>(), s.index_count = r.get<uint32_t>(), s.vertex_count = r.get<uint32_t>(), s.base_vertex = r.get<uint32_t>(), s.base_index = r.get<uint32_t>();
+                s.name = "submesh";
+            }
+            std::vector<Material::Ptr> mesh_materials(r.get<uint32_t>());
+            for (auto& m : mesh_materials) m = materials.at(r.get<uint32_t>());
+            meshes[k] = Mesh::create(backend, std::move(vertices), std::move(indices), subs, mesh_materials, uploader, "mesh" + std::to_string(k));
+        }
+        uploader.submit();
+
+        auto           root    = std::make_shared<RootNode>("root");
+        const uint32_t n_nodes = r.get<uint32_t>();
+        for (uint32_t k = 0; k < n_nodes; k++)
+        {
+            const uint32_t mesh = r.get<uint32_t>();
+            glm::mat4      model;
+            r.raw(&model, 64);
+            auto node = std::make_shared<MeshNode>("mesh_node" + std::to_string(k));
+            root->add_child(node);
+            node->set_mesh(meshes.at(mesh));
+            node->set_from_global_transform(model);
+        }
+        auto camera = std::make_shared<CameraNode>("camera");
+        root->add_child(camera);
+        camera->set_position(read_vec3(r));
+        camera->set_orientation(read_quat(r));
+        camera->set_fov(r.get<float>()), camera->set_near_plane(r.get<float>()), camera->set_far_plane(r.get<float>());
+        camera->set_focal_length(r.get<float>()), camera->set_aperture_radius(r.get<float>());
+        for (uint32_t k = 0, n = r.get<uint32_t>(); k < n; k++)
+        {
+            auto l = std::make_shared<DirectionalLightNode>("directional" + std::to_string(k));
+            root->add_child(l);
+            l->set_orientation(read_quat(r));
+            l->set_color(read_vec3(r)), l->set_intensity(r.get<float>()), l->set_radius(r.get<float>());
+        }
+        for (uint32_t k = 0, n = r.get<uint32_t>(); k < n; k++)
+        {
+            auto l = std::make_shared<PointLightNode>("point" + std::to_string(k));
+            root->add_child(l);
+            l->set_position(read_vec3(r));
+            l->set_color(read_vec3(r)), l->set_intensity(r.get<float>()), l->set_radius(r.get<float>());
+        }
+        for (uint32_t k = 0, n = r.get<uint32_t>(); k < n; k++)
+        {
+            auto l = std::make_shared<SpotLightNode>("spot" + std::to_string(k));
+            root->add_child(l);
+            l->set_position(read_vec3(r));
+            l->set_orientation(read_quat(r));
+            l->set_color(read_vec3(r)), l->set_intensity(r.get<float>()), l->set_radius(r.get<float>());
+            l->set_inner_cone_angle(r.get<float>()), l->set_outer_cone_angle(r.get<float>());
+        }
+        if (const uint32_t cube = r.get<uint32_t>())
+        {
+            std::vector<float> faces((size_t)6 * cube * cube * 4);
+            r.raw(faces.data(), faces.size() * 4);
+            auto ibl = std::make_shared<IBLNode>("ibl");
+            root->add_child(ibl);
+            ibl->set_image(TextureCube::create(backend, cube, faces.data(), "ibl"));
+        }
+
+        Scene::Ptr  scene = Scene::create(backend, "scene", root, scene_path);
+        RenderState render_state;
+        auto        cmd = std::make_shared<vk::CommandBuffer>();
+
+        if (no_device)
+        {
+            render_state.setup(width, height, cmd);
+            scene->update(render_state);
+        }
+        std::unique_ptr<Renderer> renderer;
+        double                    seconds = 0.0;
+        if (!no_device)
+        {
+            renderer.reset(new Renderer(backend));
+            renderer->path_integrator()->set_max_ray_bounces(bounces ? bounces : file_bounces);
+            renderer->path_integrator()->set_shadow_ray_bias(bias);
+            renderer->path_integrator()->set_tiled(tiled);
+            renderer->set_exposure(exposure);
+            if (tiled) renderer->path_integrator()->set_max_samples(spp); // spp per tile, tile after tile (path_integrator.cpp:48-84)
+            auto       pi   = renderer->path_integrator();
+            uint32_t   done = 0;
+            const auto t0   = std::chrono::steady_clock::now();
+            auto finished   = [&]() { return tiled ? (done > 0 && pi->tile_idx() * pi->max_samples() >= pi->num_target_samples()) : done == spp; };
+            while (!finished())
+            {
+                if (!tiled && !out_path.empty() && done + 1 == spp) renderer->save_image_to_disk(out_path);
+                render_state.setup(width, height, cmd);
+                scene->update(render_state);
+                renderer->render(render_state);
+                done++;
+            }
+            backend->wait_idle();
+            seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (tiled && !out_path.empty())
+            {
+                // one more frame would restart nothing: the bake is complete, so only tone map + save
+                const auto img = renderer->read_tone_mapped_image();
+                if (FILE* f = std::fopen(out_path.c_str(), "wb"))
+                {
+                    std::fprintf(f, "P6\n%u %u\n255\n", width, height);
+                    for (size_t i = 0; i < (size_t)width * height; i++) std::fwrite(&img[i * 4], 1, 3, f);
+                    std::fclose(f);
+                }
+            }
+            if (!accum_path.empty())
+            {
+                const auto acc = renderer->read_accumulation();
+                if (FILE* f = std::fopen(accum_path.c_str(), "wb"))
+                {
+                    std::fwrite(acc.data(), 4, acc.size(), f);
+                    std::fclose(f);
+                }
+            }
+            hl_counters c {};
+            backend->check(hl_get_counters(backend->context(), &c), "hl_get_counters");
+            std::printf("{\"scene\": \"%s\", \"width\": %u, \"height\": %u, \"launches\": %u, \"seconds\": %.6f, \"extension_rays\": %llu, \"shadow_rays\": %llu, \"mrays_per_s\": %.1f}\n",
+                        scene_path.c_str(), width, height, done, seconds, (unsigned long long)c.extension_rays, (unsigned long long)c.shadow_rays,
+                        seconds > 0 ? double(c.extension_rays + c.shadow_rays) / seconds / 1e6 : 0.0);
+        }
+        if (!tables_path.empty())
+        {
+            // materials, instances, lights, per-instance submesh pairs, last push constants, sky coefficients
+            const SceneTables& T = scene->tables();
+            FILE*              f = std::fopen(tables_path.c_str(), "wb");
+            if (!f) throw std::runtime_error("cannot write " + tables_path);
+            write_vec(f, T.materials), write_vec(f, T.instances), write_vec(f, T.lights);
+            const uint32_t ni = (uint32_t)T.submesh_info.size();
+            std::fwrite(&ni, 4, 1, f);
+            for (auto& v : T.submesh_info) write_vec(f, v);
+            hl_push_constants pc;
+            if (renderer)
+                pc = renderer->path_integrator()->last_push_constants();
+            else
+            {
+                PathIntegrator pi(backend);
+                pi.set_max_ray_bounces(bounces ? bounces : file_bounces), pi.set_shadow_ray_bias(bias);
+                pc = pi.make_push_constants(render_state, render_state.camera()->view_matrix(), render_state.camera()->projection_matrix(), glm::ivec2(0, 0), glm::ivec2(0, 0));
+            }
+            std::fwrite(&pc, sizeof(pc), 1, f);
+            std::fwrite(scene->sky_model()->coefficients(), 4, 40, f);
+            std::fclose(f);
+        }
+        // release in dependency order: scene graph and resources before the backend
+        renderer.reset();
+        scene.reset(), root.reset(), camera.reset();
+        meshes.clear(), materials.clear(), textures.clear();
+    }
+    catch (const std::exception& e)
+    {
+        std::fprintf(stderr, "helios_headless: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
