@@ -287,8 +287,12 @@ def main():
     te0 = time.time()
     for s in range(K):
         pc = scene.push_constants(frame_index(W + s))  # host-side PushConstants fill (PathIntegrator::launch_rays)
-        ctx.render_frame(pc)
-        ctx._chk(ctx.lib.hl_tonemap(ctx.h, C.c_float(1.0), C.c_int(0), C.c_float(1.0), host_img.ctypes.data_as(C.c_void_p)))
+        if dist is None:
+            ctx.render_frame_tonemapped(pc, 1.0, abi.TONE_MAP_ACES)  # fused accumulate + tone-map resolve pass
+            ctx.read_rgba8(host_img)
+        else:  # sum mode: separate tone-map pass (needs the sample scale)
+            ctx.render_frame(pc)
+            ctx._chk(ctx.lib.hl_tonemap(ctx.h, C.c_float(1.0), C.c_int(0), C.c_float(1.0 / (s + 1)), host_img.ctypes.data_as(C.c_void_p)))
     barrier()
     te = time.time() - te0
     ce = ctx.counters()

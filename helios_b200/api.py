@@ -52,6 +52,10 @@ class Context:
         self.meshes.append(m)
         return m
 
+    def destroy_mesh(self, mesh):
+        self._chk(self.lib.hl_mesh_destroy(self.h, mesh))
+        self.meshes = [m for m in self.meshes if m.value != mesh.value]
+
     def mesh_build_stats(self, mesh) -> np.ndarray:
         out = np.zeros((), abi.BUILD_STATS)
         self._chk(self.lib.hl_mesh_build_stats(self.h, mesh, _p(out)))
@@ -110,6 +114,16 @@ class Context:
         pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
         self._chk(self.lib.hl_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1])))
 
+    def render_frame_tonemapped(self, pc, exposure=1.0, op=abi.TONE_MAP_ACES, launch=(0, 0)):
+        """frame + fused accumulate / tone-map resolve pass (Renderer::render in one call)"""
+        pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
+        self._chk(self.lib.hl_render_frame_tonemapped(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), C.c_float(exposure), C.c_int(op)))
+
+    def read_rgba8(self, out=None):
+        out = np.zeros((self.height, self.width, 4), np.uint8) if out is None else out
+        self._chk(self.lib.hl_read_rgba8(self.h, _p(out)))
+        return out
+
     def accum_clear(self):
         self._chk(self.lib.hl_accum_clear(self.h))
 
@@ -123,6 +137,11 @@ class Context:
         pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
         self._chk(self.lib.hl_trace_primary_ids(self.h, _p(pcb), _p(inst), _p(geom), _p(prim), _p(t), _p(u), _p(v)))
         return inst, geom, prim, t, u, v
+
+    def trace_primary_device_only(self, pc):
+        """primary-ray closest hits without the read-back (timing: bracket with event_record)"""
+        pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
+        self._chk(self.lib.hl_trace_primary_ids(self.h, _p(pcb), None, None, None, None, None, None))
 
     def trace_rays(self, rays, flags=0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)

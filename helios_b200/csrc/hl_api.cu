@@ -69,6 +69,13 @@ hl_status hl_context_create(int device_ordinal, uint32_t width, uint32_t height,
         HL_CUDA(cudaSetDevice(device_ordinal));
         HL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         HL_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal));
+        {
+            // keep freed build scratch in the stream-ordered pool instead of returning it to the driver
+            cudaMemPool_t pool;
+            HL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
+            uint64_t keep = ~0ull;
+            HL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         c->W = width, c->H = height;
         // 8-bit decode tables (unorm, srgb, snorm), computed in double like the oracle's
         float lut[768];
@@ -361,6 +368,29 @@ hl_status hl_render_frame(hl_context ctx, const hl_push_constants* pc, uint32_t 
     HL_CATCH
 }
 
+hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h, float exposure, int op)
+{
+    HL_TRY(ctx)
+    if (!pc) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: null push constants");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_frame_tonemapped: hl_scene_set_tables has not been called since the last resource change");
+    if (c_->accum_mode != HL_ACCUM_RUNNING_MEAN) HL_FAIL(HL_ERR_STATE, "hl_render_frame_tonemapped: needs HL_ACCUM_RUNNING_MEAN (use hl_tonemap with sample_scale for sums)");
+    if (op != HL_TONE_MAP_ACES && op != HL_TONE_MAP_REINHARD) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: unknown tone map operator");
+    if (!clip_launch(c_, pc, launch_w, launch_h)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: launch_id_size.zw differs from the context extent");
+    if (pc->max_ray_bounces > HL_MAX_BOUNCES) HL_FAIL(HL_ERR_LIMIT, "hl_render_frame_tonemapped: max_ray_bounces > 64");
+    wavefront_render_frame(c_, *pc, launch_w, launch_h, true, exposure, op);
+    HL_CUDA(cudaGetLastError());
+    HL_CATCH
+}
+
+hl_status hl_read_rgba8(hl_context ctx, uint8_t* rgba8_host)
+{
+    HL_TRY(ctx)
+    if (!rgba8_host) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_read_rgba8: null pointer");
+    HL_CUDA(cudaMemcpyAsync(rgba8_host, c_->rgba8.p, (size_t)c_->W * c_->H * 4, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    HL_CATCH
+}
+
 hl_status hl_accum_clear(hl_context ctx)
 {
     HL_TRY(ctx)
@@ -383,6 +413,7 @@ hl_status hl_trace_primary_ids(hl_context ctx, const hl_push_constants* pc, uint
     if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_trace_primary_ids: scene tables not set");
     if (pc->launch_id_size[2] != c_->W || pc->launch_id_size[3] != c_->H) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_trace_primary_ids: extent mismatch");
     wavefront_primary_hits(c_, *pc);
+    if (!instance && !geometry && !primitive && !t && !u && !v) return HL_OK; // device-only: results stay in the hit buffers
     const size_t       n = (size_t)c_->W * c_->H;
     std::vector<float> ha(n * 4);
     std::vector<uint32_t> hb(n * 2);

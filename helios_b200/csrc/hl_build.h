@@ -254,10 +254,21 @@ struct WideOut
     uint32_t* node_counter; // next free wide node
     uint32_t* leaf_counter; // next free leaf slot
 };
-// Builds wide node `task.wide` from binary subtree `task.bnode`; appends one task per internal child.
+// A task is published to the work queue with ONE aligned 8-byte store, so a consumer polling the slot sees
+// either the empty pattern (all ones) or the whole task.
+HL_HD void publish_task(CollapseTask* slot, CollapseTask t)
+{
+#if defined(__CUDA_ARCH__)
+    *(volatile unsigned long long*)slot = ((unsigned long long)t.bnode << 32) | t.wide;
+#else
+    *slot = t;
+#endif
+}
+// Builds wide node `task.wide` from binary subtree `task.bnode`; appends one task per internal child to the
+// queue `next` (slots handed out by `next_count`) and returns how many it appended.
 // leaf_writer(dst_leaf_index, sorted_leaf_position) stores one leaf primitive record.
 template <class LeafWriter>
-HL_HD void collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, CollapseTask* next, uint32_t* next_count, LeafWriter& leaf_writer)
+HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, CollapseTask* next, uint32_t* next_count, LeafWriter& leaf_writer)
 {
     uint32_t ch[8];
     uint32_t ch_inner = 0; // bit k: child k becomes a wide node of its own
@@ -303,6 +314,10 @@ HL_HD void collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, Col
     int      slot_child[8];
     uint32_t child_done = 0, slot_done = 0;
     for (int s = 0; s < 8; s++) slot_child[s] = -1;
+    // cost(child, slot) once, then 8 rounds of "cheapest remaining pair"
+    float cost[64];
+    for (int k = 0; k < nch; k++)
+        for (int s = 0; s < 8; s++) cost[k * 8 + s] = ((s & 4) ? -cx[k] : cx[k]) + ((s & 2) ? -cy[k] : cy[k]) + ((s & 1) ? -cz[k] : cz[k]);
     for (int it = 0; it < nch; it++)
     {
         float bc = 3.0e38f;
@@ -313,7 +328,7 @@ HL_HD void collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, Col
             for (int s = 0; s < 8; s++)
             {
                 if (slot_done & (1u << s)) continue;
-                const float c = ((s & 4) ? -cx[k] : cx[k]) + ((s & 2) ? -cy[k] : cy[k]) + ((s & 1) ? -cz[k] : cz[k]);
+                const float c = cost[k * 8 + s];
                 if (c < bc) bc = c, bk = k, bs = s;
             }
         }
@@ -365,7 +380,7 @@ HL_HD void collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, Col
             w.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             CollapseTask nt;
             nt.wide = w.child_base + inner_rank, nt.bnode = c;
-            next[first_task + inner_rank] = nt;
+            publish_task(next + (first_task + inner_rank), nt);
             inner_rank++;
         }
         else
@@ -377,6 +392,7 @@ HL_HD void collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, Col
         }
     }
     out.nodes[task.wide] = w;
+    return n_inner;
 }
 
 // geometry lookup for a flat triangle index: tri_start[g] <= f < tri_start[g+1]
@@ -432,6 +448,13 @@ HL_HD Box triangle_box(const hl_vertex* vertices, const uint32_t* indices, const
     for (int k = 0; k < 3; k++) r.lo[k] = fminf(p0[k], fminf(p1[k], p2[k])), r.hi[k] = fmaxf(p0[k], fmaxf(p1[k], p2[k]));
     return r;
 }
+// collapse only records which sorted primitive lands in which leaf slot; a second, fully parallel pass writes
+// the records (keeps the vertex fetches out of the collapse's parent -> child dependency chain)
+struct DeferredLeafWriter
+{
+    uint32_t*  leaf_pos;
+    HL_HD void operator()(uint32_t dst, uint32_t sorted_pos) const { leaf_pos[dst] = sorted_pos; }
+};
 struct InstLeafWriter
 {
     const uint32_t* sorted_prim;

@@ -8,9 +8,9 @@
 //   morton         24 read, 8 + 4 written                                36
 //   radix sort     8 passes x (12 read + 12 written)  (CUB, 63 key bits) 192
 //   radix_tree     ~2 x 8 key reads (cached), 24 written                 40
-//   fit            24 read (sorted box) + 2 x 24 written + 48 read       120
-//   collapse       ~48 read (boxes) + 0.2 x 80 node + 48 leaf + 48 src   160
-//   total                                                              ~ 640 B / triangle
+//   fit            24 read (sorted box) + 2 x 24 written + 48 read + 2 x 28 cost-table rows written, 56 read   232
+//   collapse       ~48 read (boxes) + 8 decisions + 0.12 x 80 node + 48 leaf + 48 src + 2 x 8 queue   ~180
+//   total                                                              ~ 780 B / triangle
 #include "hl_internal.h"
 #include <cub/cub.cuh>
 
@@ -65,11 +65,50 @@ __global__ void k_fit(BinaryTree t, const Box* prim_boxes, const uint32_t* sorte
     }
 }
 
+// Collapse as ONE persistent launch over a device-side work queue (no host round trip per tree level):
+// queue[0] holds the root task; a thread takes the next queue index, polls the slot until its task is published
+// (a parent publishes one task per internal child while it writes its own node) and processes it.
+// ctl[0] = node counter, ctl[1] = leaf counter, ctl[2] = queue tail, ctl[3] = queue head,
+// ctl[4] = outstanding tasks (published - finished), ctl[5] = done flag.
 template <class LeafWriter>
-__global__ void k_collapse(BinaryTree t, const CollapseTask* tasks, uint32_t n_tasks, WideOut out, CollapseTask* next, uint32_t* next_count, LeafWriter writer)
+__global__ void k_write_leaves(LeafWriter writer, const uint32_t* leaf_pos, uint32_t n)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_tasks) collapse_one(t, tasks[i], out, next, next_count, writer);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) writer(i, leaf_pos[i]);
+}
+
+__global__ void __launch_bounds__(128) k_collapse(BinaryTree t, WideOut out, CollapseTask* queue, uint32_t capacity, uint32_t* ctl, DeferredLeafWriter writer)
+{
+    volatile uint32_t* vdone = ctl + 5;
+    uint32_t           idx   = 0;
+    bool               have  = false;
+    for (;;)
+    {
+        if (!have) idx = atomicAdd(ctl + 3, 1u), have = true;
+        bool ready = false;
+        CollapseTask task;
+        task.wide = task.bnode = 0xFFFFFFFFu;
+        if (idx < capacity)
+        {
+            const unsigned long long raw = *(volatile unsigned long long*)(queue + idx);
+            task.wide = (uint32_t)raw, task.bnode = (uint32_t)(raw >> 32);
+            ready = raw != ~0ull;
+        }
+        if (ready)
+        {
+            const uint32_t spawned = collapse_one(t, task, out, queue, ctl + 2, writer);
+            have                   = false;
+            // outstanding += spawned - 1; the thread that brings it to zero ends the launch
+            if (atomicAdd(ctl + 4, spawned - 1u) + spawned - 1u == 0u)
+            {
+                __threadfence();
+                *vdone = 1u;
+            }
+        }
+        else if (*vdone)
+            break;
+        else
+            __nanosleep(64); // waiting lanes yield the issue slots to the lanes of the warp that hold a task
+    }
 }
 
 static inline int grid_for(uint32_t n, int block, int cap) { return (int)std::min<uint64_t>(((uint64_t)n + block - 1) / block, (uint64_t)cap); }
@@ -89,41 +128,47 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         out.leaves.alloc(leaf_bytes);
         return;
     }
-    cudaEvent_t e0, e1;
-    HL_CUDA(cudaEventCreate(&e0));
-    HL_CUDA(cudaEventCreate(&e1));
-    HL_CUDA(cudaEventRecord(e0, st));
-
-    const int cap = ctx->sm_count * 8;
-    // scene box
-    DevBuf partial, scene;
-    const int rb = grid_for(n, 256, 1024);
-    partial.alloc(sizeof(Box) * rb);
-    scene.alloc(sizeof(Box));
-    k_box_reduce<<<rb, 256, 0, st>>>(d_boxes, n, partial.as<Box>());
-    k_box_reduce<<<1, 256, 0, st>>>(partial.as<Box>(), (uint32_t)rb, scene.as<Box>());
-    ctx->launches += 2;
-    // Morton keys + sort
-    DevBuf keys_a, keys_b, vals_a, vals_b, cub_tmp;
-    keys_a.alloc(8ull * n), keys_b.alloc(8ull * n), vals_a.alloc(4ull * n), vals_b.alloc(4ull * n);
-    k_morton<<<grid_for(n, 256, cap), 256, 0, st>>>(d_boxes, scene.as<Box>(), n, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
-    ctx->launches++;
+    // ---- all allocations first: the timed region below contains device work only
+    const int    cap = ctx->sm_count * 8;
+    const int    rb  = grid_for(n, 256, 1024);
+    const size_t ni  = n > 1 ? n - 1 : 1;
+    ScratchBuf   partial, scene, keys_a, keys_b, vals_a, vals_b, cub_tmp, tree_u32, tree_box, tree_cost, big_nodes, queue, ctr, leaf_pos;
+    partial.alloc(sizeof(Box) * rb, st);
+    scene.alloc(sizeof(Box), st);
+    keys_a.alloc(8ull * n, st), keys_b.alloc(8ull * n, st), vals_a.alloc(4ull * n, st), vals_b.alloc(4ull * n, st);
     cub::DoubleBuffer<uint64_t> dk(keys_a.as<uint64_t>(), keys_b.as<uint64_t>());
     cub::DoubleBuffer<uint32_t> dv(vals_a.as<uint32_t>(), vals_b.as<uint32_t>());
     size_t                      tmp_bytes = 0;
     HL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, 63, st));
-    cub_tmp.alloc(tmp_bytes);
+    cub_tmp.alloc(tmp_bytes, st);
+    tree_u32.alloc(4ull * (ni * 5 + 2ull * n), st);
+    tree_box.alloc(sizeof(Box) * (2ull * n), st);
+    tree_cost.alloc(4ull * (7ull * 2 * n + ni), st);
+    const uint32_t capacity = n + 1u; // at most one wide node per primitive
+    big_nodes.alloc(sizeof(WideNode) * (size_t)n, st);
+    queue.alloc(sizeof(CollapseTask) * (size_t)capacity, st);
+    leaf_pos.alloc(4ull * n, st);
+    ctr.alloc(32, st);
+    out.leaves.alloc(leaf_bytes * (size_t)n);
+
+    cudaEvent_t e0, e1, e2, e3;
+    HL_CUDA(cudaEventCreate(&e0));
+    HL_CUDA(cudaEventCreate(&e1));
+    HL_CUDA(cudaEventCreate(&e2));
+    HL_CUDA(cudaEventCreate(&e3));
+    HL_CUDA(cudaEventRecord(e0, st));
+    // scene box
+    k_box_reduce<<<rb, 256, 0, st>>>(d_boxes, n, partial.as<Box>());
+    k_box_reduce<<<1, 256, 0, st>>>(partial.as<Box>(), (uint32_t)rb, scene.as<Box>());
+    ctx->launches += 2;
+    // Morton keys + sort
+    k_morton<<<grid_for(n, 256, cap), 256, 0, st>>>(d_boxes, scene.as<Box>(), n, keys_a.as<uint64_t>(), vals_a.as<uint32_t>());
+    ctx->launches++;
     HL_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, dk, dv, (int)n, 0, 63, st));
-    ctx->launches += 8;
+    ctx->launches += 10;
     const uint64_t* keys   = dk.Current();
     const uint32_t* sorted = dv.Current();
     // binary radix tree
-    DevBuf     tree_u32, tree_box;
-    const size_t ni = n > 1 ? n - 1 : 1;
-    tree_u32.alloc(4ull * (ni * 5 + 2ull * n));
-    tree_box.alloc(sizeof(Box) * (2ull * n));
-    DevBuf tree_cost;
-    tree_cost.alloc(4ull * (7ull * 2 * n + ni));
     BinaryTree t;
     t.cost   = tree_cost.as<float>();
     t.dec    = (uint32_t*)(t.cost + 7ull * 2 * n);
@@ -145,45 +190,40 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     }
     k_fit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted);
     ctx->launches++;
-    // collapse, level by level
-    DevBuf big_nodes, tasks_a, tasks_b, ctr;
-    big_nodes.alloc(sizeof(WideNode) * (size_t)n);
-    out.leaves.alloc(leaf_bytes * (size_t)n);
-    tasks_a.alloc(sizeof(CollapseTask) * (size_t)n);
-    tasks_b.alloc(sizeof(CollapseTask) * (size_t)n);
-    ctr.alloc(16);
-    uint32_t h_ctr[4] = { 1u, 0u, 0u, 0u }; // node counter, leaf counter, next count
-    HL_CUDA(cudaMemcpyAsync(ctr.p, h_ctr, 16, cudaMemcpyHostToDevice, st));
+    // collapse: one persistent launch over a device-side work queue, then the leaf records in a parallel pass
+    HL_CUDA(cudaMemsetAsync(queue.p, 0xFF, sizeof(CollapseTask) * (size_t)capacity, st));
+    uint32_t h_ctr[8] = { 1u, 0u, 1u, 0u, 1u, 0u, 0u, 0u }; // nodes, leaves, tail, head, outstanding, done
+    HL_CUDA(cudaMemcpyAsync(ctr.p, h_ctr, 32, cudaMemcpyHostToDevice, st));
     CollapseTask root_task;
     root_task.wide = 0, root_task.bnode = 0;
-    HL_CUDA(cudaMemcpyAsync(tasks_a.p, &root_task, sizeof(root_task), cudaMemcpyHostToDevice, st));
+    HL_CUDA(cudaMemcpyAsync(queue.p, &root_task, sizeof(root_task), cudaMemcpyHostToDevice, st));
     WideOut wo;
     wo.nodes = big_nodes.as<WideNode>(), wo.node_counter = ctr.as<uint32_t>(), wo.leaf_counter = ctr.as<uint32_t>() + 1;
-    auto          writer  = make_writer(sorted, out.leaves.p);
-    uint32_t      n_tasks = 1;
-    CollapseTask *cur = tasks_a.as<CollapseTask>(), *nxt = tasks_b.as<CollapseTask>();
-    int           levels = 0;
-    while (n_tasks)
-    {
-        HL_CUDA(cudaMemsetAsync(ctr.as<uint32_t>() + 2, 0, 4, st));
-        k_collapse<<<(n_tasks + 127) / 128, 128, 0, st>>>(t, cur, n_tasks, wo, nxt, ctr.as<uint32_t>() + 2, writer);
-        ctx->launches++;
-        HL_CUDA(cudaMemcpyAsync(&n_tasks, ctr.as<uint32_t>() + 2, 4, cudaMemcpyDeviceToHost, st));
-        HL_CUDA(cudaStreamSynchronize(st));
-        std::swap(cur, nxt);
-        if (++levels > 256) throw CudaError(HL_ERR_CUDA, "BVH collapse did not terminate");
-    }
+    DeferredLeafWriter deferred;
+    deferred.leaf_pos = leaf_pos.as<uint32_t>();
+    k_collapse<<<cap, 128, 0, st>>>(t, wo, queue.as<CollapseTask>(), capacity, ctr.as<uint32_t>(), deferred);
+    k_write_leaves<<<grid_for(n, 256, cap), 256, 0, st>>>(make_writer(sorted, out.leaves.p), leaf_pos.as<uint32_t>(), n);
+    ctx->launches += 2;
+    HL_CUDA(cudaEventRecord(e1, st));
     HL_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, 8, cudaMemcpyDeviceToHost, st));
     HL_CUDA(cudaMemcpyAsync(&out.root, t.box, sizeof(Box), cudaMemcpyDeviceToHost, st));
+    HL_CUDA(cudaMemcpyAsync(&out.sah_cost, t.cost, 4, cudaMemcpyDeviceToHost, st));
     HL_CUDA(cudaStreamSynchronize(st));
     out.n_nodes = h_ctr[0], out.n_leaves = h_ctr[1], out.n_binary = 2 * n - 1;
+    {
+        const float a = box_half_area(out.root);
+        out.sah_cost  = a > 0.0f ? out.sah_cost / a : 0.0f; // C(root, 1) / A_root: expected cost per ray hitting the root box
+    }
     out.nodes.alloc(sizeof(WideNode) * (size_t)out.n_nodes);
+    HL_CUDA(cudaEventRecord(e2, st));
     HL_CUDA(cudaMemcpyAsync(out.nodes.p, big_nodes.p, sizeof(WideNode) * (size_t)out.n_nodes, cudaMemcpyDeviceToDevice, st));
-    HL_CUDA(cudaEventRecord(e1, st));
-    HL_CUDA(cudaEventSynchronize(e1));
-    HL_CUDA(cudaEventElapsedTime(&out.ms_build, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    HL_CUDA(cudaEventRecord(e3, st));
+    HL_CUDA(cudaEventSynchronize(e3));
+    float ms_a = 0.0f, ms_b = 0.0f;
+    HL_CUDA(cudaEventElapsedTime(&ms_a, e0, e1));
+    HL_CUDA(cudaEventElapsedTime(&ms_b, e2, e3));
+    out.ms_build = ms_a + ms_b;
+    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2), cudaEventDestroy(e3);
 }
 
 void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
@@ -195,8 +235,8 @@ void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
     const uint32_t n = tri_start[ng];
     mesh->tri_start.upload(tri_start.data(), 4ull * (ng + 1), st);
     mesh->submeshes.upload(mesh->subs.data(), sizeof(hl_submesh) * (size_t)ng, st);
-    DevBuf boxes;
-    boxes.alloc(sizeof(Box) * (size_t)std::max(n, 1u));
+    ScratchBuf boxes;
+    boxes.alloc(sizeof(Box) * (size_t)std::max(n, 1u), st);
     cudaEvent_t e0, e1;
     HL_CUDA(cudaEventCreate(&e0));
     HL_CUDA(cudaEventCreate(&e1));
@@ -225,7 +265,7 @@ void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
     mesh->stats.wide_nodes      = mesh->bvh.n_nodes;
     mesh->stats.binary_nodes    = mesh->bvh.n_binary;
     mesh->stats.ms_build        = mesh->bvh.ms_build + ms0;
-    mesh->stats.sah_cost        = 0.0f;
+    mesh->stats.sah_cost        = mesh->bvh.sah_cost;
     mesh->stats.bytes_nodes     = sizeof(WideNode) * (uint64_t)mesh->bvh.n_nodes;
     mesh->stats.bytes_triangles = sizeof(LeafTri) * (uint64_t)mesh->bvh.n_leaves;
 }

@@ -53,12 +53,36 @@ struct DevBuf
     T* as() const { return (T*)p; }
 };
 
+// build scratch: stream-ordered allocation from the device's default memory pool (cudaMallocAsync); the
+// context raises the pool's release threshold so a second build reuses the first build's memory
+struct ScratchBuf
+{
+    void*        p = nullptr;
+    cudaStream_t s = nullptr;
+    ScratchBuf() {}
+    ScratchBuf(const ScratchBuf&)            = delete;
+    ScratchBuf& operator=(const ScratchBuf&) = delete;
+    ~ScratchBuf()
+    {
+        if (p) cudaFreeAsync(p, s);
+    }
+    void alloc(size_t n, cudaStream_t stream)
+    {
+        if (p) cudaFreeAsync(p, s), p = nullptr;
+        s = stream;
+        HL_CUDA(cudaMallocAsync(&p, n ? n : 16, stream));
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
 struct WideBVHDev
 {
     DevBuf   nodes, leaves;
     uint32_t n_nodes = 0, n_leaves = 0, n_binary = 0;
     Box      root;
     float    ms_build = 0.0f;
+    float    sah_cost = 0.0f; // C(root, 1) / A(root) of the collapse DP (hl_build.h)
 };
 
 #define HL_MAX_BOUNCES 64
@@ -134,7 +158,7 @@ void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh);
 void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes);
 // hl_wavefront.cu
 void wavefront_alloc(hl_context_t* ctx);
-void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh);
+void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, bool fused_tonemap = false, float exposure = 1.0f, int op = 0);
 void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc);
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits);
 void film_clear(hl_context_t* ctx);

@@ -486,7 +486,7 @@ static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounc
     }
 }
 
-void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh)
+void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, bool fused_tonemap, float exposure, int op)
 {
     cudaStream_t st = ctx->stream;
     FrameParams  fp;
@@ -505,7 +505,7 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
     run_bounces(ctx, fp, bounces, true);
     const size_t last = 2 + 4 * (size_t)bounces;
     if (prof) HL_CUDA(cudaEventRecord(ctx->ev[last], st));
-    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, ctx->rgba8.as<uint32_t>(), 0, 1.0f, 0);
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, ctx->rgba8.as<uint32_t>(), fused_tonemap ? 1 : 0, exposure, op);
     k_totals<<<1, 32, 0, st>>>(ctr, (unsigned long long*)((char*)ctx->counters.p + CTR_TOTALS_OFFSET), bounces);
     ctx->launches += 2;
     if (prof)

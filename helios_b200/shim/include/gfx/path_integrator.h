@@ -37,6 +37,11 @@ public:
     void on_window_resize();
     void set_tiled(bool tiled);
 
+    // Renderer::render hands the tone-map settings down so that the launch can resolve accumulation and tone map
+    // in one fused pass (hl_render_frame_tonemapped); launched_last_render() tells it whether a launch happened
+    inline void set_resolve_tone_map(bool enabled, float exposure, int tone_map_operator) { m_fuse_tone_map = enabled, m_fuse_exposure = exposure, m_fuse_operator = tone_map_operator; }
+    inline bool launched_last_render() const { return m_launched; }
+
     // the block the last launch used (tests compare it with the Python host's restatement)
     inline const hl_push_constants& last_push_constants() const { return m_last_push_constants; }
     // fills a PushConstants block for (camera, counters) without launching
@@ -57,5 +62,8 @@ private:
     std::vector<glm::uvec2>    m_tile_coords;
     std::weak_ptr<vk::Backend> m_backend;
     hl_push_constants          m_last_push_constants {};
+    bool                       m_fuse_tone_map = false, m_launched = false;
+    float                      m_fuse_exposure = 1.0f;
+    int                        m_fuse_operator = HL_TONE_MAP_ACES;
 };
 } // namespace helios

@@ -20,6 +20,7 @@ void PathIntegrator::render(RenderState& render_state)
         m_tile_idx                = 0;
         m_num_accumulated_samples = 0;
     }
+    m_launched = false;
     if (m_tile_idx < m_tile_coords.size())
     {
         if (!render_state.camera())
@@ -31,6 +32,7 @@ void PathIntegrator::render(RenderState& render_state)
         launch_rays(render_state, m_tile_size.x, m_tile_size.y, 1, render_state.camera()->view_matrix(), render_state.camera()->projection_matrix(), glm::ivec2((int)tile.x, (int)tile.y),
                     glm::ivec2(0, 0));
         m_num_accumulated_samples++;
+        m_launched = true;
     }
     if (m_num_accumulated_samples == m_max_samples)
     {
@@ -91,7 +93,11 @@ void PathIntegrator::launch_rays(RenderState& render_state, const uint32_t& x, c
     (void)z;
     auto backend          = m_backend.lock();
     m_last_push_constants = make_push_constants(render_state, view, projection, tile_coord, pixel_coord);
-    backend->check(hl_render_frame(backend->require_device("PathIntegrator::launch_rays"), &m_last_push_constants, x, y), "hl_render_frame");
+    hl_context ctx = backend->require_device("PathIntegrator::launch_rays");
+    if (m_fuse_tone_map)
+        backend->check(hl_render_frame_tonemapped(ctx, &m_last_push_constants, x, y, m_fuse_exposure, m_fuse_operator), "hl_render_frame_tonemapped");
+    else
+        backend->check(hl_render_frame(ctx, &m_last_push_constants, x, y), "hl_render_frame");
 }
 
 // :312-336

@@ -24,13 +24,20 @@ void Renderer::render(RenderState& render_state)
         backend->check(hl_accum_clear(ctx), "hl_accum_clear");
         m_output_image_recreated = false;
     }
+    // the launch resolves accumulation + tone map in one fused pass; a frame without a launch (bake complete) or a
+    // tiled launch (only the tile's pixels are resolved) still runs the separate tone-map pass over the image
+    const int op = m_tone_map_operator == TONE_MAP_OPERATOR_ACES ? HL_TONE_MAP_ACES : HL_TONE_MAP_REINHARD;
+    m_path_integrator->set_resolve_tone_map(!m_path_integrator->is_tiled(), m_exposure, op);
     if (render_state.m_scene) m_path_integrator->render(render_state);
-    // tone map into the RGBA8 target (device only unless a save is pending)
+    const bool resolved = render_state.m_scene && m_path_integrator->launched_last_render() && !m_path_integrator->is_tiled();
     if (m_save_image_to_disk)
     {
         const auto           ext = backend->swap_chain_extents();
         std::vector<uint8_t> img((size_t)ext.width * ext.height * 4);
-        tone_map(img.data());
+        if (resolved)
+            backend->check(hl_read_rgba8(ctx, img.data()), "hl_read_rgba8");
+        else
+            tone_map(img.data());
         bool              ok  = false;
         const std::string& p  = m_image_save_path;
         const bool        pfm = p.size() > 4 && p.substr(p.size() - 4) == ".pfm";
@@ -54,7 +61,7 @@ void Renderer::render(RenderState& render_state)
         if (!ok) HELIOS_LOG_ERROR("Renderer::save_image_to_disk: cannot write " + p);
         m_save_image_to_disk = false;
     }
-    else
+    else if (!resolved)
         tone_map(nullptr);
 }
 

@@ -160,7 +160,7 @@ typedef struct hl_build_stats
     uint32_t wide_nodes;
     uint32_t binary_nodes;
     float    ms_build;     /* device time of the whole BLAS build (CUDA events) */
-    float    sah_cost;     /* SAH cost of the final wide BVH (Ct = Ci = 1) */
+    float    sah_cost;     /* SAH cost of the wide BVH per unit root area (node visit = 1, triangle test = 0.35) */
     uint64_t bytes_nodes;
     uint64_t bytes_triangles;
 } hl_build_stats;
@@ -215,6 +215,14 @@ HL_API hl_status hl_scene_set_tables(hl_context ctx, const hl_material* material
  * into the accumulation image exactly as path_trace_rgen.glsl:217-248.  launch_w/h = 0 -> full frame.
  * Asynchronous on the context's stream. */
 HL_API hl_status hl_render_frame(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h);
+/* The same frame with the progressive blend and the tone map fused into ONE resolve pass (reads the frame's radiance
+ * and the previous accumulation, writes RGBA32F + RGBA8): Renderer::render = PathIntegrator::render + tone_map
+ * (renderer.cpp:225-330, :369-428) in a single call.  Running-mean mode only (HL_ACCUM_SUM needs the sample
+ * count of the final reduction: use hl_tonemap with sample_scale there).  Asynchronous. */
+HL_API hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h,
+                                            float exposure, int tone_map_operator);
+/* copies the RGBA8 target written by the last hl_tonemap / hl_render_frame_tonemapped to host memory (synchronises) */
+HL_API hl_status hl_read_rgba8(hl_context ctx, uint8_t* rgba8_host);
 /* Renderer::render's restart branch (renderer.cpp:212-223): clears the accumulation image. */
 HL_API hl_status hl_accum_clear(hl_context ctx);
 HL_API hl_status hl_set_accum_mode(hl_context ctx, int mode);

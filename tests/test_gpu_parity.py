@@ -150,3 +150,25 @@ def test_errors_are_reported(api):
         bad[0] = 10_000_000
         ctx.create_mesh(s.meshes[0].vertices, bad, s.meshes[0].submeshes)
     ctx.close()
+
+
+def test_fused_resolve_equals_separate_tone_map():
+    """hl_render_frame_tonemapped (progressive blend + ACES/Reinhard in one pass) writes the same RGBA32F accumulation
+    and the same RGBA8 image as hl_render_frame followed by hl_tonemap"""
+    from helios_b200 import abi, api
+
+    s = scenes.cornell_box(160, 96)
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    for op, exposure in ((abi.TONE_MAP_ACES, 1.0), (abi.TONE_MAP_REINHARD, 0.6)):
+        ctx.accum_clear()
+        for f in range(4):
+            ctx.render_frame(s.push_constants(f))
+        a0, i0 = ctx.read_accum(), ctx.tonemap(exposure, op)
+        ctx.accum_clear()
+        for f in range(4):
+            ctx.render_frame_tonemapped(s.push_constants(f), exposure, op)
+        a1, i1 = ctx.read_accum(), ctx.read_rgba8()
+        assert np.array_equal(a0, a1) and np.array_equal(i0, i1)
+        assert i1[..., :3].max() > 0
+    ctx.close()
