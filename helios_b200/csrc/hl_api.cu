@@ -10,12 +10,17 @@ using namespace hl;
 
 static thread_local std::string g_create_error;
 
-#define HL_TRY(ctx_)                                      \
+// HL_TRY makes the main stream wait for the frames in flight (hl_wave_slot) before the call enqueues anything;
+// HL_TRY_FRAME is for the frame entry points themselves, which order their own streams.
+#define HL_TRY_FRAME(ctx_)                                \
     hl_context_t* c_ = (ctx_);                            \
     if (!c_) return HL_ERR_INVALID_ARGUMENT;              \
     try                                                   \
     {                                                     \
         HL_CUDA(cudaSetDevice(c_->device));
+#define HL_TRY(ctx_)   \
+    HL_TRY_FRAME(ctx_) \
+    hl::wavefront_join(c_);
 #define HL_CATCH                                          \
     }                                                     \
     catch (const hl::CudaError& e)                        \
@@ -112,6 +117,12 @@ hl_status hl_context_destroy(hl_context ctx)
         for (auto& e : ctx->ev) cudaEventDestroy(e);
     if (ctx->user_ev_ready)
         for (auto& e : ctx->user_ev) cudaEventDestroy(e);
+    for (hl_wave_slot& w : ctx->slot)
+    {
+        if (w.stream) cudaStreamSynchronize(w.stream), cudaStreamDestroy(w.stream);
+        if (w.resolved) cudaEventDestroy(w.resolved);
+    }
+    if (ctx->main_ev) cudaEventDestroy(ctx->main_ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HL_OK;
@@ -123,9 +134,7 @@ hl_status hl_context_resize(hl_context ctx, uint32_t width, uint32_t height)
     if (width == 0 || height == 0) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_context_resize: zero extent");
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     c_->W = width, c_->H = height;
-    c_->accum.release(), c_->rgba8.release(), c_->state_a.release(), c_->state_b.release();
-    for (int k = 0; k < 2; k++) c_->ext_o[k].release(), c_->ext_d[k].release();
-    c_->hit_a.release(), c_->hit_b.release(), c_->sh_o.release(), c_->sh_d.release(), c_->sh_c.release();
+    wavefront_release(c_);
     wavefront_alloc(c_);
     HL_CATCH
 }
@@ -358,7 +367,7 @@ static bool clip_launch(hl_context_t* c, const hl_push_constants* pc, uint32_t& 
 
 hl_status hl_render_frame(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h)
 {
-    HL_TRY(ctx)
+    HL_TRY_FRAME(ctx)
     if (!pc) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame: null push constants");
     if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_frame: hl_scene_set_tables has not been called since the last resource change");
     if (!clip_launch(c_, pc, launch_w, launch_h)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame: launch_id_size.zw differs from the context extent");
@@ -370,7 +379,7 @@ hl_status hl_render_frame(hl_context ctx, const hl_push_constants* pc, uint32_t 
 
 hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h, float exposure, int op)
 {
-    HL_TRY(ctx)
+    HL_TRY_FRAME(ctx)
     if (!pc) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: null push constants");
     if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_frame_tonemapped: hl_scene_set_tables has not been called since the last resource change");
     if (c_->accum_mode != HL_ACCUM_RUNNING_MEAN) HL_FAIL(HL_ERR_STATE, "hl_render_frame_tonemapped: needs HL_ACCUM_RUNNING_MEAN (use hl_tonemap with sample_scale for sums)");
@@ -417,8 +426,8 @@ hl_status hl_trace_primary_ids(hl_context ctx, const hl_push_constants* pc, uint
     const size_t       n = (size_t)c_->W * c_->H;
     std::vector<float> ha(n * 4);
     std::vector<uint32_t> hb(n * 2);
-    HL_CUDA(cudaMemcpyAsync(ha.data(), c_->hit_a.p, n * 16, cudaMemcpyDeviceToHost, c_->stream));
-    HL_CUDA(cudaMemcpyAsync(hb.data(), c_->hit_b.p, n * 8, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaMemcpyAsync(ha.data(), c_->slot[0].hit_a.p, n * 16, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaMemcpyAsync(hb.data(), c_->slot[0].hit_b.p, n * 8, cudaMemcpyDeviceToHost, c_->stream));
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     for (size_t i = 0; i < n; i++)
     {
@@ -497,18 +506,18 @@ hl_status hl_get_counters(hl_context ctx, hl_counters* out)
 {
     HL_TRY(ctx)
     if (!out) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_get_counters: null pointer");
-    uint64_t totals[2];
-    HL_CUDA(cudaMemcpyAsync(totals, (char*)c_->counters.p + CTR_TOTALS_OFFSET, 16, cudaMemcpyDeviceToHost, c_->stream));
+    uint64_t totals[2][2];
+    for (int k = 0; k < 2; k++) HL_CUDA(cudaMemcpyAsync(totals[k], (char*)c_->slot[k].counters.p + CTR_TOTALS_OFFSET, 16, cudaMemcpyDeviceToHost, c_->stream));
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     *out                = c_->last;
-    out->extension_rays = totals[0], out->shadow_rays = totals[1], out->frames = c_->frames;
+    out->extension_rays = totals[0][0] + totals[1][0], out->shadow_rays = totals[0][1] + totals[1][1], out->frames = c_->frames;
     HL_CATCH
 }
 
 hl_status hl_reset_counters(hl_context ctx)
 {
     HL_TRY(ctx)
-    HL_CUDA(cudaMemsetAsync((char*)c_->counters.p + CTR_TOTALS_OFFSET, 0, 16, c_->stream));
+    for (int k = 0; k < 2; k++) HL_CUDA(cudaMemsetAsync((char*)c_->slot[k].counters.p + CTR_TOTALS_OFFSET, 0, 16, c_->stream));
     c_->frames = 0;
     HL_CATCH
 }
@@ -549,6 +558,8 @@ hl_status hl_set_option(hl_context ctx, int option, int64_t value)
         c_->tail_threshold = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 0x7FFFFFFF));
     else if (option == HL_OPT_TAIL_START)
         c_->tail_start = (uint32_t)std::max<int64_t>(1, value);
+    else if (option == HL_OPT_PIPELINE)
+        c_->pipeline = value != 0;
     else
         HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_set_option: unknown option");
     HL_CATCH

@@ -111,6 +111,21 @@ struct hl_mesh_t
     hl_build_stats          stats {};
 };
 
+// Wavefront state of ONE frame in flight.  The context keeps two: frame f runs on slot f & 1 with its own CUDA
+// stream, so the latency-bound late bounces of frame f overlap the throughput-bound first bounces of frame f + 1
+// (the frames share nothing but the read-only scene; their resolve passes are chained by events).
+struct hl_wave_slot
+{
+    hl::DevBuf state_a, state_b;   // per path: (T.xyz, rng.x), (L.xyz, rng.y)
+    hl::DevBuf ext_o[2], ext_d[2]; // extension queue: (o.xyz, path), (d.xyz, -)
+    hl::DevBuf hit_a, hit_b;       // (t,u,v,prim), (instance, geometry)
+    hl::DevBuf sh_o, sh_d, sh_c;   // shadow queue: (o.xyz, path), (d.xyz, tmax), (contribution.xyz, -)
+    hl::DevBuf counters;           // uint32: ext_count[65], sh_count[64], fetch_ext[64], fetch_sh[64], tail; then uint64 totals[2]
+    cudaStream_t stream   = nullptr;
+    cudaEvent_t  resolved = nullptr; // recorded after the slot's last resolve pass
+    bool         pending  = false;   // frames were issued on `stream` since the last join with the main stream
+};
+
 struct hl_context_t
 {
     int          device = 0;
@@ -135,13 +150,12 @@ struct hl_context_t
     hl::SceneView   view {};
     bool            scene_ready = false;
     // film + wavefront state
-    hl::DevBuf accum, rgba8;
-    hl::DevBuf state_a, state_b;         // per path: (T.xyz, rng.x), (L.xyz, rng.y)
-    hl::DevBuf ext_o[2], ext_d[2];       // extension queue: (o.xyz, path), (d.xyz, -)
-    hl::DevBuf hit_a, hit_b;             // (t,u,v,prim), (instance, geometry)
-    hl::DevBuf sh_o, sh_d, sh_c;         // shadow queue: (o.xyz, path), (d.xyz, tmax), (contribution.xyz, -)
-    hl::DevBuf counters;                 // uint32: ext_count[65], sh_count[64], fetch_ext[64], fetch_sh[64]; then uint64 totals[2]
-    size_t     queue_capacity = 0;
+    hl::DevBuf   accum, rgba8;
+    hl_wave_slot slot[2];
+    uint64_t     frame_seq   = 0;       // frames issued; frame f uses slot[f & 1]
+    int          pipeline    = 1;       // 0: every frame on the main stream (also forced while profiling)
+    cudaEvent_t  main_ev     = nullptr; // orders work enqueued on the main stream before the next frame
+    size_t       queue_capacity = 0;
     // profiling
     cudaEvent_t ev[2 + 4 * HL_MAX_BOUNCES + 4] {};
     bool        ev_ready = false;
@@ -158,6 +172,8 @@ void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh);
 void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes);
 // hl_wavefront.cu
 void wavefront_alloc(hl_context_t* ctx);
+void wavefront_release(hl_context_t* ctx);
+void wavefront_join(hl_context_t* ctx); // main stream waits for every frame in flight
 void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, bool fused_tonemap = false, float exposure = 1.0f, int op = 0);
 void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc);
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits);

@@ -397,14 +397,44 @@ void wavefront_alloc(hl_context_t* ctx)
 {
     const size_t n = (size_t)ctx->W * ctx->H;
     ctx->accum.alloc(n * 16), ctx->rgba8.alloc(n * 4);
-    ctx->state_a.alloc(n * 16), ctx->state_b.alloc(n * 16);
-    for (int k = 0; k < 2; k++) ctx->ext_o[k].alloc(n * 16), ctx->ext_d[k].alloc(n * 16);
-    ctx->hit_a.alloc(n * 16), ctx->hit_b.alloc(n * 8);
-    ctx->sh_o.alloc(n * 16), ctx->sh_d.alloc(n * 16), ctx->sh_c.alloc(n * 16);
-    ctx->counters.alloc(CTR_BYTES);
-    HL_CUDA(cudaMemsetAsync(ctx->counters.p, 0, CTR_BYTES, ctx->stream));
+    for (hl_wave_slot& w : ctx->slot)
+    {
+        w.state_a.alloc(n * 16), w.state_b.alloc(n * 16);
+        for (int k = 0; k < 2; k++) w.ext_o[k].alloc(n * 16), w.ext_d[k].alloc(n * 16);
+        w.hit_a.alloc(n * 16), w.hit_b.alloc(n * 8);
+        w.sh_o.alloc(n * 16), w.sh_d.alloc(n * 16), w.sh_c.alloc(n * 16);
+        w.counters.alloc(CTR_BYTES);
+        HL_CUDA(cudaMemsetAsync(w.counters.p, 0, CTR_BYTES, ctx->stream));
+        if (!w.stream) HL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        if (!w.resolved) HL_CUDA(cudaEventCreateWithFlags(&w.resolved, cudaEventDisableTiming));
+        w.pending = false;
+    }
+    if (!ctx->main_ev) HL_CUDA(cudaEventCreateWithFlags(&ctx->main_ev, cudaEventDisableTiming));
     ctx->queue_capacity = n;
     film_clear(ctx);
+}
+
+void wavefront_release(hl_context_t* ctx)
+{
+    ctx->accum.release(), ctx->rgba8.release();
+    for (hl_wave_slot& w : ctx->slot)
+    {
+        w.state_a.release(), w.state_b.release();
+        for (int k = 0; k < 2; k++) w.ext_o[k].release(), w.ext_d[k].release();
+        w.hit_a.release(), w.hit_b.release(), w.sh_o.release(), w.sh_d.release(), w.sh_c.release();
+    }
+}
+
+// every frame in flight happens-before whatever is enqueued on the main stream next
+void wavefront_join(hl_context_t* ctx)
+{
+    for (hl_wave_slot& w : ctx->slot)
+        if (w.pending)
+        {
+            HL_CUDA(cudaEventRecord(w.resolved, w.stream));
+            HL_CUDA(cudaStreamWaitEvent(ctx->stream, w.resolved, 0));
+            w.pending = false;
+        }
 }
 
 void film_clear(hl_context_t* ctx)
@@ -441,10 +471,9 @@ static void ensure_events(hl_context_t* ctx)
     ctx->ev_ready = true;
 }
 
-static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounces, bool shade)
+static void run_bounces(hl_context_t* ctx, hl_wave_slot& w, cudaStream_t st, const FrameParams& fp, uint32_t bounces, bool shade)
 {
-    cudaStream_t st   = ctx->stream;
-    uint32_t*    ctr  = ctx->counters.as<uint32_t>();
+    uint32_t*    ctr  = w.counters.as<uint32_t>();
     const int    tgrid = ctx->sm_count * 8; // persistent: 8 blocks of 128 threads per SM
     const int    sgrid = ctx->sm_count * 8;
     ShadeParams  prm;
@@ -460,18 +489,18 @@ static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounc
         if (shade && b >= ctx->tail_start && ctx->tail_threshold > 0)
         {
             // sparse late bounces: finish the surviving paths in one launch when the queue is small (see k_tail)
-            k_tail<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, prm, b, ctx->tail_threshold, ctr, ctx->ext_o[cur].as<float4>(), ctx->ext_d[cur].as<float4>(), ctx->state_a.as<float4>(),
-                                                     ctx->state_b.as<float4>());
+            k_tail<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, prm, b, ctx->tail_threshold, ctr, w.ext_o[cur].as<float4>(), w.ext_d[cur].as<float4>(), w.state_a.as<float4>(),
+                                                     w.state_b.as<float4>());
             ctx->launches++;
         }
-        k_extend<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, ctx->ext_o[cur].as<float4>(), ctx->ext_d[cur].as<float4>(), ctr + CTR_EXT_COUNT + b, ctr + CTR_EXT_FETCH + b, ext_tmin,
-                                                   10000.0f, ext_flags, ctx->hit_a.as<float4>(), ctx->hit_b.as<uint2>());
+        k_extend<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, w.ext_o[cur].as<float4>(), w.ext_d[cur].as<float4>(), ctr + CTR_EXT_COUNT + b, ctr + CTR_EXT_FETCH + b, ext_tmin,
+                                                   10000.0f, ext_flags, w.hit_a.as<float4>(), w.hit_b.as<uint2>());
         ctx->launches++;
         if (!shade) break;
         if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 1], st));
-        k_shade<<<sgrid, HL_SHADE_BLOCK, 0, st>>>(ctx->view, prm, b, ctr + CTR_EXT_COUNT + b, ctx->ext_o[cur].as<float4>(), ctx->ext_d[cur].as<float4>(), ctx->hit_a.as<float4>(),
-                                                  ctx->hit_b.as<uint2>(), ctx->state_a.as<float4>(), ctx->state_b.as<float4>(), ctx->ext_o[nxt].as<float4>(), ctx->ext_d[nxt].as<float4>(),
-                                                  ctr + CTR_EXT_COUNT + b + 1, ctx->sh_o.as<float4>(), ctx->sh_d.as<float4>(), ctx->sh_c.as<float4>(), ctr + CTR_SH_COUNT + b);
+        k_shade<<<sgrid, HL_SHADE_BLOCK, 0, st>>>(ctx->view, prm, b, ctr + CTR_EXT_COUNT + b, w.ext_o[cur].as<float4>(), w.ext_d[cur].as<float4>(), w.hit_a.as<float4>(),
+                                                  w.hit_b.as<uint2>(), w.state_a.as<float4>(), w.state_b.as<float4>(), w.ext_o[nxt].as<float4>(), w.ext_d[nxt].as<float4>(),
+                                                  ctr + CTR_EXT_COUNT + b + 1, w.sh_o.as<float4>(), w.sh_d.as<float4>(), w.sh_c.as<float4>(), ctr + CTR_SH_COUNT + b);
         ctx->launches++;
         if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 2], st));
         // shadow rays: depth 0 -> flags 0 (any-hit runs); deeper -> Opaque | TerminateOnFirstHit (rchit:286-290).
@@ -479,8 +508,8 @@ static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounc
         // per-candidate test (alpha), independent of order — so the depth-0 query may also stop at its first
         // accepted hit: the result is identical to the reference's closest-hit + shadow.rchit sequence.
         const uint32_t sh_flags = b == 0 ? HL_RAY_TERMINATE : (HL_RAY_OPAQUE | HL_RAY_TERMINATE);
-        k_connect<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, ctx->sh_o.as<float4>(), ctx->sh_d.as<float4>(), ctx->sh_c.as<float4>(), ctr + CTR_SH_COUNT + b, ctr + CTR_SH_FETCH + b, 0.0001f,
-                                                    sh_flags, ctx->state_b.as<float4>());
+        k_connect<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, w.sh_o.as<float4>(), w.sh_d.as<float4>(), w.sh_c.as<float4>(), ctr + CTR_SH_COUNT + b, ctr + CTR_SH_FETCH + b, 0.0001f,
+                                                    sh_flags, w.state_b.as<float4>());
         ctx->launches++;
         if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 3], st));
     }
@@ -488,25 +517,42 @@ static void run_bounces(hl_context_t* ctx, const FrameParams& fp, uint32_t bounc
 
 void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, bool fused_tonemap, float exposure, int op)
 {
-    cudaStream_t st = ctx->stream;
-    FrameParams  fp;
+    FrameParams fp;
     fp.pc = pc;
     fp.lw = lw, fp.lh = lh;
     const uint32_t n = lw * lh;
     if (n == 0) return;
     const uint32_t bounces = std::min<uint32_t>(pc.max_ray_bounces, HL_MAX_BOUNCES);
     const bool     prof    = ctx->profiling;
+    const bool     piped   = ctx->pipeline && !prof;
+    if (!piped) wavefront_join(ctx);
+    hl_wave_slot& w     = ctx->slot[piped ? (ctx->frame_seq & 1) : 0];
+    hl_wave_slot& other = ctx->slot[piped ? ((ctx->frame_seq & 1) ^ 1) : 1];
+    cudaStream_t  st    = piped ? w.stream : ctx->stream;
+    if (piped)
+    {
+        // whatever the caller enqueued on the main stream (uploads, clears, table updates) precedes this frame
+        HL_CUDA(cudaEventRecord(ctx->main_ev, ctx->stream));
+        HL_CUDA(cudaStreamWaitEvent(st, ctx->main_ev, 0));
+    }
     if (prof) ensure_events(ctx);
-    uint32_t* ctr = ctx->counters.as<uint32_t>();
+    uint32_t* ctr = w.counters.as<uint32_t>();
     HL_CUDA(cudaMemsetAsync(ctr, 0, CTR_U32_TOTAL * 4, st));
     if (prof) HL_CUDA(cudaEventRecord(ctx->ev[0], st));
-    k_generate<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_a.as<float4>(), ctx->state_b.as<float4>(), ctx->ext_o[0].as<float4>(), ctx->ext_d[0].as<float4>(), ctr);
+    k_generate<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_a.as<float4>(), w.state_b.as<float4>(), w.ext_o[0].as<float4>(), w.ext_d[0].as<float4>(), ctr);
     ctx->launches++;
-    run_bounces(ctx, fp, bounces, true);
+    run_bounces(ctx, w, st, fp, bounces, true);
     const size_t last = 2 + 4 * (size_t)bounces;
     if (prof) HL_CUDA(cudaEventRecord(ctx->ev[last], st));
-    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, ctx->rgba8.as<uint32_t>(), fused_tonemap ? 1 : 0, exposure, op);
-    k_totals<<<1, 32, 0, st>>>(ctr, (unsigned long long*)((char*)ctx->counters.p + CTR_TOTALS_OFFSET), bounces);
+    // progressive blends are applied in frame order: wait for the previous frame's resolve pass
+    if (piped && other.pending) HL_CUDA(cudaStreamWaitEvent(st, other.resolved, 0));
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, ctx->rgba8.as<uint32_t>(), fused_tonemap ? 1 : 0, exposure, op);
+    if (piped)
+    {
+        HL_CUDA(cudaEventRecord(w.resolved, st));
+        w.pending = true;
+    }
+    k_totals<<<1, 32, 0, st>>>(ctr, (unsigned long long*)((char*)w.counters.p + CTR_TOTALS_OFFSET), bounces);
     ctx->launches += 2;
     if (prof)
     {
@@ -532,21 +578,24 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
         c.ms_frame = ms;
     }
     ctx->frames++;
+    ctx->frame_seq++;
 }
 
+// primary-ray closest hits into slot 0's hit buffers, on the main stream (callers join first)
 void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc)
 {
-    cudaStream_t st = ctx->stream;
-    FrameParams  fp;
+    cudaStream_t  st = ctx->stream;
+    hl_wave_slot& w  = ctx->slot[0];
+    FrameParams   fp;
     fp.pc = pc;
     fp.pc.launch_id_size[0] = fp.pc.launch_id_size[1] = 0;
     fp.lw = ctx->W, fp.lh = ctx->H;
     const uint32_t n   = fp.lw * fp.lh;
-    uint32_t*      ctr = ctx->counters.as<uint32_t>();
+    uint32_t*      ctr = w.counters.as<uint32_t>();
     HL_CUDA(cudaMemsetAsync(ctr, 0, CTR_U32_TOTAL * 4, st));
-    k_generate<<<(n + 255) / 256, 256, 0, st>>>(fp, ctx->state_a.as<float4>(), ctx->state_b.as<float4>(), ctx->ext_o[0].as<float4>(), ctx->ext_d[0].as<float4>(), ctr);
+    k_generate<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_a.as<float4>(), w.state_b.as<float4>(), w.ext_o[0].as<float4>(), w.ext_d[0].as<float4>(), ctr);
     ctx->launches++;
-    run_bounces(ctx, fp, 1, false);
+    run_bounces(ctx, w, st, fp, 1, false);
 }
 
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits)

@@ -254,6 +254,8 @@ HL_API hl_status hl_event_elapsed_ms(hl_context ctx, int slot_begin, int slot_en
 /* tuning knobs of the wavefront scheduler (results do not depend on them) */
 #define HL_OPT_TAIL_THRESHOLD 1 /* queue size at or below which the late bounces are finished by one per-path kernel; 0 = never */
 #define HL_OPT_TAIL_START 2     /* first bounce at which that switch may happen (>= 1) */
+#define HL_OPT_PIPELINE 3       /* 1 (default): consecutive frames alternate between two wavefront state slots / streams so the
+                                   sparse late bounces of frame f overlap the first bounces of frame f + 1; 0: one frame at a time */
 HL_API hl_status hl_set_option(hl_context ctx, int option, int64_t value);
 /* number of kernels launched by this library on this context since creation */
 HL_API hl_status hl_kernel_launches(hl_context ctx, uint64_t* out);

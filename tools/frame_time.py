@@ -1,6 +1,6 @@
 """ms/frame, Mrays/s and per-stage times of one BASELINE config on the GPU, plus an image checksum (so that
 tuning variants can be checked for identical results).  python tools/frame_time.py [terrain|foliage|city|cornell]"""
-import sys, json, hashlib
+import sys, json, hashlib, os
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
@@ -13,6 +13,7 @@ s = {"terrain": lambda: scenes.terrain_scene(), "foliage": lambda: scenes.foliag
      "cornell": lambda: scenes.cornell_box(1024, 1024)}[name]()
 ctx = api.Context(s.width, s.height)
 ctx.load_scene(s)
+ctx.set_option(3, int(os.environ.get('HL_PIPELINE', '1')))  # HL_OPT_PIPELINE
 pcs = [s.push_constants(f) for f in range(1, frames + 5)]
 ctx.accum_clear()
 for pc in pcs[:4]: ctx.render_frame(pc)
@@ -24,7 +25,7 @@ ms = ctx.event_elapsed_ms(0, 1) / frames
 c = ctx.counters()
 rays = float(c["extension_rays"] + c["shadow_rays"]) / frames
 acc = ctx.read_accum()
-out = {"scene": name, "tris": int(s.num_triangles), "ms_per_frame": round(ms, 4), "mrays_s": round(rays / ms / 1e3, 1), "rays_per_frame": rays,
+out = {"scene": name, "pipeline": int(os.environ.get('HL_PIPELINE', '1')), "tris": int(s.num_triangles), "ms_per_frame": round(ms, 4), "mrays_s": round(rays / ms / 1e3, 1), "rays_per_frame": rays,
        "sha": hashlib.sha256(acc.tobytes()).hexdigest()[:16]}
 ctx.set_profiling(True)
 st = {k: 0.0 for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_resolve", "ms_frame")}
