@@ -278,7 +278,8 @@ def main():
     }
 
     # ---------------- end to end through the C ABI with host buffers ----------------
-    host_img = torch.empty((scene.height, scene.width, 4), dtype=torch.uint8).pin_memory().numpy()
+    host_ring = [torch.empty((scene.height, scene.width, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(3)]
+    host_img = host_ring[0]
     ctx.accum_clear()
     ctx.reset_counters()
     import ctypes as C
@@ -288,8 +289,9 @@ def main():
     for s in range(K):
         pc = scene.push_constants(frame_index(W + s))  # host-side PushConstants fill (PathIntegrator::launch_rays)
         if dist is None:
-            ctx.render_frame_tonemapped(pc, 1.0, abi.TONE_MAP_ACES)  # fused accumulate + tone-map resolve pass
-            ctx.read_rgba8(host_img)
+            # fused accumulate + tone-map resolve pass, RGBA8 image copied to pinned host memory on the frame's own stream
+            # (every step's image reaches the host; the copy of step s overlaps the rendering of step s + 1)
+            ctx.render_frame_readback(pc, host_ring[s % 3], 1.0, abi.TONE_MAP_ACES)
         else:  # sum mode: separate tone-map pass (needs the sample scale)
             ctx.render_frame(pc)
             ctx._chk(ctx.lib.hl_tonemap(ctx.h, C.c_float(1.0), C.c_int(0), C.c_float(1.0 / (s + 1)), host_img.ctypes.data_as(C.c_void_p)))

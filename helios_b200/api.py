@@ -119,6 +119,13 @@ class Context:
         pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
         self._chk(self.lib.hl_render_frame_tonemapped(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), C.c_float(exposure), C.c_int(op)))
 
+    def render_frame_readback(self, pc, host_rgba8, exposure=1.0, op=abi.TONE_MAP_ACES, launch=(0, 0)):
+        """frame + fused resolve + asynchronous read-back of the RGBA8 image into `host_rgba8` (pinned uint8 [H, W, 4]);
+        complete after synchronize()"""
+        pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
+        assert host_rgba8.dtype == np.uint8 and host_rgba8.size == self.width * self.height * 4 and host_rgba8.flags["C_CONTIGUOUS"]
+        self._chk(self.lib.hl_render_frame_readback(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), C.c_float(exposure), C.c_int(op), _p(host_rgba8)))
+
     def read_rgba8(self, out=None):
         out = np.zeros((self.height, self.width, 4), np.uint8) if out is None else out
         self._chk(self.lib.hl_read_rgba8(self.h, _p(out)))

@@ -386,7 +386,25 @@ hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_constants* pc
     if (op != HL_TONE_MAP_ACES && op != HL_TONE_MAP_REINHARD) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: unknown tone map operator");
     if (!clip_launch(c_, pc, launch_w, launch_h)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: launch_id_size.zw differs from the context extent");
     if (pc->max_ray_bounces > HL_MAX_BOUNCES) HL_FAIL(HL_ERR_LIMIT, "hl_render_frame_tonemapped: max_ray_bounces > 64");
-    wavefront_render_frame(c_, *pc, launch_w, launch_h, true, exposure, op);
+    ResolveOptions opt;
+    opt.tone_map = true, opt.exposure = exposure, opt.op = op;
+    wavefront_render_frame(c_, *pc, launch_w, launch_h, opt);
+    HL_CUDA(cudaGetLastError());
+    HL_CATCH
+}
+
+hl_status hl_render_frame_readback(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h, float exposure, int op, uint8_t* rgba8_host)
+{
+    HL_TRY_FRAME(ctx)
+    if (!pc || !rgba8_host) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_readback: null argument");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_frame_readback: hl_scene_set_tables has not been called since the last resource change");
+    if (c_->accum_mode != HL_ACCUM_RUNNING_MEAN) HL_FAIL(HL_ERR_STATE, "hl_render_frame_readback: needs HL_ACCUM_RUNNING_MEAN");
+    if (op != HL_TONE_MAP_ACES && op != HL_TONE_MAP_REINHARD) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_readback: unknown tone map operator");
+    if (!clip_launch(c_, pc, launch_w, launch_h)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_readback: launch_id_size.zw differs from the context extent");
+    if (pc->max_ray_bounces > HL_MAX_BOUNCES) HL_FAIL(HL_ERR_LIMIT, "hl_render_frame_readback: max_ray_bounces > 64");
+    ResolveOptions opt;
+    opt.tone_map = true, opt.exposure = exposure, opt.op = op, opt.host = rgba8_host;
+    wavefront_render_frame(c_, *pc, launch_w, launch_h, opt);
     HL_CUDA(cudaGetLastError());
     HL_CATCH
 }
@@ -395,7 +413,7 @@ hl_status hl_read_rgba8(hl_context ctx, uint8_t* rgba8_host)
 {
     HL_TRY(ctx)
     if (!rgba8_host) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_read_rgba8: null pointer");
-    HL_CUDA(cudaMemcpyAsync(rgba8_host, c_->rgba8.p, (size_t)c_->W * c_->H * 4, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaMemcpyAsync(rgba8_host, c_->rgba8_cur ? c_->rgba8_cur : c_->rgba8.p, (size_t)c_->W * c_->H * 4, cudaMemcpyDeviceToHost, c_->stream));
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     HL_CATCH
 }

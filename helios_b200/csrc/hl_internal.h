@@ -120,6 +120,8 @@ struct hl_wave_slot
     hl::DevBuf ext_o[2], ext_d[2]; // extension queue: (o.xyz, path), (d.xyz, -)
     hl::DevBuf hit_a, hit_b;       // (t,u,v,prim), (instance, geometry)
     hl::DevBuf sh_o, sh_d, sh_c;   // shadow queue: (o.xyz, path), (d.xyz, tmax), (contribution.xyz, -)
+    hl::DevBuf rgba8;              // tone-map target of the fused resolve pass (per slot: an asynchronous read-back of
+                                   // frame f must not race with frame f + 1's resolve)
     hl::DevBuf counters;           // uint32: ext_count[65], sh_count[64], fetch_ext[64], fetch_sh[64], tail; then uint64 totals[2]
     cudaStream_t stream   = nullptr;
     cudaEvent_t  resolved = nullptr; // recorded after the slot's last resolve pass
@@ -150,7 +152,8 @@ struct hl_context_t
     hl::SceneView   view {};
     bool            scene_ready = false;
     // film + wavefront state
-    hl::DevBuf   accum, rgba8;
+    hl::DevBuf   accum, rgba8;          // rgba8: target of the stand-alone tone-map pass (hl_tonemap)
+    void*        rgba8_cur = nullptr;   // the RGBA8 image written last (ctx->rgba8 or a slot's)
     hl_wave_slot slot[2];
     uint64_t     frame_seq   = 0;       // frames issued; frame f uses slot[f & 1]
     int          pipeline    = 1;       // 0: every frame on the main stream (also forced while profiling)
@@ -174,7 +177,14 @@ void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes);
 void wavefront_alloc(hl_context_t* ctx);
 void wavefront_release(hl_context_t* ctx);
 void wavefront_join(hl_context_t* ctx); // main stream waits for every frame in flight
-void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, bool fused_tonemap = false, float exposure = 1.0f, int op = 0);
+struct ResolveOptions
+{
+    bool     tone_map = false; // also produce the RGBA8 image (fused into the resolve pass for full-frame launches)
+    float    exposure = 1.0f;
+    int      op       = 0;
+    uint8_t* host     = nullptr; // asynchronous read-back of that image on the frame's stream
+};
+void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, const ResolveOptions& opt = ResolveOptions());
 void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc);
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits);
 void film_clear(hl_context_t* ctx);

@@ -403,6 +403,7 @@ void wavefront_alloc(hl_context_t* ctx)
         for (int k = 0; k < 2; k++) w.ext_o[k].alloc(n * 16), w.ext_d[k].alloc(n * 16);
         w.hit_a.alloc(n * 16), w.hit_b.alloc(n * 8);
         w.sh_o.alloc(n * 16), w.sh_d.alloc(n * 16), w.sh_c.alloc(n * 16);
+        w.rgba8.alloc(n * 4);
         w.counters.alloc(CTR_BYTES);
         HL_CUDA(cudaMemsetAsync(w.counters.p, 0, CTR_BYTES, ctx->stream));
         if (!w.stream) HL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
@@ -421,7 +422,7 @@ void wavefront_release(hl_context_t* ctx)
     {
         w.state_a.release(), w.state_b.release();
         for (int k = 0; k < 2; k++) w.ext_o[k].release(), w.ext_d[k].release();
-        w.hit_a.release(), w.hit_b.release(), w.sh_o.release(), w.sh_d.release(), w.sh_c.release();
+        w.hit_a.release(), w.hit_b.release(), w.sh_o.release(), w.sh_d.release(), w.sh_c.release(), w.rgba8.release();
     }
 }
 
@@ -443,12 +444,15 @@ void film_clear(hl_context_t* ctx)
     k_clear<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->accum.as<float4>(), n);
     ctx->launches++;
     HL_CUDA(cudaMemsetAsync(ctx->rgba8.p, 0, n * 4, ctx->stream));
+    for (hl_wave_slot& w : ctx->slot) HL_CUDA(cudaMemsetAsync(w.rgba8.p, 0, n * 4, ctx->stream));
+    ctx->rgba8_cur = ctx->rgba8.p;
 }
 
 void film_tonemap(hl_context_t* ctx, float exposure, int op, float scale)
 {
     const size_t n = (size_t)ctx->W * ctx->H;
     k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->accum.as<float4>(), ctx->W, ctx->H, exposure, op, scale, ctx->rgba8.as<uint32_t>());
+    ctx->rgba8_cur = ctx->rgba8.p;
     ctx->launches++;
 }
 
@@ -515,7 +519,7 @@ static void run_bounces(hl_context_t* ctx, hl_wave_slot& w, cudaStream_t st, con
     }
 }
 
-void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, bool fused_tonemap, float exposure, int op)
+void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, const ResolveOptions& opt)
 {
     FrameParams fp;
     fp.pc = pc;
@@ -546,7 +550,20 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
     if (prof) HL_CUDA(cudaEventRecord(ctx->ev[last], st));
     // progressive blends are applied in frame order: wait for the previous frame's resolve pass
     if (piped && other.pending) HL_CUDA(cudaStreamWaitEvent(st, other.resolved, 0));
-    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, ctx->rgba8.as<uint32_t>(), fused_tonemap ? 1 : 0, exposure, op);
+    const bool full  = lw == ctx->W && lh == ctx->H;
+    const bool fused = opt.tone_map && full;
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, w.rgba8.as<uint32_t>(), fused ? 1 : 0, opt.exposure, opt.op);
+    if (opt.tone_map)
+    {
+        if (!fused) // a tile launch resolves only its own pixels: tone map the whole image, as the reference's full-screen pass does
+        {
+            const size_t px = (size_t)ctx->W * ctx->H;
+            k_tonemap<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(ctx->accum.as<float4>(), ctx->W, ctx->H, opt.exposure, opt.op, 1.0f, w.rgba8.as<uint32_t>());
+            ctx->launches++;
+        }
+        ctx->rgba8_cur = w.rgba8.p;
+        if (opt.host) HL_CUDA(cudaMemcpyAsync(opt.host, w.rgba8.p, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost, st));
+    }
     if (piped)
     {
         HL_CUDA(cudaEventRecord(w.resolved, st));

@@ -24,12 +24,12 @@ void Renderer::render(RenderState& render_state)
         backend->check(hl_accum_clear(ctx), "hl_accum_clear");
         m_output_image_recreated = false;
     }
-    // the launch resolves accumulation + tone map in one fused pass; a frame without a launch (bake complete) or a
-    // tiled launch (only the tile's pixels are resolved) still runs the separate tone-map pass over the image
+    // the launch resolves accumulation + tone map itself (one fused pass for full-frame launches); only a frame
+    // without a launch (bake complete) runs the stand-alone tone-map pass
     const int op = m_tone_map_operator == TONE_MAP_OPERATOR_ACES ? HL_TONE_MAP_ACES : HL_TONE_MAP_REINHARD;
-    m_path_integrator->set_resolve_tone_map(!m_path_integrator->is_tiled(), m_exposure, op);
+    m_path_integrator->set_resolve_tone_map(true, m_exposure, op);
     if (render_state.m_scene) m_path_integrator->render(render_state);
-    const bool resolved = render_state.m_scene && m_path_integrator->launched_last_render() && !m_path_integrator->is_tiled();
+    const bool resolved = render_state.m_scene && m_path_integrator->launched_last_render();
     if (m_save_image_to_disk)
     {
         const auto           ext = backend->swap_chain_extents();

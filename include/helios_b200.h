@@ -221,6 +221,13 @@ HL_API hl_status hl_render_frame(hl_context ctx, const hl_push_constants* pc, ui
  * count of the final reduction: use hl_tonemap with sample_scale there).  Asynchronous. */
 HL_API hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h,
                                             float exposure, int tone_map_operator);
+/* The same, plus an asynchronous device->host copy of the frame's RGBA8 image into rgba8_host (W*H*4 bytes, pinned memory
+ * for a truly asynchronous copy) on the frame's own stream: the read-back of frame f overlaps the rendering of frame
+ * f + 1 (the reference's save path also trails the frame, renderer.cpp:637-711).  The image is complete after
+ * hl_synchronize(); the caller must not reuse rgba8_host before that (or before two later frames were issued and
+ * synchronised).  Full-frame or tiled launches. */
+HL_API hl_status hl_render_frame_readback(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h,
+                                          float exposure, int tone_map_operator, uint8_t* rgba8_host);
 /* copies the RGBA8 target written by the last hl_tonemap / hl_render_frame_tonemapped to host memory (synchronises) */
 HL_API hl_status hl_read_rgba8(hl_context ctx, uint8_t* rgba8_host);
 /* Renderer::render's restart branch (renderer.cpp:212-223): clears the accumulation image. */
