@@ -28,7 +28,117 @@ struct WideBVH
     std::vector<uint32_t> inst_leaf;
     Box                   root;
     uint32_t              n_binary = 0;
+    float                 sah      = 0.0f; // C(root, 1) / A(root) of the collapse DP
 };
+
+// ---- experiment: binned-SAH re-split of the LBVH's upper levels over Morton clusters (HLBVH style) --------------
+// clusters = maximal LBVH subtrees with <= C primitives; the K-1 internal nodes above the cut are re-linked by a
+// top-down 16-bin SAH build over the cluster boxes.  Sequential reference used to MEASURE the quality gain
+// (tools/bvh_stats.py, HL_EMUL_SAH_TOP=C) before deciding on a GPU version.
+static int g_sah_top_cluster = 0;
+EM_API void em_set_sah_top(int cluster_prims) { g_sah_top_cluster = cluster_prims; }
+static uint32_t refine_rec(BinaryTree& t, std::vector<uint32_t>& cl, size_t lo, size_t hi, std::vector<uint32_t>& free_nodes, size_t& next_free, uint32_t self)
+{
+    // builds the subtree over clusters cl[lo, hi) into binary node `self`; returns prims below
+    const size_t n = hi - lo;
+    Box cb;
+    for (int k = 0; k < 3; k++) cb.lo[k] = 3e38f, cb.hi[k] = -3e38f;
+    auto centroid = [&](uint32_t m, int k) { return 0.5f * (t.box[m].lo[k] + t.box[m].hi[k]); };
+    for (size_t i = lo; i < hi; i++)
+        for (int k = 0; k < 3; k++) cb.lo[k] = fminf(cb.lo[k], centroid(cl[i], k)), cb.hi[k] = fmaxf(cb.hi[k], centroid(cl[i], k));
+    const int NB = 16;
+    float best = 3e38f;
+    int   bax = -1, bsplit = -1;
+    for (int ax = 0; ax < 3; ax++)
+    {
+        const float ext = cb.hi[ax] - cb.lo[ax];
+        if (!(ext > 0.0f)) continue;
+        Box      bb[NB];
+        uint32_t cnt[NB] = {};
+        for (auto& b : bb)
+            for (int k = 0; k < 3; k++) b.lo[k] = 3e38f, b.hi[k] = -3e38f;
+        for (size_t i = lo; i < hi; i++)
+        {
+            int b = (int)((centroid(cl[i], ax) - cb.lo[ax]) / ext * NB);
+            b     = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+            bb[b] = box_union(bb[b], t.box[cl[i]]);
+            cnt[b] += subtree_prims(t, cl[i]);
+        }
+        Box      R[NB];
+        uint32_t rc[NB];
+        Box      acc;
+        for (int k = 0; k < 3; k++) acc.lo[k] = 3e38f, acc.hi[k] = -3e38f;
+        uint32_t c = 0;
+        for (int b = NB - 1; b > 0; b--)
+        {
+            acc = box_union(acc, bb[b]), c += cnt[b];
+            R[b] = acc, rc[b] = c;
+        }
+        for (int k = 0; k < 3; k++) acc.lo[k] = 3e38f, acc.hi[k] = -3e38f;
+        c = 0;
+        for (int b = 0; b < NB - 1; b++)
+        {
+            acc = box_union(acc, bb[b]), c += cnt[b];
+            if (c == 0 || rc[b + 1] == 0) continue;
+            const float cost = box_half_area(acc) * c + box_half_area(R[b + 1]) * rc[b + 1];
+            if (cost < best) best = cost, bax = ax, bsplit = b;
+        }
+    }
+    size_t mid;
+    if (bax < 0)
+        mid = lo + n / 2;
+    else
+    {
+        const float ext = cb.hi[bax] - cb.lo[bax];
+        auto        it  = std::partition(cl.begin() + lo, cl.begin() + hi, [&](uint32_t m) {
+            int b = (int)((centroid(m, bax) - cb.lo[bax]) / ext * NB);
+            b     = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+            return b <= bsplit;
+        });
+        mid = (size_t)(it - cl.begin());
+        if (mid == lo || mid == hi) mid = lo + n / 2;
+    }
+    uint32_t child[2], prims = 0;
+    for (int side = 0; side < 2; side++)
+    {
+        const size_t a = side ? mid : lo, b = side ? hi : mid;
+        if (b - a == 1)
+            child[side] = cl[a], prims += subtree_prims(t, cl[a]);
+        else
+        {
+            child[side] = free_nodes[next_free++];
+            prims += refine_rec(t, cl, a, b, free_nodes, next_free, child[side]);
+        }
+        t.parent[child[side]] = self;
+    }
+    t.left[self] = child[0], t.right[self] = child[1];
+    t.first[self] = 0, t.last[self] = prims - 1; // only the count is meaningful above the cut
+    const Box b = box_union(t.box[child[0]], t.box[child[1]]);
+    t.box[self] = b;
+    sah_node_costs(t, self, box_half_area(b));
+    return prims;
+}
+static void refine_top(BinaryTree& t, uint32_t C)
+{
+    if (t.n <= C) return;
+    std::vector<uint32_t> clusters, top; // top = internal nodes above the cut, root first
+    std::vector<uint32_t> stack { 0u };
+    while (!stack.empty())
+    {
+        const uint32_t m = stack.back();
+        stack.pop_back();
+        if (subtree_prims(t, m) <= C)
+        {
+            clusters.push_back(m);
+            continue;
+        }
+        top.push_back(m);
+        stack.push_back(t.right[m]), stack.push_back(t.left[m]);
+    }
+    size_t next_free = 1; // top[0] is the root (node 0)
+    refine_rec(t, clusters, 0, clusters.size(), top, next_free, 0u);
+    t.parent[0] = 0xFFFFFFFFu;
+}
 
 template <class MakeWriter>
 static void build_wide(const std::vector<Box>& prim, WideBVH& out, MakeWriter make_writer, bool tri_leaves)
@@ -56,8 +166,10 @@ static void build_wide(const std::vector<Box>& prim, WideBVH& out, MakeWriter ma
     for (int i = 0; i + 1 < (int)n; i++) radix_tree_node(skeys.data(), t, i);
     for (uint32_t j = 0; j < n; j++) box[(n - 1) + j] = prim[order[j]];
     for (uint32_t j = 0; j < n; j++) fit_from_leaf(t, j, [] {});
+    if (g_sah_top_cluster > 0 && tri_leaves) refine_top(t, (uint32_t)g_sah_top_cluster);
     out.root     = box[0];
     out.n_binary = 2 * n - 1;
+    out.sah      = cost[0] / box_half_area(box[0]);
     out.nodes.resize(n);
     if (tri_leaves)
         out.tris.resize(n);
@@ -447,6 +559,7 @@ EM_API void em_tonemap(const float* accum, uint32_t W, uint32_t H, float exposur
             ((uint32_t*)out)[(size_t)r * W + x] = tone_map_rgba8(mk3(a[0] * scale, a[1] * scale, a[2] * scale), exposure, op);
         }
 }
+EM_API float em_mesh_sah(const EmScene* s, int mesh) { return s->meshes[mesh]->bvh.sah; }
 EM_API void em_mesh_stats(const EmScene* s, int mesh, uint32_t* out3)
 {
     out3[0] = (uint32_t)s->meshes[mesh]->bvh.tris.size();

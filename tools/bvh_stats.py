@@ -46,6 +46,9 @@ def main():
     faces = None
     if s.env_cube is None and getattr(s, "sun_direction", None) is not None:
         faces = emul.sky_bake(sky.sky_coefficients(s.sun_direction), s.sun_direction, 64)
+    import os
+    if os.environ.get("HL_EMUL_SAH_TOP"):
+        emul.lib().em_set_sah_top(C.c_int(int(os.environ["HL_EMUL_SAH_TOP"])))
     t0 = time.time()
     e = emul.EmulScene(s, sky_faces=faces)
     t1 = time.time()
@@ -56,6 +59,8 @@ def main():
     e.render_frame(s.push_constants(1), accum)
     emul.lib().em_set_node_log(None, C.c_size_t(0))
     print(f"{a.scene}: {s.num_triangles} triangles, build {t1 - t0:.1f}s, mesh0 stats (tris, wide nodes, binary) = {e.mesh_stats(0)}")
+    emul.lib().em_mesh_sah.restype = C.c_float
+    print("  SAH cost per mesh (DP, per unit root area):", [round(float(emul.lib().em_mesh_sah(e.h, C.c_int(k))), 2) for k in range(len(s.meshes))])
     tot_n = tot_l = tot_r = 0
     for d in range(a.depths):
         v = log[d]
