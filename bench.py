@@ -16,8 +16,10 @@ A "step" is one progressive frame (one hl_render_frame over the full image).
   cpu_baseline  the CPU oracle (restatement of the reference's GLSL integrator, OpenMP) on a bounded sample
 N > 1: samples-per-pixel sharding — every rank renders its own frame indices (weak scaling: K steps per rank)
 into a per-GPU sum buffer; one NCCL all-reduce of the accumulation image at the end (inside the timed region).
---impl reference times the reference's own algorithm on the host CPU: the oracle port (the reference cannot be
-built or run here: Vulkan-RT + MSVC only).
+--impl reference times the reference's own shaders on the host CPU: oracle/_ref/libhelios_glsl_ref.so, i.e. the
+reference's GLSL files compiled as C++ (oracle/ref_glsl/; cpu_baseline.kind = "reference"), over the oracle's
+traversal and texture units (the engine itself is Vulkan-RT + MSVC only and cannot run here).  If that
+library is absent the restatement is timed instead (kind = "port").
 """
 from __future__ import annotations
 
@@ -107,6 +109,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic_bytes():
+    """DRAM bytes per k_extend launch from the committed `ncu --set full` capture (profiles/*_extend_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches of one frame), or None"""
+    files = sorted((ROOT / "profiles").glob("*_extend_traffic.json"))
+    if not files:
+        return None
+    try:
+        return float(json.loads(files[-1].read_text())["mean_mb"]) * 1e6
+    except Exception:
+        return None
+
+
 def build_scene():
     from helios_b200 import scenes
 
@@ -138,7 +152,8 @@ def cpu_sample(scene, oracle, sky_cf, frames=1, target_s=8.0):
 
 
 def run_reference(args):
-    """reference arm: the reference's algorithm on the host CPU (oracle port), all host threads"""
+    """reference arm: the reference's own shaders on the host CPU, all host threads — oracle/_ref (the reference's GLSL
+    compiled as C++, kind "reference") when that library exists, else the restatement (kind "port")"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -146,7 +161,8 @@ def run_reference(args):
 
     scene = build_scene()
     cf = orc.sky_coeffs(scene.sun_direction)
-    o = orc.OracleScene(scene, sky_coeffs_override=cf)
+    kind = "reference" if orc.ref_lib() is not None else "port"
+    o = orc.GlslRefScene(scene, sky_coeffs_override=cf) if kind == "reference" else orc.OracleScene(scene, sky_coeffs_override=cf)
     cores = os.cpu_count() or 1
     per_step = []
     sample = ""
@@ -160,7 +176,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "each step = bounded sample of the frame on the host CPU"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -281,7 +297,8 @@ def main():
     peak, peak_src = measured_peak_gbs()
     achieved = ext_rays * a_ray / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic_bytes(),
+        "algorithmic_bytes_per_launch": ext_rays * a_ray / max(nprof * int(scene.max_ray_bounces), 1),
         "peak_source": peak_src, "algorithmic_bytes_per_ray": a_ray, "launches_timed": nprof * int(scene.max_ray_bounces),
         "stage_share_of_frame": {"extend": ext_ms / frame_ms, "shade": sh_ms / frame_ms, "connect": con_ms / frame_ms} if frame_ms else None,
     }
@@ -322,9 +339,10 @@ def main():
         from oracle import oracle as orc
 
         cf = orc.sky_coeffs(scene.sun_direction)
-        o = orc.OracleScene(scene, sky_coeffs_override=cf)
+        kind = "reference" if orc.ref_lib() is not None else "port"  # oracle/_ref = the reference's GLSL compiled as C++
+        o = orc.GlslRefScene(scene, sky_coeffs_override=cf) if kind == "reference" else orc.OracleScene(scene, sky_coeffs_override=cf)
         v, dt, sample = cpu_sample(scene, o, cf, target_s=10.0)
-        cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": kind, "sample": sample}
 
     if rank == 0:
         line = {

@@ -2,11 +2,14 @@
 // only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
 //
 // CPU restatement ("port") of the path-tracing hot path of diharaw/helios, following the
-// reference's GLSL recursively and bug-for-bug.  PARITY UNPINNED BY THE REFERENCE: upstream has
-// no tests, fixtures or golden vectors for this path and cannot be built or run here (Windows /
-// Vulkan-RT only); the pins are (a) the public xoroshiro64* reference sequence,
-// (b) closed-form checks (ACES, Hosek-Wilkie formula) and (c) self-consistency (brute force ==
-// BVH) — see tests/test_oracle_*.py and tests/golden/.
+// reference's GLSL recursively and bug-for-bug.  PINNED AGAINST THE REFERENCE ITSELF: upstream has
+// no tests or golden vectors and the engine cannot run here (Windows / Vulkan-RT only, SURVEY.md
+// §0), but its shader files and the host half of its sky model do compile as C++ — oracle/ref_glsl/
+// builds them from /root/reference into oracle/_ref/libhelios_glsl_ref.so, and every frame, ray
+// count, RNG / BRDF / sky / tone-map value of this restatement is bit-identical to that library on
+// all scene types (tests/test_ref_glsl.py; outputs committed as tests/golden/ref_glsl_golden.npz).
+// What the reference leaves to the Vulkan driver (traversal, texture filtering) is shared by both.
+// Further pins: the public xoroshiro64* sequence, closed forms, brute force == BVH (tests/test_oracle_kat.py).
 //
 // Reference files restated (paths relative to the reference checkout, src/engine/shader/ unless noted):
 //   random.glsl:11-50, sampling.glsl:6-36, brdf.glsl:6-167, common.glsl:130-141,
@@ -468,6 +471,11 @@ static inline bool hit_better(float t, uint32_t i, uint32_t g, uint32_t p, const
     return p < best.primitive;
 }
 
+// oracle/ref_glsl/runtime.cpp (the reference's own any-hit shader compiled as C++) installs itself here; the
+// restatement's any_hit_ignores() is used otherwise
+typedef bool (*AnyHitOverride)(uint32_t inst, uint32_t geom, uint32_t prim, float bu, float bv);
+static thread_local AnyHitOverride t_any_hit_override = nullptr;
+
 // traceRayEXT: closest accepted hit with tmin < t < tmax; ties -> min (instance, geometry, primitive)
 static Hit trace(const Scene& s, vec3 o, float tmin, vec3 d, float tmax, uint32_t flags)
 {
@@ -499,7 +507,7 @@ static Hit trace(const Scene& s, vec3 o, float tmin, vec3 d, float tmax, uint32_
             if (!tri_test(oo, od, vec3(a[0], a[1], a[2]), vec3(b[0], b[1], b[2]), vec3(c[0], c[1], c[2]), t, u, v)) return;
             if (!(t > tmin && t < tmax)) return;
             if (!hit_better(t, ii, g, p, best)) return;
-            if (!ray_opaque && !sm.opaque && any_hit_ignores(s, ii, g, p, u, v)) return;
+            if (!ray_opaque && !sm.opaque && (t_any_hit_override ? t_any_hit_override(ii, g, p, u, v) : any_hit_ignores(s, ii, g, p, u, v))) return;
             best.valid     = true;
             best.t         = t;
             best.u         = u;

@@ -37,6 +37,37 @@ def lib():
     return _lib
 
 
+# ---- oracle/_ref: the reference's own GLSL compiled as C++ (oracle/ref_glsl/) -----------------------------------
+_REF_PATH = _HERE / "_ref" / "libhelios_glsl_ref.so"
+_REF_SHADERS = Path("/root/reference/src/engine/shader")
+_ref_lib = None
+
+
+def build_ref(force: bool = False):
+    """(Re)build oracle/_ref/libhelios_glsl_ref.so where the reference checkout is mounted; elsewhere (the GPU box)
+    the prebuilt file that travelled with the snapshot is used.  Returns its path, or None if there is neither."""
+    if _REF_SHADERS.is_dir():
+        subprocess.check_call(["make", "-C", str(_HERE), "-s", "ref"] + (["-B"] if force else []))
+    return _REF_PATH if _REF_PATH.exists() else None
+
+
+def ref_lib():
+    """ctypes handle of the reference-GLSL library (contains the restatement's or_* entry points as well), or None"""
+    global _ref_lib
+    if _ref_lib is None:
+        path = build_ref()
+        if path is None:
+            return None
+        _ref_lib = C.CDLL(str(path))
+        _ref_lib.or_scene_new.restype = C.c_void_p
+        _ref_lib.or_scene_add_mesh.restype = C.c_int
+        _ref_lib.or_scene_add_texture.restype = C.c_int
+        _ref_lib.or_rng_hash.restype = C.c_uint32
+        _ref_lib.ref_rng_hash.restype = C.c_uint32
+        _ref_lib.or_tri_test.restype = C.c_int
+    return _ref_lib
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
@@ -66,8 +97,8 @@ def sky_bake(coeffs, sun_direction, size=512) -> np.ndarray:
 class OracleScene:
     """CPU scene built from a helios_b200.scenes.SceneData."""
 
-    def __init__(self, scene, brute_force: bool = False, sky_size: int = 512, sky_coeffs_override=None):
-        L = lib()
+    def __init__(self, scene, brute_force: bool = False, sky_size: int = 512, sky_coeffs_override=None, library=None):
+        L = self.L = library if library is not None else lib()
         self.scene = scene
         self.h = C.c_void_p(L.or_scene_new())
         self._keep = []
@@ -97,17 +128,17 @@ class OracleScene:
 
     def __del__(self):
         try:
-            lib().or_scene_free(self.h)
+            self.L.or_scene_free(self.h)
         except Exception:
             pass
 
     def set_brute_force(self, on: bool):
-        lib().or_scene_set_brute_force(self.h, C.c_int(1 if on else 0))
+        self.L.or_scene_set_brute_force(self.h, C.c_int(1 if on else 0))
 
     def render_frame(self, pc, accum: np.ndarray, launch=(0, 0), raw_L: np.ndarray | None = None):
         """one launch; accum (H,W,4 float32) is updated in place (prev == cur, pixels are independent)"""
         pcb = np.ascontiguousarray(pc)
-        lib().or_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), _p(accum), _p(accum), _p(self.counters), _p(raw_L))
+        self.L.or_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), _p(accum), _p(accum), _p(self.counters), _p(raw_L))
 
     def render(self, n_launches: int, **kw) -> np.ndarray:
         """Renderer::render loop: clear, then launches num_frames = 0 .. n_launches-1 (frame 0 is discarded
@@ -125,14 +156,51 @@ class OracleScene:
         inst, geom, prim = (np.zeros(n, np.uint32) for _ in range(3))
         t, u, v = (np.zeros(n, np.float32) for _ in range(3))
         pcb = np.ascontiguousarray(pc)
-        lib().or_trace_primary_ids(self.h, _p(pcb), _p(inst), _p(geom), _p(prim), _p(t), _p(u), _p(v))
+        self.L.or_trace_primary_ids(self.h, _p(pcb), _p(inst), _p(geom), _p(prim), _p(t), _p(u), _p(v))
         return inst, geom, prim, t, u, v
 
     def trace_rays(self, rays: np.ndarray, flags: int = 0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((len(rays), 6), np.float32)
-        lib().or_trace_rays(self.h, _p(rays), C.c_uint32(len(rays)), C.c_uint32(flags), _p(hits))
+        self.L.or_trace_rays(self.h, _p(rays), C.c_uint32(len(rays)), C.c_uint32(flags), _p(hits))
         return hits
+
+
+class GlslRefScene(OracleScene):
+    """The same scene rendered by the REFERENCE'S OWN SHADERS (oracle/_ref/libhelios_glsl_ref.so): render_frame runs
+    path_trace_rgen/rchit/rahit/rmiss.glsl + path_trace_shadow.* as compiled from /root/reference; `restated_frame`
+    runs the restatement inside the same library on the same scene object, for side-by-side checks."""
+
+    def __init__(self, scene, **kw):
+        L = ref_lib()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libhelios_glsl_ref.so is not available (no /root/reference and no prebuilt copy)")
+        super().__init__(scene, library=L, **kw)
+        self.restated_counters = np.zeros(2, np.uint64)
+
+    def restated_frame(self, pc, accum, launch=(0, 0)):
+        pcb = np.ascontiguousarray(pc)
+        self.L.or_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), _p(accum), _p(accum), _p(self.restated_counters), None)
+
+    def render_frame(self, pc, accum: np.ndarray, launch=(0, 0), raw_L=None):
+        pcb = np.ascontiguousarray(pc)
+        self.L.ref_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), _p(accum), _p(accum), _p(self.counters))
+
+
+def ref_tonemap(accum: np.ndarray, exposure=1.0, op=0) -> np.ndarray:
+    H, W = accum.shape[:2]
+    out = np.zeros((H, W, 4), np.uint8)
+    a = np.ascontiguousarray(accum, np.float32)
+    ref_lib().ref_tonemap(_p(a), C.c_uint32(W), C.c_uint32(H), C.c_float(exposure), C.c_int(op), _p(out))
+    return out
+
+
+def ref_sky_bake(coeffs, sun_direction, size=64) -> np.ndarray:
+    out = np.zeros((6, size, size, 4), np.float32)
+    cf = np.ascontiguousarray(coeffs, np.float32)
+    d = np.ascontiguousarray(sun_direction, np.float32)
+    ref_lib().ref_sky_bake(_p(cf), _p(d), C.c_uint32(size), _p(out))
+    return out
 
 
 def tonemap(accum: np.ndarray, exposure=1.0, op=0, sample_scale=1.0) -> np.ndarray:
