@@ -43,7 +43,7 @@ public:
     void render(RenderState& render_state);
     void on_window_resize();
     // queues a save of the tone-mapped image; it is written at the end of the next render(), as in the reference
-    // (.ppm / .pfm here: the reference's stb_image_write PNG encoder is not part of this path)
+    // (8-bit RGBA PNG as in the reference, :651; a path ending in .ppm / .pfm selects those formats instead)
     void save_image_to_disk(const std::string& path);
 
     // headless read-backs (the reference presents to a swap chain instead)

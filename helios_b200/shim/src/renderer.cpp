@@ -1,6 +1,7 @@
 // renderer.cpp — Renderer (reference: src/engine/gfx/renderer.cpp:106-330 render, :369-428 tone_map,
 // :637-711 copy_and_save_tone_mapped_image, :715-726 on_window_resize).
 #include <gfx/renderer.h>
+#include <utility/png_writer.h>
 #include <cstdio>
 
 namespace helios
@@ -38,26 +39,33 @@ void Renderer::render(RenderState& render_state)
             backend->check(hl_read_rgba8(ctx, img.data()), "hl_read_rgba8");
         else
             tone_map(img.data());
-        bool              ok  = false;
-        const std::string& p  = m_image_save_path;
-        const bool        pfm = p.size() > 4 && p.substr(p.size() - 4) == ".pfm";
-        if (FILE* f = std::fopen(p.c_str(), "wb"))
+        bool               ok  = false;
+        const std::string& p   = m_image_save_path;
+        auto               ext_is = [&](const char* e) { return p.size() > 4 && p.compare(p.size() - 4, 4, e) == 0; };
+        if (ext_is(".pfm") || ext_is(".ppm"))
         {
-            if (pfm)
+            // headless extras: raw radiance (.pfm) / binary pixmap (.ppm)
+            if (FILE* f = std::fopen(p.c_str(), "wb"))
             {
-                const std::vector<float> acc = read_accumulation();
-                std::fprintf(f, "PF\n%u %u\n-1.0\n", ext.width, ext.height);
-                // PFM rows run bottom-up, and so does the accumulation image (launch row 0 is the bottom of the view:
-                // the tone-map pass flips it, tone_map.frag + the negative-height viewport)
-                for (size_t i = 0; i < (size_t)ext.width * ext.height; i++) std::fwrite(&acc[i * 4], 4, 3, f);
+                if (ext_is(".pfm"))
+                {
+                    const std::vector<float> acc = read_accumulation();
+                    std::fprintf(f, "PF\n%u %u\n-1.0\n", ext.width, ext.height);
+                    // PFM rows run bottom-up, and so does the accumulation image (launch row 0 is the bottom of the
+                    // view: the tone-map pass flips it, tone_map.frag + the negative-height viewport)
+                    for (size_t i = 0; i < (size_t)ext.width * ext.height; i++) std::fwrite(&acc[i * 4], 4, 3, f);
+                }
+                else
+                {
+                    std::fprintf(f, "P6\n%u %u\n255\n", ext.width, ext.height);
+                    for (size_t i = 0; i < (size_t)ext.width * ext.height; i++) std::fwrite(&img[i * 4], 1, 3, f);
+                }
+                ok = std::fclose(f) == 0;
             }
-            else
-            {
-                std::fprintf(f, "P6\n%u %u\n255\n", ext.width, ext.height);
-                for (size_t i = 0; i < (size_t)ext.width * ext.height; i++) std::fwrite(&img[i * 4], 1, 3, f);
-            }
-            ok = std::fclose(f) == 0;
         }
+        else
+            // the reference's format, :651: 4-channel 8-bit PNG of the tone-mapped image
+            ok = write_png_rgba8(p, ext.width, ext.height, img.data(), (size_t)ext.width * 4);
         if (!ok) HELIOS_LOG_ERROR("Renderer::save_image_to_disk: cannot write " + p);
         m_save_image_to_disk = false;
     }
@@ -80,6 +88,11 @@ void Renderer::on_window_resize()
 
 void Renderer::save_image_to_disk(const std::string& path)
 {
+    if (path.length() == 0)
+    {
+        HELIOS_LOG_ERROR("A valid path is required to save an image to disk");
+        return;
+    }
     m_save_image_to_disk = true;
     m_image_save_path    = path;
 }

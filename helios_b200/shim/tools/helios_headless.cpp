@@ -5,7 +5,7 @@
 // renderer->render(render_state), once per sample.
 //
 //   helios_headless --scene file.hlsc [--spp N] [--device D] [--tiled] [--bounces B] [--exposure E]
-//                   [--out image.ppm|.pfm] [--dump-accum raw.f32] [--dump-tables tables.bin] [--no-device]
+//                   [--out image.png|.ppm|.pfm] [--dump-accum raw.f32] [--dump-tables tables.bin] [--no-device]
 //
 // --no-device builds the scene graph and the tables on the host only (for inspection); rendering needs a GPU.
 #include <gfx/renderer.h>
@@ -107,7 +107,7 @@ int main(int argc, char** argv)
     }
     if (scene_path.empty())
     {
-        std::fprintf(stderr, "usage: helios_headless --scene file.hlsc [--spp N] [--out image.ppm] ...\n");
+        std::fprintf(stderr, "usage: helios_headless --scene file.hlsc [--spp N] [--out image.png] ...\n");
         return 2;
     }
     try

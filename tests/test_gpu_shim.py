@@ -23,9 +23,9 @@ def python_render(s, launches):
     return acc
 
 
-def headless_render(s, tmp_path, spp, extra=()):
+def headless_render(s, tmp_path, spp, extra=(), out="out.ppm"):
     exe = str(build_shim())
-    f, a, img = tmp_path / "s.hlsc", tmp_path / "acc.f32", tmp_path / "out.ppm"
+    f, a, img = tmp_path / "s.hlsc", tmp_path / "acc.f32", tmp_path / out
     scene_io.export_scene(s, f)
     r = subprocess.run([exe, "--scene", str(f), "--spp", str(spp), "--dump-accum", str(a), "--out", str(img), *extra], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -62,3 +62,17 @@ def test_tiled_bake_equals_full_frame(tmp_path):
     tiled, stats, _ = headless_render(s, tmp_path, 4, extra=("--tiled",))
     assert stats["launches"] == 4 * 2 * 2
     assert np.array_equal(full, tiled)
+
+
+def test_save_image_to_disk_png(tmp_path):
+    """Renderer::save_image_to_disk writes the tone-mapped image as 8-bit RGBA PNG (renderer.cpp:637-711, :651);
+    decoded with the independent decoder of tests/test_png_writer.py it must equal the .ppm of the same render"""
+    from tests.test_png_writer import decode_png
+
+    s = scenes.cornell_box(160, 96)
+    _, _, ppm = headless_render(s, tmp_path, 3)
+    _, _, png = headless_render(s, tmp_path, 3, out="out.png")
+    raw = ppm.read_bytes()
+    rgb = np.frombuffer(raw[len(raw) - 160 * 96 * 3 :], np.uint8).reshape(96, 160, 3)
+    img = decode_png(png.read_bytes())
+    assert img.shape == (96, 160, 4) and np.array_equal(img[..., :3], rgb) and rgb.max() > 0
