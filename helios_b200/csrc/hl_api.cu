@@ -578,6 +578,8 @@ hl_status hl_set_option(hl_context ctx, int option, int64_t value)
         c_->tail_start = (uint32_t)std::max<int64_t>(1, value);
     else if (option == HL_OPT_PIPELINE)
         c_->pipeline = value != 0;
+    else if (option == HL_OPT_SAH_CLUSTER)
+        c_->sah_cluster = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else
         HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_set_option: unknown option");
     HL_CATCH

@@ -213,6 +213,484 @@ HL_HD void fit_from_leaf(BinaryTree& t, uint32_t leaf, Fence fence)
     }
 }
 
+// ---- binned-SAH re-split of the upper levels ------------------------------------------------------------
+// The LBVH above a cut is rebuilt top-down with the binned surface-area heuristic (16 bins per axis; the
+// HLBVH scheme of Garanzha, Pantaleoni, McAllister, HPG 2011, written from the paper's description):
+//   * clusters = the maximal radix-tree subtrees with <= C primitives (they keep their Morton-built interior);
+//   * the K-1 internal nodes above the cut are re-linked, level by level: every level runs three data-parallel
+//     phases — BIN (each cluster adds its box to the 3 x 16 bins of the node it currently sits in), SPLIT (each
+//     node sweeps its bins for the cheapest area(L)·prims(L) + area(R)·prims(R) plane, CHOOSE; then takes a binary
+//     node id from the free list, links itself to its parent and creates its two children in the next level's
+//     array, COMMIT) and ASSIGN (each cluster moves to the child on its side of the plane and grows that child's centroid
+//     bounds).  Nothing is physically partitioned: a cluster only carries the index of its current node.
+//   * a node with <= HL_TOP_SMALL clusters leaves the level loop: its clusters register in a per-node list during
+//     the next BIN phase, and after the last level one thread per such node builds the whole subtree with exact
+//     (sorted sweep) SAH splits — no bins, and the long tail of nearly-empty levels disappears;
+//   * nodes without a usable plane (all centroids equal), nodes that found no free bin slot and levels beyond
+//     HL_TOP_SAH_LEVELS split by arrival order (first half left), which bounds the number of levels;
+//   * a node holding one cluster is not materialised: the cluster links itself to the parent.
+// Afterwards top_refit_from_cluster() recomputes boxes, primitive counts and the collapse cost tables of the
+// re-linked nodes bottom-up.  Tree shape never changes a traversal RESULT (closest hit + tie rule are order
+// independent), so the arrival-order splits may differ from run to run.
+#define HL_TOP_BINS 16
+#ifndef HL_DEFAULT_SAH_CLUSTER
+#define HL_DEFAULT_SAH_CLUSTER 2 /* primitives per cluster below the cut (triangle trees; instance trees use 1) */
+#endif
+#define HL_TOP_MAX_LEVELS 160
+#define HL_TOP_SAH_LEVELS 120
+#define HL_TOP_DONE 0xFFFFFFFFu
+#define HL_TOP_MODE_BINNED 0u
+#define HL_TOP_MODE_ARRIVAL 1u
+#define HL_TOP_MODE_SINGLE 2u
+#define HL_TOP_MODE_SMALL 3u
+#define HL_TOP_SMALL 16u
+#define HL_ORD_POS_INF 0xFF800000u /* f2ord(+inf) */
+#define HL_ORD_NEG_INF 0x007FFFFFu /* f2ord(-inf) */
+
+// order-preserving float <-> uint32 map, so that float min / max can be done with integer atomics
+HL_HD uint32_t f2ord(float f)
+{
+    const uint32_t u = f2u(f);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+HL_HD float ord2f(uint32_t o) { return u2f((o >> 31) ? (o & 0x7FFFFFFFu) : ~o); }
+
+#if defined(__CUDA_ARCH__)
+HL_HD uint32_t hl_atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+HL_HD uint32_t hl_atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
+HL_HD uint32_t hl_load_cg(const uint32_t* p) { return __ldcg(p); }
+#else
+inline uint32_t hl_atomic_min(uint32_t* p, uint32_t v)
+{
+    const uint32_t o = *p;
+    if (v < o) *p = v;
+    return o;
+}
+inline uint32_t hl_atomic_max(uint32_t* p, uint32_t v)
+{
+    const uint32_t o = *p;
+    if (v > o) *p = v;
+    return o;
+}
+inline uint32_t hl_load_cg(const uint32_t* p) { return *p; }
+#endif
+
+// counter += amount, returns the old value.  The SPLIT phase hands out node ids, child slots, bin slots and
+// small-node records through a few global counters; on the GPU the lanes of a warp that allocate from the same
+// counter together (same amount) are served by ONE atomic.
+HL_HD uint32_t hl_alloc(uint32_t* counter, uint32_t amount)
+{
+#if defined(__CUDA_ARCH__)
+    const unsigned act = __activemask();
+    int            same_c, same_a;
+    __match_all_sync(act, (unsigned long long)counter, &same_c);
+    __match_all_sync(act, amount, &same_a);
+    if (same_c && same_a)
+    {
+        unsigned lane;
+        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+        const int leader = __ffs(act) - 1;
+        uint32_t  base   = 0;
+        if ((int)lane == leader) base = atomicAdd(counter, amount * (uint32_t)__popc(act));
+        base = __shfl_sync(act, base, leader);
+        return base + amount * (uint32_t)__popc(act & ((1u << lane) - 1u));
+    }
+#endif
+    return hl_atomic_add(counter, amount);
+}
+
+struct TopBin
+{
+    uint32_t lo[3], hi[3]; // union of the cluster boxes, f2ord encoding
+    uint32_t prims, clusters;
+}; // 32 B
+struct TopNode
+{
+    uint32_t cb_lo[3], cb_hi[3]; // bounds of the cluster centroids (f2ord), grown by the ASSIGN phase of the level above
+    uint32_t count;              // clusters in the node
+    uint32_t link;               // (binary node id of the parent << 1) | side; 0xFFFFFFFF = root
+    uint32_t mode;
+    uint32_t bins;     // BINNED: bin slot of this node in the level's bin array; SMALL: index of its TopSmall record
+    uint32_t split;    // BINNED, after SPLIT: axis | (last bin of the left side << 2)
+    uint32_t n_left;   // clusters that go left
+    uint32_t child;    // index of the left child in the next level's node array (right = + 1)
+    uint32_t arrivals; // ARRIVAL: ticket counter
+    uint32_t pad[2];
+}; // 64 B
+struct TopSmall
+{
+    uint32_t count, link, list_base, arrivals; // arrivals: ticket counter of the registering clusters
+}; // 16 B
+struct TopBuild
+{
+    uint32_t        cluster_prims; // C
+    uint32_t        k_cap;         // capacity of the per-cluster / per-level arrays
+    uint32_t        bins_cap;      // bin slots per level parity
+    const uint32_t* n_clusters;    // K (device resident)
+    const uint32_t* cluster;       // [K] binary node id of each cluster root
+    const uint32_t* free_nodes;    // [K - 1] internal nodes above the cut, the root (id 0) first
+    uint32_t*       cnode;         // [K] index of the level node each cluster sits in, HL_TOP_DONE once linked
+    TopNode*        level[2];      // node arrays of the even / odd levels
+    TopBin*         bins[2];       // bin arrays of the even / odd levels, 3 * HL_TOP_BINS per slot
+    TopSmall*       small;         // [K / 2 + 1] nodes with 2..HL_TOP_SMALL clusters, finished after the level loop
+    uint32_t*       small_count;
+    uint32_t*       list;          // [(K / 2 + 1) * HL_TOP_SMALL] their cluster lists, HL_TOP_SMALL entries per record
+    uint32_t*       level_count;   // [HL_TOP_MAX_LEVELS + 1] nodes per level
+    uint32_t*       bins_used;     // [HL_TOP_MAX_LEVELS + 1] bin slots handed out per level
+    uint32_t*       free_next;     // next unused entry of free_nodes
+};
+
+HL_HD uint32_t subtree_prims_cg(const BinaryTree& t, uint32_t node) { return node >= t.n - 1 ? 1u : hl_load_cg(t.last + node) - hl_load_cg(t.first + node) + 1u; }
+// the two predicates that define the cut (evaluated on the radix tree before anything is re-linked)
+HL_HD bool top_is_cluster_root(const BinaryTree& t, uint32_t m, uint32_t C) { return m != 0u && subtree_prims(t, m) <= C && subtree_prims(t, t.parent[m]) > C; }
+HL_HD bool top_is_upper_node(const BinaryTree& t, uint32_t m, uint32_t C) { return m < t.n - 1 && subtree_prims(t, m) > C; }
+
+HL_HD void top_cluster_centroid(const BinaryTree& t, uint32_t m, float c[3])
+{
+    const Box& b = t.box[m];
+    for (int k = 0; k < 3; k++) c[k] = 0.5f * (b.lo[k] + b.hi[k]);
+}
+// bin of centroid coordinate c inside [lo, hi]; -1 when the axis has no extent
+HL_HD int top_bin_of(float c, float lo, float hi)
+{
+    const float ext = hi - lo;
+    if (!(ext > 0.0f)) return -1;
+    int b = (int)((c - lo) / ext * (float)HL_TOP_BINS);
+    return b < 0 ? 0 : (b >= HL_TOP_BINS ? HL_TOP_BINS - 1 : b);
+}
+// dst.lo = min(dst.lo, vlo), dst.hi = max(dst.hi, vhi), optional counters += (prims, 1).  On the GPU the lanes
+// of a warp that arrive here together with the same destination (the common case near the root: clusters are
+// in Morton order, so neighbours share node and bin) are combined with warp reductions into one set of atomics
+// per distinct destination.
+HL_HD void top_merge(uint32_t* lo, uint32_t* hi, uint32_t* counters, const uint32_t vlo[3], const uint32_t vhi[3], uint32_t prims)
+{
+#if defined(__CUDA_ARCH__)
+    // lanes with the same destination form a group; every group reduces on its own (disjoint masks)
+    const unsigned grp = __match_any_sync(__activemask(), (unsigned long long)lo);
+    if (grp & (grp - 1u))
+    {
+        uint32_t rl[3], rh[3];
+        for (int k = 0; k < 3; k++) rl[k] = __reduce_min_sync(grp, vlo[k]), rh[k] = __reduce_max_sync(grp, vhi[k]);
+        const uint32_t rp = counters ? __reduce_add_sync(grp, prims) : 0u;
+        unsigned       lane;
+        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+        if (lane == (unsigned)(__ffs(grp) - 1))
+        {
+            for (int k = 0; k < 3; k++) atomicMin(lo + k, rl[k]), atomicMax(hi + k, rh[k]);
+            if (counters) atomicAdd(counters, rp), atomicAdd(counters + 1, (uint32_t)__popc(grp));
+        }
+        return;
+    }
+#endif
+    for (int k = 0; k < 3; k++) hl_atomic_min(lo + k, vlo[k]), hl_atomic_max(hi + k, vhi[k]);
+    if (counters) hl_atomic_add(counters, prims), hl_atomic_add(counters + 1, 1u);
+}
+HL_HD TopBin load_bin_coherent(const TopBin* p)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 a = __ldcg((const uint4*)p), b = __ldcg((const uint4*)p + 1);
+    TopBin      r;
+    r.lo[0] = a.x, r.lo[1] = a.y, r.lo[2] = a.z, r.hi[0] = a.w, r.hi[1] = b.x, r.hi[2] = b.y, r.prims = b.z, r.clusters = b.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+HL_HD void top_clear_bin(TopBin* b)
+{
+#if defined(__CUDA_ARCH__)
+    ((uint4*)b)[0] = make_uint4(HL_ORD_POS_INF, HL_ORD_POS_INF, HL_ORD_POS_INF, HL_ORD_NEG_INF);
+    ((uint4*)b)[1] = make_uint4(HL_ORD_NEG_INF, HL_ORD_NEG_INF, 0u, 0u);
+#else
+    for (int k = 0; k < 3; k++) b->lo[k] = HL_ORD_POS_INF, b->hi[k] = HL_ORD_NEG_INF;
+    b->prims = 0, b->clusters = 0;
+#endif
+}
+// mode of a node that holds `count` clusters at `level`; BINNED nodes get a bin slot (or fall back when none is left)
+HL_HD void top_init_node(TopBuild& tb, uint32_t level, TopNode& n, uint32_t count, uint32_t link)
+{
+    for (int k = 0; k < 3; k++) n.cb_lo[k] = HL_ORD_POS_INF, n.cb_hi[k] = HL_ORD_NEG_INF;
+    n.count = count, n.link = link, n.bins = 0, n.split = 0, n.n_left = 0, n.child = 0, n.arrivals = 0;
+    n.pad[0] = n.pad[1] = 0;
+    n.mode = count == 1u ? HL_TOP_MODE_SINGLE : HL_TOP_MODE_ARRIVAL;
+    if (count >= 2u && count <= HL_TOP_SMALL)
+    {
+        n.mode = HL_TOP_MODE_SMALL, n.bins = hl_alloc(tb.small_count, 1u);
+        TopSmall& r = tb.small[n.bins];
+        r.count = count, r.link = link, r.list_base = n.bins * HL_TOP_SMALL, r.arrivals = 0u;
+    }
+    else if (count > HL_TOP_SMALL && level < HL_TOP_SAH_LEVELS)
+    {
+        const uint32_t slot = hl_alloc(tb.bins_used + level, 1u);
+        if (slot < tb.bins_cap)
+        {
+            n.mode = HL_TOP_MODE_BINNED, n.bins = slot; // (the caller's phase clears the bins)
+        }
+    }
+}
+// level 0: one node over all K clusters (run by ONE thread before top_seed_cluster)
+HL_HD void top_begin(TopBuild& tb, uint32_t K)
+{
+    tb.level_count[0] = 1u;
+    top_init_node(tb, 0u, tb.level[0][0], K, 0xFFFFFFFFu);
+    for (uint32_t b = 0; b < 3u * HL_TOP_BINS; b++) top_clear_bin(tb.bins[0] + b);
+}
+// every cluster starts in the root node and contributes its centroid to the root's centroid bounds
+HL_HD void top_seed_cluster(const BinaryTree& t, TopBuild& tb, uint32_t i)
+{
+    tb.cnode[i] = 0u;
+    float c[3];
+    top_cluster_centroid(t, tb.cluster[i], c);
+    uint32_t oc[3];
+    for (int k = 0; k < 3; k++) oc[k] = f2ord(c[k]);
+    TopNode& root = tb.level[0][0];
+    top_merge(root.cb_lo, root.cb_hi, nullptr, oc, oc, 0u);
+}
+HL_HD void top_link(BinaryTree& t, uint32_t link, uint32_t node)
+{
+    if (link == 0xFFFFFFFFu)
+    {
+        t.parent[node] = 0xFFFFFFFFu;
+        return;
+    }
+    const uint32_t p = link >> 1;
+    if (link & 1u)
+        t.right[p] = node;
+    else
+        t.left[p] = node;
+    t.parent[node] = p;
+}
+// BIN phase, one cluster
+HL_HD void top_bin_cluster(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t i)
+{
+    const uint32_t nd = tb.cnode[i];
+    if (nd == HL_TOP_DONE) return;
+    TopNode&       N    = tb.level[level & 1u][nd];
+    const uint32_t mode = hl_load_cg(&N.mode);
+    const uint32_t m    = tb.cluster[i];
+    if (mode == HL_TOP_MODE_SINGLE)
+    {
+        top_link(t, hl_load_cg(&N.link), m);
+        tb.cnode[i] = HL_TOP_DONE;
+        return;
+    }
+    if (mode == HL_TOP_MODE_SMALL)
+    {
+        // register with the node's record; top_small_node() links the cluster after the level loop
+        TopSmall& r = tb.small[hl_load_cg(&N.bins)];
+        tb.list[hl_load_cg(&r.list_base) + hl_atomic_add(&r.arrivals, 1u)] = i;
+        tb.cnode[i] = HL_TOP_DONE;
+        return;
+    }
+    if (mode != HL_TOP_MODE_BINNED) return;
+    float c[3];
+    top_cluster_centroid(t, m, c);
+    const Box& b = t.box[m];
+    uint32_t   olo[3], ohi[3];
+    for (int k = 0; k < 3; k++) olo[k] = f2ord(b.lo[k]), ohi[k] = f2ord(b.hi[k]);
+    const uint32_t prims = subtree_prims(t, m);
+    TopBin*        bins  = tb.bins[level & 1u] + (size_t)hl_load_cg(&N.bins) * (3 * HL_TOP_BINS);
+    for (int ax = 0; ax < 3; ax++)
+    {
+        const int bi = top_bin_of(c[ax], ord2f(hl_load_cg(&N.cb_lo[ax])), ord2f(hl_load_cg(&N.cb_hi[ax])));
+        if (bi < 0) continue;
+        TopBin& B = bins[ax * HL_TOP_BINS + bi];
+        top_merge(B.lo, B.hi, &B.prims, olo, ohi, prims);
+    }
+}
+// A node with 2..HL_TOP_SMALL clusters: the whole subtree, built by one thread with exact SAH splits (clusters
+// sorted along each axis, every position between two neighbours is a candidate).
+// the number of binary node ids top_small_node() takes from free_nodes[free_base ...]
+HL_HD uint32_t top_small_node_ids(const TopBuild& tb, uint32_t record) { return hl_load_cg(&tb.small[record].count) - 1u; }
+HL_HD void top_small_node(BinaryTree& t, TopBuild& tb, uint32_t record, uint32_t free_base)
+{
+    const uint32_t count = hl_load_cg(&tb.small[record].count), link = hl_load_cg(&tb.small[record].link), list_base = hl_load_cg(&tb.small[record].list_base);
+    uint32_t       ids[HL_TOP_SMALL], pr[HL_TOP_SMALL];
+    Box            bx[HL_TOP_SMALL];
+    uint8_t        ord[HL_TOP_SMALL]; // permutation of the clusters; sub-ranges of it are the nodes being built
+    for (uint32_t k = 0; k < count; k++)
+    {
+        ids[k] = tb.cluster[hl_load_cg(tb.list + list_base + k)];
+        bx[k] = t.box[ids[k]], pr[k] = subtree_prims(t, ids[k]), ord[k] = (uint8_t)k;
+    }
+    uint32_t       used = 0;
+    uint8_t        slo[HL_TOP_SMALL], shi[HL_TOP_SMALL];
+    uint32_t       slink[HL_TOP_SMALL];
+    int            sp = 0;
+    slo[0] = 0, shi[0] = (uint8_t)count, slink[0] = link, sp = 1;
+    while (sp > 0)
+    {
+        sp--;
+        const int      lo = slo[sp], hi = shi[sp];
+        const uint32_t lk = slink[sp];
+        if (hi - lo == 1)
+        {
+            top_link(t, lk, ids[ord[lo]]);
+            continue;
+        }
+        const uint32_t self = tb.free_nodes[free_base + used++];
+        top_link(t, lk, self);
+        t.visits[self] = 0u;
+        float best = hl_inf();
+        int   bax = 2, bk = (lo + hi) / 2;
+        for (int pass = 0; pass < 4; pass++)
+        {
+            // passes 0..2 evaluate the axes; pass 3 restores the order of the winning axis (unless it was sorted last)
+            const int ax = pass < 3 ? pass : bax;
+            if (pass == 3 && bax == 2) break;
+            for (int a = lo + 1; a < hi; a++)
+            {
+                const uint8_t m  = ord[a];
+                const float   cm = bx[m].lo[ax] + bx[m].hi[ax];
+                int           b  = a - 1;
+                while (b >= lo && bx[ord[b]].lo[ax] + bx[ord[b]].hi[ax] > cm) ord[b + 1] = ord[b], b--;
+                ord[b + 1] = m;
+            }
+            if (pass == 3) break;
+            float    rarea[HL_TOP_SMALL];
+            uint32_t rprims[HL_TOP_SMALL];
+            Box      acc = bx[ord[hi - 1]];
+            uint32_t p   = pr[ord[hi - 1]];
+            rarea[hi - 1] = box_half_area(acc), rprims[hi - 1] = p;
+            for (int k = hi - 2; k > lo; k--)
+            {
+                acc = box_union(acc, bx[ord[k]]), p += pr[ord[k]];
+                rarea[k] = box_half_area(acc), rprims[k] = p;
+            }
+            acc = bx[ord[lo]], p = pr[ord[lo]];
+            for (int k = lo + 1; k < hi; k++)
+            {
+                // left = [lo, k), right = [k, hi)
+                const float cost = box_half_area(acc) * (float)p + rarea[k] * (float)rprims[k];
+                if (cost < best) best = cost, bax = ax, bk = k;
+                acc = box_union(acc, bx[ord[k]]), p += pr[ord[k]];
+            }
+        }
+        slo[sp] = (uint8_t)bk, shi[sp] = (uint8_t)hi, slink[sp] = (self << 1) | 1u, sp++;
+        slo[sp] = (uint8_t)lo, shi[sp] = (uint8_t)bk, slink[sp] = self << 1, sp++;
+    }
+}
+// SPLIT phase, step 1 (CHOOSE), one BINNED node of `level`: sweep the bins for the cheapest plane and record it in
+// the node (split, n_left), or turn the node into an ARRIVAL node when no plane separates its clusters.  This is
+// the one-thread form (emulator); the CUDA builder runs the same selection with one warp per node, a bin per
+// lane and shuffle scans (hl_builder.cu: top_choose_node_warp).
+HL_HD void top_choose_node(TopBuild& tb, uint32_t level, uint32_t j)
+{
+    TopNode& N = tb.level[level & 1u][j];
+    if (hl_load_cg(&N.mode) != HL_TOP_MODE_BINNED) return;
+    const TopBin* bins = tb.bins[level & 1u] + (size_t)hl_load_cg(&N.bins) * (3 * HL_TOP_BINS);
+    float         best = hl_inf();
+    uint32_t      split = 0u, n_left = 0u;
+    for (int ax = 0; ax < 3; ax++)
+    {
+        // suffix unions, then a prefix sweep over the 15 candidate planes (an empty bin is the identity of the union)
+        Box      bb[HL_TOP_BINS];
+        uint32_t bp[HL_TOP_BINS], bc[HL_TOP_BINS];
+        for (int b = 0; b < HL_TOP_BINS; b++)
+        {
+            const TopBin B = load_bin_coherent(bins + ax * HL_TOP_BINS + b);
+            for (int k = 0; k < 3; k++) bb[b].lo[k] = ord2f(B.lo[k]), bb[b].hi[k] = ord2f(B.hi[k]);
+            bp[b] = B.prims, bc[b] = B.clusters;
+        }
+        float    rarea[HL_TOP_BINS];
+        uint32_t rp[HL_TOP_BINS], rc[HL_TOP_BINS];
+        Box      acc = bb[HL_TOP_BINS - 1];
+        uint32_t p = bp[HL_TOP_BINS - 1], c = bc[HL_TOP_BINS - 1];
+        rarea[HL_TOP_BINS - 1] = box_half_area(acc), rp[HL_TOP_BINS - 1] = p, rc[HL_TOP_BINS - 1] = c;
+        for (int b = HL_TOP_BINS - 2; b > 0; b--)
+        {
+            acc = box_union(acc, bb[b]), p += bp[b], c += bc[b];
+            rarea[b] = box_half_area(acc), rp[b] = p, rc[b] = c;
+        }
+        acc = bb[0], p = bp[0], c = bc[0];
+        for (int b = 0; b < HL_TOP_BINS - 1; b++)
+        {
+            // left = bins 0..b, right = bins b+1..15
+            if (c != 0u && rc[b + 1] != 0u)
+            {
+                const float cost = box_half_area(acc) * (float)p + rarea[b + 1] * (float)rp[b + 1];
+                if (cost < best) best = cost, split = (uint32_t)ax | ((uint32_t)b << 2), n_left = c;
+            }
+            acc = box_union(acc, bb[b + 1]), p += bp[b + 1], c += bc[b + 1];
+        }
+    }
+    if (best < hl_inf())
+        N.split = split, N.n_left = n_left;
+    else
+        N.mode = HL_TOP_MODE_ARRIVAL;
+}
+// SPLIT phase, step 2 (COMMIT), one node of `level` (after every node of the level has chosen): take a binary node
+// id, link it to the parent, create the two children in the next level's array.  Their bins are cleared by
+// top_clear_bin() calls spread over all threads during the ASSIGN phase.
+HL_HD void top_commit_node(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t j)
+{
+    // (fields written by other thread blocks are read past the L1)
+    TopNode&       N    = tb.level[level & 1u][j];
+    const uint32_t mode = hl_load_cg(&N.mode), count = hl_load_cg(&N.count);
+    if (mode == HL_TOP_MODE_SINGLE || mode == HL_TOP_MODE_SMALL) return;
+    const uint32_t self = tb.free_nodes[hl_alloc(tb.free_next, 1u)];
+    top_link(t, hl_load_cg(&N.link), self);
+    t.visits[self]       = 0u;
+    const uint32_t n_left = mode == HL_TOP_MODE_BINNED ? hl_load_cg(&N.n_left) : count / 2u;
+    const uint32_t child  = hl_alloc(tb.level_count + (level + 1u), 2u);
+    N.n_left = n_left, N.child = child, N.arrivals = 0u;
+    TopNode* next = tb.level[(level + 1u) & 1u];
+    top_init_node(tb, level + 1u, next[child], n_left, self << 1);
+    top_init_node(tb, level + 1u, next[child + 1u], count - n_left, (self << 1) | 1u);
+}
+// bin entries of `level` that must be empty before its BIN phase
+HL_HD uint32_t top_bins_to_clear(const TopBuild& tb, uint32_t level)
+{
+    const uint32_t used = hl_load_cg(tb.bins_used + level);
+    return (used < tb.bins_cap ? used : tb.bins_cap) * (3u * HL_TOP_BINS);
+}
+// ASSIGN phase, one cluster
+HL_HD void top_assign_cluster(const BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t i)
+{
+    const uint32_t nd = tb.cnode[i];
+    if (nd == HL_TOP_DONE) return;
+    TopNode& N = tb.level[level & 1u][nd];
+    float    c[3];
+    top_cluster_centroid(t, tb.cluster[i], c);
+    uint32_t side;
+    if (hl_load_cg(&N.mode) == HL_TOP_MODE_BINNED)
+    {
+        const uint32_t split = hl_load_cg(&N.split);
+        const int      ax    = (int)(split & 3u);
+        side                 = top_bin_of(c[ax], ord2f(hl_load_cg(&N.cb_lo[ax])), ord2f(hl_load_cg(&N.cb_hi[ax]))) > (int)(split >> 2) ? 1u : 0u;
+    }
+    else
+        side = hl_atomic_add(&N.arrivals, 1u) >= hl_load_cg(&N.n_left) ? 1u : 0u;
+    const uint32_t child = hl_load_cg(&N.child) + side;
+    tb.cnode[i]          = child;
+    TopNode& Cn          = tb.level[(level + 1u) & 1u][child];
+    uint32_t oc[3];
+    for (int k = 0; k < 3; k++) oc[k] = f2ord(c[k]);
+    top_merge(Cn.cb_lo, Cn.cb_hi, nullptr, oc, oc, 0u);
+}
+// bottom-up over the re-linked nodes, started once per cluster (own launch, after the re-split): box, primitive
+// count (kept in `last` with first = 0; ranges above the cut are no longer contiguous in Morton order, so the
+// stored count is floored at HL_MAX_LEAF_PRIMS + 1 — such a node can never be emitted as a leaf) and the
+// collapse cost table.
+template <class Fence>
+HL_HD void top_refit_from_cluster(BinaryTree& t, uint32_t cluster_root, Fence fence)
+{
+    uint32_t node = t.parent[cluster_root];
+    while (node != 0xFFFFFFFFu)
+    {
+        fence();
+        if (hl_atomic_add(&t.visits[node], 1u) == 0u) return;
+        fence();
+        const uint32_t l = t.left[node], r = t.right[node];
+        const Box      b = box_union(load_box_coherent(&t.box[l]), load_box_coherent(&t.box[r]));
+        t.box[node]      = b;
+        const uint32_t p = subtree_prims_cg(t, l) + subtree_prims_cg(t, r);
+        t.first[node] = 0u, t.last[node] = (p > HL_MAX_LEAF_PRIMS ? p : HL_MAX_LEAF_PRIMS + 1u) - 1u;
+        sah_node_costs(t, node, box_half_area(b));
+        node = t.parent[node];
+    }
+}
+
 // ---- collapse to 8-wide, top-down half -------------------------------------------------------------
 
 // smallest biased exponent e with 255 * 2^(e-127) >= extent (0 for a flat axis)

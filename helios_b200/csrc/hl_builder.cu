@@ -9,10 +9,14 @@
 //   radix sort     8 passes x (12 read + 12 written)  (CUB, 63 key bits) 192
 //   radix_tree     ~2 x 8 key reads (cached), 24 written                 40
 //   fit            24 read (sorted box) + 2 x 24 written + 48 read + 2 x 28 cost-table rows written, 56 read   232
+//   top re-split   clusters of <= C primitives (K ~ N / C..N): 2 selects over the node ids (8), then per level
+//                  K x (24 box + 4 node id) read twice + 21 + 6 atomics per cluster still above a small node;
+//                  ~log2(K / 16) + imbalance levels; refit of the K - 1 re-linked nodes (as `fit`)       ~150 (C = 2)
 //   collapse       ~48 read (boxes) + 8 decisions + 0.12 x 80 node + 48 leaf + 48 src + 2 x 8 queue   ~180
-//   total                                                              ~ 780 B / triangle
+//   total                                                              ~ 930 B / triangle
 #include "hl_internal.h"
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 namespace hl
 {
@@ -63,6 +67,186 @@ __global__ void k_fit(BinaryTree t, const Box* prim_boxes, const uint32_t* sorte
         t.box[(t.n - 1) + j] = prim_boxes[sorted[j]];
         fit_from_leaf(t, j, DeviceFence());
     }
+}
+
+// ---- binned-SAH re-split of the upper levels (hl_build.h: top_*): one persistent launch, the three phases of
+// every level separated by a grid-wide barrier (the launch is cooperative, so all blocks are resident).
+struct IsClusterRoot
+{
+    BinaryTree t;
+    uint32_t   C;
+    __device__ bool operator()(uint32_t m) const { return top_is_cluster_root(t, m, C); }
+};
+struct IsUpperNode
+{
+    BinaryTree t;
+    uint32_t   C;
+    __device__ bool operator()(uint32_t m) const { return top_is_upper_node(t, m, C); }
+};
+// bar[0] = arrivals, bar[1] = generation
+__device__ __forceinline__ void grid_barrier(uint32_t* bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        volatile uint32_t* gen = bar + 1;
+        const uint32_t     g   = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1u)
+        {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        }
+        else
+            while (*gen == g) __nanosleep(40);
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void top_trace(unsigned long long* trace, uint32_t& n)
+{
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0 && n < 1000u)
+    {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        trace[n++] = ns;
+    }
+}
+// CHOOSE for one BINNED node by one warp (same selection as top_choose_node, hl_build.h): lane b < 16 holds bin b
+// of the current axis, inclusive prefix / suffix unions by shuffle scans, candidate plane b = prefix(b) | suffix(b+1),
+// warp arg-min over the 3 x 15 candidates.  All in registers.
+__device__ __forceinline__ void top_choose_node_warp(TopBuild& tb, uint32_t level, uint32_t j, uint32_t lane)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    TopNode&       N    = tb.level[level & 1u][j];
+    if (__ldcg(&N.mode) != HL_TOP_MODE_BINNED) return; // warp-uniform
+    const TopBin* bins = tb.bins[level & 1u] + (size_t)__ldcg(&N.bins) * (3 * HL_TOP_BINS);
+    float         best = hl_inf();
+    uint32_t      split = 0xFFFFFFFFu, n_left = 0u;
+    for (int ax = 0; ax < 3; ax++)
+    {
+        float    lo[3], hi[3];
+        uint32_t p = 0u, c = 0u;
+        for (int k = 0; k < 3; k++) lo[k] = hl_inf(), hi[k] = -hl_inf();
+        if (lane < HL_TOP_BINS)
+        {
+            const TopBin B = load_bin_coherent(bins + ax * HL_TOP_BINS + lane);
+            for (int k = 0; k < 3; k++) lo[k] = ord2f(B.lo[k]), hi[k] = ord2f(B.hi[k]);
+            p = B.prims, c = B.clusters;
+        }
+        float    plo[3] = { lo[0], lo[1], lo[2] }, phi[3] = { hi[0], hi[1], hi[2] }, slo[3] = { lo[0], lo[1], lo[2] }, shi[3] = { hi[0], hi[1], hi[2] };
+        uint32_t pp = p, pc = c, sp = p, sc = c;
+#pragma unroll
+        for (int d = 1; d < HL_TOP_BINS; d <<= 1)
+        {
+            // lanes >= 16 hold the identity, so the suffix scan may pull from them without a range check below lane 16
+            const bool up = (int)lane >= d, dn = lane + d < 32u;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                const float a = __shfl_up_sync(FULL, plo[k], d), b = __shfl_up_sync(FULL, phi[k], d);
+                const float e = __shfl_down_sync(FULL, slo[k], d), f = __shfl_down_sync(FULL, shi[k], d);
+                if (up) plo[k] = fminf(plo[k], a), phi[k] = fmaxf(phi[k], b);
+                if (dn) slo[k] = fminf(slo[k], e), shi[k] = fmaxf(shi[k], f);
+            }
+            const uint32_t a = __shfl_up_sync(FULL, pp, d), b = __shfl_up_sync(FULL, pc, d);
+            const uint32_t e = __shfl_down_sync(FULL, sp, d), f = __shfl_down_sync(FULL, sc, d);
+            if (up) pp += a, pc += b;
+            if (dn) sp += e, sc += f;
+        }
+        // suffix of the bins right of this lane
+        const float    sarea = (shi[0] - slo[0]) * (shi[1] - slo[1]) + (shi[1] - slo[1]) * (shi[2] - slo[2]) + (shi[2] - slo[2]) * (shi[0] - slo[0]);
+        const float    rarea = __shfl_down_sync(FULL, sarea, 1);
+        const uint32_t rp = __shfl_down_sync(FULL, sp, 1), rc = __shfl_down_sync(FULL, sc, 1);
+        if (lane < HL_TOP_BINS - 1u && pc != 0u && rc != 0u)
+        {
+            const float parea = (phi[0] - plo[0]) * (phi[1] - plo[1]) + (phi[1] - plo[1]) * (phi[2] - plo[2]) + (phi[2] - plo[2]) * (phi[0] - plo[0]);
+            const float cost  = parea * (float)pp + rarea * (float)rp;
+            if (cost < best) best = cost, split = (uint32_t)ax | (lane << 2), n_left = pc;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const float    ob = __shfl_xor_sync(FULL, best, d);
+        const uint32_t os = __shfl_xor_sync(FULL, split, d), on = __shfl_xor_sync(FULL, n_left, d);
+        if (ob < best || (ob == best && os < split)) best = ob, split = os, n_left = on;
+    }
+    if (lane == 0u)
+    {
+        if (best < hl_inf())
+            N.split = split, N.n_left = n_left;
+        else
+            N.mode = HL_TOP_MODE_ARRIVAL;
+    }
+}
+// `trace` (debug, HL_TOP_TRACE=1): global timer after every phase, read back and printed by the host
+__global__ void __launch_bounds__(256, 4) k_top_build(BinaryTree t, TopBuild tb, uint32_t* bar, unsigned long long* trace)
+{
+    uint32_t       ntrace = 1;
+    const uint32_t K      = *tb.n_clusters;
+    if (K < 2u || K > tb.k_cap) return; // (uniform) cut too fine for the scratch arrays: keep the radix tree
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = tid >> 5, nwarps = nthr >> 5;
+    top_trace(trace, ntrace);
+    if (tid == 0) top_begin(tb, K);
+    grid_barrier(bar);
+    for (uint32_t i = tid; i < K; i += nthr) top_seed_cluster(t, tb, i);
+    grid_barrier(bar);
+    top_trace(trace, ntrace);
+    for (uint32_t level = 0; level + 1u < HL_TOP_MAX_LEVELS; level++)
+    {
+        for (uint32_t i = tid; i < K; i += nthr) top_bin_cluster(t, tb, level, i);
+        grid_barrier(bar);
+        top_trace(trace, ntrace);
+        const uint32_t nodes = __ldcg(tb.level_count + level);
+        for (uint32_t j = warp; j < nodes; j += nwarps) top_choose_node_warp(tb, level, j, lane);
+        grid_barrier(bar);
+        top_trace(trace, ntrace);
+        for (uint32_t j = tid; j < nodes; j += nthr) top_commit_node(t, tb, level, j);
+        grid_barrier(bar);
+        top_trace(trace, ntrace);
+        if (__ldcg(tb.level_count + level + 1u) == 0u) break; // only single / small nodes were left
+        TopBin* next_bins = tb.bins[(level + 1u) & 1u];
+        for (uint32_t b = tid, nb = top_bins_to_clear(tb, level + 1u); b < nb; b += nthr) top_clear_bin(next_bins + b);
+        for (uint32_t i = tid; i < K; i += nthr) top_assign_cluster(t, tb, level, i);
+        grid_barrier(bar);
+        top_trace(trace, ntrace);
+    }
+    if (trace && tid == 0) trace[0] = ntrace;
+}
+// the nodes that left the level loop with 2..HL_TOP_SMALL clusters: one thread each (own launch with few threads
+// per SM, so that the per-thread work arrays stay in the L1).  Their binary node ids: one allocation per warp, a
+// prefix sum over the lanes' needs.
+__global__ void __launch_bounds__(128) k_top_small(BinaryTree t, TopBuild tb)
+{
+    const uint32_t K = *tb.n_clusters;
+    if (K < 2u || K > tb.k_cap) return;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const uint32_t small = *tb.small_count;
+    const uint32_t lane  = threadIdx.x & 31u;
+    for (uint32_t r0 = tid - lane; r0 < small; r0 += nthr)
+    {
+        const uint32_t r    = r0 + lane;
+        const uint32_t need = r < small ? top_small_node_ids(tb, r) : 0u;
+        uint32_t       incl = need;
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        uint32_t base = 0;
+        if (lane == 31u) base = atomicAdd(tb.free_next, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31);
+        if (r < small) top_small_node(t, tb, r, base + incl - need);
+    }
+}
+__global__ void k_top_refit(BinaryTree t, TopBuild tb)
+{
+    const uint32_t K = *tb.n_clusters;
+    if (K < 2u || K > tb.k_cap) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) top_refit_from_cluster(t, tb.cluster[i], DeviceFence());
 }
 
 // Collapse as ONE persistent launch over a device-side work queue (no host round trip per tree level):
@@ -150,6 +334,40 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     leaf_pos.alloc(4ull * n, st);
     ctr.alloc(32, st);
     out.leaves.alloc(leaf_bytes * (size_t)n);
+    // binned-SAH re-split of the upper levels: cluster size C (triangle trees: the context option, doubled until the
+    // cut has at most ~4M clusters; instance trees: single instances), scratch sized for k_cap clusters
+    const bool tri_tree = leaf_bytes == sizeof(LeafTri);
+    uint32_t   C        = ctx->sah_cluster == 0 ? 0u : (tri_tree ? ctx->sah_cluster : 1u);
+    while (C && tri_tree && n / C > (4u << 20)) C *= 2;
+    const bool     resplit  = C != 0 && n >= 2 && n > C;
+    const uint32_t k_cap    = resplit ? (uint32_t)std::min<uint64_t>(n, 4ull * n / C + 1024) : 0u;
+    const uint32_t bins_cap = k_cap / (HL_TOP_SMALL + 1u) + 2u;
+    const size_t   top_ctl_words = 8 + 2 * (HL_TOP_MAX_LEVELS + 1);
+    ScratchBuf     top_clusters, top_free, top_cnode, top_level[2], top_bins[2], top_list, top_small, top_ctl, top_tmp, top_trace_buf;
+    size_t         top_tmp_bytes = 0;
+    int            top_grid      = 0;
+    if (resplit)
+    {
+        top_clusters.alloc(4ull * n, st), top_free.alloc(4ull * n, st), top_cnode.alloc(4ull * k_cap, st);
+        for (int p = 0; p < 2; p++)
+        {
+            top_level[p].alloc(sizeof(TopNode) * ((size_t)k_cap + 2), st);
+            top_bins[p].alloc(sizeof(TopBin) * (size_t)bins_cap * (3 * HL_TOP_BINS), st);
+        }
+        top_list.alloc(4ull * ((size_t)k_cap / 2 + 1) * HL_TOP_SMALL, st), top_small.alloc(sizeof(TopSmall) * ((size_t)k_cap / 2 + 1), st);
+        top_ctl.alloc(4ull * top_ctl_words, st);
+        if (getenv("HL_TOP_TRACE")) top_trace_buf.alloc(8000, st);
+        size_t a = 0, b = 0;
+        thrust::counting_iterator<uint32_t> ids(0u);
+        HL_CUDA(cub::DeviceSelect::If(nullptr, a, ids, top_clusters.as<uint32_t>(), top_ctl.as<uint32_t>(), (int)(2 * n - 1), IsClusterRoot { BinaryTree(), C }, st));
+        HL_CUDA(cub::DeviceSelect::If(nullptr, b, ids, top_free.as<uint32_t>(), top_ctl.as<uint32_t>() + 1, (int)(n - 1), IsUpperNode { BinaryTree(), C }, st));
+        top_tmp_bytes = std::max(a, b);
+        top_tmp.alloc(top_tmp_bytes, st);
+        int per_sm = 0;
+        HL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_top_build, 256, 0));
+        top_grid = ctx->sm_count * std::max(1, std::min(per_sm, 4));
+        top_grid = std::max(1, std::min<int>(top_grid, (int)((k_cap + 255u) / 256u)));
+    }
 
     cudaEvent_t e0, e1, e2, e3;
     HL_CUDA(cudaEventCreate(&e0));
@@ -190,6 +408,41 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     }
     k_fit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted);
     ctx->launches++;
+    if (resplit)
+    {
+        uint32_t* ctl = top_ctl.as<uint32_t>(); // [0] K, [1] upper nodes, [2] next free node, [4..5] barrier, [6] small nodes, [8..] per-level counters
+        HL_CUDA(cudaMemsetAsync(ctl, 0, 4ull * top_ctl_words, st));
+        thrust::counting_iterator<uint32_t> ids(0u);
+        HL_CUDA(cub::DeviceSelect::If(top_tmp.p, top_tmp_bytes, ids, top_clusters.as<uint32_t>(), ctl, (int)(2 * n - 1), IsClusterRoot { t, C }, st));
+        HL_CUDA(cub::DeviceSelect::If(top_tmp.p, top_tmp_bytes, ids, top_free.as<uint32_t>(), ctl + 1, (int)(n - 1), IsUpperNode { t, C }, st));
+        TopBuild tb;
+        tb.cluster_prims = C, tb.k_cap = k_cap, tb.bins_cap = bins_cap;
+        tb.n_clusters = ctl, tb.cluster = top_clusters.as<uint32_t>(), tb.free_nodes = top_free.as<uint32_t>(), tb.cnode = top_cnode.as<uint32_t>();
+        for (int p = 0; p < 2; p++) tb.level[p] = top_level[p].as<TopNode>(), tb.bins[p] = top_bins[p].as<TopBin>();
+        tb.free_next   = ctl + 2;
+        tb.list = top_list.as<uint32_t>(), tb.small = top_small.as<TopSmall>(), tb.small_count = ctl + 6;
+        tb.level_count = ctl + 8, tb.bins_used = tb.level_count + (HL_TOP_MAX_LEVELS + 1);
+        uint32_t*           bar    = ctl + 4;
+        unsigned long long* trace  = top_trace_buf.p ? top_trace_buf.as<unsigned long long>() : nullptr;
+        void*               args[] = { (void*)&t, (void*)&tb, (void*)&bar, (void*)&trace };
+        HL_CUDA(cudaLaunchCooperativeKernel((const void*)k_top_build, dim3((unsigned)top_grid), dim3(256), args, 0, st));
+        k_top_small<<<ctx->sm_count * 2, 128, 0, st>>>(t, tb);
+        k_top_refit<<<grid_for(k_cap, 256, cap), 256, 0, st>>>(t, tb);
+        ctx->launches += 9;
+        if (trace)
+        {
+            std::vector<unsigned long long> h(1000);
+            std::vector<uint32_t>           hc(top_ctl_words);
+            HL_CUDA(cudaMemcpyAsync(h.data(), trace, 8000, cudaMemcpyDeviceToHost, st));
+            HL_CUDA(cudaMemcpyAsync(hc.data(), ctl, 4 * top_ctl_words, cudaMemcpyDeviceToHost, st));
+            HL_CUDA(cudaStreamSynchronize(st));
+            fprintf(stderr, "[top re-split] n %u C %u K %u small %u grid %d: phase us:", n, C, hc[0], hc[6], top_grid);
+            for (uint32_t k = 2; k < h[0] && k < 1000; k++) fprintf(stderr, " %.1f", (double)(h[k] - h[k - 1]) * 1e-3);
+            fprintf(stderr, "\n  nodes per level:");
+            for (uint32_t k = 0; k < HL_TOP_MAX_LEVELS && hc[8 + k]; k++) fprintf(stderr, " %u", hc[8 + k]);
+            fprintf(stderr, "\n");
+        }
+    }
     // collapse: one persistent launch over a device-side work queue, then the leaf records in a parallel pass
     HL_CUDA(cudaMemsetAsync(queue.p, 0xFF, sizeof(CollapseTask) * (size_t)capacity, st));
     uint32_t h_ctr[8] = { 1u, 0u, 1u, 0u, 1u, 0u, 0u, 0u }; // nodes, leaves, tail, head, outstanding, done

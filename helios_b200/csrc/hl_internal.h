@@ -139,6 +139,7 @@ struct hl_context_t
     bool         profiling = false;
     int          accum_mode = HL_ACCUM_RUNNING_MEAN;
     uint32_t     tail_start = 2, tail_threshold = 98304; // see k_tail (hl_wavefront.cu)
+    uint32_t     sah_cluster = HL_DEFAULT_SAH_CLUSTER;   // binned-SAH re-split of the BVHs' upper levels (hl_build.h); 0 = off
 
     // resources
     std::vector<hl_mesh_t*>  meshes;

@@ -263,6 +263,9 @@ HL_API hl_status hl_event_elapsed_ms(hl_context ctx, int slot_begin, int slot_en
 #define HL_OPT_TAIL_START 2     /* first bounce at which that switch may happen (>= 1) */
 #define HL_OPT_PIPELINE 3       /* 1 (default): consecutive frames alternate between two wavefront state slots / streams so the
                                    sparse late bounces of frame f overlap the first bounces of frame f + 1; 0: one frame at a time */
+/* builder knob (applies to meshes / scene tables created afterwards; changes the tree, never a traversal result) */
+#define HL_OPT_SAH_CLUSTER 4    /* binned-SAH re-split of the LBVH above a cut: primitives per cluster below the cut
+                                   (default 2; larger = faster build, coarser refinement); 0 = plain LBVH topology */
 HL_API hl_status hl_set_option(hl_context ctx, int option, int64_t value);
 /* number of kernels launched by this library on this context since creation */
 HL_API hl_status hl_kernel_launches(hl_context ctx, uint64_t* out);

@@ -31,113 +31,60 @@ struct WideBVH
     float                 sah      = 0.0f; // C(root, 1) / A(root) of the collapse DP
 };
 
-// ---- experiment: binned-SAH re-split of the LBVH's upper levels over Morton clusters (HLBVH style) --------------
-// clusters = maximal LBVH subtrees with <= C primitives; the K-1 internal nodes above the cut are re-linked by a
-// top-down 16-bin SAH build over the cluster boxes.  Sequential reference used to MEASURE the quality gain
-// (tools/bvh_stats.py, HL_EMUL_SAH_TOP=C) before deciding on a GPU version.
-static int g_sah_top_cluster = 0;
+// ---- binned-SAH re-split of the LBVH's upper levels: sequential driver of the per-element phase functions of
+// hl_build.h (the CUDA builder runs the same functions from one persistent kernel, hl_builder.cu k_top_build).
+// cluster size 0 = off.
+static int g_sah_top_cluster = HL_DEFAULT_SAH_CLUSTER;
 EM_API void em_set_sah_top(int cluster_prims) { g_sah_top_cluster = cluster_prims; }
-static uint32_t refine_rec(BinaryTree& t, std::vector<uint32_t>& cl, size_t lo, size_t hi, std::vector<uint32_t>& free_nodes, size_t& next_free, uint32_t self)
-{
-    // builds the subtree over clusters cl[lo, hi) into binary node `self`; returns prims below
-    const size_t n = hi - lo;
-    Box cb;
-    for (int k = 0; k < 3; k++) cb.lo[k] = 3e38f, cb.hi[k] = -3e38f;
-    auto centroid = [&](uint32_t m, int k) { return 0.5f * (t.box[m].lo[k] + t.box[m].hi[k]); };
-    for (size_t i = lo; i < hi; i++)
-        for (int k = 0; k < 3; k++) cb.lo[k] = fminf(cb.lo[k], centroid(cl[i], k)), cb.hi[k] = fmaxf(cb.hi[k], centroid(cl[i], k));
-    const int NB = 16;
-    float best = 3e38f;
-    int   bax = -1, bsplit = -1;
-    for (int ax = 0; ax < 3; ax++)
-    {
-        const float ext = cb.hi[ax] - cb.lo[ax];
-        if (!(ext > 0.0f)) continue;
-        Box      bb[NB];
-        uint32_t cnt[NB] = {};
-        for (auto& b : bb)
-            for (int k = 0; k < 3; k++) b.lo[k] = 3e38f, b.hi[k] = -3e38f;
-        for (size_t i = lo; i < hi; i++)
-        {
-            int b = (int)((centroid(cl[i], ax) - cb.lo[ax]) / ext * NB);
-            b     = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-            bb[b] = box_union(bb[b], t.box[cl[i]]);
-            cnt[b] += subtree_prims(t, cl[i]);
-        }
-        Box      R[NB];
-        uint32_t rc[NB];
-        Box      acc;
-        for (int k = 0; k < 3; k++) acc.lo[k] = 3e38f, acc.hi[k] = -3e38f;
-        uint32_t c = 0;
-        for (int b = NB - 1; b > 0; b--)
-        {
-            acc = box_union(acc, bb[b]), c += cnt[b];
-            R[b] = acc, rc[b] = c;
-        }
-        for (int k = 0; k < 3; k++) acc.lo[k] = 3e38f, acc.hi[k] = -3e38f;
-        c = 0;
-        for (int b = 0; b < NB - 1; b++)
-        {
-            acc = box_union(acc, bb[b]), c += cnt[b];
-            if (c == 0 || rc[b + 1] == 0) continue;
-            const float cost = box_half_area(acc) * c + box_half_area(R[b + 1]) * rc[b + 1];
-            if (cost < best) best = cost, bax = ax, bsplit = b;
-        }
-    }
-    size_t mid;
-    if (bax < 0)
-        mid = lo + n / 2;
-    else
-    {
-        const float ext = cb.hi[bax] - cb.lo[bax];
-        auto        it  = std::partition(cl.begin() + lo, cl.begin() + hi, [&](uint32_t m) {
-            int b = (int)((centroid(m, bax) - cb.lo[bax]) / ext * NB);
-            b     = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-            return b <= bsplit;
-        });
-        mid = (size_t)(it - cl.begin());
-        if (mid == lo || mid == hi) mid = lo + n / 2;
-    }
-    uint32_t child[2], prims = 0;
-    for (int side = 0; side < 2; side++)
-    {
-        const size_t a = side ? mid : lo, b = side ? hi : mid;
-        if (b - a == 1)
-            child[side] = cl[a], prims += subtree_prims(t, cl[a]);
-        else
-        {
-            child[side] = free_nodes[next_free++];
-            prims += refine_rec(t, cl, a, b, free_nodes, next_free, child[side]);
-        }
-        t.parent[child[side]] = self;
-    }
-    t.left[self] = child[0], t.right[self] = child[1];
-    t.first[self] = 0, t.last[self] = prims - 1; // only the count is meaningful above the cut
-    const Box b = box_union(t.box[child[0]], t.box[child[1]]);
-    t.box[self] = b;
-    sah_node_costs(t, self, box_half_area(b));
-    return prims;
-}
+static uint32_t g_top_levels = 0;
+EM_API uint32_t em_last_top_levels() { return g_top_levels; }
 static void refine_top(BinaryTree& t, uint32_t C)
 {
-    if (t.n <= C) return;
-    std::vector<uint32_t> clusters, top; // top = internal nodes above the cut, root first
-    std::vector<uint32_t> stack { 0u };
-    while (!stack.empty())
+    g_top_levels = 0;
+    if (t.n < 2 || t.n <= C) return;
+    std::vector<uint32_t> clusters, upper;
+    for (uint32_t m = 0; m < 2 * t.n - 1; m++)
+        if (top_is_cluster_root(t, m, C)) clusters.push_back(m);
+    for (uint32_t m = 0; m + 1 < t.n; m++)
+        if (top_is_upper_node(t, m, C)) upper.push_back(m);
+    const uint32_t K = (uint32_t)clusters.size();
+    if (K < 2 || upper.size() != K - 1 || upper[0] != 0u) abort();
+    std::vector<uint32_t> cnode(K), level_count(HL_TOP_MAX_LEVELS + 1, 0), bins_used(HL_TOP_MAX_LEVELS + 1, 0);
+    std::vector<TopNode>  lv[2] = { std::vector<TopNode>(K + 2), std::vector<TopNode>(K + 2) };
+    const uint32_t        bins_cap = K / (HL_TOP_SMALL + 1) + 2;
+    std::vector<uint32_t> list((size_t)(K / 2 + 1) * HL_TOP_SMALL);
+    std::vector<TopSmall> small(K / 2 + 1);
+    uint32_t              small_count = 0;
+    std::vector<TopBin>   bins[2]  = { std::vector<TopBin>((size_t)bins_cap * 3 * HL_TOP_BINS), std::vector<TopBin>((size_t)bins_cap * 3 * HL_TOP_BINS) };
+    uint32_t free_next = 0, kdev = K;
+    TopBuild tb;
+    tb.cluster_prims = C, tb.k_cap = K, tb.bins_cap = bins_cap, tb.n_clusters = &kdev, tb.cluster = clusters.data(), tb.free_nodes = upper.data();
+    tb.cnode = cnode.data(), tb.level[0] = lv[0].data(), tb.level[1] = lv[1].data(), tb.bins[0] = bins[0].data(), tb.bins[1] = bins[1].data();
+    tb.list = list.data(), tb.small = small.data(), tb.small_count = &small_count;
+    tb.level_count = level_count.data(), tb.bins_used = bins_used.data(), tb.free_next = &free_next;
+    top_begin(tb, K);
+    for (uint32_t i = 0; i < K; i++) top_seed_cluster(t, tb, i);
+    for (uint32_t L = 0;; L++)
     {
-        const uint32_t m = stack.back();
-        stack.pop_back();
-        if (subtree_prims(t, m) <= C)
-        {
-            clusters.push_back(m);
-            continue;
-        }
-        top.push_back(m);
-        stack.push_back(t.right[m]), stack.push_back(t.left[m]);
+        if (L + 1 >= HL_TOP_MAX_LEVELS) abort();
+        for (uint32_t i = 0; i < K; i++) top_bin_cluster(t, tb, L, i);
+        for (uint32_t j = 0; j < level_count[L]; j++) top_choose_node(tb, L, j);
+        for (uint32_t j = 0; j < level_count[L]; j++) top_commit_node(t, tb, L, j);
+        for (uint32_t b = 0, nb = top_bins_to_clear(tb, L + 1); b < nb; b++) top_clear_bin(tb.bins[(L + 1) & 1u] + b);
+        g_top_levels = L + 1;
+        if (level_count[L + 1] == 0) break;
+        for (uint32_t i = 0; i < K; i++) top_assign_cluster(t, tb, L, i);
     }
-    size_t next_free = 1; // top[0] is the root (node 0)
-    refine_rec(t, clusters, 0, clusters.size(), top, next_free, 0u);
-    t.parent[0] = 0xFFFFFFFFu;
+    for (uint32_t r = 0; r < small_count; r++)
+    {
+        const uint32_t ids = top_small_node_ids(tb, r);
+        top_small_node(t, tb, r, free_next);
+        free_next += ids;
+    }
+    if (free_next != K - 1) abort();
+    for (uint32_t i = 0; i < K; i++)
+        if (cnode[i] != HL_TOP_DONE) abort();
+    for (uint32_t i = 0; i < K; i++) top_refit_from_cluster(t, clusters[i], [] {});
 }
 
 template <class MakeWriter>
@@ -166,7 +113,7 @@ static void build_wide(const std::vector<Box>& prim, WideBVH& out, MakeWriter ma
     for (int i = 0; i + 1 < (int)n; i++) radix_tree_node(skeys.data(), t, i);
     for (uint32_t j = 0; j < n; j++) box[(n - 1) + j] = prim[order[j]];
     for (uint32_t j = 0; j < n; j++) fit_from_leaf(t, j, [] {});
-    if (g_sah_top_cluster > 0 && tri_leaves) refine_top(t, (uint32_t)g_sah_top_cluster);
+    if (g_sah_top_cluster > 0) refine_top(t, tri_leaves ? (uint32_t)g_sah_top_cluster : 1u);
     out.root     = box[0];
     out.n_binary = 2 * n - 1;
     out.sah      = cost[0] / box_half_area(box[0]);

@@ -97,6 +97,27 @@ def test_soup_primary_ids_bit_exact(api, oracle_mod, n_tris):
     ctx.close()
 
 
+@pytest.mark.parametrize("scene", ["soup", "city"])
+def test_builder_sah_cluster_never_changes_a_result(api, oracle_mod, scene):
+    """HL_OPT_SAH_CLUSTER (binned-SAH re-split of the upper BVH levels, hl_build.h top_*): every setting builds a
+    different tree (plain LBVH, SAH over single triangles / pairs / coarse clusters, instance tree re-split or
+    not) and every tree must return the oracle's hits bit for bit — closest hit and tie rule are order independent"""
+    s = scenes.triangle_soup(60_000, 320, 180) if scene == "soup" else scenes.city_scene(n_instances=40, n_meshes=4, width=320, height=180, floors=(2, 5), detail=(1, 3))
+    o = oracle_mod.OracleScene(s)
+    pc = s.push_constants(1)
+    ref = o.trace_primary_ids(pc)
+    nodes = {}
+    for c in (0, 1, 2, 7, 64, 100_000):
+        ctx = api.Context(s.width, s.height)
+        ctx.set_option(4, c)  # HL_OPT_SAH_CLUSTER
+        handles = ctx.load_scene(s)
+        nodes[c] = int(ctx.mesh_build_stats(handles[0])["wide_nodes"])
+        check_ids(ctx.trace_primary_ids(pc), ref)
+        ctx.close()
+    assert nodes[0] != nodes[2]  # the re-split really changed the tree
+    assert nodes[100_000] == nodes[0]  # a cut above the root leaves the radix tree alone
+
+
 def test_terrain_sky_scene(api, oracle_mod):
     from helios_b200.sky import sky_coefficients
 

@@ -12,7 +12,9 @@ s = {"terrain": lambda: scenes.terrain_scene(), "foliage": lambda: scenes.foliag
      "foliage_small": lambda: scenes.foliage_scene(n_clusters=5000), "city_1080": lambda: scenes.city_scene(width=1920, height=1080),
      "cornell": lambda: scenes.cornell_box(1024, 1024)}[name]()
 ctx = api.Context(s.width, s.height)
-ctx.load_scene(s)
+if os.environ.get('HL_SAH_CLUSTER') is not None:
+    ctx.set_option(4, int(os.environ['HL_SAH_CLUSTER']))  # HL_OPT_SAH_CLUSTER
+handles = ctx.load_scene(s)
 ctx.set_option(3, int(os.environ.get('HL_PIPELINE', '1')))  # HL_OPT_PIPELINE
 pcs = [s.push_constants(f) for f in range(1, frames + 5)]
 ctx.accum_clear()
@@ -25,7 +27,7 @@ ms = ctx.event_elapsed_ms(0, 1) / frames
 c = ctx.counters()
 rays = float(c["extension_rays"] + c["shadow_rays"]) / frames
 acc = ctx.read_accum()
-out = {"scene": name, "pipeline": int(os.environ.get('HL_PIPELINE', '1')), "tris": int(s.num_triangles), "ms_per_frame": round(ms, 4), "mrays_s": round(rays / ms / 1e3, 1), "rays_per_frame": rays,
+out = {"scene": name, "pipeline": int(os.environ.get('HL_PIPELINE', '1')), "tris": int(s.num_triangles), "sah_cluster": os.environ.get('HL_SAH_CLUSTER', 'default'), "build_ms": [round(float(ctx.mesh_build_stats(h)["ms_build"]), 3) for h in handles[:3]], "sah": [round(float(ctx.mesh_build_stats(h)["sah_cost"]), 2) for h in handles[:3]], "ms_per_frame": round(ms, 4), "mrays_s": round(rays / ms / 1e3, 1), "rays_per_frame": rays,
        "sha": hashlib.sha256(acc.tobytes()).hexdigest()[:16]}
 ctx.set_profiling(True)
 st = {k: 0.0 for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_resolve", "ms_frame")}
