@@ -139,19 +139,23 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
     const float adjx = u2f((n0.w & 0xFFu) << 23) * r.idir.x;
     const float adjy = u2f(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
     const float adjz = u2f(((n0.w >> 16) & 0xFFu) << 23) * r.idir.z;
-    const float orgx = (u2f(n0.x) - r.o.x) * r.idir.x;
-    const float orgy = (u2f(n0.y) - r.o.y) * r.idir.y;
-    const float orgz = (u2f(n0.z) - r.o.z) * r.idir.z;
+    const float dx = u2f(n0.x) - r.o.x, dy = u2f(n0.y) - r.o.y, dz = u2f(n0.z) - r.o.z;
+    const float orgx = dx * r.idir.x, orgy = dy * r.idir.y, orgz = dz * r.idir.z;
     // conservative per-axis slack (in t): covers the rounding of org/adj/B/fma and the fact that the fp32
-    // triangle test can accept rays that miss the exact box by a few ulp of the ray-box distance.  It is
-    // folded into the fma addend: near planes use org - s, far planes org + s.  (Per axis, not a common
-    // maximum: an axis with a near-zero direction component has a huge |idir| and would otherwise open
-    // every box of the tree.)  2^-19 * 1536 |adj| = 2^-8.4 |adj| > 2^-9 |adj| (rounding of B) + the
-    // 2^-19 * 255 |adj| of the exact-byte formulation.
+    // triangle test can accept rays that miss the exact triangle (hence its box) by a few ulp of the DISTANCE
+    // between ray origin and triangle — the distance over all axes (D below), not the one along the axis being
+    // tested: a ray that runs almost parallel to an axis-aligned wall is close to the box in that axis and far
+    // away in the others (measured with tools/tree_invariance.py: with a slack relative to |org| alone, 1 of
+    // 2.6e8 secondary rays of the city scene lost an edge hit, u + v = 0.99999, in one tree and not in another).
+    // The slack is folded into the fma addend: near planes use org - s, far planes org + s.  (Scaled per axis
+    // by |idir|, not a common maximum in t: an axis with a near-zero direction component has a huge |idir| and
+    // would otherwise open every box of the tree.)  2^-19 * 1536 |adj| = 2^-8.4 |adj| > 2^-9 |adj| (rounding of
+    // B) + the 2^-19 * 255 |adj| of the exact-byte formulation.
     const float C  = 1.9073486e-6f; /* 2^-19 */
-    const float sx = C * (fabsf(orgx) + 1536.0f * fabsf(adjx));
-    const float sy = C * (fabsf(orgy) + 1536.0f * fabsf(adjy));
-    const float sz = C * (fabsf(orgz) + 1536.0f * fabsf(adjz));
+    const float D  = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+    const float sx = C * (fabsf(r.idir.x) * D + 1536.0f * fabsf(adjx));
+    const float sy = C * (fabsf(r.idir.y) * D + 1536.0f * fabsf(adjy));
+    const float sz = C * (fabsf(r.idir.z) * D + 1536.0f * fabsf(adjz));
     const float Ax = adjx * 32768.0f, Ay = adjy * 32768.0f, Az = adjz * 32768.0f;
     const float Bnx = (orgx - sx) - Ax, Bfx = (orgx + sx) - Ax;
     const float Bny = (orgy - sy) - Ay, Bfy = (orgy + sy) - Ay;
