@@ -4,10 +4,14 @@
 // loop (src/viewer/main.cpp:66-76):  render_state.setup(w, h, cmd) -> scene->update(render_state) ->
 // renderer->render(render_state), once per sample.
 //
+//   helios_headless --ast-scene scene.json [--asset-root DIR] [--width W] [--height H] [--focal-length F] [--aperture A] ...
+//       loads an AssetCore scene description (scene JSON -> mesh .ast -> material JSON -> image .ast) through
+//       ResourceManager::load_scene, the reference's own asset route
 //   helios_headless --scene file.hlsc [--spp N] [--device D] [--tiled] [--bounces B] [--exposure E]
 //                   [--out image.png|.ppm|.pfm] [--dump-accum raw.f32] [--dump-tables tables.bin] [--no-device]
 //
 // --no-device builds the scene graph and the tables on the host only (for inspection); rendering needs a GPU.
+#include <core/resource_manager.h>
 #include <gfx/renderer.h>
 #include <resource/material.h>
 #include <resource/mesh.h>
@@ -69,8 +73,9 @@ void write_vec(FILE* f, const std::vector<T>& v)
 
 int main(int argc, char** argv)
 {
-    std::string scene_path, out_path, accum_path, tables_path;
-    uint32_t    spp = 16, bounces = 0;
+    std::string scene_path, ast_scene_path, asset_root, out_path, accum_path, tables_path;
+    uint32_t    spp = 16, bounces = 0, arg_width = 1280, arg_height = 720;
+    float       focal_length = -1.0f, aperture = -1.0f;
     int         device = 0;
     bool        tiled = false, no_device = false;
     float       exposure = 1.0f;
@@ -84,6 +89,12 @@ int main(int argc, char** argv)
         try
         {
             if (a == "--scene") scene_path = next();
+            else if (a == "--ast-scene") ast_scene_path = next();
+            else if (a == "--asset-root") asset_root = next();
+            else if (a == "--width") arg_width = (uint32_t)std::stoul(next());
+            else if (a == "--height") arg_height = (uint32_t)std::stoul(next());
+            else if (a == "--focal-length") focal_length = std::stof(next());
+            else if (a == "--aperture") aperture = std::stof(next());
             else if (a == "--spp") spp = (uint32_t)std::stoul(next());
             else if (a == "--device") device = std::stoi(next());
             else if (a == "--bounces") bounces = (uint32_t)std::stoul(next());
@@ -105,21 +116,43 @@ int main(int argc, char** argv)
             return 2;
         }
     }
-    if (scene_path.empty())
+    if (scene_path.empty() == ast_scene_path.empty())
     {
-        std::fprintf(stderr, "usage: helios_headless --scene file.hlsc [--spp N] [--out image.png] ...\n");
+        std::fprintf(stderr, "usage: helios_headless (--scene file.hlsc | --ast-scene scene.json [--asset-root DIR] [--width W] [--height H]) [--spp N] [--out image.png] ...\n");
         return 2;
     }
     try
     {
+      uint32_t         width = arg_width, height = arg_height, file_bounces = 8;
+      float            bias  = 0.0f;
+      vk::Backend::Ptr backend;
+      Scene::Ptr       scene;
+      if (!ast_scene_path.empty())
+      {
+        // the reference's own asset route: ResourceManager::load_scene on an AssetCore scene description
+        // (src/viewer/main.cpp: m_resource_manager->load_scene(path)); camera lens values are not serialised
+        backend = no_device ? vk::Backend::create_without_device(width, height) : vk::Backend::create(device, width, height);
+        ResourceManager rm(backend);
+        if (!asset_root.empty()) rm.set_asset_root(asset_root);
+        scene = rm.load_scene(ast_scene_path);
+        if (!scene) throw std::runtime_error("cannot load scene " + ast_scene_path);
+        if (auto camera = scene->find_camera())
+        {
+            if (focal_length >= 0.0f) camera->set_focal_length(focal_length);
+            if (aperture >= 0.0f) camera->set_aperture_radius(aperture);
+        }
+        scene_path = ast_scene_path;
+      }
+      else
+      {
         Reader r(scene_path);
         char   magic[8];
         r.raw(magic, 8);
         if (std::memcmp(magic, "HLSC0001", 8) != 0) throw std::runtime_error("not a HLSC0001 scene file");
-        const uint32_t width = r.get<uint32_t>(), height = r.get<uint32_t>(), file_bounces = r.get<uint32_t>();
-        const float    bias = r.get<float>();
+        width = r.get<uint32_t>(), height = r.get<uint32_t>(), file_bounces = r.get<uint32_t>();
+        bias  = r.get<float>();
 
-        vk::Backend::Ptr  backend = no_device ? vk::Backend::create_without_device(width, height) : vk::Backend::create(device, width, height);
+        backend = no_device ? vk::Backend::create_without_device(width, height) : vk::Backend::create(device, width, height);
         vk::BatchUploader uploader(backend);
 
         std::vector<Texture2D::Ptr> textures(r.get<uint32_t>());
@@ -224,7 +257,8 @@ int main(int argc, char** argv)
             ibl->set_image(TextureCube::create(backend, cube, faces.data(), "ibl"));
         }
 
-        Scene::Ptr  scene = Scene::create(backend, "scene", root, scene_path);
+        scene = Scene::create(backend, "scene", root, scene_path);
+      }
         RenderState render_state;
         auto        cmd = std::make_shared<vk::CommandBuffer>();
 
@@ -308,8 +342,7 @@ int main(int argc, char** argv)
         }
         // release in dependency order: scene graph and resources before the backend
         renderer.reset();
-        scene.reset(), root.reset(), camera.reset();
-        meshes.clear(), materials.clear(), textures.clear();
+        scene.reset();
     }
     catch (const std::exception& e)
     {

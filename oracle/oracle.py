@@ -51,6 +51,18 @@ def build_ref(force: bool = False):
     return _REF_PATH if _REF_PATH.exists() else None
 
 
+_REF_AST_TOOL = _HERE / "_ref" / "ref_ast_tool"
+
+
+def build_ref_ast(force: bool = False):
+    """(Re)build oracle/_ref/ref_ast_tool (the reference's AssetCore loader and exporters behind a dump / fixture
+    command line, oracle/ref_ast/) where the reference checkout is mounted; elsewhere the prebuilt file is used.
+    Returns its path, or None if there is neither."""
+    if Path("/root/reference/external/AssetCore/src/loader/loader.cpp").is_file():
+        subprocess.check_call(["make", "-C", str(_HERE), "-s", "ref_ast"] + (["-B"] if force else []))
+    return _REF_AST_TOOL if _REF_AST_TOOL.exists() else None
+
+
 def ref_lib():
     """ctypes handle of the reference-GLSL library (contains the restatement's or_* entry points as well), or None"""
     global _ref_lib

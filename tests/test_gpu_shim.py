@@ -76,3 +76,28 @@ def test_save_image_to_disk_png(tmp_path):
     rgb = np.frombuffer(raw[len(raw) - 160 * 96 * 3 :], np.uint8).reshape(96, 160, 3)
     img = decode_png(png.read_bytes())
     assert img.shape == (96, 160, 4) and np.array_equal(img[..., :3], rgb) and rgb.max() > 0
+
+
+@pytest.mark.parametrize("name", ["cornell", "foliage"])
+def test_asset_route_renders_like_the_direct_route(name, tmp_path):
+    """the scene written as AssetCore files (scene JSON -> mesh .ast -> material JSON -> image .ast) and
+    loaded through ResourceManager::load_scene renders like the scene built through the engine API directly"""
+    from helios_b200 import ast_io
+
+    s = {
+        "cornell": lambda: scenes.cornell_box(128, 96),
+        "foliage": lambda: scenes.foliage_scene(n_clusters=200, cards_per_cluster=10, width=128, height=72, ground_grid=8, tex_size=32),
+    }[name]()
+    direct, _, _ = headless_render(s, tmp_path, 5)
+    rel = ast_io.export_assets(s, tmp_path, name)
+    exe, a = str(build_shim()), tmp_path / "ast.f32"
+    r = subprocess.run([exe, "--ast-scene", rel, "--asset-root", str(tmp_path), "--width", str(s.width), "--height", str(s.height), "--focal-length", str(s.camera.focal_length), "--aperture",
+                        str(s.camera.aperture_radius), "--bounces", str(s.max_ray_bounces), "--spp", "5", "--dump-accum", str(a), "--out", str(tmp_path / "ast.png")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    acc = np.fromfile(a, np.float32).reshape(s.height, s.width, 4)
+    if name == "cornell":
+        assert np.array_equal(acc, direct)  # identical tables and push constants (tests/test_ast_loader.py) -> identical image
+    else:
+        d = np.abs(acc[..., :3] - direct[..., :3]).max(-1)
+        assert (d > 1e-3).mean() < 0.03, (d > 1e-3).mean()
+        assert abs(float(acc[..., :3].mean()) - float(direct[..., :3].mean())) < 3e-3 * max(1.0, float(direct[..., :3].mean()))
