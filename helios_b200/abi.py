@@ -76,5 +76,6 @@ assert INSTANCE.itemsize == 144 and PUSH_CONSTANTS.itemsize == 192 and SUBMESH.i
 LIGHT_DIRECTIONAL, LIGHT_SPOT, LIGHT_POINT, LIGHT_ENVIRONMENT_MAP, LIGHT_AREA = 0, 1, 2, 3, 4
 TONE_MAP_ACES, TONE_MAP_REINHARD = 0, 1
 TEX_RGBA8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA8_SNORM, TEX_RGBA32F = 0, 1, 2, 3
+OUTPUT_BUFFER_ALBEDO, OUTPUT_BUFFER_NORMALS, OUTPUT_BUFFER_ROUGHNESS, OUTPUT_BUFFER_METALLIC, OUTPUT_BUFFER_EMISSIVE = 0, 1, 2, 3, 4  # include/gfx/renderer.h:25-33
 ACCUM_RUNNING_MEAN, ACCUM_SUM = 0, 1
 MISS_ID = 0xFFFFFFFF

@@ -150,6 +150,13 @@ class Context:
         pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
         self._chk(self.lib.hl_trace_primary_ids(self.h, _p(pcb), None, None, None, None, None, None))
 
+    def render_output_buffer(self, pc, output_buffer: int) -> np.ndarray:
+        """debug output buffer (abi.OUTPUT_BUFFER_*) of the surfaces seen by the primary rays of `pc`: [H, W, 4] float32"""
+        pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        self._chk(self.lib.hl_render_output_buffer(self.h, _p(pcb), C.c_int(output_buffer), _p(out)))
+        return out
+
     def trace_rays(self, rays, flags=0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((len(rays), 6), np.float32)

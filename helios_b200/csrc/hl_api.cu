@@ -460,6 +460,23 @@ hl_status hl_trace_primary_ids(hl_context ctx, const hl_push_constants* pc, uint
     HL_CATCH
 }
 
+hl_status hl_render_output_buffer(hl_context ctx, const hl_push_constants* pc, int output_buffer, float* rgba32f_host)
+{
+    HL_TRY(ctx)
+    if (!pc || !rgba32f_host) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_output_buffer: null argument");
+    if (output_buffer < HL_OUTPUT_BUFFER_ALBEDO || output_buffer > HL_OUTPUT_BUFFER_EMISSIVE) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_output_buffer: unknown output buffer");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_output_buffer: scene tables not set");
+    if (pc->launch_id_size[2] != c_->W || pc->launch_id_size[3] != c_->H) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_output_buffer: extent mismatch");
+    wavefront_join(c_);
+    const size_t n = (size_t)c_->W * c_->H;
+    DevBuf       out;
+    out.alloc(n * 16);
+    wavefront_output_buffer(c_, *pc, output_buffer, out.as<float4>());
+    HL_CUDA(cudaMemcpyAsync(rgba32f_host, out.p, n * 16, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    HL_CATCH
+}
+
 hl_status hl_trace_rays(hl_context ctx, const float* rays, uint32_t n_rays, uint32_t flags, void* hits)
 {
     HL_TRY(ctx)

@@ -29,6 +29,7 @@ struct Surface // SurfaceProperties, common.glsl:67-78 (only the members the pat
     f3    emissive;
     f3    F0;
     float roughness;
+    float roughness_unclamped, metallic; // as fetched, before the MIN_ROUGHNESS floor / the F0 mix (debug output buffers only)
 };
 
 // ---- BRDF (brdf.glsl) ---------------------------------------------------------------------------
@@ -174,8 +175,32 @@ HL_HD void load_surface(const SceneView& s, const Hit& h, Surface& p)
         const f4 e = sample_texture_lod0(s, mat.texture_indices1[0], tu, tv);
         p.emissive = mk3(e.x, e.y, e.z);
     }
+    p.roughness_unclamped = p.roughness, p.metallic = metallic;
     p.roughness = fmaxf(p.roughness, HL_MIN_ROUGHNESS);
     p.F0        = mix3(mk3(0.03f), p.albedo, metallic);
+}
+
+// Debug output buffers (debug_visualization.frag:144-161): one material channel of the surface a primary ray hit —
+// 0 albedo, 1 shading normal * 0.5 + 0.5, 2 roughness, 3 metallic (both as fetched: no floor, no F0 mix), 4 emissive;
+// alpha 1; a miss is the pass's clear colour (0,0,0,1).
+HL_HD f4 output_buffer_value(const SceneView& s, const Hit& h, int which)
+{
+    f4 c;
+    c.x = c.y = c.z = 0.0f, c.w = 1.0f;
+    if (h.instance == HL_MISS) return c;
+    Surface p;
+    load_surface(s, h, p);
+    if (which == 0)
+        c.x = p.albedo.x, c.y = p.albedo.y, c.z = p.albedo.z;
+    else if (which == 1)
+        c.x = p.normal.x * 0.5f + 0.5f, c.y = p.normal.y * 0.5f + 0.5f, c.z = p.normal.z * 0.5f + 0.5f;
+    else if (which == 2)
+        c.x = c.y = c.z = p.roughness_unclamped;
+    else if (which == 3)
+        c.x = c.y = c.z = p.metallic;
+    else
+        c.x = p.emissive.x, c.y = p.emissive.y, c.z = p.emissive.z;
+    return c;
 }
 
 // ---- next-event estimation ------------------------------------------------------------------------

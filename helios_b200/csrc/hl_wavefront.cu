@@ -392,6 +392,23 @@ __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_trace_generic(SceneView s, c
     }
 }
 
+// Debug output buffers (Renderer::set_current_output_buffer, include/gfx/renderer.h:25-33): what the reference
+// rasterises with debug_visualization.frag:144-161 — albedo, shading normal * 0.5 + 0.5, roughness, metallic,
+// emissive of the surface seen through each pixel — evaluated here on the primary hits with the path's own
+// surface fetch (path_trace_rchit.glsl:206-252 and debug_visualization.frag:74-135 are the same fetch_* functions).
+__global__ void k_output_buffer(SceneView s, const float4* __restrict__ hit_a, const uint2* __restrict__ hit_b, uint32_t n, int which, float4* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 ha = hit_a[i];
+        const uint2  hb = hit_b[i];
+        Hit          h;
+        h.t = ha.x, h.u = ha.y, h.v = ha.z, h.primitive = __float_as_uint(ha.w), h.instance = hb.x, h.geometry = hb.y;
+        const f4 c = output_buffer_value(s, h, which);
+        out[i] = make_float4(c.x, c.y, c.z, c.w);
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 void wavefront_alloc(hl_context_t* ctx)
 {
@@ -613,6 +630,14 @@ void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc)
     k_generate<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_a.as<float4>(), w.state_b.as<float4>(), w.ext_o[0].as<float4>(), w.ext_d[0].as<float4>(), ctr);
     ctx->launches++;
     run_bounces(ctx, w, st, fp, 1, false);
+}
+
+void wavefront_output_buffer(hl_context_t* ctx, const hl_push_constants& pc, int which, float4* d_out)
+{
+    wavefront_primary_hits(ctx, pc);
+    const uint32_t n = ctx->W * ctx->H;
+    k_output_buffer<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->view, ctx->slot[0].hit_a.as<float4>(), ctx->slot[0].hit_b.as<uint2>(), n, which, d_out);
+    ctx->launches++;
 }
 
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits)

@@ -49,6 +49,10 @@ public:
     // headless read-backs (the reference presents to a swap chain instead)
     std::vector<uint8_t> read_tone_mapped_image(); // RGBA8, row 0 = top
     std::vector<float>   read_accumulation();      // RGBA32F, row 0 = v 0
+    // the debug view selected with set_current_output_buffer (albedo / normals / roughness / metallic / emissive of
+    // the surfaces the camera sees; reference: renderer.cpp:459-547 + debug_visualization.frag), RGBA32F, row 0 = v 0.
+    // OUTPUT_BUFFER_FINAL returns the accumulation image.
+    std::vector<float> read_output_buffer(RenderState& render_state);
 
 private:
     void tone_map(uint8_t* rgba8_host);

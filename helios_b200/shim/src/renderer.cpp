@@ -106,6 +106,23 @@ std::vector<uint8_t> Renderer::read_tone_mapped_image()
     return img;
 }
 
+std::vector<float> Renderer::read_output_buffer(RenderState& render_state)
+{
+    if (m_current_output_buffer == OUTPUT_BUFFER_FINAL) return read_accumulation();
+    auto backend = m_backend.lock();
+    if (!render_state.camera())
+    {
+        HELIOS_LOG_FATAL("Renderer::read_output_buffer: the render state has no camera");
+        throw std::runtime_error("Renderer::read_output_buffer: the render state has no camera");
+    }
+    const auto              ext = backend->swap_chain_extents();
+    std::vector<float>      out((size_t)ext.width * ext.height * 4);
+    const hl_push_constants pc  = m_path_integrator->make_push_constants(render_state, render_state.camera()->view_matrix(), render_state.camera()->projection_matrix(), glm::ivec2(0, 0), glm::ivec2(0, 0));
+    static const int        map[] = { HL_OUTPUT_BUFFER_ALBEDO, HL_OUTPUT_BUFFER_NORMALS, HL_OUTPUT_BUFFER_ROUGHNESS, HL_OUTPUT_BUFFER_METALLIC, HL_OUTPUT_BUFFER_EMISSIVE };
+    backend->check(hl_render_output_buffer(backend->require_device("Renderer::read_output_buffer"), &pc, map[m_current_output_buffer], out.data()), "hl_render_output_buffer");
+    return out;
+}
+
 std::vector<float> Renderer::read_accumulation()
 {
     auto               backend = m_backend.lock();

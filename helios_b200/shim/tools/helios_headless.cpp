@@ -73,7 +73,7 @@ void write_vec(FILE* f, const std::vector<T>& v)
 
 int main(int argc, char** argv)
 {
-    std::string scene_path, ast_scene_path, asset_root, out_path, accum_path, tables_path;
+    std::string scene_path, ast_scene_path, asset_root, out_path, accum_path, tables_path, output_buffer, output_buffer_path;
     uint32_t    spp = 16, bounces = 0, arg_width = 1280, arg_height = 720;
     float       focal_length = -1.0f, aperture = -1.0f;
     int         device = 0;
@@ -102,6 +102,8 @@ int main(int argc, char** argv)
             else if (a == "--out") out_path = next();
             else if (a == "--dump-accum") accum_path = next();
             else if (a == "--dump-tables") tables_path = next();
+            else if (a == "--output-buffer") output_buffer = next();           // albedo | normals | roughness | metallic | emissive
+            else if (a == "--dump-output-buffer") output_buffer_path = next(); // raw RGBA32F of that debug view
             else if (a == "--tiled") tiled = true;
             else if (a == "--no-device") no_device = true;
             else
@@ -308,6 +310,22 @@ int main(int argc, char** argv)
                 if (FILE* f = std::fopen(accum_path.c_str(), "wb"))
                 {
                     std::fwrite(acc.data(), 4, acc.size(), f);
+                    std::fclose(f);
+                }
+            }
+            if (!output_buffer.empty() && !output_buffer_path.empty())
+            {
+                static const char* names[] = { "albedo", "normals", "roughness", "metallic", "emissive" };
+                int                which   = -1;
+                for (int k = 0; k < 5; k++)
+                    if (output_buffer == names[k]) which = k;
+                if (which < 0) throw std::runtime_error("unknown output buffer " + output_buffer);
+                renderer->set_current_output_buffer((OutputBuffer)which);
+                const auto img = renderer->read_output_buffer(render_state);
+                renderer->set_current_output_buffer(OUTPUT_BUFFER_FINAL);
+                if (FILE* f = std::fopen(output_buffer_path.c_str(), "wb"))
+                {
+                    std::fwrite(img.data(), 4, img.size(), f);
                     std::fclose(f);
                 }
             }

@@ -237,6 +237,16 @@ HL_API hl_status hl_set_accum_mode(hl_context ctx, int mode);
  * miss = 0xFFFFFFFF ids and t = +inf.  Any pointer may be NULL. */
 HL_API hl_status hl_trace_primary_ids(hl_context ctx, const hl_push_constants* pc, uint32_t* instance,
                                       uint32_t* geometry, uint32_t* primitive, float* t, float* u, float* v);
+/* debug output buffers: Renderer::set_current_output_buffer (include/gfx/renderer.h:25-33, src/engine/gfx/renderer.cpp:
+ * 459-547 + debug_visualization.frag:144-161 in the reference, a rasterised view of one material channel).  Here:
+ * the channel of the surface hit by each pixel's primary ray of `pc` (camera rays as in hl_render_frame), RGBA32F,
+ * row 0 = v 0; pixels that see no surface are (0,0,0,1).  Normals are encoded n * 0.5 + 0.5 as in the reference. */
+#define HL_OUTPUT_BUFFER_ALBEDO 0
+#define HL_OUTPUT_BUFFER_NORMALS 1
+#define HL_OUTPUT_BUFFER_ROUGHNESS 2
+#define HL_OUTPUT_BUFFER_METALLIC 3
+#define HL_OUTPUT_BUFFER_EMISSIVE 4
+HL_API hl_status hl_render_output_buffer(hl_context ctx, const hl_push_constants* pc, int output_buffer, float* rgba32f_host);
 /* generic closest-hit / visibility query on caller-supplied rays (8 floats per ray: o.xyz, tmin, d.xyz, tmax);
  * flags: bit0 = opaque (skip any-hit), bit1 = terminate on first hit. hit = 6 x 4 B per ray:
  * t,u,v (float) instance,geometry,primitive (u32). */

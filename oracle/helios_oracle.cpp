@@ -1148,6 +1148,43 @@ OR_API void or_trace_primary_ids(const Scene* s, const PushConstants* pcp, uint3
         }
 }
 
+// debug output buffers (debug_visualization.frag:144-161: albedo, normal * 0.5 + 0.5, roughness, metallic, emissive
+// as fetched — no MIN_ROUGHNESS floor) of the surface each pixel's primary ray hits; (0,0,0,1) where nothing is hit
+OR_API void or_output_buffer(const Scene* s, const PushConstants* pcp, int which, float* out)
+{
+    const PushConstants& pc = *pcp;
+    const uint32_t       W = pc.launch_id_size[2], H = pc.launch_id_size[3];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t y = 0; y < (int64_t)H; y++)
+        for (uint32_t x = 0; x < W; x++)
+        {
+            RNG  rng = rng_init(x, (uint32_t)y, pc.num_frames);
+            vec3 o, d;
+            generate_ray(pc, rng, x, (uint32_t)y, o, d);
+            Hit    h = trace(*s, o, 0.001f, d, 10000.0f, 0);
+            float* c = out + ((size_t)y * W + x) * 4;
+            c[0] = c[1] = c[2] = 0.0f, c[3] = 1.0f;
+            if (!h.valid) continue;
+            SurfaceProperties p;
+            populate_surface_properties(*s, h, p);
+            const Material& material = s->materials[s->submesh_info[h.instance][h.geometry * 2 + 1]];
+            if (which == 0)
+                c[0] = p.albedo.x, c[1] = p.albedo.y, c[2] = p.albedo.z;
+            else if (which == 1)
+                c[0] = p.normal.x * 0.5f + 0.5f, c[1] = p.normal.y * 0.5f + 0.5f, c[2] = p.normal.z * 0.5f + 0.5f;
+            else if (which == 2)
+            {
+                // fetch_roughness without the floor populate_surface_properties applies afterwards
+                const float r = material.texture_indices0[2] == -1 ? material.roughness_metallic[0] : texture_lod0(s->textures[material.texture_indices0[2]], p.tex_coord.x, p.tex_coord.y)[material.texture_indices1[2] & 3];
+                c[0] = c[1] = c[2] = r;
+            }
+            else if (which == 3)
+                c[0] = c[1] = c[2] = p.metallic;
+            else
+                c[0] = p.emissive.x, c[1] = p.emissive.y, c[2] = p.emissive.z;
+        }
+}
+
 // generic ray batch: rays = 8 floats (o, tmin, d, tmax); hits = t,u,v,inst,geom,prim (24 B)
 OR_API void or_trace_rays(const Scene* s, const float* rays, uint32_t n, uint32_t flags_hl, void* hits)
 {

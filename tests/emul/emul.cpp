@@ -342,6 +342,23 @@ EM_API void em_trace_primary_ids(const EmScene* s, const hl_push_constants* pc, 
             t[i] = hit ? h.t : hl_inf(), u[i] = hit ? h.u : 0.0f, v[i] = hit ? h.v : 0.0f;
         }
 }
+EM_API void em_output_buffer(const EmScene* s, const hl_push_constants* pc, int which, float* out)
+{
+    const uint32_t W = pc->launch_id_size[2], H = pc->launch_id_size[3];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < (int64_t)H; y++)
+        for (uint32_t x = 0; x < W; x++)
+        {
+            Rng rng = rng_seed(x, (uint32_t)y, pc->num_frames);
+            f3  o, d;
+            primary_ray(*pc, x, (uint32_t)y, rng, o, d);
+            Hit h;
+            trace_one(s->view, o, 0.001f, d, 10000.0f, 0, h);
+            const f4 c = output_buffer_value(s->view, h, which);
+            float*   q = out + ((size_t)y * W + x) * 4;
+            q[0] = c.x, q[1] = c.y, q[2] = c.z, q[3] = c.w;
+        }
+}
 EM_API void em_trace_rays(const EmScene* s, const float* rays, uint32_t n, uint32_t flags, void* hits)
 {
 #pragma omp parallel for schedule(dynamic, 256)

@@ -97,6 +97,13 @@ class EmulScene:
         lib().em_trace_primary_ids(self.h, _p(pcb), _p(inst), _p(geom), _p(prim), _p(t), _p(u), _p(v))
         return inst, geom, prim, t, u, v
 
+    def output_buffer(self, pc, which):
+        s = self.scene
+        out = np.zeros((s.height, s.width, 4), np.float32)
+        pcb = np.ascontiguousarray(pc)
+        lib().em_output_buffer(self.h, _p(pcb), C.c_int(which), _p(out))
+        return out
+
     def trace_rays(self, rays, flags=0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((len(rays), 6), np.float32)

@@ -151,3 +151,23 @@ def test_tonemap_and_sky_match_oracle(oracle_mod, emul):
     sun /= np.linalg.norm(sun)
     cf = sky_coefficients(sun)
     assert np.allclose(emul.sky_bake(cf, sun, 16), oracle_mod.sky_bake(cf, sun, 16), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["cornell", "terrain_textured", "foliage", "city"])
+def test_debug_output_buffers(name, oracle_mod, emul):
+    """albedo / normals / roughness / metallic / emissive views (debug_visualization.frag:144-161)"""
+    s = SCENES[name]()
+    o, e = pair(s, oracle_mod, emul)
+    pc = s.push_constants(1)
+    hit = o.trace_primary_ids(pc)[0].reshape(s.height, s.width) != abi.MISS_ID
+    for which in range(5):
+        a, b = o.output_buffer(pc, which), e.output_buffer(pc, which)
+        assert np.array_equal(a[~hit], np.broadcast_to(np.float32([0, 0, 0, 1]), a[~hit].shape))  # the pass's clear colour
+        assert np.all(a[..., 3] == 1.0)
+        # same hits (bit-exact above) and the same fetch; contraction differences only in the interpolated normal
+        assert np.abs(a - b).max() < 2e-6, (which, np.abs(a - b).max())
+    rough = o.output_buffer(pc, abi.OUTPUT_BUFFER_ROUGHNESS)
+    mats = s.materials
+    if all(int(m["texture_indices0"][2]) == -1 for m in mats):  # constant roughness: the view shows the table's value, un-floored
+        vals = {np.float32(m["roughness_metallic"][0]) for m in mats}
+        assert set(np.unique(rough[hit][:, 0])) <= vals

@@ -279,3 +279,22 @@ def test_gpu_matches_reference_shaders_side_by_side(name, api, oracle_mod):
     assert (d > 1e-4).mean() < 0.01, f"{(d > 1e-4).sum()} of {d.size} pixels differ by more than 1e-4"
     assert rel_mse(a, b) < 2e-3
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["cornell", "terrain_textured", "foliage"])
+def test_debug_output_buffers(name, api, oracle_mod):
+    """SURVEY §8 f4: hl_render_output_buffer (Renderer::set_current_output_buffer, debug_visualization.frag:144-161)"""
+    from helios_b200 import abi as A
+
+    G, _ = _golden()
+    s = G.GOLDEN_SCENES[name]()
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s)
+    pc = s.push_constants(1)
+    for which in (A.OUTPUT_BUFFER_ALBEDO, A.OUTPUT_BUFFER_NORMALS, A.OUTPUT_BUFFER_ROUGHNESS, A.OUTPUT_BUFFER_METALLIC, A.OUTPUT_BUFFER_EMISSIVE):
+        a, b = ctx.render_output_buffer(pc, which), o.output_buffer(pc, which)
+        assert np.abs(a - b).max() < 2e-6, (which, float(np.abs(a - b).max()))
+    with pytest.raises(api.HeliosError):
+        ctx.render_output_buffer(pc, 7)
+    ctx.close()

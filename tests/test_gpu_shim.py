@@ -101,3 +101,16 @@ def test_asset_route_renders_like_the_direct_route(name, tmp_path):
         d = np.abs(acc[..., :3] - direct[..., :3]).max(-1)
         assert (d > 1e-3).mean() < 0.03, (d > 1e-3).mean()
         assert abs(float(acc[..., :3].mean()) - float(direct[..., :3].mean())) < 3e-3 * max(1.0, float(direct[..., :3].mean()))
+
+
+def test_output_buffer_views(tmp_path):
+    """SURVEY 8 f4: Renderer::set_current_output_buffer + read_output_buffer (include/gfx/renderer.h:25-33) — the
+    albedo view of the Cornell box shows exactly the material table's albedos (and the clear colour off-surface)"""
+    s = scenes.cornell_box(96, 96)
+    ob = tmp_path / "albedo.f32"
+    headless_render(s, tmp_path, 1, extra=("--output-buffer", "albedo", "--dump-output-buffer", str(ob)))
+    img = np.fromfile(ob, np.float32).reshape(s.height, s.width, 4)
+    assert np.all(img[..., 3] == 1.0)
+    table = {tuple(np.float32(m["albedo"][:3])) for m in s.materials} | {(0.0, 0.0, 0.0)}
+    seen = {tuple(c) for c in np.unique(img[..., :3].reshape(-1, 3), axis=0)}
+    assert seen <= table and len(seen) >= 3
