@@ -111,6 +111,7 @@ def test_output_buffer_views(tmp_path):
     headless_render(s, tmp_path, 1, extra=("--output-buffer", "albedo", "--dump-output-buffer", str(ob)))
     img = np.fromfile(ob, np.float32).reshape(s.height, s.width, 4)
     assert np.all(img[..., 3] == 1.0)
-    table = {tuple(np.float32(m["albedo"][:3])) for m in s.materials} | {(0.0, 0.0, 0.0)}
-    seen = {tuple(c) for c in np.unique(img[..., :3].reshape(-1, 3), axis=0)}
-    assert seen <= table and len(seen) >= 3
+    table = np.float32([m["albedo"][:3] for m in s.materials] + [[0.0, 0.0, 0.0]])
+    seen = np.unique(img[..., :3].reshape(-1, 3), axis=0)
+    assert 3 <= len(seen) <= len(table)
+    assert all(np.abs(table - c).max(-1).min() < 1e-6 for c in seen)  # the two hosts' tables agree to float rounding
