@@ -541,18 +541,19 @@ hl_status hl_get_counters(hl_context ctx, hl_counters* out)
 {
     HL_TRY(ctx)
     if (!out) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_get_counters: null pointer");
-    uint64_t totals[2][2];
-    for (int k = 0; k < 2; k++) HL_CUDA(cudaMemcpyAsync(totals[k], (char*)c_->slot[k].counters.p + CTR_TOTALS_OFFSET, 16, cudaMemcpyDeviceToHost, c_->stream));
+    uint64_t totals[HL_MAX_WAVE_SLOTS][2];
+    for (int k = 0; k < c_->n_slots; k++) HL_CUDA(cudaMemcpyAsync(totals[k], (char*)c_->slot[k].counters.p + CTR_TOTALS_OFFSET, 16, cudaMemcpyDeviceToHost, c_->stream));
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     *out                = c_->last;
-    out->extension_rays = totals[0][0] + totals[1][0], out->shadow_rays = totals[0][1] + totals[1][1], out->frames = c_->frames;
+    out->extension_rays = out->shadow_rays = 0, out->frames = c_->frames;
+    for (int k = 0; k < c_->n_slots; k++) out->extension_rays += totals[k][0], out->shadow_rays += totals[k][1];
     HL_CATCH
 }
 
 hl_status hl_reset_counters(hl_context ctx)
 {
     HL_TRY(ctx)
-    for (int k = 0; k < 2; k++) HL_CUDA(cudaMemsetAsync((char*)c_->slot[k].counters.p + CTR_TOTALS_OFFSET, 0, 16, c_->stream));
+    for (int k = 0; k < c_->n_slots; k++) HL_CUDA(cudaMemsetAsync((char*)c_->slot[k].counters.p + CTR_TOTALS_OFFSET, 0, 16, c_->stream));
     c_->frames = 0;
     HL_CATCH
 }
@@ -595,6 +596,12 @@ hl_status hl_set_option(hl_context ctx, int option, int64_t value)
         c_->tail_start = (uint32_t)std::max<int64_t>(1, value);
     else if (option == HL_OPT_PIPELINE)
         c_->pipeline = value != 0;
+    else if (option == HL_OPT_FRAMES_IN_FLIGHT)
+    {
+        if (value < 1 || value > HL_MAX_WAVE_SLOTS) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_set_option: frames in flight must be 1..8");
+        // (HL_TRY joined the frames in flight) ray totals of slots that go out of use move into slot 0
+        wavefront_set_slots(c_, (int)value);
+    }
     else if (option == HL_OPT_SAH_CLUSTER)
         c_->sah_cluster = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else

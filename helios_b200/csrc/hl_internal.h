@@ -114,6 +114,12 @@ struct hl_mesh_t
 // Wavefront state of ONE frame in flight.  The context keeps two: frame f runs on slot f & 1 with its own CUDA
 // stream, so the latency-bound late bounces of frame f overlap the throughput-bound first bounces of frame f + 1
 // (the frames share nothing but the read-only scene; their resolve passes are chained by events).
+// frames in flight: consecutive frames rotate through ctx->n_slots wavefront state slots / streams (hl_wavefront.cu,
+// HL_OPT_FRAMES_IN_FLIGHT); slots beyond n_slots stay unallocated
+#define HL_MAX_WAVE_SLOTS 8
+#ifndef HL_DEFAULT_WAVE_SLOTS
+#define HL_DEFAULT_WAVE_SLOTS 4
+#endif
 struct hl_wave_slot
 {
     hl::DevBuf state_a, state_b;   // per path: (T.xyz, rng.x), (L.xyz, rng.y)
@@ -138,7 +144,7 @@ struct hl_context_t
     uint64_t     launches = 0;
     bool         profiling = false;
     int          accum_mode = HL_ACCUM_RUNNING_MEAN;
-    uint32_t     tail_start = 2, tail_threshold = 98304; // see k_tail (hl_wavefront.cu)
+    uint32_t     tail_start = 4, tail_threshold = 98304; // see k_tail (hl_wavefront.cu); tuned with 4 frames in flight (tools/gpu/slot_sweep.sh)
     uint32_t     sah_cluster = HL_DEFAULT_SAH_CLUSTER;   // binned-SAH re-split of the BVHs' upper levels (hl_build.h); 0 = off
 
     // resources
@@ -155,8 +161,9 @@ struct hl_context_t
     // film + wavefront state
     hl::DevBuf   accum, rgba8;          // rgba8: target of the stand-alone tone-map pass (hl_tonemap)
     void*        rgba8_cur = nullptr;   // the RGBA8 image written last (ctx->rgba8 or a slot's)
-    hl_wave_slot slot[2];
-    uint64_t     frame_seq   = 0;       // frames issued; frame f uses slot[f & 1]
+    hl_wave_slot slot[HL_MAX_WAVE_SLOTS];
+    int          n_slots     = HL_DEFAULT_WAVE_SLOTS;
+    uint64_t     frame_seq   = 0;       // frames issued; frame f uses slot[f % n_slots]
     int          pipeline    = 1;       // 0: every frame on the main stream (also forced while profiling)
     cudaEvent_t  main_ev     = nullptr; // orders work enqueued on the main stream before the next frame
     size_t       queue_capacity = 0;
@@ -177,6 +184,7 @@ void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes);
 // hl_wavefront.cu
 void wavefront_alloc(hl_context_t* ctx);
 void wavefront_release(hl_context_t* ctx);
+void wavefront_set_slots(hl_context_t* ctx, int n_slots); // HL_OPT_FRAMES_IN_FLIGHT
 void wavefront_join(hl_context_t* ctx); // main stream waits for every frame in flight
 struct ResolveOptions
 {

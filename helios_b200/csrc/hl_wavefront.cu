@@ -18,7 +18,20 @@
 
 namespace hl
 {
+#ifndef HL_TRACE_BLOCK
 #define HL_TRACE_BLOCK 128
+#endif
+// register cap of the persistent trace kernels.  Measured on configs[1] (tools/tune_trace.py, set "occ"): the
+// compiler's own choice under __launch_bounds__(128) — 72 registers, 7 CTAs/SM — 1.81 ms/frame; capped to 64
+// (8 CTAs/SM, spills) 1.89 ms; uncapped (113 registers, 4 CTAs/SM) 2.21 ms.
+#ifdef HL_TRACE_MIN_BLOCKS
+#define HL_TRACE_BOUNDS __launch_bounds__(HL_TRACE_BLOCK, HL_TRACE_MIN_BLOCKS)
+#else
+#define HL_TRACE_BOUNDS __launch_bounds__(HL_TRACE_BLOCK)
+#endif
+#ifndef HL_TRACE_GRID_MULT
+#define HL_TRACE_GRID_MULT 8 /* persistent trace kernels: CTAs launched per SM */
+#endif
 #define HL_SHADE_BLOCK 128
 
 struct FrameParams
@@ -115,7 +128,7 @@ struct ExtendQueue
         hit_b[i] = make_uint2(h.instance, h.geometry);
     }
 };
-__global__ void __launch_bounds__(HL_TRACE_BLOCK) k_extend(SceneView s, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
+__global__ void HL_TRACE_BOUNDS k_extend(SceneView s, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
                                                            uint32_t* fetch, float tmin, float tmax, uint32_t flags, float4* __restrict__ hit_a, uint2* __restrict__ hit_b)
 {
     __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
@@ -223,7 +236,7 @@ struct ConnectQueue
         state_b[path] = sb;
     }
 };
-__global__ void __launch_bounds__(HL_TRACE_BLOCK) k_connect(SceneView s, const float4* __restrict__ sh_o, const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
+__global__ void HL_TRACE_BOUNDS k_connect(SceneView s, const float4* __restrict__ sh_o, const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                             const uint32_t* __restrict__ count_ptr, uint32_t* fetch, float tmin, uint32_t flags, float4* state_b)
 {
     __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
@@ -410,37 +423,67 @@ __global__ void k_output_buffer(SceneView s, const float4* __restrict__ hit_a, c
 }
 
 // ---- host side -------------------------------------------------------------------------------------
+static void slot_alloc(hl_context_t* ctx, hl_wave_slot& w, size_t n)
+{
+    w.state_a.alloc(n * 16), w.state_b.alloc(n * 16);
+    for (int k = 0; k < 2; k++) w.ext_o[k].alloc(n * 16), w.ext_d[k].alloc(n * 16);
+    w.hit_a.alloc(n * 16), w.hit_b.alloc(n * 8);
+    w.sh_o.alloc(n * 16), w.sh_d.alloc(n * 16), w.sh_c.alloc(n * 16);
+    w.rgba8.alloc(n * 4);
+    HL_CUDA(cudaMemsetAsync(w.rgba8.p, 0, n * 4, ctx->stream));
+    if (!w.counters.p)
+    {
+        w.counters.alloc(CTR_BYTES);
+        HL_CUDA(cudaMemsetAsync(w.counters.p, 0, CTR_BYTES, ctx->stream));
+    }
+    if (!w.stream) HL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    if (!w.resolved) HL_CUDA(cudaEventCreateWithFlags(&w.resolved, cudaEventDisableTiming));
+    w.pending = false;
+}
+static void slot_release(hl_wave_slot& w)
+{
+    w.state_a.release(), w.state_b.release();
+    for (int k = 0; k < 2; k++) w.ext_o[k].release(), w.ext_d[k].release();
+    w.hit_a.release(), w.hit_b.release(), w.sh_o.release(), w.sh_d.release(), w.sh_c.release(), w.rgba8.release();
+}
+
 void wavefront_alloc(hl_context_t* ctx)
 {
     const size_t n = (size_t)ctx->W * ctx->H;
     ctx->accum.alloc(n * 16), ctx->rgba8.alloc(n * 4);
-    for (hl_wave_slot& w : ctx->slot)
-    {
-        w.state_a.alloc(n * 16), w.state_b.alloc(n * 16);
-        for (int k = 0; k < 2; k++) w.ext_o[k].alloc(n * 16), w.ext_d[k].alloc(n * 16);
-        w.hit_a.alloc(n * 16), w.hit_b.alloc(n * 8);
-        w.sh_o.alloc(n * 16), w.sh_d.alloc(n * 16), w.sh_c.alloc(n * 16);
-        w.rgba8.alloc(n * 4);
-        w.counters.alloc(CTR_BYTES);
-        HL_CUDA(cudaMemsetAsync(w.counters.p, 0, CTR_BYTES, ctx->stream));
-        if (!w.stream) HL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
-        if (!w.resolved) HL_CUDA(cudaEventCreateWithFlags(&w.resolved, cudaEventDisableTiming));
-        w.pending = false;
-    }
+    for (int k = 0; k < ctx->n_slots; k++) slot_alloc(ctx, ctx->slot[k], n);
     if (!ctx->main_ev) HL_CUDA(cudaEventCreateWithFlags(&ctx->main_ev, cudaEventDisableTiming));
     ctx->queue_capacity = n;
     film_clear(ctx);
 }
 
+// HL_OPT_FRAMES_IN_FLIGHT; the caller has joined the frames in flight with the main stream
+void wavefront_set_slots(hl_context_t* ctx, int n_slots)
+{
+    const size_t n = (size_t)ctx->W * ctx->H;
+    for (int k = ctx->n_slots; k < n_slots; k++) slot_alloc(ctx, ctx->slot[k], n);
+    if (n_slots < ctx->n_slots)
+    {
+        HL_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int k = n_slots; k < ctx->n_slots; k++)
+        {
+            // keep the ray totals (hl_get_counters sums the slots in use)
+            unsigned long long t[2], t0[2];
+            HL_CUDA(cudaMemcpy(t, (char*)ctx->slot[k].counters.p + CTR_TOTALS_OFFSET, 16, cudaMemcpyDeviceToHost));
+            HL_CUDA(cudaMemcpy(t0, (char*)ctx->slot[0].counters.p + CTR_TOTALS_OFFSET, 16, cudaMemcpyDeviceToHost));
+            t0[0] += t[0], t0[1] += t[1], t[0] = t[1] = 0;
+            HL_CUDA(cudaMemcpy((char*)ctx->slot[0].counters.p + CTR_TOTALS_OFFSET, t0, 16, cudaMemcpyHostToDevice));
+            HL_CUDA(cudaMemcpy((char*)ctx->slot[k].counters.p + CTR_TOTALS_OFFSET, t, 16, cudaMemcpyHostToDevice));
+            slot_release(ctx->slot[k]);
+        }
+    }
+    ctx->n_slots = n_slots;
+}
+
 void wavefront_release(hl_context_t* ctx)
 {
     ctx->accum.release(), ctx->rgba8.release();
-    for (hl_wave_slot& w : ctx->slot)
-    {
-        w.state_a.release(), w.state_b.release();
-        for (int k = 0; k < 2; k++) w.ext_o[k].release(), w.ext_d[k].release();
-        w.hit_a.release(), w.hit_b.release(), w.sh_o.release(), w.sh_d.release(), w.sh_c.release(), w.rgba8.release();
-    }
+    for (hl_wave_slot& w : ctx->slot) slot_release(w);
 }
 
 // every frame in flight happens-before whatever is enqueued on the main stream next
@@ -461,7 +504,8 @@ void film_clear(hl_context_t* ctx)
     k_clear<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->accum.as<float4>(), n);
     ctx->launches++;
     HL_CUDA(cudaMemsetAsync(ctx->rgba8.p, 0, n * 4, ctx->stream));
-    for (hl_wave_slot& w : ctx->slot) HL_CUDA(cudaMemsetAsync(w.rgba8.p, 0, n * 4, ctx->stream));
+    for (hl_wave_slot& w : ctx->slot)
+        if (w.rgba8.p) HL_CUDA(cudaMemsetAsync(w.rgba8.p, 0, n * 4, ctx->stream));
     ctx->rgba8_cur = ctx->rgba8.p;
 }
 
@@ -495,7 +539,7 @@ static void ensure_events(hl_context_t* ctx)
 static void run_bounces(hl_context_t* ctx, hl_wave_slot& w, cudaStream_t st, const FrameParams& fp, uint32_t bounces, bool shade)
 {
     uint32_t*    ctr  = w.counters.as<uint32_t>();
-    const int    tgrid = ctx->sm_count * 8; // persistent: 8 blocks of 128 threads per SM
+    const int    tgrid = ctx->sm_count * HL_TRACE_GRID_MULT; // persistent trace kernels
     const int    sgrid = ctx->sm_count * 8;
     ShadeParams  prm;
     prm.num_lights = fp.pc.num_lights, prm.max_ray_bounces = fp.pc.max_ray_bounces, prm.shadow_ray_bias = fp.pc.shadow_ray_bias;
@@ -545,10 +589,11 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
     if (n == 0) return;
     const uint32_t bounces = std::min<uint32_t>(pc.max_ray_bounces, HL_MAX_BOUNCES);
     const bool     prof    = ctx->profiling;
-    const bool     piped   = ctx->pipeline && !prof;
+    const bool     piped   = ctx->pipeline && ctx->n_slots > 1 && !prof;
     if (!piped) wavefront_join(ctx);
-    hl_wave_slot& w     = ctx->slot[piped ? (ctx->frame_seq & 1) : 0];
-    hl_wave_slot& other = ctx->slot[piped ? ((ctx->frame_seq & 1) ^ 1) : 1];
+    const uint64_t ns   = (uint64_t)ctx->n_slots;
+    hl_wave_slot& w     = ctx->slot[piped ? ctx->frame_seq % ns : 0];
+    hl_wave_slot& other = ctx->slot[piped ? (ctx->frame_seq + ns - 1) % ns : 0]; // the previous frame's
     cudaStream_t  st    = piped ? w.stream : ctx->stream;
     if (piped)
     {

@@ -271,8 +271,11 @@ HL_API hl_status hl_event_elapsed_ms(hl_context ctx, int slot_begin, int slot_en
 /* tuning knobs of the wavefront scheduler (results do not depend on them) */
 #define HL_OPT_TAIL_THRESHOLD 1 /* queue size at or below which the late bounces are finished by one per-path kernel; 0 = never */
 #define HL_OPT_TAIL_START 2     /* first bounce at which that switch may happen (>= 1) */
-#define HL_OPT_PIPELINE 3       /* 1 (default): consecutive frames alternate between two wavefront state slots / streams so the
-                                   sparse late bounces of frame f overlap the first bounces of frame f + 1; 0: one frame at a time */
+#define HL_OPT_PIPELINE 3       /* 1 (default): consecutive frames rotate through several wavefront state slots / streams so the
+                                   sparse late bounces of frame f overlap the first bounces of the frames after it (blends stay
+                                   in frame order); 0: one frame at a time */
+#define HL_OPT_FRAMES_IN_FLIGHT 5 /* number of those slots, 1..8 (default 4; the reference keeps up to 3 frames in flight,
+                                   include/gfx/vk.h:66); each costs 172 B per pixel of device memory */
 /* builder knob (applies to meshes / scene tables created afterwards; changes the tree, never a traversal result) */
 #define HL_OPT_SAH_CLUSTER 4    /* binned-SAH re-split of the LBVH above a cut: primitives per cluster below the cut
                                    (default 2; larger = faster build, coarser refinement); 0 = plain LBVH topology */

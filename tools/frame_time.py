@@ -16,6 +16,9 @@ if os.environ.get('HL_SAH_CLUSTER') is not None:
     ctx.set_option(4, int(os.environ['HL_SAH_CLUSTER']))  # HL_OPT_SAH_CLUSTER
 handles = ctx.load_scene(s)
 ctx.set_option(3, int(os.environ.get('HL_PIPELINE', '1')))  # HL_OPT_PIPELINE
+if os.environ.get('HL_TAIL_THRESHOLD') is not None: ctx.set_option(1, int(os.environ['HL_TAIL_THRESHOLD']))
+if os.environ.get('HL_SLOTS') is not None: ctx.set_option(5, int(os.environ['HL_SLOTS']))
+if os.environ.get('HL_TAIL_START') is not None: ctx.set_option(2, int(os.environ['HL_TAIL_START']))
 pcs = [s.push_constants(f) for f in range(1, frames + 5)]
 ctx.accum_clear()
 for pc in pcs[:4]: ctx.render_frame(pc)

@@ -1,21 +1,39 @@
 """Compile-time tuning of the persistent trace loop.  `build` (run where nvcc is) compiles one library per
 variant under build/variants/; `run` (on the GPU box) times configs[1] with each and prints one JSON line per
-variant.  python tools/tune_trace.py build|run [scene]"""
+variant.  HL_TUNE_SET=occ|sched python tools/tune_trace.py build|run [scene]"""
 import os, subprocess, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-VARIANTS = {
-    "tmin1": ["-DHL_TRI_MIN_LANES=1"], "tmin4": ["-DHL_TRI_MIN_LANES=4"], "tmin8": ["-DHL_TRI_MIN_LANES=8"], "tmin12": ["-DHL_TRI_MIN_LANES=12"],
-    "tmin16": ["-DHL_TRI_MIN_LANES=16"], "tmin8_tri24": ["-DHL_TRI_MIN_LANES=8", "-DHL_TRI_PER_STEP=24"], "tmin12_tri24": ["-DHL_TRI_MIN_LANES=12", "-DHL_TRI_PER_STEP=24"],
-    "tmin8_tri3": ["-DHL_TRI_MIN_LANES=8", "-DHL_TRI_PER_STEP=3"], "tmin8_refill4": ["-DHL_TRI_MIN_LANES=8", "-DHL_REFILL_MIN=4"],
-    "tmin8_refill12": ["-DHL_TRI_MIN_LANES=8", "-DHL_REFILL_MIN=12"],
+VARIANT_SETS = {
+    "sched": {
+        "tmin1": ["-DHL_TRI_MIN_LANES=1"], "tmin4": ["-DHL_TRI_MIN_LANES=4"], "tmin8": ["-DHL_TRI_MIN_LANES=8"], "tmin12": ["-DHL_TRI_MIN_LANES=12"],
+        "tmin16": ["-DHL_TRI_MIN_LANES=16"], "tmin8_tri24": ["-DHL_TRI_MIN_LANES=8", "-DHL_TRI_PER_STEP=24"], "tmin12_tri24": ["-DHL_TRI_MIN_LANES=12", "-DHL_TRI_PER_STEP=24"],
+        "tmin8_tri3": ["-DHL_TRI_MIN_LANES=8", "-DHL_TRI_PER_STEP=3"], "tmin8_refill4": ["-DHL_TRI_MIN_LANES=8", "-DHL_REFILL_MIN=4"],
+        "tmin8_refill12": ["-DHL_TRI_MIN_LANES=8", "-DHL_REFILL_MIN=12"],
+    },
+    # occupancy of the persistent trace kernels: register cap (launch bounds), CTA size, fast-stack depth, CTAs per SM
+    "occ": {
+        "base": [],
+        "mb8": ["-DHL_TRACE_MIN_BLOCKS=8"],
+        "mb8_s8": ["-DHL_TRACE_MIN_BLOCKS=8", "-DHL_STACK_FAST=8"],
+        "mb10_s8": ["-DHL_TRACE_MIN_BLOCKS=10", "-DHL_STACK_FAST=8", "-DHL_TRACE_GRID_MULT=10"],
+        "b64_mb16": ["-DHL_TRACE_BLOCK=64", "-DHL_TRACE_MIN_BLOCKS=16", "-DHL_TRACE_GRID_MULT=16"],
+        "b256_mb4": ["-DHL_TRACE_BLOCK=256", "-DHL_TRACE_MIN_BLOCKS=4", "-DHL_TRACE_GRID_MULT=4"],
+        "g7": ["-DHL_TRACE_GRID_MULT=7"],
+        "g6": ["-DHL_TRACE_GRID_MULT=6"],
+        "s16": ["-DHL_STACK_FAST=16"],
+        "refill4": ["-DHL_REFILL_MIN=4"], "refill16": ["-DHL_REFILL_MIN=16"],
+    },
 }
+VARIANT_SETS["slots"] = {"base": [], "slots3": ["-DHL_WAVE_SLOTS=3"], "slots2": ["-DHL_WAVE_SLOTS=2"], "slots4": ["-DHL_WAVE_SLOTS=4"], "slots6": ["-DHL_WAVE_SLOTS=6"], "mb7": ["-DHL_TRACE_MIN_BLOCKS=7"], "mb6": ["-DHL_TRACE_MIN_BLOCKS=6", "-DHL_TRACE_GRID_MULT=6"]}
+VARIANTS = VARIANT_SETS[os.environ.get("HL_TUNE_SET", "occ")]
 OUT = ROOT / "build" / "variants"
 if sys.argv[1] == "build":
+    from concurrent.futures import ThreadPoolExecutor
     from helios_b200.build import build_library
-    for n, d in VARIANTS.items():
-        build_library(defines=d, out=OUT / f"lib_{n}.so")
+    with ThreadPoolExecutor(int(os.environ.get("HL_TUNE_JOBS", "6"))) as ex:  # nvcc runs as subprocesses
+        list(ex.map(lambda nd: build_library(force=True, defines=nd[1], out=OUT / f"lib_{nd[0]}.so"), VARIANTS.items()))
 else:
     scene = sys.argv[2:] or ["terrain"]
     for n in VARIANTS:
