@@ -157,6 +157,15 @@ class Context:
         self._chk(self.lib.hl_render_output_buffer(self.h, _p(pcb), C.c_int(output_buffer), _p(out)))
         return out
 
+    def gather_debug_rays(self, pc, num_debug_rays: int, max_vertices: int = 2 * abi.MAX_DEBUG_RAY_DRAW_COUNT):
+        """ray debug view (PathIntegrator::gather_debug_rays): (vertices [min(count, max_vertices)] of abi.DEBUG_RAY_VERTEX,
+        count) — two vertices per secondary-ray segment of num_debug_rays paths through pc.ray_debug_pixel_coord"""
+        pcb = np.ascontiguousarray(pc, abi.PUSH_CONSTANTS)
+        out = np.zeros(max_vertices, abi.DEBUG_RAY_VERTEX)
+        n = C.c_uint32(0)
+        self._chk(self.lib.hl_gather_debug_rays(self.h, _p(pcb), C.c_uint32(num_debug_rays), _p(out), C.c_uint32(max_vertices), C.byref(n)))
+        return out[: min(n.value, max_vertices)], n.value
+
     def trace_rays(self, rays, flags=0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((len(rays), 6), np.float32)

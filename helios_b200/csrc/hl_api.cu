@@ -477,6 +477,27 @@ hl_status hl_render_output_buffer(hl_context ctx, const hl_push_constants* pc, i
     HL_CATCH
 }
 
+hl_status hl_gather_debug_rays(hl_context ctx, const hl_push_constants* pc, uint32_t num_debug_rays, hl_debug_ray_vertex* vertices_host, uint32_t max_vertices, uint32_t* vertex_count)
+{
+    HL_TRY(ctx)
+    if (!pc || !vertex_count || (!vertices_host && max_vertices)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_gather_debug_rays: null argument");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_gather_debug_rays: scene tables not set");
+    *vertex_count = 0;
+    if (num_debug_rays == 0) return HL_OK;
+    DevBuf verts, count;
+    verts.alloc((size_t)max_vertices * sizeof(hl_debug_ray_vertex));
+    count.alloc(4);
+    HL_CUDA(cudaMemsetAsync(count.p, 0, 4, c_->stream));
+    wavefront_debug_rays(c_, *pc, num_debug_rays, verts.as<float4>(), max_vertices, count.as<uint32_t>());
+    uint32_t n = 0;
+    HL_CUDA(cudaMemcpyAsync(&n, count.p, 4, cudaMemcpyDeviceToHost, c_->stream));
+    HL_CUDA(cudaStreamSynchronize(c_->stream));
+    *vertex_count = n;
+    const uint32_t m = n < max_vertices ? n : max_vertices;
+    if (m) HL_CUDA(cudaMemcpy(vertices_host, verts.p, (size_t)m * sizeof(hl_debug_ray_vertex), cudaMemcpyDeviceToHost));
+    HL_CATCH
+}
+
 hl_status hl_trace_rays(hl_context ctx, const float* rays, uint32_t n_rays, uint32_t flags, void* hits)
 {
     HL_TRY(ctx)

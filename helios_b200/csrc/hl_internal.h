@@ -196,6 +196,7 @@ struct ResolveOptions
 void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint32_t lw, uint32_t lh, const ResolveOptions& opt = ResolveOptions());
 void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc);
 void wavefront_output_buffer(hl_context_t* ctx, const hl_push_constants& pc, int which, float4* d_out); // debug output buffers
+void wavefront_debug_rays(hl_context_t* ctx, const hl_push_constants& pc, uint32_t n, float4* d_verts, uint32_t capacity, uint32_t* d_count); // ray debug view
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits);
 void film_clear(hl_context_t* ctx);
 void film_tonemap(hl_context_t* ctx, float exposure, int op, float scale);

@@ -302,6 +302,7 @@ struct ShadeParams
 {
     uint32_t num_lights, max_ray_bounces;
     float    shadow_ray_bias;
+    uint32_t ray_debug_view = 0; // 1 = the RAY_DEBUG_VIEW variant of the closest-hit shader: no Russian roulette (hl_debug.h)
 };
 struct ShadeResult
 {
@@ -363,9 +364,9 @@ HL_HD void shade_hit(const SceneView& s, const ShadeParams& prm, uint32_t depth,
         const float ct   = clampf(dot(p.normal, Wi), 0.0f, 1.0f);
         f3          Tn   = T * (brdf * ct) / pdf;
         const float prob = fmaxf(Tn.x, fmaxf(Tn.y, Tn.z));
-        if (!(rand01(rng) > prob)) // Russian roulette, rchit:501-504
+        if (prm.ray_debug_view || !(rand01(rng) > prob)) // Russian roulette, rchit:500-509 (#if !defined(RAY_DEBUG_VIEW))
         {
-            Tn          = Tn * (1.0f / prob);
+            if (!prm.ray_debug_view) Tn = Tn * (1.0f / prob);
             r.continues = true;
             r.next_o    = p.position;
             r.next_d    = Wi;

@@ -12,6 +12,7 @@
 // kernels that pull 32 rays per warp from an atomic cursor, shade is a grid-stride loop.
 #include "hl_bvh.h"
 #include "hl_camera.h"
+#include "hl_debug.h"
 #include "hl_film.h"
 #include "hl_internal.h"
 #include "hl_shade.h"
@@ -422,6 +423,29 @@ __global__ void k_output_buffer(SceneView s, const float4* __restrict__ hit_a, c
     }
 }
 
+// Ray debug view (hl_debug.h): one path per lane; segments appended with one atomic per segment, as the reference's
+// shaders do (rchit:552, rmiss:44) — their order in the buffer is not defined there either.
+struct DebugRayOut
+{
+    float4*   verts; // two float4 per vertex: position.xyz 1, colour.rgb 1 (DebugRayVertex, common.glsl:54-58)
+    uint32_t* count;
+    uint32_t  capacity;
+    __device__ __forceinline__ uint32_t alloc2() { return atomicAdd(count, 2u); }
+    __device__ __forceinline__ void     put(uint32_t k, f3 p, f3 c)
+    {
+        if (k < capacity) verts[2 * (size_t)k] = make_float4(p.x, p.y, p.z, 1.0f), verts[2 * (size_t)k + 1] = make_float4(c.x, c.y, c.z, 1.0f);
+    }
+};
+__global__ void __launch_bounds__(HL_TRACE_BLOCK) k_debug_rays(SceneView s, hl_push_constants pc, uint32_t n, DebugRayOut out)
+{
+    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
+    TravStack     st;
+    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x)
+        debug_ray_path(s, pc, base + lane, base + lane < n, st, out);
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 static void slot_alloc(hl_context_t* ctx, hl_wave_slot& w, size_t n)
 {
@@ -682,6 +706,16 @@ void wavefront_output_buffer(hl_context_t* ctx, const hl_push_constants& pc, int
     wavefront_primary_hits(ctx, pc);
     const uint32_t n = ctx->W * ctx->H;
     k_output_buffer<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->view, ctx->slot[0].hit_a.as<float4>(), ctx->slot[0].hit_b.as<uint2>(), n, which, d_out);
+    ctx->launches++;
+}
+
+void wavefront_debug_rays(hl_context_t* ctx, const hl_push_constants& pc, uint32_t n, float4* d_verts, uint32_t capacity, uint32_t* d_count)
+{
+    if (!n) return;
+    DebugRayOut out;
+    out.verts = d_verts, out.count = d_count, out.capacity = capacity;
+    const uint32_t blocks = std::min<uint32_t>((n + HL_TRACE_BLOCK - 1) / HL_TRACE_BLOCK, (uint32_t)ctx->sm_count * 8u);
+    k_debug_rays<<<blocks, HL_TRACE_BLOCK, 0, ctx->stream>>>(ctx->view, pc, n, out);
     ctx->launches++;
 }
 

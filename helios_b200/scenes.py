@@ -74,7 +74,7 @@ class SceneData:
     def num_triangles(self) -> int:
         return int(sum(int(self.meshes[i["mesh_index"]].indices.size) // 3 for i in self.instances))
 
-    def push_constants(self, num_frames: int, tile=(0, 0), max_ray_bounces=None, shadow_ray_bias=None) -> np.ndarray:
+    def push_constants(self, num_frames: int, tile=(0, 0), max_ray_bounces=None, shadow_ray_bias=None, pixel_coord=(0, 0)) -> np.ndarray:
         """PathIntegrator::launch_rays, src/engine/gfx/path_integrator.cpp:136-161."""
         cam = self.camera
         W, H = self.width, self.height
@@ -99,7 +99,7 @@ class SceneData:
         fpp = cam.position + view_dir * np.float32(cam.focal_length)
         fp = -view_dir
         pc["focal_plane"] = [*fp, -(fp[0] * fpp[0] + fp[1] * fpp[1] + fp[2] * fpp[2])]
-        pc["ray_debug_pixel_coord"] = [0, H, W, H]
+        pc["ray_debug_pixel_coord"] = [pixel_coord[0], H - pixel_coord[1], W, H]  # path_integrator.cpp:146 (gather_debug_rays passes the clicked pixel)
         pc["launch_id_size"] = [tile[0], tile[1], W, H]
         pc["accumulation"] = num_frames / (num_frames + 1.0)
         pc["num_lights"] = len(self.lights)

@@ -34,6 +34,10 @@ public:
     inline void set_shadow_ray_bias(const float& bias) { m_shadow_ray_bias = bias; }
 
     void render(RenderState& render_state);
+    // the ray debug view (reference: path_integrator.cpp:88-104): num_debug_rays paths through pixel_coord, one line segment
+    // per secondary ray; the vertices land in `vertices` (appended, 2 per segment; capacity as the reference's buffer)
+    void gather_debug_rays(const glm::ivec2& pixel_coord, const uint32_t& num_debug_rays, const glm::mat4& view, const glm::mat4& projection, RenderState& render_state,
+                           std::vector<hl_debug_ray_vertex>& vertices, uint32_t max_vertices);
     void on_window_resize();
     void set_tiled(bool tiled);
 

@@ -1,7 +1,8 @@
 // gfx/renderer.h — Renderer (reference: include/gfx/renderer.h:35-120, src/engine/gfx/renderer.cpp:106-330
 // render, :369-428 tone_map, :637-711 save path).  render(RenderState&) = (re)build the top level when the
 // hierarchy changed, clear the accumulation when the bake restarts, one PathIntegrator iteration, tone map.
-// The swap-chain copy, ImGui, ray-debug and G-buffer debug views of the reference are outside the path.
+// The swap-chain copy and ImGui of the reference are outside the path; its ray-debug and G-buffer debug views are
+// offered as data (segment vertices / channel images) instead of rasterised overlays.
 #pragma once
 #include <gfx/path_integrator.h>
 #include <resource/scene.h>
@@ -10,6 +11,16 @@
 
 namespace helios
 {
+#define MAX_DEBUG_RAY_DRAW_COUNT 1024 // include/gfx/renderer.h:9
+
+struct RayDebugView // include/gfx/renderer.h:13-19
+{
+    glm::ivec2 pixel_coord;
+    uint32_t   num_debug_rays;
+    glm::mat4  view;
+    glm::mat4  projection;
+};
+
 enum ToneMapOperator
 {
     TONE_MAP_OPERATOR_ACES,
@@ -42,6 +53,12 @@ public:
 
     void render(RenderState& render_state);
     void on_window_resize();
+    // ray debug views (reference: renderer.cpp:229-250, :733-751): the view added last is gathered by the next render()
+    // (PathIntegrator::gather_debug_rays); the first view after a clear resets the segment buffer, later ones append.
+    void                                    add_ray_debug_view(const glm::ivec2& pixel_coord, const uint32_t& num_debug_rays, const glm::mat4& view, const glm::mat4& projection);
+    const std::vector<RayDebugView>&        ray_debug_views();
+    void                                    clear_ray_debug_views();
+    const std::vector<hl_debug_ray_vertex>& ray_debug_vertices() const { return m_ray_debug_vertices; } // what the reference draws as a line list
     // queues a save of the tone-mapped image; it is written at the end of the next render(), as in the reference
     // (8-bit RGBA PNG as in the reference, :651; a path ending in .ppm / .pfm selects those formats instead)
     void save_image_to_disk(const std::string& path);
@@ -57,6 +74,9 @@ public:
 private:
     void tone_map(uint8_t* rgba8_host);
 
+    std::vector<RayDebugView>        m_ray_debug_views;
+    bool                             m_ray_debug_view_added = false;
+    std::vector<hl_debug_ray_vertex> m_ray_debug_vertices;
     std::weak_ptr<vk::Backend> m_backend;
     PathIntegrator::Ptr        m_path_integrator;
     bool                       m_output_image_recreated = true;

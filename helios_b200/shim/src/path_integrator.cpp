@@ -1,5 +1,6 @@
 // path_integrator.cpp — PathIntegrator (reference: src/engine/gfx/path_integrator.cpp).
 #include <gfx/path_integrator.h>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -54,6 +55,20 @@ void PathIntegrator::set_tiled(bool tiled)
 }
 
 // :136-161
+void PathIntegrator::gather_debug_rays(const glm::ivec2& pixel_coord, const uint32_t& num_debug_rays, const glm::mat4& view, const glm::mat4& projection, RenderState& render_state,
+                                       std::vector<hl_debug_ray_vertex>& vertices, uint32_t max_vertices)
+{
+    auto backend = m_backend.lock();
+    // launch_rays(render_state, ray-debug pipeline, num_debug_rays, 1, 1, view, projection, tile (0, 0), pixel_coord)
+    const hl_push_constants pc   = make_push_constants(render_state, view, projection, glm::ivec2(0, 0), pixel_coord);
+    const size_t            have = vertices.size();
+    const uint32_t          room = have < max_vertices ? max_vertices - (uint32_t)have : 0;
+    vertices.resize(have + room);
+    uint32_t count = 0;
+    backend->check(hl_gather_debug_rays(backend->require_device("PathIntegrator::gather_debug_rays"), &pc, num_debug_rays, vertices.data() + have, room, &count), "hl_gather_debug_rays");
+    vertices.resize(have + std::min(count, room));
+}
+
 hl_push_constants PathIntegrator::make_push_constants(RenderState& render_state, const glm::mat4& view, const glm::mat4& projection, const glm::ivec2& tile_coord, const glm::ivec2& pixel_coord)
 {
     auto           backend = m_backend.lock();

@@ -31,6 +31,14 @@ void Renderer::render(RenderState& render_state)
     m_path_integrator->set_resolve_tone_map(true, m_exposure, op);
     if (render_state.m_scene) m_path_integrator->render(render_state);
     const bool resolved = render_state.m_scene && m_path_integrator->launched_last_render();
+    if (m_ray_debug_view_added) // renderer.cpp:229-250
+    {
+        m_ray_debug_view_added = false;
+        if (m_ray_debug_views.size() == 1) m_ray_debug_vertices.clear(); // the draw arguments are reset for the first view
+        const auto& view = m_ray_debug_views.back();
+        if (render_state.m_scene)
+            m_path_integrator->gather_debug_rays(view.pixel_coord, view.num_debug_rays, view.view, view.projection, render_state, m_ray_debug_vertices, MAX_DEBUG_RAY_DRAW_COUNT * 2);
+    }
     if (m_save_image_to_disk)
     {
         const auto           ext = backend->swap_chain_extents();
@@ -85,6 +93,16 @@ void Renderer::on_window_resize()
     m_output_image_recreated = true;
     m_path_integrator->on_window_resize();
 }
+
+void Renderer::add_ray_debug_view(const glm::ivec2& pixel_coord, const uint32_t& num_debug_rays, const glm::mat4& view, const glm::mat4& projection)
+{
+    m_ray_debug_views.push_back({ pixel_coord, num_debug_rays, view, projection });
+    m_ray_debug_view_added = true;
+}
+
+const std::vector<RayDebugView>& Renderer::ray_debug_views() { return m_ray_debug_views; }
+
+void Renderer::clear_ray_debug_views() { m_ray_debug_views.clear(); }
 
 void Renderer::save_image_to_disk(const std::string& path)
 {

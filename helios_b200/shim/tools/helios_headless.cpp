@@ -73,7 +73,8 @@ void write_vec(FILE* f, const std::vector<T>& v)
 
 int main(int argc, char** argv)
 {
-    std::string scene_path, ast_scene_path, asset_root, out_path, accum_path, tables_path, output_buffer, output_buffer_path;
+    std::string scene_path, ast_scene_path, asset_root, out_path, accum_path, tables_path, output_buffer, output_buffer_path, ray_debug_path;
+    int         ray_debug[3] = { 0, 0, 0 };
     uint32_t    spp = 16, bounces = 0, arg_width = 1280, arg_height = 720;
     float       focal_length = -1.0f, aperture = -1.0f;
     int         device = 0;
@@ -104,6 +105,11 @@ int main(int argc, char** argv)
             else if (a == "--dump-tables") tables_path = next();
             else if (a == "--output-buffer") output_buffer = next();           // albedo | normals | roughness | metallic | emissive
             else if (a == "--dump-output-buffer") output_buffer_path = next(); // raw RGBA32F of that debug view
+            else if (a == "--ray-debug") // x y n : ray debug view through pixel (x, y) with n paths, gathered after the last frame
+            {
+                ray_debug[0] = std::atoi(next().c_str()), ray_debug[1] = std::atoi(next().c_str()), ray_debug[2] = std::atoi(next().c_str());
+            }
+            else if (a == "--dump-ray-debug") ray_debug_path = next(); // raw vertices, 8 floats each
             else if (a == "--tiled") tiled = true;
             else if (a == "--no-device") no_device = true;
             else
@@ -310,6 +316,20 @@ int main(int argc, char** argv)
                 if (FILE* f = std::fopen(accum_path.c_str(), "wb"))
                 {
                     std::fwrite(acc.data(), 4, acc.size(), f);
+                    std::fclose(f);
+                }
+            }
+            if (ray_debug[2] > 0 && !ray_debug_path.empty())
+            {
+                // the editor's click (src/editor/main.cpp:516-523): add a view with the camera's matrices; the next render() gathers it
+                renderer->add_ray_debug_view(glm::ivec2(ray_debug[0], ray_debug[1]), (uint32_t)ray_debug[2], render_state.camera()->view_matrix(), render_state.camera()->projection_matrix());
+                render_state.setup(width, height, cmd);
+                scene->update(render_state);
+                renderer->render(render_state);
+                const auto& v = renderer->ray_debug_vertices();
+                if (FILE* f = std::fopen(ray_debug_path.c_str(), "wb"))
+                {
+                    std::fwrite(v.data(), sizeof(hl_debug_ray_vertex), v.size(), f);
                     std::fclose(f);
                 }
             }

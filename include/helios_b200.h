@@ -247,6 +247,22 @@ HL_API hl_status hl_trace_primary_ids(hl_context ctx, const hl_push_constants* p
 #define HL_OUTPUT_BUFFER_METALLIC 3
 #define HL_OUTPUT_BUFFER_EMISSIVE 4
 HL_API hl_status hl_render_output_buffer(hl_context ctx, const hl_push_constants* pc, int output_buffer, float* rgba32f_host);
+/* ray debug view: PathIntegrator::gather_debug_rays (src/engine/gfx/path_integrator.cpp:88-104) + the RAY_DEBUG_VIEW variant
+ * of the pipeline (:259-307; path_trace_rgen.glsl:137-147,193-195, path_trace_rchit.glsl:500-514,548-567,
+ * path_trace_rmiss.glsl:40-58) + the vertex / draw-argument buffers of Renderer::create_ray_debug_buffers
+ * (src/engine/gfx/renderer.cpp:1473-1479).  num_debug_rays paths (launch ids (tile x + i, tile y)) start through pixel
+ * pc->ray_debug_pixel_coord.xy (extent .zw), are never ended by Russian roulette, and every ray after the primary one
+ * leaves a line segment = two vertices (origin; hit point, or origin + direction * 10000 on a miss) in the path's colour.
+ * Writes min(*vertex_count, max_vertices) vertices (segment order is unspecified, as in the reference: atomicAdd);
+ * *vertex_count is the full count (the reference's DebugRayDrawArgs.count; its buffer holds MAX_DEBUG_RAY_DRAW_COUNT * 2
+ * = 2048 vertices, include/gfx/renderer.h:9).  Synchronous. */
+typedef struct hl_debug_ray_vertex
+{
+    float position[4];
+    float color[4];
+} hl_debug_ray_vertex; /* 32 B, DebugRayVertex common.glsl:54-58 */
+HL_API hl_status hl_gather_debug_rays(hl_context ctx, const hl_push_constants* pc, uint32_t num_debug_rays,
+                                      hl_debug_ray_vertex* vertices_host, uint32_t max_vertices, uint32_t* vertex_count);
 /* generic closest-hit / visibility query on caller-supplied rays (8 floats per ray: o.xyz, tmin, d.xyz, tmax);
  * flags: bit0 = opaque (skip any-hit), bit1 = terminate on first hit. hit = 6 x 4 B per ray:
  * t,u,v (float) instance,geometry,primitive (u32). */

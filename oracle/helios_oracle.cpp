@@ -708,6 +708,7 @@ struct PathTracePayload // common.glsl:26-35
     vec3     L, T;
     uint32_t depth;
     RNG      rng;
+    vec3     debug_color; // RAY_DEBUG_VIEW only (common.glsl:32-34)
 };
 struct Counters
 {
@@ -718,7 +719,16 @@ struct TraceCtx
     const Scene*         scene;
     const PushConstants* pc;
     Counters*            counters;
+    // non-null = the RAY_DEBUG_VIEW variant of the pipeline (path_integrator.cpp:259-307): DebugRayVertexBuffer, 8 floats
+    // per vertex (position.xyz 1, color.rgb 1); DebugRayDrawArgs.count = size() / 8
+    std::vector<float>* debug_vertices = nullptr;
 };
+static void debug_ray_segment(const TraceCtx& c, const PathTracePayload& payload, vec3 a, vec3 b) // rchit:551-565, rmiss:43-57
+{
+    const float v[16] = { a.x, a.y, a.z, 1.0f, payload.debug_color.x, payload.debug_color.y, payload.debug_color.z, 1.0f,
+                          b.x, b.y, b.z, 1.0f, payload.debug_color.x, payload.debug_color.y, payload.debug_color.z, 1.0f };
+    c.debug_vertices->insert(c.debug_vertices->end(), v, v + 16);
+}
 
 static inline bool is_black(vec3 c) { return c.x == 0.0f && c.y == 0.0f && c.z == 0.0f; } // common.glsl:123-126
 static inline vec3 v3(const float* p) { return vec3(p[0], p[1], p[2]); }
@@ -904,7 +914,7 @@ static vec3 sample_light(const TraceCtx& c, PathTracePayload& payload, const Sur
     return Li * (visibility ? 1.0f : 0.0f);
 }
 
-static void closest_hit(const TraceCtx& c, PathTracePayload& payload, vec3 ray_dir, const Hit& hit);
+static void closest_hit(const TraceCtx& c, PathTracePayload& payload, vec3 ray_origin, vec3 ray_dir, const Hit& hit);
 
 // traceRayEXT on the path-trace hit group: miss shader or closest-hit shader
 static void trace_path(const TraceCtx& c, PathTracePayload& payload, vec3 origin, float tmin, vec3 dir, float tmax, uint32_t flags)
@@ -913,6 +923,11 @@ static void trace_path(const TraceCtx& c, PathTracePayload& payload, vec3 origin
     Hit h = trace(*c.scene, origin, tmin, dir, tmax, flags);
     if (!h.valid)
     {
+        if (c.debug_vertices) // rmiss:40-58: the segment of a secondary ray that leaves the scene, nothing else
+        {
+            if (payload.depth > 0) debug_ray_segment(c, payload, origin, origin + dir * tmax);
+            return;
+        }
         // path_trace_rmiss.glsl:60-65
         vec3 e = env_sample(c.scene->env, dir);
         if (payload.depth == 0)
@@ -921,7 +936,7 @@ static void trace_path(const TraceCtx& c, PathTracePayload& payload, vec3 origin
             payload.L = payload.T * e;
         return;
     }
-    closest_hit(c, payload, dir, h);
+    closest_hit(c, payload, origin, dir, h);
 }
 
 static vec3 direct_lighting(const TraceCtx& c, PathTracePayload& payload, vec3 ray_dir, const SurfaceProperties& p) // rchit:455-483
@@ -960,20 +975,25 @@ static vec3 indirect_lighting(const TraceCtx& c, PathTracePayload& payload, vec3
     PathTracePayload indirect;
     indirect.L = vec3(0.0f);
     indirect.T = payload.T * (brdf * cos_theta) / pdf;
-    // Russian roulette
-    float probability = std::fmax(indirect.T.x, std::fmax(indirect.T.y, indirect.T.z));
-    if (next_float(payload.rng) > probability) return vec3(0.0f);
-    indirect.T *= 1.0f / probability;
+    if (!c.debug_vertices) // rchit:500-509: #if !defined(RAY_DEBUG_VIEW)
+    {
+        // Russian roulette
+        float probability = std::fmax(indirect.T.x, std::fmax(indirect.T.y, indirect.T.z));
+        if (next_float(payload.rng) > probability) return vec3(0.0f);
+        indirect.T *= 1.0f / probability;
+    }
     indirect.depth = payload.depth + 1;
     indirect.rng   = payload.rng;
+    indirect.debug_color = payload.debug_color; // rchit:512-514
     trace_path(c, indirect, p.position, 0.0001f, Wi, 10000.0f, RAY_FLAG_OPAQUE);
     return indirect.L;
 }
 
-static void closest_hit(const TraceCtx& c, PathTracePayload& payload, vec3 ray_dir, const Hit& hit) // rchit:542-580
+static void closest_hit(const TraceCtx& c, PathTracePayload& payload, vec3 ray_origin, vec3 ray_dir, const Hit& hit) // rchit:542-580
 {
     SurfaceProperties p;
     populate_surface_properties(*c.scene, hit, p);
+    if (c.debug_vertices && payload.depth > 0) debug_ray_segment(c, payload, ray_origin, ray_origin + ray_dir * hit.t); // rchit:548-567
     payload.L = vec3(0.0f);
     if (payload.depth == 0 && !is_black(p.emissive)) payload.L += p.emissive;
     payload.L += direct_lighting(c, payload, ray_dir, p);
@@ -983,13 +1003,14 @@ static void closest_hit(const TraceCtx& c, PathTracePayload& payload, vec3 ray_d
 // ------------------------------------------------------------------------------------------------
 // path_trace_rgen.glsl
 // ------------------------------------------------------------------------------------------------
-static void generate_ray(const PushConstants& pc, RNG& rng, uint32_t lx, uint32_t ly, vec3& origin, vec3& direction) // rgen:132-174
+static void generate_ray(const PushConstants& pc, RNG& rng, uint32_t lx, uint32_t ly, vec3& origin, vec3& direction, bool ray_debug_view = false) // rgen:132-174
 {
     float pcx = (float)lx + 0.5f, pcy = (float)ly + 0.5f;
+    if (ray_debug_view) pcx = (float)pc.ray_debug_pixel_coord[0] + 0.5f, pcy = (float)pc.ray_debug_pixel_coord[1] + 0.5f; // rgen:137-138
     float jx  = next_float(rng);
     float jy  = next_float(rng);
-    float tcx = (pcx + jx) / (float)pc.launch_id_size[2];
-    float tcy = (pcy + jy) / (float)pc.launch_id_size[3];
+    float tcx = (pcx + jx) / (ray_debug_view ? (float)pc.ray_debug_pixel_coord[2] : (float)pc.launch_id_size[2]); // rgen:143-147
+    float tcy = (pcy + jy) / (ray_debug_view ? (float)pc.ray_debug_pixel_coord[3] : (float)pc.launch_id_size[3]);
     float nx = tcx * 2.0f - 1.0f, ny = tcy * 2.0f - 1.0f;
     vec3  cam    = v3(pc.camera_pos);
     vec4  target = mul(mat4_from(pc.view_proj_inverse), vec4(nx, ny, 0.0f, 1.0f));
@@ -1146,6 +1167,33 @@ OR_API void or_trace_primary_ids(const Scene* s, const PushConstants* pcp, uint3
             if (u) u[i] = h.valid ? h.u : 0.0f;
             if (v) v[i] = h.valid ? h.v : 0.0f;
         }
+}
+
+// PathIntegrator::gather_debug_rays (path_integrator.cpp:88-104): a num_debug_rays x 1 x 1 launch of the RAY_DEBUG_VIEW
+// pipeline; every path starts through pixel ray_debug_pixel_coord, never ends by Russian roulette, and leaves one line
+// segment per secondary ray.  Returns the vertex count (DebugRayDrawArgs.count); writes at most max_vertices.
+OR_API uint32_t or_gather_debug_rays(const Scene* s, const PushConstants* pcp, uint32_t num_debug_rays, float* out, uint32_t max_vertices)
+{
+    const PushConstants& pc = *pcp;
+    std::vector<float>   verts;
+    TraceCtx             ctx { s, &pc, nullptr };
+    ctx.debug_vertices = &verts;
+    for (uint32_t i = 0; i < num_debug_rays; i++)
+    {
+        const uint32_t lx = pc.launch_id_size[0] + i, ly = pc.launch_id_size[1]; // rgen:182
+        if (!(lx < pc.launch_id_size[2] && ly < pc.launch_id_size[3])) continue;  // rgen:185
+        PathTracePayload payload;
+        payload.L = vec3(0.0f), payload.T = vec3(1.0f), payload.depth = 0;
+        payload.rng = rng_init(lx, ly, pc.num_frames);
+        const float r = next_float(payload.rng) * 0.5f + 0.5f, g = next_float(payload.rng) * 0.5f + 0.5f, b = next_float(payload.rng) * 0.5f + 0.5f; // rgen:193-195
+        payload.debug_color = vec3(r, g, b);
+        vec3 o, d;
+        generate_ray(pc, payload.rng, lx, ly, o, d, true);
+        trace_path(ctx, payload, o, 0.001f, d, 10000.0f, 0);
+    }
+    const size_t n = verts.size() / 8;
+    if (out) std::memcpy(out, verts.data(), std::min<size_t>(n, max_vertices) * 32);
+    return (uint32_t)n;
 }
 
 // debug output buffers (debug_visualization.frag:144-161: albedo, normal * 0.5 + 0.5, roughness, metallic, emissive

@@ -178,6 +178,13 @@ class OracleScene:
         self.L.or_output_buffer(self.h, _p(pcb), C.c_int(which), _p(out))
         return out
 
+    def gather_debug_rays(self, pc, num_debug_rays: int, max_vertices: int = 2048):
+        out = np.zeros((max_vertices, 8), np.float32)
+        pcb = np.ascontiguousarray(pc)
+        self.L.or_gather_debug_rays.restype = C.c_uint32
+        n = self.L.or_gather_debug_rays(self.h, _p(pcb), C.c_uint32(num_debug_rays), _p(out), C.c_uint32(max_vertices))
+        return out[: min(n, max_vertices)], n
+
     def trace_rays(self, rays: np.ndarray, flags: int = 0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((len(rays), 6), np.float32)

@@ -10,6 +10,7 @@
 #include "../../helios_b200/csrc/hl_build.h"
 #include "../../helios_b200/csrc/hl_bvh.h"
 #include "../../helios_b200/csrc/hl_camera.h"
+#include "../../helios_b200/csrc/hl_debug.h"
 #include "../../helios_b200/csrc/hl_film.h"
 #include "../../helios_b200/csrc/hl_shade.h"
 #include <algorithm>
@@ -341,6 +342,36 @@ EM_API void em_trace_primary_ids(const EmScene* s, const hl_push_constants* pc, 
             inst[i] = h.instance, geom[i] = h.geometry, prim[i] = h.primitive;
             t[i] = hit ? h.t : hl_inf(), u[i] = hit ? h.u : 0.0f, v[i] = hit ? h.v : 0.0f;
         }
+}
+struct EmDebugOut
+{
+    float*   verts;
+    uint32_t count = 0, capacity;
+    uint32_t alloc2()
+    {
+        const uint32_t k = count;
+        count += 2;
+        return k;
+    }
+    void put(uint32_t k, f3 p, f3 c)
+    {
+        if (k >= capacity) return;
+        float* q = verts + (size_t)k * 8;
+        q[0] = p.x, q[1] = p.y, q[2] = p.z, q[3] = 1.0f, q[4] = c.x, q[5] = c.y, q[6] = c.z, q[7] = 1.0f;
+    }
+};
+EM_API uint32_t em_gather_debug_rays(const EmScene* s, const hl_push_constants* pc, uint32_t n, float* out, uint32_t max_vertices)
+{
+    EmDebugOut o;
+    o.verts = out, o.capacity = max_vertices;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        u2        fast[HL_STACK_FAST];
+        TravStack st;
+        st.fast = fast, st.stride = 1, st.sp = 0;
+        debug_ray_path(s->view, *pc, i, true, st, o);
+    }
+    return o.count;
 }
 EM_API void em_output_buffer(const EmScene* s, const hl_push_constants* pc, int which, float* out)
 {

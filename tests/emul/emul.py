@@ -104,6 +104,13 @@ class EmulScene:
         lib().em_output_buffer(self.h, _p(pcb), C.c_int(which), _p(out))
         return out
 
+    def gather_debug_rays(self, pc, num_debug_rays, max_vertices=2048):
+        out = np.zeros((max_vertices, 8), np.float32)
+        pcb = np.ascontiguousarray(pc)
+        lib().em_gather_debug_rays.restype = C.c_uint32
+        n = lib().em_gather_debug_rays(self.h, _p(pcb), C.c_uint32(num_debug_rays), _p(out), C.c_uint32(max_vertices))
+        return out[: min(n, max_vertices)], n
+
     def trace_rays(self, rays, flags=0):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((len(rays), 6), np.float32)

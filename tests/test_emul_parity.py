@@ -171,3 +171,30 @@ def test_debug_output_buffers(name, oracle_mod, emul):
     if all(int(m["texture_indices0"][2]) == -1 for m in mats):  # constant roughness: the view shows the table's value, un-floored
         vals = {np.float32(m["roughness_metallic"][0]) for m in mats}
         assert set(np.unique(rough[hit][:, 0])) <= vals
+
+
+@pytest.mark.parametrize("name", ["cornell", "terrain", "foliage", "city"])
+def test_ray_debug_view(name, oracle_mod, emul):
+    """SURVEY §8 f4: PathIntegrator::gather_debug_rays — the RAY_DEBUG_VIEW pipeline (no Russian roulette, one line segment
+    per secondary ray through one pixel)"""
+    s = SCENES[name]()
+    o, e = pair(s, oracle_mod, emul)
+    # a pixel that sees geometry (the push constant holds (x, H - y): path_integrator.cpp:146)
+    hit = o.trace_primary_ids(s.push_constants(3))[0].reshape(s.height, s.width) != abi.MISS_ID
+    ys, xs = np.nonzero(hit)
+    k = len(ys) // 2
+    pc = s.push_constants(3, pixel_coord=(int(xs[k]), s.height - int(ys[k])), max_ray_bounces=5)
+    a, na = o.gather_debug_rays(pc, 40)
+    b, nb = e.gather_debug_rays(pc, 40)
+    assert na == nb and na % 2 == 0 and na > 0
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-5)  # same hits, same random numbers; fp contraction differences only
+    seg = a.reshape(-1, 2, 8)
+    assert np.array_equal(seg[:, 0, 4:], seg[:, 1, 4:]) and np.all(seg[..., 3] == 1.0) and np.all(seg[..., 7] == 1.0)
+    assert np.all((seg[..., 4:7] >= 0.5) & (seg[..., 4:7] < 1.0))  # rgen:193-195: next_float * 0.5 + 0.5
+    # no Russian roulette: a path that keeps hitting geometry leaves max_ray_bounces - 1 segments, each starting where the
+    # previous one ended (the indirect ray starts at the hit position, rchit:521)
+    colours, counts = np.unique(seg[:, 0, 4:7], axis=0, return_counts=True)
+    assert counts.max() <= 4 and len(colours) <= 40
+    # capacity: the count keeps growing past the buffer like the reference's draw argument, writes stop
+    c, nc = e.gather_debug_rays(pc, 40, max_vertices=6)
+    assert nc == nb and len(c) == 6 and np.array_equal(c, b[:6])

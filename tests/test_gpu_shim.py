@@ -115,3 +115,21 @@ def test_output_buffer_views(tmp_path):
     seen = np.unique(img[..., :3].reshape(-1, 3), axis=0)
     assert 3 <= len(seen) <= len(table)
     assert all(np.abs(table - c).max(-1).min() < 1e-6 for c in seen)  # the two hosts' tables agree to float rounding
+
+
+def test_ray_debug_view_through_renderer(tmp_path):
+    """Renderer::add_ray_debug_view -> render() -> PathIntegrator::gather_debug_rays (renderer.cpp:229-250): segments of
+    25 paths through the image centre, 7 bounces (the integrator's default), consecutive segments of a path chained"""
+    s = scenes.cornell_box(96, 96)
+    f = tmp_path / "rays.f32"
+    headless_render(s, tmp_path, 1, extra=("--ray-debug", "48", "48", "25", "--dump-ray-debug", str(f)))
+    v = np.fromfile(f, np.float32).reshape(-1, 2, 8)
+    assert 0 < len(v) <= 1024
+    assert np.array_equal(v[:, 0, 4:], v[:, 1, 4:]) and np.all(v[..., 3] == 1.0)
+    colours = np.unique(v[:, 0, 4:7], axis=0)
+    assert len(colours) <= 25 and np.all((colours >= 0.5) & (colours < 1.0))
+    for c in colours[:5]:  # inside the closed box every secondary ray hits: each segment starts where another one ended
+        seg = v[(v[:, 0, 4:7] == c).all(-1)]
+        starts, ends = seg[:, 0, :3], seg[:, 1, :3]
+        linked = [(np.abs(ends - st).max(-1) < 1e-4).any() for st in starts]
+        assert sum(linked) >= len(seg) - 1
