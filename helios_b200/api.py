@@ -27,6 +27,11 @@ class Context:
         self.meshes = []
         self._keep = []
 
+    def resize(self, width: int, height: int):
+        """Renderer::on_window_resize: new extent, accumulation cleared; meshes, textures and tables stay"""
+        self._chk(self.lib.hl_context_resize(self.h, C.c_uint32(width), C.c_uint32(height)))
+        self.width, self.height = width, height
+
     def close(self):
         if self.h:
             self.lib.hl_context_destroy(self.h)

@@ -611,7 +611,8 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
     fp.lw = lw, fp.lh = lh;
     const uint32_t n = lw * lh;
     if (n == 0) return;
-    const uint32_t bounces = std::min<uint32_t>(pc.max_ray_bounces, HL_MAX_BOUNCES);
+    // max_ray_bounces = 0 still traces and shades the primary ray (rgen:205; the closest-hit shader only skips the indirect ray)
+    const uint32_t bounces = std::max<uint32_t>(1u, std::min<uint32_t>(pc.max_ray_bounces, HL_MAX_BOUNCES));
     const bool     prof    = ctx->profiling;
     const bool     piped   = ctx->pipeline && ctx->n_slots > 1 && !prof;
     if (!piped) wavefront_join(ctx);

@@ -458,7 +458,7 @@ EM_API void em_render_frame(const EmScene* sc, const hl_push_constants* pcp, uin
     }
     ShadeParams prm;
     prm.num_lights = pc.num_lights, prm.max_ray_bounces = pc.max_ray_bounces, prm.shadow_ray_bias = pc.shadow_ray_bias;
-    for (uint32_t depth = 0; depth < pc.max_ray_bounces && !q.empty(); depth++)
+    for (uint32_t depth = 0; depth < std::max(1u, pc.max_ray_bounces) && !q.empty(); depth++)
     {
         const uint32_t ext_flags = depth == 0 ? 0u : HL_RAY_OPAQUE;
         const float    ext_tmin  = depth == 0 ? 0.001f : 0.0001f;

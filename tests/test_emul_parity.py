@@ -198,3 +198,12 @@ def test_ray_debug_view(name, oracle_mod, emul):
     # capacity: the count keeps growing past the buffer like the reference's draw argument, writes stop
     c, nc = e.gather_debug_rays(pc, 40, max_vertices=6)
     assert nc == nb and len(c) == 6 and np.array_equal(c, b[:6])
+
+
+@pytest.mark.parametrize("bounces", [0, 1, 2])
+def test_bounce_limits(bounces, oracle_mod, emul):
+    """max_ray_bounces = 0 still traces and shades the primary ray (rgen:205, rchit:575 only guards the indirect ray)"""
+    s = SCENES["cornell"]()
+    o, e = pair(s, oracle_mod, emul)
+    a, b = o.render(3, max_ray_bounces=bounces), e.render(3, max_ray_bounces=bounces)
+    assert np.abs(a - b)[..., :3].max() < 2e-6 and a[..., :3].max() > 0

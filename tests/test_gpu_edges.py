@@ -1,0 +1,192 @@
+"""GPU: edge cases of the path against the oracle through the C ABI — empty and tiny meshes, coincident and degenerate
+triangles (tie rule), no lights, the instance limit of the reference (scene.h:14-17), odd image extents and clipped
+tiles, bounce limits, axis-parallel rays, context resize, frames-in-flight settings."""
+import numpy as np
+import pytest
+
+from helios_b200 import abi, scenes
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+@pytest.fixture(scope="module")
+def api():
+    from helios_b200 import api as a
+
+    return a
+
+
+def ids_equal(g, r):
+    return all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(g, r))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 9, 33])
+def test_tiny_meshes(n, api, oracle_mod):
+    s = scenes.triangle_soup(max(n, 1), 48, 27, seed=100 + n)
+    if n == 0:  # empty geometry: a submesh with zero triangles
+        s.meshes[0].submeshes[0]["index_count"] = 0
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    pc = s.push_constants(1)
+    assert ids_equal(ctx.trace_primary_ids(pc), o.trace_primary_ids(pc))
+    a, b = ctx.render(s, 3), o.render(3)
+    assert np.abs(a - b)[..., :3].max() < 1e-4
+    ctx.close()
+
+
+def test_coincident_and_degenerate_triangles(api, oracle_mod):
+    """equal t -> the lexicographically smallest (instance, geometry, primitive) wins, whatever the tree; zero-area
+    triangles are never hit"""
+    s = scenes.triangle_soup(300, 64, 36, seed=7)
+    m = s.meshes[0]
+    v, idx = m.vertices, m.indices
+    # triangles 100..199 become exact copies of 0..99 (same vertices through the index buffer); 200..249 collapse to a point / a line
+    idx[300:600] = idx[0:300]
+    v["position"][idx[600:675], :3] = v["position"][idx[600], :3]
+    for t in range(225, 250):
+        v["position"][idx[3 * t + 2], :3] = 0.5 * (v["position"][idx[3 * t], :3] + v["position"][idx[3 * t + 1], :3])
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    for frame in (0, 1, 2):
+        pc = s.push_constants(frame)
+        g, r = ctx.trace_primary_ids(pc), o.trace_primary_ids(pc)
+        assert ids_equal(g, r)
+        prim = g[2][g[0] != abi.MISS_ID]
+        assert not np.any((prim >= 100) & (prim < 200)), "a duplicate with the larger primitive id won a tie"
+        assert not np.any((prim >= 200) & (prim < 225)), "a point-sized triangle was hit"
+    ctx.close()
+
+
+def test_no_lights(api, oracle_mod):
+    """num_lights = 0: next_uint(rng, 0) = 0 indexes an empty table; the term is multiplied by num_lights = 0 (SURVEY C-4)"""
+    s = scenes.cornell_box(64, 64)
+    s.lights = s.lights[:0]
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    a, b = ctx.render(s, 4), o.render(4)
+    assert np.isfinite(a).all() and np.abs(a - b)[..., :3].max() < 1e-4
+    assert a[..., :3].max() > 0  # the emissive quad is still seen directly
+    ctx.close()
+
+
+def test_instance_limit_1024(api, oracle_mod):
+    """MAX_SCENE_MESH_INSTANCE_COUNT = 1024 (include/resource/scene.h:14): a full table of instances of two small meshes"""
+    s = scenes.city_scene(n_instances=1023, n_meshes=2, width=96, height=54, floors=(1, 2), detail=(1, 1))  # + the ground instance
+    assert len(s.instances) == 1024
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s)
+    pc = s.push_constants(1)
+    g, r = ctx.trace_primary_ids(pc), o.trace_primary_ids(pc)
+    same = (g[0] == r[0]) & (g[1] == r[1]) & (g[2] == r[2])
+    assert same.mean() >= 1 - 1e-4
+    assert len(np.unique(g[0][g[0] != abi.MISS_ID])) > 20
+    ctx.close()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 5), (257, 3), (130, 129)])
+def test_odd_extents_and_clipped_tiles(w, h, api, oracle_mod):
+    s = scenes.cornell_box(w, h)
+    ctx = api.Context(w, h)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    pc = s.push_constants(1)
+    assert ids_equal(ctx.trace_primary_ids(pc), o.trace_primary_ids(pc))
+    full = ctx.render(s, 3)
+    assert np.abs(full - o.render(3))[..., :3].max() < 1e-4
+    # 128^2 tiles like PathIntegrator::compute_tile_coords; the last row / column of tiles hangs over the image edge
+    ctx.accum_clear()
+    for f in range(3):
+        for ty in range(0, h, 128):
+            for tx in range(0, w, 128):
+                ctx.render_frame(s.push_constants(f, tile=(tx, ty)), launch=(128, 128))
+    assert np.array_equal(ctx.read_accum(), full)
+    ctx.close()
+
+
+@pytest.mark.parametrize("bounces", [0, 1, 2, 64, 100])
+def test_bounce_limits(bounces, api, oracle_mod):
+    """max_ray_bounces = 0 still traces the primary ray (the raygen shader does, rgen:205); 1 = direct light only; more
+    than 64 is refused (HL_ERR_LIMIT; the reference's UI offers 1..8)"""
+    s = scenes.cornell_box(48, 48)
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    if bounces > 64:
+        from helios_b200._lib import HeliosError
+
+        with pytest.raises(HeliosError, match="max_ray_bounces > 64"):
+            ctx.render_frame(s.push_constants(0, max_ray_bounces=bounces))
+        ctx.close()
+        return
+    ctx.accum_clear()
+    acc = np.zeros((s.height, s.width, 4), np.float32)
+    acc[..., 3] = 1.0
+    for f in range(3):
+        pc = s.push_constants(f, max_ray_bounces=bounces)
+        ctx.render_frame(pc)
+        o.render_frame(pc, acc)  # in place
+    a = ctx.read_accum()
+    assert np.abs(a - acc)[..., :3].max() < 1e-4, float(np.abs(a - acc)[..., :3].max())
+    ctx.close()
+
+
+@pytest.mark.parametrize("flags", [0, 1, 3])
+def test_axis_parallel_and_grazing_rays(flags, api, oracle_mod):
+    s = scenes.foliage_scene(n_clusters=40, cards_per_cluster=10, width=32, height=18, ground_grid=6, tex_size=16)
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s)
+    rng = np.random.default_rng(10 + flags)
+    n = 20000
+    org = (rng.random((n, 3)) - 0.5) * np.array([50, 4, 50]) + np.array([0, 4, 0])
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[::7] = np.eye(3)[rng.integers(0, 3, len(d[::7]))] * rng.choice([-1.0, 1.0], (len(d[::7]), 1))  # exactly along an axis
+    d[1::50, 0] = 0.0
+    d[2::77, 1] = 1e-12
+    d[3::91, 1] = -0.0
+    org[4::13, 1] = 0.0  # origins on the ground plane
+    rays = np.concatenate([org, np.full((n, 1), 1e-3), d, np.full((n, 1), 30.0)], 1).astype(np.float32)
+    rays[5::101, 7] = 0.0  # empty interval: tmax < tmin
+    a, b = ctx.trace_rays(rays, flags), o.trace_rays(rays, flags)
+    if flags & 2:  # terminate on first hit: only hit / miss is defined
+        assert np.array_equal(np.isinf(a[:, 0]), np.isinf(b[:, 0]))
+    else:
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.isfinite(a[:, 0]).mean() > 0.05
+    ctx.close()
+
+
+def test_resize_and_frames_in_flight(api, oracle_mod):
+    """hl_context_resize (Renderer::on_window_resize) and HL_OPT_FRAMES_IN_FLIGHT 1..8: same image for every setting,
+    ray counters survive a change of the setting, bad values are refused"""
+    from helios_b200._lib import HeliosError
+
+    s0 = scenes.cornell_box(40, 40)
+    ctx = api.Context(s0.width, s0.height)
+    ctx.load_scene(s0)
+    ctx.render(s0, 2)
+    s = scenes.cornell_box(96, 64)
+    ctx.resize(s.width, s.height)
+    ref = None
+    total = 0
+    ctx.reset_counters()
+    for n in (4, 1, 8, 2, 3):
+        ctx.set_option(abi.OPT_FRAMES_IN_FLIGHT, n)
+        a = ctx.render(s, 9)
+        total += 9
+        if ref is None:
+            ref = a
+            assert np.abs(a - oracle_mod.OracleScene(s, brute_force=True).render(9))[..., :3].max() < 1e-4
+        else:
+            assert np.array_equal(a, ref), n
+        c = ctx.counters()
+        assert int(c["extension_rays"]) >= total * s.width * s.height
+    for bad in (0, 9, -1):
+        with pytest.raises(HeliosError):
+            ctx.set_option(abi.OPT_FRAMES_IN_FLIGHT, bad)
+    ctx.close()
