@@ -33,7 +33,17 @@ namespace hl
 #ifndef HL_TRACE_GRID_MULT
 #define HL_TRACE_GRID_MULT 8 /* persistent trace kernels: CTAs launched per SM */
 #endif
+#ifndef HL_SHADE_BLOCK
 #define HL_SHADE_BLOCK 128
+#endif
+#ifdef HL_SHADE_MIN_BLOCKS
+#define HL_SHADE_BOUNDS __launch_bounds__(HL_SHADE_BLOCK, HL_SHADE_MIN_BLOCKS)
+#else
+#define HL_SHADE_BOUNDS __launch_bounds__(HL_SHADE_BLOCK)
+#endif
+#ifndef HL_SHADE_GRID_MULT
+#define HL_SHADE_GRID_MULT 8
+#endif
 
 struct FrameParams
 {
@@ -151,7 +161,7 @@ __device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* counter, ui
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
-__global__ void __launch_bounds__(HL_SHADE_BLOCK) k_shade(SceneView s, ShadeParams prm, uint32_t depth, const uint32_t* __restrict__ count_ptr, const float4* __restrict__ ray_o,
+__global__ void HL_SHADE_BOUNDS k_shade(SceneView s, ShadeParams prm, uint32_t depth, const uint32_t* __restrict__ count_ptr, const float4* __restrict__ ray_o,
                                                           const float4* __restrict__ ray_d, const float4* __restrict__ hit_a, const uint2* __restrict__ hit_b, float4* state_a,
                                                           float4* state_b, float4* next_o, float4* next_d, uint32_t* next_count, float4* sh_o, float4* sh_d, float4* sh_c,
                                                           uint32_t* sh_count)
@@ -564,7 +574,7 @@ static void run_bounces(hl_context_t* ctx, hl_wave_slot& w, cudaStream_t st, con
 {
     uint32_t*    ctr  = w.counters.as<uint32_t>();
     const int    tgrid = ctx->sm_count * HL_TRACE_GRID_MULT; // persistent trace kernels
-    const int    sgrid = ctx->sm_count * 8;
+    const int    sgrid = ctx->sm_count * HL_SHADE_GRID_MULT;
     ShadeParams  prm;
     prm.num_lights = fp.pc.num_lights, prm.max_ray_bounces = fp.pc.max_ray_bounces, prm.shadow_ray_bias = fp.pc.shadow_ray_bias;
     const bool prof = ctx->profiling;

@@ -213,6 +213,47 @@ class GlslRefScene(OracleScene):
         self.L.ref_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), _p(accum), _p(accum), _p(self.counters))
 
 
+_REF_DEBUG_PATH = _HERE / "_ref" / "libhelios_glsl_ref_raydebug.so"
+_ref_debug_lib = None
+
+
+def ref_debug_lib():
+    """ctypes handle of the RAY_DEBUG_VIEW build of the reference's shaders (oracle/_ref/libhelios_glsl_ref_raydebug.so:
+    the same sources compiled with -DRAY_DEBUG_VIEW, as path_integrator.cpp:259-307 builds its second pipeline), or None"""
+    global _ref_debug_lib
+    if _ref_debug_lib is None:
+        build_ref()
+        if not _REF_DEBUG_PATH.exists():
+            return None
+        _ref_debug_lib = C.CDLL(str(_REF_DEBUG_PATH))
+        _ref_debug_lib.or_scene_new.restype = C.c_void_p
+        _ref_debug_lib.or_scene_add_mesh.restype = C.c_int
+        _ref_debug_lib.or_scene_add_texture.restype = C.c_int
+        _ref_debug_lib.ref_gather_debug_rays.restype = C.c_uint32
+        _ref_debug_lib.or_gather_debug_rays.restype = C.c_uint32
+    return _ref_debug_lib
+
+
+class GlslRefDebugScene(OracleScene):
+    """The scene under the reference's RAY_DEBUG_VIEW pipeline: gather_debug_rays runs the reference's own shader files
+    (compiled with that define); `restated_debug_rays` runs the restatement inside the same library."""
+
+    def __init__(self, scene, **kw):
+        L = ref_debug_lib()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libhelios_glsl_ref_raydebug.so is not available (no /root/reference and no prebuilt copy)")
+        super().__init__(scene, library=L, **kw)
+
+    def gather_debug_rays(self, pc, num_debug_rays: int, max_vertices: int = 2048):
+        out = np.zeros((max_vertices, 8), np.float32)
+        pcb = np.ascontiguousarray(pc)
+        n = self.L.ref_gather_debug_rays(self.h, _p(pcb), C.c_uint32(num_debug_rays), _p(out), C.c_uint32(max_vertices))
+        return out[: min(n, max_vertices)], n
+
+    def restated_debug_rays(self, pc, num_debug_rays: int, max_vertices: int = 2048):
+        return OracleScene.gather_debug_rays(self, pc, num_debug_rays, max_vertices)
+
+
 def ref_tonemap(accum: np.ndarray, exposure=1.0, op=0) -> np.ndarray:
     H, W = accum.shape[:2]
     out = np.zeros((H, W, 4), np.uint8)

@@ -38,6 +38,19 @@ void ref_drv_texture2d(int index, float u, float v, float* out4);
 void ref_drv_texture_cube(const float* dir3, float* out4);
 void ref_drv_trace(uint32_t flags, uint32_t sbt_offset, uint32_t miss_index, const float* origin3, float tmin, const float* dir3, float tmax, void* payload);
 
+// RAY_DEBUG_VIEW builds: descriptor set 5 (DebugRayVertexBuffer / DebugRayDrawArgs, rchit:64-77) is ONE pair of storage
+// buffers shared by every stage; the generated per-stage declarations are routed to these two blocks (stage_common.h)
+struct RefDebugVertexBlock
+{
+    void* vertices; // DebugRayVertex[] (2 x vec4)
+};
+struct RefDebugDrawArgs
+{
+    uint32_t count, instance_count, first, base_instance;
+};
+RefDebugVertexBlock* ref_drv_debug_vertex_block();
+RefDebugDrawArgs*    ref_drv_debug_draw_args();
+
 // stage entry points (stage_*.cpp)
 void ref_rgen_bind(const RefBindings* b);
 void ref_rgen_invoke(uint32_t launch_x, uint32_t launch_y);

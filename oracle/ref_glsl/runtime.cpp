@@ -52,6 +52,39 @@ extern "C" void ref_drv_trace(uint32_t flags, uint32_t sbt_offset, uint32_t miss
         ref_shadow_rmiss_invoke(payload);
 }
 
+// descriptor set 5 of the RAY_DEBUG_VIEW pipeline: one vertex buffer + one draw-argument block for all stages
+static RefDebugVertexBlock g_debug_vertex_block = { nullptr };
+static RefDebugDrawArgs    g_debug_draw_args    = { 0, 1, 0, 0 }; // renderer.cpp:236
+extern "C" RefDebugVertexBlock* ref_drv_debug_vertex_block() { return &g_debug_vertex_block; }
+extern "C" RefDebugDrawArgs*    ref_drv_debug_draw_args() { return &g_debug_draw_args; }
+
+#if defined(RAY_DEBUG_VIEW)
+// PathIntegrator::gather_debug_rays (path_integrator.cpp:88-104): launch_rays(ray-debug pipeline, num_debug_rays, 1, 1):
+// same framing as or_gather_debug_rays.  `out` must hold max_vertices vertices of 8 floats; the shaders do not check the
+// capacity (nor does the reference: its buffer has room for 2048), so the launch runs into a scratch buffer sized for the
+// worst case (max_ray_bounces segments per path) and min(count, max_vertices) vertices are copied out.
+OR_API uint32_t ref_gather_debug_rays(const Scene* s, const PushConstants* pcp, uint32_t num_debug_rays, float* out, uint32_t max_vertices)
+{
+    std::vector<void*> vb, ib, sb;
+    for (auto m : s->meshes) vb.push_back((void*)m->verts.data()), ib.push_back((void*)m->indices.data());
+    for (auto& t : s->submesh_info) sb.push_back((void*)t.data());
+    RefBindings b;
+    b.materials = s->materials.data(), b.instances = s->instances.data(), b.lights = s->lights.data();
+    b.vertices = vb.data(), b.indices = ib.data(), b.submesh_info = sb.data();
+    b.previous_color = nullptr, b.current_color = nullptr, b.width = (int)pcp->launch_id_size[2], b.height = (int)pcp->launch_id_size[3], b.push_constants = pcp;
+    g_ref_scene = s;
+    ref_rgen_bind(&b), ref_rchit_bind(&b), ref_rahit_bind(&b);
+    std::vector<float> scratch((size_t)num_debug_rays * (pcp->max_ray_bounces + 1) * 2 * 8 + 16);
+    g_debug_vertex_block.vertices = scratch.data();
+    g_debug_draw_args             = { 0, 1, 0, 0 };
+    for (uint32_t i = 0; i < num_debug_rays; i++) ref_rgen_invoke(i, 0);
+    const uint32_t n = g_debug_draw_args.count;
+    if (out) std::memcpy(out, scratch.data(), (size_t)std::min(n, max_vertices) * 32);
+    g_debug_vertex_block.vertices = nullptr;
+    return n;
+}
+#endif
+
 // same signature and semantics as or_render_frame (minus raw_L): one launch of the ray-tracing pipeline
 OR_API void ref_render_frame(const Scene* s, const PushConstants* pcp, uint32_t lw, uint32_t lh, const float* prev, float* cur, uint64_t* counters)
 {

@@ -14,6 +14,7 @@ static thread_local bool t_ignored;
 #define main glsl_main
 #include "path_trace_rahit.glsl.inc"
 #undef main
+GLSL_DEBUG_BLOCKS
 } // namespace rahit
 } // namespace glsl
 

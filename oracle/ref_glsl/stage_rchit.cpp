@@ -6,11 +6,14 @@ namespace rchit
 {
 static thread_local int  gl_InstanceCustomIndexEXT, gl_GeometryIndexEXT, gl_PrimitiveID;
 static thread_local vec3 gl_WorldRayDirectionEXT;
+static thread_local vec3 gl_WorldRayOriginEXT; // the two below are only read by the RAY_DEBUG_VIEW blocks (rchit:548-567)
+static thread_local float gl_HitTEXT;
 /* layout(location = 1) p_IndirectPayload, layout(location = 2) p_Visibility, rchit:123-125 */
 #define GLSL_PAYLOAD_AT(loc) ((loc) == 1 ? (void*)&p_IndirectPayload : (void*)&p_Visibility)
 #define main glsl_main
 #include "path_trace_rchit.glsl.inc"
 #undef main
+GLSL_DEBUG_BLOCKS
 static_assert(sizeof(PathTraceConsts) == 192 && sizeof(Instance) == 144 && sizeof(Vertex) == 80 && sizeof(Material) == 80 && sizeof(Light) == 64, "std430 layout");
 } // namespace rchit
 } // namespace glsl
@@ -36,7 +39,8 @@ extern "C" void ref_rchit_invoke(void* payload, const RefHit* hit, const RefRay*
     const bool             s_vis  = p_Visibility;
     const glsl::vec2       s_attr = b_HitAttribs;
     const int              s_i = gl_InstanceCustomIndexEXT, s_g = gl_GeometryIndexEXT, s_p = gl_PrimitiveID;
-    const glsl::vec3       s_d = gl_WorldRayDirectionEXT;
+    const glsl::vec3       s_d = gl_WorldRayDirectionEXT, s_o = gl_WorldRayOriginEXT;
+    const float            s_t = gl_HitTEXT;
 
     p_PathTracePayload        = *(const PathTracePayload*)payload;
     b_HitAttribs              = glsl::vec2(hit->u, hit->v);
@@ -44,10 +48,12 @@ extern "C" void ref_rchit_invoke(void* payload, const RefHit* hit, const RefRay*
     gl_GeometryIndexEXT       = (int)hit->geometry;
     gl_PrimitiveID            = (int)hit->primitive;
     gl_WorldRayDirectionEXT   = glsl::vec3(ray->direction[0], ray->direction[1], ray->direction[2]);
+    gl_WorldRayOriginEXT      = glsl::vec3(ray->origin[0], ray->origin[1], ray->origin[2]);
+    gl_HitTEXT                = hit->t;
     glsl_main();
     const PathTracePayload out = p_PathTracePayload;
 
     p_PathTracePayload = s_in, p_IndirectPayload = s_indirect, p_Visibility = s_vis, b_HitAttribs = s_attr;
-    gl_InstanceCustomIndexEXT = s_i, gl_GeometryIndexEXT = s_g, gl_PrimitiveID = s_p, gl_WorldRayDirectionEXT = s_d;
+    gl_InstanceCustomIndexEXT = s_i, gl_GeometryIndexEXT = s_g, gl_PrimitiveID = s_p, gl_WorldRayDirectionEXT = s_d, gl_WorldRayOriginEXT = s_o, gl_HitTEXT = s_t;
     *(PathTracePayload*)payload = out;
 }

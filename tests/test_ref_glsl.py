@@ -99,6 +99,18 @@ def test_product_sky_fit_matches_reference_host_code():
         np.testing.assert_allclose(np.asarray(cf, np.float32).ravel(), GOLD[f"sky/coeffs/{k}"], rtol=2e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", list(G.GOLDEN_SCENES))
+def test_restatement_reproduces_reference_ray_debug_view(name, oracle_mod):
+    """gather_debug_rays: the restatement of the RAY_DEBUG_VIEW blocks against the committed output of the reference's shaders
+    compiled with that define (same vertices, same order: both run the launch sequentially, depth first)"""
+    s = G.GOLDEN_SCENES[name]()
+    o = oracle_mod.OracleScene(s, sky_size=G.GOLDEN_SKY_SIZE)
+    v, n = o.gather_debug_rays(G.raydebug_push_constants(s, o), G.RAYDEBUG_RAYS, max_vertices=4096)
+    gold = GOLD[f"raydebug/{name}"]
+    assert n == len(gold) and same_bits(v, gold)
+    assert name in ("soup",) or n > 0
+
+
 # ---- side-by-side layer: needs the reference-GLSL library ---------------------------------------------------------
 def test_golden_file_is_current(ref, oracle_mod):
     """the committed fixture is what the reference shaders produce today (guards against a stale .npz)"""
@@ -124,6 +136,24 @@ def test_side_by_side_frames_bit_identical(name, ref, oracle_mod):
         r.restated_frame(pc, b)
         assert same_bits(a, b), f"{name} frame {f}: max |diff| {np.abs(a - b).max()}"
     assert np.array_equal(r.counters, r.restated_counters)
+
+
+@pytest.mark.parametrize("name", ["cornell", "terrain_textured", "foliage", "city"])
+def test_side_by_side_ray_debug_view(name, oracle_mod):
+    """the reference's shaders built with -DRAY_DEBUG_VIEW (oracle/_ref/libhelios_glsl_ref_raydebug.so) vs the restatement in
+    the same library: every vertex bit-identical, for several pixels, frames and bounce limits"""
+    if oracle_mod.ref_debug_lib() is None:
+        pytest.skip("oracle/_ref/libhelios_glsl_ref_raydebug.so not available")
+    s = G.GOLDEN_SCENES[name]()
+    r = oracle_mod.GlslRefDebugScene(s, sky_size=G.GOLDEN_SKY_SIZE)
+    total = 0
+    for frame, bounces, px in ((0, 1, (3, 5)), (2, 4, (s.width // 2, s.height // 2)), (9, 8, (s.width // 3, s.height - 4)), (4, 6, (s.width - 2, 2 * s.height // 3))):
+        pc = s.push_constants(frame, pixel_coord=px, max_ray_bounces=bounces)
+        a, na = r.gather_debug_rays(pc, 48, max_vertices=8192)
+        b, nb = r.restated_debug_rays(pc, 48, max_vertices=8192)
+        assert na == nb and same_bits(a, b), f"{name} frame {frame}: {na} vs {nb}"
+        total += na
+    assert total > 0
 
 
 def test_side_by_side_tiles_and_depths(ref, oracle_mod):

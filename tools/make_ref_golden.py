@@ -34,6 +34,17 @@ RNG_SEEDS = [(1, 2), (123456789, 987654321), (0xDEADBEEF, 0x12345678), (42, 4242
 SKY_CASES = [((0.0, 0.7071068, 0.7071068), 4.0, 0.1, 1.15), ((0.3, 0.2, -0.9327379), 2.5, 0.3, 1.15), ((0.0, 1.0, 0.0), 7.75, 0.0, 0.0), ((0.6, -0.1, 0.7937254), 4.0, 0.1, 1.15)]
 
 
+RAYDEBUG_RAYS, RAYDEBUG_BOUNCES, RAYDEBUG_FRAME = 24, 5, 3
+
+
+def raydebug_push_constants(s, oracle_scene):
+    """the push constants of a gather_debug_rays launch through a pixel of `s` that sees geometry"""
+    hit = oracle_scene.trace_primary_ids(s.push_constants(RAYDEBUG_FRAME))[0].reshape(s.height, s.width) != 0xFFFFFFFF
+    ys, xs = np.nonzero(hit)
+    k = len(ys) // 2
+    return s.push_constants(RAYDEBUG_FRAME, pixel_coord=(int(xs[k]), s.height - int(ys[k])), max_ray_bounces=RAYDEBUG_BOUNCES)
+
+
 def brdf_cases():
     rng = np.random.default_rng(11)
     out = []
@@ -97,6 +108,14 @@ def main():
     img = tonemap_image()
     for op in (0, 1, 2):
         g[f"tonemap/{op}"] = oracle.ref_tonemap(img, 0.8, op)
+    # the RAY_DEBUG_VIEW build of the same shaders (second library): segment vertices of gather_debug_rays
+    if oracle.ref_debug_lib() is not None:
+        for name, mk in GOLDEN_SCENES.items():
+            s = mk()
+            r = oracle.GlslRefDebugScene(s, sky_size=GOLDEN_SKY_SIZE)
+            v, n = r.gather_debug_rays(raydebug_push_constants(s, r), RAYDEBUG_RAYS, max_vertices=4096)
+            assert n == len(v)
+            g[f"raydebug/{name}"] = v
     out = ROOT / "tests" / "golden" / "ref_glsl_golden.npz"
     np.savez_compressed(out, **g)
     print(f"wrote {out} ({out.stat().st_size} bytes, {len(g)} arrays)")

@@ -26,6 +26,16 @@ VARIANT_SETS = {
         "refill4": ["-DHL_REFILL_MIN=4"], "refill16": ["-DHL_REFILL_MIN=16"],
     },
 }
+VARIANT_SETS["sched2"] = {
+    "base": [], "tri1": ["-DHL_TRI_PER_STEP=1"], "tri3": ["-DHL_TRI_PER_STEP=3"], "tri4": ["-DHL_TRI_PER_STEP=4"], "tri24": ["-DHL_TRI_PER_STEP=24"],
+    "tmin4": ["-DHL_TRI_MIN_LANES=4"], "tmin8": ["-DHL_TRI_MIN_LANES=8"], "refill4": ["-DHL_REFILL_MIN=4"], "refill12": ["-DHL_REFILL_MIN=12"], "refill16": ["-DHL_REFILL_MIN=16"],
+    "refill1": ["-DHL_REFILL_MIN=1"], "s8": ["-DHL_STACK_FAST=8"],
+}
+VARIANT_SETS["shade"] = {
+    "base": [], "mb5": ["-DHL_SHADE_MIN_BLOCKS=5"], "mb6": ["-DHL_SHADE_MIN_BLOCKS=6"], "mb8": ["-DHL_SHADE_MIN_BLOCKS=8"],
+    "b64_mb12": ["-DHL_SHADE_BLOCK=64", "-DHL_SHADE_MIN_BLOCKS=12", "-DHL_SHADE_GRID_MULT=16"], "b256_mb3": ["-DHL_SHADE_BLOCK=256", "-DHL_SHADE_MIN_BLOCKS=3", "-DHL_SHADE_GRID_MULT=4"],
+    "g16": ["-DHL_SHADE_GRID_MULT=16"], "g4": ["-DHL_SHADE_GRID_MULT=4"],
+}
 VARIANT_SETS["slots"] = {"base": [], "slots3": ["-DHL_WAVE_SLOTS=3"], "slots2": ["-DHL_WAVE_SLOTS=2"], "slots4": ["-DHL_WAVE_SLOTS=4"], "slots6": ["-DHL_WAVE_SLOTS=6"], "mb7": ["-DHL_TRACE_MIN_BLOCKS=7"], "mb6": ["-DHL_TRACE_MIN_BLOCKS=6", "-DHL_TRACE_GRID_MULT=6"]}
 VARIANTS = VARIANT_SETS[os.environ.get("HL_TUNE_SET", "occ")]
 OUT = ROOT / "build" / "variants"
