@@ -121,6 +121,22 @@ def profiled_traffic_bytes():
         return None
 
 
+def profiled_limits():
+    """what ncu says bounds k_extend (same committed capture; first launch = bounce 0): the kernel is instruction-issue bound,
+    so the HBM fraction above is small by nature — these are the numbers that describe how close to ITS wall it runs"""
+    files = sorted((ROOT / "profiles").glob("*_extend_traffic.json"))
+    if not files:
+        return None
+    try:
+        j = json.loads(files[-1].read_text())
+        keys = ("issue_active_pct", "lanes_per_instruction", "alu_pipe_pct", "fma_pipe_pct", "dram_throughput_pct", "l2_throughput_pct", "l1_hit_pct", "l2_hit_pct", "warps_active_pct")
+        out = {k: j[k][0] for k in keys if j.get(k)}
+        out["source"] = j.get("source")
+        return out or None
+    except Exception:
+        return None
+
+
 def build_scene():
     from helios_b200 import scenes
 
@@ -301,6 +317,7 @@ def main():
         "algorithmic_bytes_per_launch": ext_rays * a_ray / max(nprof * int(scene.max_ray_bounces), 1),
         "peak_source": peak_src, "algorithmic_bytes_per_ray": a_ray, "launches_timed": nprof * int(scene.max_ray_bounces),
         "stage_share_of_frame": {"extend": ext_ms / frame_ms, "shade": sh_ms / frame_ms, "connect": con_ms / frame_ms} if frame_ms else None,
+        "ncu_bounce0": profiled_limits(),
     }
 
     # ---------------- end to end through the C ABI with host buffers ----------------

@@ -36,7 +36,15 @@ def main():
     us = [float(r[col["gpu__time_duration.sum"]]) for r in data]
     # mean over the launches that carry the step (a capture of an almost empty queue would only dilute it)
     big = [p for p, t in zip(per, us) if t > 0.05 * max(us)]
-    json.dump({"kernel": kernel, "launches": len(per), "dram_bytes_per_launch_mb": per, "duration_us": us, "mean_mb": sum(big) / len(big), "mean_over": len(big), "source": out + "_ncu_full.md"},
+    def pct(m):
+        return [float(r[col[m]]) for r in data] if m in col else None
+
+    json.dump({"kernel": kernel, "launches": len(per), "dram_bytes_per_launch_mb": per, "duration_us": us, "mean_mb": sum(big) / len(big), "mean_over": len(big), "source": out + "_ncu_full.md",
+               # what actually bounds the kernel (first captured launch = the largest one)
+               "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"), "lanes_per_instruction": pct("smsp__thread_inst_executed_per_inst_executed.ratio"),
+               "alu_pipe_pct": pct("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), "fma_pipe_pct": pct("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+               "dram_throughput_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), "l2_throughput_pct": pct("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+               "l1_hit_pct": pct("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": pct("lts__t_sector_hit_rate.pct"), "warps_active_pct": pct("sm__warps_active.avg.pct_of_peak_sustained_active")},
               open(out + "_traffic.json", "w"), indent=1)
     print("\n".join(lines))
 
