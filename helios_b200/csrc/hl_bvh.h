@@ -208,7 +208,7 @@ HL_HD bool any_hit_ignores(const SceneView& s, uint32_t inst, uint32_t geom, uin
     const float  b0 = 1.0f - bu - bv;
     const float  tu = t0[0] * b0 + t1[0] * bu + t2[0] * bv;
     const float  tv = t0[1] * b0 + t1[1] * bu + t2[1] * bv;
-    return sample_texture_lod0(s, mat.texture_indices0[0], tu, tv).w < 0.1f;
+    return sample_texture_alpha_lod0(s, mat.texture_indices0[0], tu, tv) < 0.1f;
 }
 
 // Moeller-Trumbore against one 48-byte leaf record; updates `best` per the closest-hit / tie rule.

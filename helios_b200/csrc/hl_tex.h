@@ -28,21 +28,54 @@ HL_HD f4 bilinear(f4 t00, f4 t10, f4 t01, f4 t11, float fx, float fy)
     const f4 b = t01 * (1.0f - fx) + t11 * fx;
     return a * (1.0f - fy) + b * fy;
 }
-HL_HD f4 sample_texture_lod0(const SceneView& s, int index, float u, float v)
+// REPEAT addressing of the bilinear footprint.  After u -= floor(u), u is in [0, 1] (1.0 when a tiny negative u rounds
+// up), so x = u * W - 0.5 lies in [-0.5, W - 0.5] and floor(x) in [-1, W - 1]: the wrap is one conditional add, not
+// an integer modulo (four of those were ~100 instructions per sample).
+struct TexFootprint
 {
-    if (!(fabsf(u) < 1e30f) || !(fabsf(v) < 1e30f)) return mk4(0.0f, 0.0f, 0.0f, 0.0f);
-    const TexView t = s.textures[index];
+    int   ix0, iy0, ix1, iy1;
+    float fx, fy;
+};
+HL_HD TexFootprint texture_footprint(const TexView& t, float u, float v)
+{
+    TexFootprint f;
     u -= floorf(u);
     v -= floorf(v);
     const float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
     const float x0 = floorf(x), y0 = floorf(y);
-    const float fx = x - x0, fy = y - y0;
-    const int   W = (int)t.w, H = (int)t.h;
-    int         ix0 = (int)x0, iy0 = (int)y0;
-    ix0 = ((ix0 % W) + W) % W;
-    iy0 = ((iy0 % H) + H) % H;
-    const int ix1 = (ix0 + 1) % W, iy1 = (iy0 + 1) % H;
-    return bilinear(texel_load(t, s.lut8, ix0, iy0), texel_load(t, s.lut8, ix1, iy0), texel_load(t, s.lut8, ix0, iy1), texel_load(t, s.lut8, ix1, iy1), fx, fy);
+    f.fx = x - x0, f.fy = y - y0;
+    const int W = (int)t.w, H = (int)t.h;
+    f.ix0 = (int)x0, f.iy0 = (int)y0;
+    if (f.ix0 < 0) f.ix0 += W;
+    if (f.iy0 < 0) f.iy0 += H;
+    f.ix1 = f.ix0 + 1 == W ? 0 : f.ix0 + 1;
+    f.iy1 = f.iy0 + 1 == H ? 0 : f.iy0 + 1;
+    return f;
+}
+HL_HD f4 sample_texture_lod0(const SceneView& s, int index, float u, float v)
+{
+    if (!(fabsf(u) < 1e30f) || !(fabsf(v) < 1e30f)) return mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    const TexView      t = s.textures[index];
+    const TexFootprint f = texture_footprint(t, u, v);
+    return bilinear(texel_load(t, s.lut8, f.ix0, f.iy0), texel_load(t, s.lut8, f.ix1, f.iy0), texel_load(t, s.lut8, f.ix0, f.iy1), texel_load(t, s.lut8, f.ix1, f.iy1), f.fx, f.fy);
+}
+// .w of sample_texture_lod0, bit for bit (the channels filter independently): what the any-hit shader needs
+// (path_trace_rahit.glsl:162-188 reads only albedo.a)
+HL_HD float texel_alpha(const TexView& t, const float* lut8, int x, int y)
+{
+    const size_t i = (size_t)y * t.w + (size_t)x;
+    if (t.format == HL_TEX_RGBA32F) return ((const float*)t.texels)[i * 4 + 3];
+    const uint32_t px = ((const uint32_t*)t.texels)[i];
+    return lut8[(t.format == HL_TEX_RGBA8_SNORM ? 512 : 0) + (px >> 24)]; // sRGB alpha is linear (UNORM table)
+}
+HL_HD float sample_texture_alpha_lod0(const SceneView& s, int index, float u, float v)
+{
+    if (!(fabsf(u) < 1e30f) || !(fabsf(v) < 1e30f)) return 0.0f;
+    const TexView      t = s.textures[index];
+    const TexFootprint f = texture_footprint(t, u, v);
+    const float a = texel_alpha(t, s.lut8, f.ix0, f.iy0) * (1.0f - f.fx) + texel_alpha(t, s.lut8, f.ix1, f.iy0) * f.fx;
+    const float b = texel_alpha(t, s.lut8, f.ix0, f.iy1) * (1.0f - f.fx) + texel_alpha(t, s.lut8, f.ix1, f.iy1) * f.fx;
+    return a * (1.0f - f.fy) + b * f.fy;
 }
 
 HL_HD f3 sample_environment(const EnvView& e, f3 r)
