@@ -78,7 +78,7 @@ TONE_MAP_ACES, TONE_MAP_REINHARD = 0, 1
 TEX_RGBA8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA8_SNORM, TEX_RGBA32F = 0, 1, 2, 3
 OUTPUT_BUFFER_ALBEDO, OUTPUT_BUFFER_NORMALS, OUTPUT_BUFFER_ROUGHNESS, OUTPUT_BUFFER_METALLIC, OUTPUT_BUFFER_EMISSIVE = 0, 1, 2, 3, 4  # include/gfx/renderer.h:25-33
 ACCUM_RUNNING_MEAN, ACCUM_SUM = 0, 1
-OPT_TAIL_THRESHOLD, OPT_TAIL_START, OPT_PIPELINE, OPT_SAH_CLUSTER, OPT_FRAMES_IN_FLIGHT = 1, 2, 3, 4, 5  # hl_set_option
+OPT_TAIL_THRESHOLD, OPT_TAIL_START, OPT_PIPELINE, OPT_SAH_CLUSTER, OPT_FRAMES_IN_FLIGHT, OPT_CUDA_GRAPH = 1, 2, 3, 4, 5, 6  # hl_set_option
 DEBUG_RAY_VERTEX = np.dtype([("position", "<f4", 4), ("color", "<f4", 4)])  # common.glsl:54-58
 MAX_DEBUG_RAY_DRAW_COUNT = 1024  # include/gfx/renderer.h:9
 MISS_ID = 0xFFFFFFFF

@@ -119,7 +119,9 @@ hl_status hl_context_destroy(hl_context ctx)
         for (auto& e : ctx->user_ev) cudaEventDestroy(e);
     for (hl_wave_slot& w : ctx->slot)
     {
-        if (w.stream) cudaStreamSynchronize(w.stream), cudaStreamDestroy(w.stream);
+        if (w.stream) cudaStreamSynchronize(w.stream);
+        if (w.graph_exec) cudaGraphExecDestroy(w.graph_exec);
+        if (w.stream) cudaStreamDestroy(w.stream);
         if (w.resolved) cudaEventDestroy(w.resolved);
     }
     if (ctx->main_ev) cudaEventDestroy(ctx->main_ev);
@@ -623,6 +625,8 @@ hl_status hl_set_option(hl_context ctx, int option, int64_t value)
         // (HL_TRY joined the frames in flight) ray totals of slots that go out of use move into slot 0
         wavefront_set_slots(c_, (int)value);
     }
+    else if (option == HL_OPT_CUDA_GRAPH)
+        c_->use_graphs = value != 0;
     else if (option == HL_OPT_SAH_CLUSTER)
         c_->sah_cluster = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else

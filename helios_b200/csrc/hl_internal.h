@@ -132,6 +132,16 @@ struct hl_wave_slot
     cudaStream_t stream   = nullptr;
     cudaEvent_t  resolved = nullptr; // recorded after the slot's last resolve pass
     bool         pending  = false;   // frames were issued on `stream` since the last join with the main stream
+    // the bounce loop of a frame (tail / extend / shade / connect per bounce: ~30 launches with arguments that only change
+    // with the scene tables or the integrator settings) as an instantiated CUDA graph; rebuilt when `graph_key` changes
+    cudaGraphExec_t graph_exec     = nullptr;
+    uint32_t        graph_launches = 0; // kernel nodes in it
+    struct GraphKey
+    {
+        hl::SceneView view;
+        uint32_t      num_lights, max_ray_bounces, bounces, tail_start, tail_threshold, W, H;
+        float         shadow_ray_bias;
+    } graph_key;
 };
 
 struct hl_context_t
@@ -165,6 +175,7 @@ struct hl_context_t
     int          n_slots     = HL_DEFAULT_WAVE_SLOTS;
     uint64_t     frame_seq   = 0;       // frames issued; frame f uses slot[f % n_slots]
     int          pipeline    = 1;       // 0: every frame on the main stream (also forced while profiling)
+    int          use_graphs  = 1;       // pipelined frames replay their bounce loop from a CUDA graph (HL_OPT_CUDA_GRAPH)
     cudaEvent_t  main_ev     = nullptr; // orders work enqueued on the main stream before the next frame
     size_t       queue_capacity = 0;
     // profiling

@@ -292,6 +292,8 @@ HL_API hl_status hl_event_elapsed_ms(hl_context ctx, int slot_begin, int slot_en
                                    in frame order); 0: one frame at a time */
 #define HL_OPT_FRAMES_IN_FLIGHT 5 /* number of those slots, 1..8 (default 4; the reference keeps up to 3 frames in flight,
                                    include/gfx/vk.h:66); each costs 172 B per pixel of device memory */
+#define HL_OPT_CUDA_GRAPH 6     /* 1 (default): the bounce loop of a pipelined frame is replayed from a CUDA graph (one launch instead
+                                   of ~30; captured per frame slot, re-captured when scene tables or integrator settings change) */
 /* builder knob (applies to meshes / scene tables created afterwards; changes the tree, never a traversal result) */
 #define HL_OPT_SAH_CLUSTER 4    /* binned-SAH re-split of the LBVH above a cut: primitives per cluster below the cut
                                    (default 2; larger = faster build, coarser refinement); 0 = plain LBVH topology */

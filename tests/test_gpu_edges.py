@@ -190,3 +190,34 @@ def test_resize_and_frames_in_flight(api, oracle_mod):
         with pytest.raises(HeliosError):
             ctx.set_option(abi.OPT_FRAMES_IN_FLIGHT, bad)
     ctx.close()
+
+
+def test_cuda_graph_replay_follows_every_setting(api):
+    """HL_OPT_CUDA_GRAPH: the bounce loop replayed from a per-slot CUDA graph must be re-captured whenever something its
+    launches carry by value changes — bounce limit, shadow bias, number of lights, the scene tables, the extent, the tail
+    settings — and give the image of the plain launch sequence"""
+
+    def run(ctx, s, n, **kw):
+        ctx.accum_clear()
+        for f in range(n):
+            ctx.render_frame(s.push_constants(f, **kw))
+        return ctx.read_accum()
+
+    a = scenes.cornell_box(64, 48)
+    b = scenes.foliage_scene(n_clusters=40, cards_per_cluster=10, width=64, height=48, ground_grid=6, tex_size=16)
+    g, p = api.Context(64, 48), api.Context(64, 48)
+    p.set_option(abi.OPT_CUDA_GRAPH, 0)
+    steps = [(a, {}), (a, {"max_ray_bounces": 3}), (a, {"max_ray_bounces": 3, "shadow_ray_bias": 1e-3}), (b, {}), (b, {"max_ray_bounces": 2}), (a, {})]
+    loaded = None
+    for s, kw in steps:
+        if s is not loaded:
+            g.load_scene(s), p.load_scene(s)
+            loaded = s
+        assert np.array_equal(run(g, s, 9, **kw), run(p, s, 9, **kw)), kw
+    g.set_option(abi.OPT_TAIL_START, 1), p.set_option(abi.OPT_TAIL_START, 1)
+    assert np.array_equal(run(g, a, 9), run(p, a, 9))
+    g.resize(80, 40), p.resize(80, 40)
+    a2 = scenes.cornell_box(80, 40)
+    assert np.array_equal(run(g, a2, 9), run(p, a2, 9))
+    assert g.kernel_launches() == p.kernel_launches()  # graph nodes are counted like plain launches
+    g.close(), p.close()

@@ -17,6 +17,7 @@ if os.environ.get('HL_SAH_CLUSTER') is not None:
 handles = ctx.load_scene(s)
 ctx.set_option(3, int(os.environ.get('HL_PIPELINE', '1')))  # HL_OPT_PIPELINE
 if os.environ.get('HL_TAIL_THRESHOLD') is not None: ctx.set_option(1, int(os.environ['HL_TAIL_THRESHOLD']))
+if os.environ.get('HL_GRAPH') is not None: ctx.set_option(6, int(os.environ['HL_GRAPH']))
 if os.environ.get('HL_SLOTS') is not None: ctx.set_option(5, int(os.environ['HL_SLOTS']))
 if os.environ.get('HL_TAIL_START') is not None: ctx.set_option(2, int(os.environ['HL_TAIL_START']))
 pcs = [s.push_constants(f) for f in range(1, frames + 5)]
