@@ -20,32 +20,32 @@ public:
     ResourceManager(vk::Backend::Ptr backend);
     ~ResourceManager();
 
-    Texture2D::Ptr   load_texture_2d(const std::string& path, bool srgb = false);
+    Texture2D::Ptr load_texture_2d(const std::string& path, bool srgb = false);
     TextureCube::Ptr load_texture_cube(const std::string& path, bool srgb = false);
-    Material::Ptr    load_material(const std::string& path);
-    Mesh::Ptr        load_mesh(const std::string& path);
-    Scene::Ptr       load_scene(const std::string& path);
+    Material::Ptr load_material(const std::string& path);
+    Mesh::Ptr load_mesh(const std::string& path);
+    Scene::Ptr load_scene(const std::string& path);
 
     // directory that contains "assets/" (the reference always uses the executable's directory)
-    void               set_asset_root(const std::string& dir) { m_asset_root = dir; }
+    void set_asset_root(const std::string& dir) { m_asset_root = dir; }
     const std::string& asset_root() const { return m_asset_root; }
 
 private:
-    std::string               full_path(const std::string& path) const;
-    Texture2D::Ptr            load_texture_2d_internal(const std::string& path, bool srgb, vk::BatchUploader& uploader);
-    TextureCube::Ptr          load_texture_cube_internal(const std::string& path, bool srgb, vk::BatchUploader& uploader);
-    Material::Ptr             load_material_internal(const std::string& path, vk::BatchUploader& uploader);
-    Mesh::Ptr                 load_mesh_internal(const std::string& path, vk::BatchUploader& uploader);
-    Node::Ptr                 create_node(std::shared_ptr<ast::SceneNode> ast_node, vk::BatchUploader& uploader);
-    void                      populate_scene_node(Node::Ptr node, std::shared_ptr<ast::SceneNode> ast_node, vk::BatchUploader& uploader);
-    void                      populate_transform_node(TransformNode::Ptr node, std::shared_ptr<ast::SceneNode> ast_node);
+    std::string full_path(const std::string& path) const;
+    Texture2D::Ptr fetch_texture_2d(const std::string& path, bool srgb, vk::BatchUploader& uploader);
+    TextureCube::Ptr fetch_texture_cube(const std::string& path, bool srgb, vk::BatchUploader& uploader);
+    Material::Ptr fetch_material(const std::string& path, vk::BatchUploader& uploader);
+    Mesh::Ptr fetch_mesh(const std::string& path, vk::BatchUploader& uploader);
+    Node::Ptr node_from_description(std::shared_ptr<ast::SceneNode> ast_node, vk::BatchUploader& uploader);
+    void fill_node(Node::Ptr node, std::shared_ptr<ast::SceneNode> ast_node, vk::BatchUploader& uploader);
+    void fill_transform(TransformNode::Ptr node, std::shared_ptr<ast::SceneNode> ast_node);
 
-    std::weak_ptr<vk::Backend>                        m_backend;
-    std::string                                       m_asset_root;
-    std::unordered_map<std::string, Texture2D::Ptr>   m_textures_2d;
-    std::unordered_map<std::string, TextureCube::Ptr> m_textures_cube;
-    std::unordered_map<std::string, Material::Ptr>    m_materials;
-    std::unordered_map<std::string, Mesh::Ptr>        m_meshes;
+    std::weak_ptr<vk::Backend> m_backend;
+    std::string m_asset_root;
+    std::unordered_map<std::string, Texture2D::Ptr> m_cache_2d;
+    std::unordered_map<std::string, TextureCube::Ptr> m_cache_cube;
+    std::unordered_map<std::string, Material::Ptr> m_materials;
+    std::unordered_map<std::string, Mesh::Ptr> m_meshes;
 };
 
 // ImGuizmo::RecomposeMatrixFromComponents (external/ImGuizmo/ImGuizmo.cpp:2069-2097) restated: rows right / up /

@@ -21,7 +21,7 @@ public:
     void update(vk::CommandBuffer::Ptr cmd_buf, glm::vec3 direction);
 
     // the uniform block of the last update: A,B,C,D,E,F,G,H,I,Z as vec4 (w = 0)
-    inline const float* coefficients() const { return m_coeffs; }
+    const float* coefficients() const { return m_block; }
     // host-only evaluation of the fit (no device call); out40 receives the same block
     void evaluate_coefficients(glm::vec3 direction, float out40[40]);
 
@@ -29,10 +29,10 @@ private:
     void load_dataset();
 
     std::weak_ptr<vk::Backend> m_backend;
-    std::vector<double>        m_dataset; // 3600 doubles
-    float                      m_coeffs[40];
-    float                      m_normalized_sun_y = 1.15f;
-    float                      m_albedo           = 0.1f;
-    float                      m_turbidity        = 4.0f;
+    std::vector<double> m_rgb_dataset; // 3600 doubles
+    float m_block[40];
+    float m_sun_luminance_target = 1.15f;
+    float m_ground_albedo = 0.1f;
+    float m_turbidity = 4.0f;
 };
 } // namespace helios

@@ -17,21 +17,21 @@ public:
     PathIntegrator(vk::Backend::Ptr backend);
     ~PathIntegrator();
 
-    inline uint32_t max_ray_bounces() { return m_max_ray_bounces; }
-    inline uint32_t max_samples() { return m_max_samples; }
-    inline uint32_t num_accumulated_samples() { return m_max_samples * m_tile_idx + m_num_accumulated_samples; }
-    inline uint32_t num_target_samples() { return m_max_samples * (uint32_t)m_tile_coords.size(); }
-    inline uint32_t tile_idx() { return m_tile_idx; }
-    inline bool     is_tiled() { return m_tiled; }
-    inline float    shadow_ray_bias() { return m_shadow_ray_bias; }
-    inline void     restart_bake()
+    uint32_t max_ray_bounces() { return m_cfg.max_bounces; }
+    uint32_t max_samples() { return m_cfg.max_samples; }
+    uint32_t num_accumulated_samples() { return m_cfg.max_samples * m_bake.tile + m_bake.samples; }
+    uint32_t num_target_samples() { return m_cfg.max_samples * (uint32_t)m_tiles.size(); }
+    uint32_t tile_idx() { return m_bake.tile; }
+    bool is_tiled() { return m_cfg.tiled; }
+    float shadow_ray_bias() { return m_cfg.shadow_bias; }
+    inline void restart_bake()
     {
-        m_num_accumulated_samples = 0;
-        m_tile_idx                = 0;
+        m_bake.samples = 0;
+        m_bake.tile = 0;
     }
-    inline void set_max_ray_bounces(const uint32_t& n) { m_max_ray_bounces = n; }
-    inline void set_max_samples(const uint32_t& n) { m_max_samples = n; }
-    inline void set_shadow_ray_bias(const float& bias) { m_shadow_ray_bias = bias; }
+    void set_max_ray_bounces(const uint32_t& n) { m_cfg.max_bounces = n; }
+    void set_max_samples(const uint32_t& n) { m_cfg.max_samples = n; }
+    void set_shadow_ray_bias(const float& bias) { m_cfg.shadow_bias = bias; }
 
     void render(RenderState& render_state);
     // the ray debug view (reference: path_integrator.cpp:88-104): num_debug_rays paths through pixel_coord, one line segment
@@ -43,11 +43,11 @@ public:
 
     // Renderer::render hands the tone-map settings down so that the launch can resolve accumulation and tone map
     // in one fused pass (hl_render_frame_tonemapped); launched_last_render() tells it whether a launch happened
-    inline void set_resolve_tone_map(bool enabled, float exposure, int tone_map_operator) { m_fuse_tone_map = enabled, m_fuse_exposure = exposure, m_fuse_operator = tone_map_operator; }
-    inline bool launched_last_render() const { return m_launched; }
+    void set_resolve_tone_map(bool enabled, float exposure, int tone_map_operator) { m_fuse_tone_map = enabled, m_fuse_exposure = exposure, m_fuse_operator = tone_map_operator; }
+    bool launched_last_render() const { return m_launched; }
 
     // the block the last launch used (tests compare it with the Python host's restatement)
-    inline const hl_push_constants& last_push_constants() const { return m_last_push_constants; }
+    const hl_push_constants& last_push_constants() const { return m_last_push_constants; }
     // fills a PushConstants block for (camera, counters) without launching
     hl_push_constants make_push_constants(RenderState& render_state, const glm::mat4& view, const glm::mat4& projection, const glm::ivec2& tile_coord, const glm::ivec2& pixel_coord);
 
@@ -55,19 +55,23 @@ private:
     void launch_rays(RenderState& render_state, const uint32_t& x, const uint32_t& y, const uint32_t& z, const glm::mat4& view, const glm::mat4& projection, const glm::ivec2& tile_coord,
                      const glm::ivec2& pixel_coord);
     void compute_tile_coords();
-
-    bool                       m_tiled                   = false;
-    uint32_t                   m_max_ray_bounces         = 7;
-    uint32_t                   m_max_samples             = 5000;
-    uint32_t                   m_num_accumulated_samples = 0;
-    uint32_t                   m_tile_idx                = 0;
-    float                      m_shadow_ray_bias         = 0.0f;
-    glm::uvec2                 m_tile_size;
-    std::vector<glm::uvec2>    m_tile_coords;
+    // integrator settings (defaults of the reference: 7 bounces, 5000 samples, no bias, full-frame launches) and bake progress
+    struct
+    {
+        bool tiled = false;
+        uint32_t max_bounces = 7, max_samples = 5000;
+        float shadow_bias = 0.0f;
+    } m_cfg;
+    struct
+    {
+        uint32_t samples = 0, tile = 0; // launches accumulated into the current tile; index of the tile being baked
+    } m_bake;
+    glm::uvec2 m_tile_extent;
+    std::vector<glm::uvec2> m_tiles;
     std::weak_ptr<vk::Backend> m_backend;
-    hl_push_constants          m_last_push_constants {};
-    bool                       m_fuse_tone_map = false, m_launched = false;
-    float                      m_fuse_exposure = 1.0f;
-    int                        m_fuse_operator = HL_TONE_MAP_ACES;
+    hl_push_constants m_last_push_constants {};
+    bool m_fuse_tone_map = false, m_launched = false;
+    float m_fuse_exposure = 1.0f;
+    int m_fuse_operator = HL_TONE_MAP_ACES;
 };
 } // namespace helios

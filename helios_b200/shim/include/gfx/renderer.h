@@ -16,9 +16,9 @@ namespace helios
 struct RayDebugView // include/gfx/renderer.h:13-19
 {
     glm::ivec2 pixel_coord;
-    uint32_t   num_debug_rays;
-    glm::mat4  view;
-    glm::mat4  projection;
+    uint32_t num_debug_rays;
+    glm::mat4 view;
+    glm::mat4 projection;
 };
 
 enum ToneMapOperator
@@ -43,21 +43,21 @@ public:
     Renderer(vk::Backend::Ptr backend);
     ~Renderer();
 
-    inline void                set_tone_map_operator(const ToneMapOperator& tone_map) { m_tone_map_operator = tone_map; }
-    inline void                set_exposure(const float& exposure) { m_exposure = exposure; }
-    inline void                set_current_output_buffer(OutputBuffer buffer) { m_current_output_buffer = buffer; }
-    inline PathIntegrator::Ptr path_integrator() { return m_path_integrator; }
-    inline ToneMapOperator     tone_map_operator() { return m_tone_map_operator; }
-    inline OutputBuffer        current_output_buffer() { return m_current_output_buffer; }
-    inline float               exposure() { return m_exposure; }
+    void set_tone_map_operator(const ToneMapOperator& tone_map) { m_tone_map_operator = tone_map; }
+    void set_exposure(const float& exposure) { m_exposure = exposure; }
+    void set_current_output_buffer(OutputBuffer buffer) { m_current_output_buffer = buffer; }
+    PathIntegrator::Ptr path_integrator() { return m_path_integrator; }
+    ToneMapOperator tone_map_operator() { return m_tone_map_operator; }
+    OutputBuffer current_output_buffer() { return m_current_output_buffer; }
+    float exposure() { return m_exposure; }
 
     void render(RenderState& render_state);
     void on_window_resize();
     // ray debug views (reference: renderer.cpp:229-250, :733-751): the view added last is gathered by the next render()
     // (PathIntegrator::gather_debug_rays); the first view after a clear resets the segment buffer, later ones append.
-    void                                    add_ray_debug_view(const glm::ivec2& pixel_coord, const uint32_t& num_debug_rays, const glm::mat4& view, const glm::mat4& projection);
-    const std::vector<RayDebugView>&        ray_debug_views();
-    void                                    clear_ray_debug_views();
+    void add_ray_debug_view(const glm::ivec2& pixel_coord, const uint32_t& num_debug_rays, const glm::mat4& view, const glm::mat4& projection);
+    const std::vector<RayDebugView>& ray_debug_views();
+    void clear_ray_debug_views();
     const std::vector<hl_debug_ray_vertex>& ray_debug_vertices() const { return m_ray_debug_vertices; } // what the reference draws as a line list
     // queues a save of the tone-mapped image; it is written at the end of the next render(), as in the reference
     // (8-bit RGBA PNG as in the reference, :651; a path ending in .ppm / .pfm selects those formats instead)
@@ -65,7 +65,7 @@ public:
 
     // headless read-backs (the reference presents to a swap chain instead)
     std::vector<uint8_t> read_tone_mapped_image(); // RGBA8, row 0 = top
-    std::vector<float>   read_accumulation();      // RGBA32F, row 0 = v 0
+    std::vector<float> read_accumulation(); // RGBA32F, row 0 = v 0
     // the debug view selected with set_current_output_buffer (albedo / normals / roughness / metallic / emissive of
     // the surfaces the camera sees; reference: renderer.cpp:459-547 + debug_visualization.frag), RGBA32F, row 0 = v 0.
     // OUTPUT_BUFFER_FINAL returns the accumulation image.
@@ -74,16 +74,16 @@ public:
 private:
     void tone_map(uint8_t* rgba8_host);
 
-    std::vector<RayDebugView>        m_ray_debug_views;
-    bool                             m_ray_debug_view_added = false;
+    std::vector<RayDebugView> m_ray_debug_views;
+    bool m_ray_debug_view_added = false;
     std::vector<hl_debug_ray_vertex> m_ray_debug_vertices;
     std::weak_ptr<vk::Backend> m_backend;
-    PathIntegrator::Ptr        m_path_integrator;
-    bool                       m_output_image_recreated = true;
-    bool                       m_save_image_to_disk     = false;
+    PathIntegrator::Ptr m_path_integrator;
+    bool m_output_image_recreated = true;
+    bool m_save_image_to_disk = false;
     std::string                m_image_save_path        = "";
-    ToneMapOperator            m_tone_map_operator      = TONE_MAP_OPERATOR_ACES;
-    float                      m_exposure               = 1.0f;
-    OutputBuffer               m_current_output_buffer  = OUTPUT_BUFFER_FINAL;
+    ToneMapOperator m_tone_map_operator = TONE_MAP_OPERATOR_ACES;
+    float m_exposure = 1.0f;
+    OutputBuffer m_current_output_buffer = OUTPUT_BUFFER_FINAL;
 };
 } // namespace helios

@@ -35,11 +35,11 @@ public:
     static Ptr create_without_device(uint32_t width, uint32_t height);
     ~Backend();
 
-    inline hl_context context() { return m_ctx; }
-    inline bool       has_device() const { return m_ctx != nullptr; }
-    inline Extent2D   swap_chain_extents() const { return m_extents; }
-    void              resize(uint32_t width, uint32_t height);
-    void              wait_idle();
+    hl_context context() { return m_ctx; }
+    bool has_device() const { return m_ctx != nullptr; }
+    Extent2D swap_chain_extents() const { return m_extents; }
+    void resize(uint32_t width, uint32_t height);
+    void wait_idle();
     // throws std::runtime_error(what + hl_last_error) when st != HL_OK
     void check(hl_status st, const char* what);
     hl_context require_device(const char* what);
@@ -47,7 +47,7 @@ public:
 private:
     Backend() = default;
     hl_context m_ctx = nullptr;
-    Extent2D   m_extents { 0, 0 };
+    Extent2D m_extents { 0, 0 };
 };
 
 class Object

@@ -23,13 +23,13 @@ static_assert(sizeof(Vertex) == sizeof(hl_vertex), "Vertex must match the 80-byt
 struct SubMesh
 {
     std::string name;
-    uint32_t    mat_idx;
-    uint32_t    index_count;
-    uint32_t    vertex_count;
-    uint32_t    base_vertex;
-    uint32_t    base_index;
-    glm::vec3   max_extents;
-    glm::vec3   min_extents;
+    uint32_t mat_idx;
+    uint32_t index_count;
+    uint32_t vertex_count;
+    uint32_t base_vertex;
+    uint32_t base_index;
+    glm::vec3 max_extents;
+    glm::vec3 min_extents;
 };
 
 class Material;
@@ -43,21 +43,21 @@ public:
                             std::vector<std::shared_ptr<Material>> materials, vk::BatchUploader& uploader, const std::string& path = "");
     ~Mesh();
 
-    inline const std::vector<std::shared_ptr<Material>>& materials() { return m_materials; }
-    inline const std::vector<SubMesh>&                   sub_meshes() { return m_sub_meshes; }
-    inline hl_mesh                                       acceleration_structure() { return m_handle; } // the BLAS handle
-    inline uint32_t                                      id() { return m_id; }
-    inline std::string                                   path() { return m_path; }
-    hl_build_stats                                       build_stats();
+    const std::vector<std::shared_ptr<Material>>& materials() { return m_materials; }
+    const std::vector<SubMesh>& sub_meshes() { return m_sub_meshes; }
+    hl_mesh acceleration_structure() { return m_handle; } // the BLAS handle
+    uint32_t id() { return m_id; }
+    std::string path() { return m_path; }
+    hl_build_stats build_stats();
 
 private:
     Mesh(vk::Backend::Ptr backend, std::vector<Vertex>& vertices, std::vector<uint32_t>& indices, std::vector<SubMesh> submeshes, std::vector<std::shared_ptr<Material>> materials,
          const std::string& path);
 
-    hl_mesh                                m_handle = nullptr;
-    std::vector<SubMesh>                   m_sub_meshes;
+    hl_mesh m_handle = nullptr;
+    std::vector<SubMesh> m_sub_meshes;
     std::vector<std::shared_ptr<Material>> m_materials;
-    uint32_t                               m_id;
-    std::string                            m_path;
+    uint32_t m_id;
+    std::string m_path;
 };
 } // namespace helios

@@ -51,33 +51,33 @@ public:
 
     virtual void update(RenderState& render_state) = 0;
 
-    void      add_child(Node::Ptr child);
+    void add_child(Node::Ptr child);
     Node::Ptr find_child(const std::string& name);
     Node::Ptr find_child(const NodeType& type);
-    void      remove_child(const std::string& name);
+    void remove_child(const std::string& name);
 
-    inline bool                                      is_enabled() { return m_is_enabled; }
-    inline bool                                      is_transform_dirty() { return m_is_transform_dirty; }
-    inline void                                      enable() { m_is_enabled = true; }
-    inline void                                      disable() { m_is_enabled = false; }
-    inline const std::vector<std::shared_ptr<Node>>& children() { return m_children; }
-    inline std::string                               name() { return m_name; }
-    inline Node*                                     parent() { return m_parent; }
-    inline uint32_t                                  id() { return m_id; }
-    NodeType                                         type() { return m_type; }
+    bool is_enabled() { return m_is_enabled; }
+    bool is_transform_dirty() { return m_is_transform_dirty; }
+    void enable() { m_is_enabled = true; }
+    void disable() { m_is_enabled = false; }
+    const std::vector<std::shared_ptr<Node>>& children() { return m_children; }
+    std::string name() { return m_name; }
+    Node* parent() { return m_parent; }
+    uint32_t id() { return m_id; }
+    NodeType type() { return m_type; }
 
 protected:
     void update_children(RenderState& render_state);
     void mark_transforms_as_dirty();
 
-    NodeType                           m_type;
-    bool                               m_is_enabled         = true;
-    bool                               m_is_transform_dirty = true;
-    bool                               m_is_heirarchy_dirty = true;
-    std::string                        m_name;
-    Node*                              m_parent = nullptr;
+    NodeType m_type;
+    bool m_is_enabled = true;
+    bool m_is_transform_dirty = true;
+    bool m_is_heirarchy_dirty = true;
+    std::string m_name;
+    Node* m_parent = nullptr;
     std::vector<std::shared_ptr<Node>> m_children;
-    uint32_t                           m_id = 0;
+    uint32_t m_id = 0;
 };
 
 class TransformNode : public Node
@@ -101,23 +101,23 @@ public:
     glm::mat4 normal_matrix();
     glm::quat orientation();
     glm::vec3 scale();
-    void      set_from_local_transform(const glm::mat4& transform);
-    void      set_from_global_transform(const glm::mat4& transform);
-    void      set_orientation(const glm::quat& q);
-    void      set_orientation_from_euler_yxz(const glm::vec3& e);
-    void      set_orientation_from_euler_xyz(const glm::vec3& e);
-    void      set_position(const glm::vec3& position);
-    void      set_scale(const glm::vec3& scale);
-    void      move(const glm::vec3& displacement);
-    void      rotate_euler_yxz(const glm::vec3& e);
-    void      rotate_euler_xyz(const glm::vec3& e);
+    void set_from_local_transform(const glm::mat4& transform);
+    void set_from_global_transform(const glm::mat4& transform);
+    void set_orientation(const glm::quat& q);
+    void set_orientation_from_euler_yxz(const glm::vec3& e);
+    void set_orientation_from_euler_xyz(const glm::vec3& e);
+    void set_position(const glm::vec3& position);
+    void set_scale(const glm::vec3& scale);
+    void move(const glm::vec3& displacement);
+    void rotate_euler_yxz(const glm::vec3& e);
+    void rotate_euler_xyz(const glm::vec3& e);
 
 protected:
-    glm::vec3 m_position                   = glm::vec3(0.0f);
-    glm::quat m_orientation                = glm::quat(glm::vec3(0.0f));
-    glm::vec3 m_scale                      = glm::vec3(1.0f);
-    glm::mat4 m_prev_model_matrix          = glm::mat4(1.0f);
-    glm::mat4 m_model_matrix               = glm::mat4(1.0f);
+    glm::vec3 m_position = glm::vec3(0.0f);
+    glm::quat m_orientation = glm::quat(glm::vec3(0.0f));
+    glm::vec3 m_scale = glm::vec3(1.0f);
+    glm::mat4 m_prev_model_matrix = glm::mat4(1.0f);
+    glm::mat4 m_model_matrix = glm::mat4(1.0f);
     glm::mat4 m_model_matrix_without_scale = glm::mat4(1.0f);
 };
 
@@ -138,41 +138,48 @@ public:
     ~MeshNode();
     void update(RenderState& render_state) override;
 
-    void                             set_mesh(std::shared_ptr<Mesh> mesh);
-    void                             set_material_override(std::shared_ptr<Material> material_override);
-    inline std::shared_ptr<Mesh>     mesh() { return m_mesh; }
-    inline std::shared_ptr<Material> material_override() { return m_material_override; }
+    void set_mesh(std::shared_ptr<Mesh> mesh);
+    void set_material_override(std::shared_ptr<Material> material_override);
+    std::shared_ptr<Mesh> mesh() { return m_mesh; }
+    std::shared_ptr<Material> material_override() { return m_material_override; }
     // (primitive offset, global material index) per submesh: descriptor set 3 of the reference
-    inline std::vector<glm::uvec2>& material_indices_buffer() { return m_material_indices; }
+    std::vector<glm::uvec2>& material_indices_buffer() { return m_material_indices; }
 
 private:
-    std::shared_ptr<Mesh>     m_mesh;
+    std::shared_ptr<Mesh> m_mesh;
     std::shared_ptr<Material> m_material_override;
-    std::vector<glm::uvec2>   m_material_indices;
+    std::vector<glm::uvec2> m_material_indices;
 };
 
-class DirectionalLightNode : public TransformNode
+// colour / intensity / radius shared by the three punctual light nodes (the reference repeats these six accessors in each
+// class, include/resource/scene.h:154-232; same names and semantics here, one definition)
+class LightParameters
+{
+public:
+    void set_color(const glm::vec3& color) { m_color = color; }
+    void set_intensity(const float& intensity) { m_intensity = intensity; }
+    void set_radius(const float& r) { m_radius = r; }
+    glm::vec3 color() { return m_color; }
+    float intensity() { return m_intensity; }
+    float radius() { return m_radius; }
+
+protected:
+    explicit LightParameters(float default_radius) : m_radius(default_radius) {}
+    glm::vec3 m_color = glm::vec3(1.0f);
+    float m_intensity = 1.0f;
+    float m_radius;
+};
+
+class DirectionalLightNode : public TransformNode, public LightParameters
 {
 public:
     using Ptr = std::shared_ptr<DirectionalLightNode>;
     DirectionalLightNode(const std::string& name);
     ~DirectionalLightNode();
     void update(RenderState& render_state) override;
-
-    inline void      set_color(const glm::vec3& color) { m_color = color; }
-    inline void      set_intensity(const float& intensity) { m_intensity = intensity; }
-    inline void      set_radius(const float& r) { m_radius = r; }
-    inline glm::vec3 color() { return m_color; }
-    inline float     intensity() { return m_intensity; }
-    inline float     radius() { return m_radius; }
-
-private:
-    glm::vec3 m_color     = glm::vec3(1.0f);
-    float     m_intensity = 1.0f;
-    float     m_radius    = 0.1f;
 };
 
-class SpotLightNode : public TransformNode
+class SpotLightNode : public TransformNode, public LightParameters
 {
 public:
     using Ptr = std::shared_ptr<SpotLightNode>;
@@ -180,44 +187,23 @@ public:
     ~SpotLightNode();
     void update(RenderState& render_state) override;
 
-    inline void      set_color(const glm::vec3& color) { m_color = color; }
-    inline void      set_intensity(const float& intensity) { m_intensity = intensity; }
-    inline void      set_inner_cone_angle(const float& cone_angle) { m_inner_cone_angle = cone_angle; }
-    inline void      set_outer_cone_angle(const float& cone_angle) { m_outer_cone_angle = cone_angle; }
-    inline void      set_radius(const float& r) { m_radius = r; }
-    inline glm::vec3 color() { return m_color; }
-    inline float     intensity() { return m_intensity; }
-    inline float     radius() { return m_radius; }
-    inline float     inner_cone_angle() { return m_inner_cone_angle; }
-    inline float     outer_cone_angle() { return m_outer_cone_angle; }
+    void set_inner_cone_angle(const float& cone_angle) { m_inner_cone_angle = cone_angle; }
+    void set_outer_cone_angle(const float& cone_angle) { m_outer_cone_angle = cone_angle; }
+    float inner_cone_angle() { return m_inner_cone_angle; }
+    float outer_cone_angle() { return m_outer_cone_angle; }
 
 private:
-    glm::vec3 m_color            = glm::vec3(1.0f);
-    float     m_inner_cone_angle = 40.0f;
-    float     m_outer_cone_angle = 50.0f;
-    float     m_intensity        = 1.0f;
-    float     m_radius           = 5.0f;
+    float m_inner_cone_angle = 40.0f;
+    float m_outer_cone_angle = 50.0f;
 };
 
-class PointLightNode : public TransformNode
+class PointLightNode : public TransformNode, public LightParameters
 {
 public:
     using Ptr = std::shared_ptr<PointLightNode>;
     PointLightNode(const std::string& name);
     ~PointLightNode();
     void update(RenderState& render_state) override;
-
-    inline void      set_color(const glm::vec3& color) { m_color = color; }
-    inline void      set_intensity(const float& intensity) { m_intensity = intensity; }
-    inline void      set_radius(const float& r) { m_radius = r; }
-    inline glm::vec3 color() { return m_color; }
-    inline float     intensity() { return m_intensity; }
-    inline float     radius() { return m_radius; }
-
-private:
-    glm::vec3 m_color     = glm::vec3(1.0f);
-    float     m_intensity = 1.0f;
-    float     m_radius    = 5.0f;
 };
 
 class CameraNode : public TransformNode
@@ -228,28 +214,28 @@ public:
     ~CameraNode();
     void update(RenderState& render_state) override;
 
-    glm::vec3        camera_forward();
-    glm::vec3        camera_left();
-    inline void      set_near_plane(const float& near_plane) { m_near_plane = near_plane; }
-    inline void      set_far_plane(const float& far_plane) { m_far_plane = far_plane; }
-    inline void      set_fov(const float& fov) { m_fov = fov; }
-    inline void      set_focal_length(const float& focal_length) { m_focal_length = focal_length; }
-    inline void      set_aperture_radius(const float& aperture_radius) { m_aperture_radius = aperture_radius; }
-    inline float     near_plane() { return m_near_plane; }
-    inline float     far_plane() { return m_far_plane; }
-    inline float     fov() { return m_fov; }
-    inline float     focal_length() { return m_focal_length; }
-    inline float     aperture_radius() { return m_aperture_radius; }
-    inline glm::mat4 view_matrix() { return m_view_matrix; }
-    inline glm::mat4 projection_matrix() { return m_projection_matrix; }
+    glm::vec3 camera_forward();
+    glm::vec3 camera_left();
+    void set_near_plane(const float& near_plane) { m_near_plane = near_plane; }
+    void set_far_plane(const float& far_plane) { m_far_plane = far_plane; }
+    void set_fov(const float& fov) { m_fov = fov; }
+    void set_focal_length(const float& focal_length) { m_focal_length = focal_length; }
+    void set_aperture_radius(const float& aperture_radius) { m_aperture_radius = aperture_radius; }
+    float near_plane() { return m_near_plane; }
+    float far_plane() { return m_far_plane; }
+    float fov() { return m_fov; }
+    float focal_length() { return m_focal_length; }
+    float aperture_radius() { return m_aperture_radius; }
+    glm::mat4 view_matrix() { return m_view_matrix; }
+    glm::mat4 projection_matrix() { return m_projection_matrix; }
 
 private:
-    float     m_near_plane        = 1.0f;
-    float     m_far_plane         = 1000.0f;
-    float     m_fov               = 60.0f;
-    float     m_focal_length      = 8.0f;
-    float     m_aperture_radius   = 0.1f;
-    glm::mat4 m_view_matrix       = glm::mat4(1.0f);
+    float m_near_plane = 1.0f;
+    float m_far_plane = 1000.0f;
+    float m_fov = 60.0f;
+    float m_focal_length = 8.0f;
+    float m_aperture_radius = 0.1f;
+    glm::mat4 m_view_matrix = glm::mat4(1.0f);
     glm::mat4 m_projection_matrix = glm::mat4(1.0f);
 };
 
@@ -261,8 +247,8 @@ public:
     ~IBLNode();
     void update(RenderState& render_state) override;
 
-    void                                set_image(std::shared_ptr<TextureCube> image);
-    inline std::shared_ptr<TextureCube> image() { return m_image; }
+    void set_image(std::shared_ptr<TextureCube> image);
+    std::shared_ptr<TextureCube> image() { return m_image; }
 
 private:
     std::shared_ptr<TextureCube> m_image;
@@ -295,42 +281,42 @@ public:
     void clear();
     void setup(uint32_t width, uint32_t height, vk::CommandBuffer::Ptr cmd_buffer);
 
-    inline const std::vector<MeshNode*>&             meshes() { return m_meshes; }
-    inline const std::vector<DirectionalLightNode*>& directional_lights() { return m_directional_lights; }
-    inline const std::vector<SpotLightNode*>&        spot_lights() { return m_spot_lights; }
-    inline const std::vector<PointLightNode*>&       point_lights() { return m_point_lights; }
-    inline CameraNode*                               camera() { return m_camera; }
-    inline IBLNode*                                  ibl_environment_map() { return m_ibl_environment_map; }
-    inline SceneState                                scene_state() { return m_scene_state; }
-    inline Scene*                                    scene() { return m_scene; }
-    inline uint32_t                                  viewport_width() { return m_viewport_width; }
-    inline uint32_t                                  viewport_height() { return m_viewport_height; }
-    inline uint32_t                                  num_lights() { return m_num_lights; }
-    inline vk::CommandBuffer::Ptr                    cmd_buffer() { return m_cmd_buffer; }
+    const std::vector<MeshNode*>& meshes() { return m_meshes; }
+    const std::vector<DirectionalLightNode*>& directional_lights() { return m_directional_lights; }
+    const std::vector<SpotLightNode*>& spot_lights() { return m_spot_lights; }
+    const std::vector<PointLightNode*>& point_lights() { return m_point_lights; }
+    CameraNode* camera() { return m_camera; }
+    IBLNode* ibl_environment_map() { return m_ibl_environment_map; }
+    SceneState scene_state() { return m_scene_state; }
+    Scene* scene() { return m_scene; }
+    uint32_t viewport_width() { return m_viewport_width; }
+    uint32_t viewport_height() { return m_viewport_height; }
+    uint32_t num_lights() { return m_num_lights; }
+    vk::CommandBuffer::Ptr cmd_buffer() { return m_cmd_buffer; }
 
 private:
-    std::vector<MeshNode*>             m_meshes;
+    std::vector<MeshNode*> m_meshes;
     std::vector<DirectionalLightNode*> m_directional_lights;
-    std::vector<SpotLightNode*>        m_spot_lights;
-    std::vector<PointLightNode*>       m_point_lights;
-    CameraNode*                        m_camera              = nullptr;
-    IBLNode*                           m_ibl_environment_map = nullptr;
-    SceneState                         m_scene_state         = SCENE_STATE_READY;
-    Scene*                             m_scene               = nullptr;
-    uint32_t                           m_viewport_width      = 0;
-    uint32_t                           m_viewport_height     = 0;
-    uint32_t                           m_num_lights          = 0;
-    vk::CommandBuffer::Ptr             m_cmd_buffer;
+    std::vector<SpotLightNode*> m_spot_lights;
+    std::vector<PointLightNode*> m_point_lights;
+    CameraNode* m_camera = nullptr;
+    IBLNode* m_ibl_environment_map = nullptr;
+    SceneState m_scene_state = SCENE_STATE_READY;
+    Scene* m_scene = nullptr;
+    uint32_t m_viewport_width = 0;
+    uint32_t m_viewport_height = 0;
+    uint32_t m_num_lights = 0;
+    vk::CommandBuffer::Ptr m_cmd_buffer;
 };
 
 // the tables of the last Scene::update, as handed to hl_scene_set_tables (host copies; tools and tests read them)
 struct SceneTables
 {
-    std::vector<hl_material>             materials;
-    std::vector<hl_instance>             instances;
-    std::vector<hl_light>                lights;
+    std::vector<hl_material> materials;
+    std::vector<hl_instance> instances;
+    std::vector<hl_light> lights;
     std::vector<std::vector<glm::uvec2>> submesh_info; // per instance
-    uint32_t                             num_textures = 0;
+    uint32_t num_textures = 0;
 };
 
 class Scene : public vk::Object
@@ -341,36 +327,36 @@ public:
     static Scene::Ptr create(vk::Backend::Ptr backend, const std::string& name, Node::Ptr root = nullptr, const std::string& path = "");
     ~Scene();
 
-    void            update(RenderState& render_state);
-    void            set_root_node(Node::Ptr node);
-    Node::Ptr       root_node();
-    Node::Ptr       find_node(const std::string& name);
+    void update(RenderState& render_state);
+    void set_root_node(Node::Ptr node);
+    Node::Ptr root_node();
+    Node::Ptr find_node(const std::string& name);
     CameraNode::Ptr find_camera();
 
-    inline void                 set_name(const std::string& name) { m_name = name; }
-    inline std::string          name() { return m_name; }
-    inline std::string          path() { return m_path; }
-    inline void                 force_update() { m_force_update = true; }
-    inline HosekWilkieSkyModel* sky_model() { return m_sky_model.get(); }
-    inline const SceneTables&   tables() const { return m_tables; }
+    void set_name(const std::string& name) { m_name = name; }
+    std::string name() { return m_name; }
+    std::string path() { return m_path; }
+    void force_update() { m_force_update = true; }
+    HosekWilkieSkyModel* sky_model() { return m_sky_model.get(); }
+    const SceneTables& tables() const { return m_tables; }
 
 private:
     Scene(vk::Backend::Ptr backend, const std::string& name, Node::Ptr root = nullptr, const std::string& path = "");
     void create_gpu_resources(RenderState& render_state);
 
-    Node::Ptr                              m_root;
+    Node::Ptr m_root;
     std::unordered_map<uint32_t, uint32_t> m_global_material_indices;
     std::unordered_map<uint32_t, uint32_t> m_global_mesh_indices;
-    uint32_t                               m_num_area_lights = 0;
-    std::unique_ptr<HosekWilkieSkyModel>   m_sky_model;
-    std::weak_ptr<vk::Backend>             m_backend;
-    std::string                            m_name;
-    std::string                            m_path;
-    bool                                   m_force_update = false;
-    SceneTables                            m_tables;
+    uint32_t m_num_area_lights = 0;
+    std::unique_ptr<HosekWilkieSkyModel> m_sky_model;
+    std::weak_ptr<vk::Backend> m_backend;
+    std::string m_name;
+    std::string m_path;
+    bool m_force_update = false;
+    SceneTables m_tables;
     // state of the device-side copy
     glm::vec3 m_last_sun_direction = glm::vec3(0.0f);
-    bool      m_sky_valid          = false;
-    uint32_t  m_env_source_id      = 0xFFFFFFFFu; // TextureCube id currently uploaded (0xFFFFFFFF = none)
+    bool m_sky_valid = false;
+    uint32_t m_env_source_id = 0xFFFFFFFFu; // TextureCube id currently uploaded (0xFFFFFFFF = none)
 };
 } // namespace helios

@@ -15,12 +15,12 @@ public:
 
     Texture(vk::Backend::Ptr backend, const std::string& path);
     virtual ~Texture();
-    inline uint32_t    id() { return m_id; }
-    inline std::string path() { return m_path; }
+    uint32_t id() { return m_id; }
+    std::string path() { return m_path; }
 
 protected:
     std::string m_path;
-    uint32_t    m_id;
+    uint32_t m_id;
 };
 
 class Texture2D : public Texture
@@ -30,15 +30,15 @@ public:
     // format: HL_TEX_RGBA8_UNORM / _SRGB / _SNORM / HL_TEX_RGBA32F; texels = width * height * 4 components
     static Texture2D::Ptr create(vk::Backend::Ptr backend, int format, uint32_t width, uint32_t height, const void* level0_texels, const std::string& path = "");
     ~Texture2D();
-    inline int                         format() const { return m_format; }
-    inline uint32_t                    width() const { return m_width; }
-    inline uint32_t                    height() const { return m_height; }
-    inline const std::vector<uint8_t>& texels() const { return m_texels; }
+    int format() const { return m_format; }
+    uint32_t width() const { return m_width; }
+    uint32_t height() const { return m_height; }
+    const std::vector<uint8_t>& texels() const { return m_texels; }
 
 private:
     Texture2D(vk::Backend::Ptr backend, int format, uint32_t width, uint32_t height, const void* texels, const std::string& path);
-    int                  m_format;
-    uint32_t             m_width, m_height;
+    int m_format;
+    uint32_t m_width, m_height;
     std::vector<uint8_t> m_texels;
 };
 
@@ -49,12 +49,12 @@ public:
     // faces +X,-X,+Y,-Y,+Z,-Z, each size * size RGBA32F
     static TextureCube::Ptr create(vk::Backend::Ptr backend, uint32_t size, const float* rgba32f_faces, const std::string& path = "");
     ~TextureCube();
-    inline uint32_t                  size() const { return m_size; }
-    inline const std::vector<float>& faces() const { return m_faces; }
+    uint32_t size() const { return m_size; }
+    const std::vector<float>& faces() const { return m_faces; }
 
 private:
     TextureCube(vk::Backend::Ptr backend, uint32_t size, const float* faces, const std::string& path);
-    uint32_t           m_size;
+    uint32_t m_size;
     std::vector<float> m_faces;
 };
 } // namespace helios

@@ -59,13 +59,13 @@ std::string data_directory()
 
 HosekWilkieSkyModel::HosekWilkieSkyModel(vk::Backend::Ptr backend) : m_backend(backend)
 {
-    for (float& c : m_coeffs) c = 0.0f;
+    for (float& c : m_block) c = 0.0f;
 }
 HosekWilkieSkyModel::~HosekWilkieSkyModel() {}
 
 void HosekWilkieSkyModel::load_dataset()
 {
-    if (!m_dataset.empty()) return;
+    if (!m_rgb_dataset.empty()) return;
     const std::string path = data_directory() + "/hosek_rgb_v1_4a.f64";
     FILE*             f    = std::fopen(path.c_str(), "rb");
     if (!f)
@@ -74,12 +74,12 @@ void HosekWilkieSkyModel::load_dataset()
         HELIOS_LOG_FATAL(msg);
         throw std::runtime_error(msg);
     }
-    m_dataset.resize(3600);
-    const size_t n = std::fread(m_dataset.data(), sizeof(double), 3600, f);
+    m_rgb_dataset.resize(3600);
+    const size_t n = std::fread(m_rgb_dataset.data(), sizeof(double), 3600, f);
     std::fclose(f);
     if (n != 3600)
     {
-        m_dataset.clear();
+        m_rgb_dataset.clear();
         const std::string msg = "HosekWilkieSkyModel: " + path + " is truncated";
         HELIOS_LOG_FATAL(msg);
         throw std::runtime_error(msg);
@@ -93,20 +93,20 @@ void HosekWilkieSkyModel::evaluate_coefficients(glm::vec3 direction, float out40
     float       cf[10][3];
     for (int i = 0; i < 3; i++)
     {
-        const double* rgb = m_dataset.data() + 1080 * i;
-        const double* rad = m_dataset.data() + 3240 + 120 * i;
-        for (int k = 0; k < 7; k++) cf[k][i] = (float)evaluate(rgb + k, 9, m_turbidity, m_albedo, sun_theta);
+        const double* rgb = m_rgb_dataset.data() + 1080 * i;
+        const double* rad = m_rgb_dataset.data() + 3240 + 120 * i;
+        for (int k = 0; k < 7; k++) cf[k][i] = (float)evaluate(rgb + k, 9, m_turbidity, m_ground_albedo, sun_theta);
         // H and I are stored swapped in the dataset (:674-676)
-        cf[7][i] = (float)evaluate(rgb + 8, 9, m_turbidity, m_albedo, sun_theta);
-        cf[8][i] = (float)evaluate(rgb + 7, 9, m_turbidity, m_albedo, sun_theta);
-        cf[9][i] = (float)evaluate(rad, 1, m_turbidity, m_albedo, sun_theta);
+        cf[7][i] = (float)evaluate(rgb + 8, 9, m_turbidity, m_ground_albedo, sun_theta);
+        cf[8][i] = (float)evaluate(rgb + 7, 9, m_turbidity, m_ground_albedo, sun_theta);
+        cf[9][i] = (float)evaluate(rad, 1, m_turbidity, m_ground_albedo, sun_theta);
     }
-    if (m_normalized_sun_y != 0.0f)
+    if (m_sun_luminance_target != 0.0f)
     {
         float S[3];
         for (int i = 0; i < 3; i++) S[i] = hosek(std::cos(sun_theta), 0.0f, 1.0f, cf, i) * cf[9][i];
         const float lum = S[0] * 0.2126f + S[1] * 0.7152f + S[2] * 0.0722f;
-        for (int i = 0; i < 3; i++) cf[9][i] = cf[9][i] / lum, cf[9][i] = cf[9][i] * m_normalized_sun_y;
+        for (int i = 0; i < 3; i++) cf[9][i] = cf[9][i] / lum, cf[9][i] = cf[9][i] * m_sun_luminance_target;
     }
     for (int k = 0; k < 10; k++)
     {
@@ -117,12 +117,12 @@ void HosekWilkieSkyModel::evaluate_coefficients(glm::vec3 direction, float out40
 void HosekWilkieSkyModel::update(vk::CommandBuffer::Ptr cmd_buf, glm::vec3 direction)
 {
     (void)cmd_buf;
-    evaluate_coefficients(direction, m_coeffs);
+    evaluate_coefficients(direction, m_block);
     auto backend = m_backend.lock();
     if (backend && backend->has_device())
     {
         const float sun[3] = { direction.x, direction.y, direction.z };
-        backend->check(hl_sky_update(backend->context(), m_coeffs, sun), "hl_sky_update");
+        backend->check(hl_sky_update(backend->context(), m_block, sun), "hl_sky_update");
     }
 }
 } // namespace helios

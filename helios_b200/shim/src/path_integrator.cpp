@@ -18,27 +18,27 @@ void PathIntegrator::render(RenderState& render_state)
 {
     if (render_state.scene_state() != SCENE_STATE_READY)
     {
-        m_tile_idx                = 0;
-        m_num_accumulated_samples = 0;
+        m_bake.tile                = 0;
+        m_bake.samples = 0;
     }
     m_launched = false;
-    if (m_tile_idx < m_tile_coords.size())
+    if (m_bake.tile < m_tiles.size())
     {
         if (!render_state.camera())
         {
             HELIOS_LOG_ERROR("PathIntegrator::render: the scene has no enabled camera");
             return;
         }
-        const glm::uvec2 tile = m_tile_coords[m_tile_idx];
-        launch_rays(render_state, m_tile_size.x, m_tile_size.y, 1, render_state.camera()->view_matrix(), render_state.camera()->projection_matrix(), glm::ivec2((int)tile.x, (int)tile.y),
+        const glm::uvec2 tile = m_tiles[m_bake.tile];
+        launch_rays(render_state, m_tile_extent.x, m_tile_extent.y, 1, render_state.camera()->view_matrix(), render_state.camera()->projection_matrix(), glm::ivec2((int)tile.x, (int)tile.y),
                     glm::ivec2(0, 0));
-        m_num_accumulated_samples++;
+        m_bake.samples++;
         m_launched = true;
     }
-    if (m_num_accumulated_samples == m_max_samples)
+    if (m_bake.samples == m_cfg.max_samples)
     {
-        m_num_accumulated_samples = 0;
-        m_tile_idx++;
+        m_bake.samples = 0;
+        m_bake.tile++;
     }
 }
 
@@ -50,7 +50,7 @@ void PathIntegrator::on_window_resize()
 
 void PathIntegrator::set_tiled(bool tiled)
 {
-    m_tiled = tiled;
+    m_cfg.tiled = tiled;
     compute_tile_coords();
 }
 
@@ -91,11 +91,11 @@ hl_push_constants PathIntegrator::make_push_constants(RenderState& render_state,
     pc.ray_debug_pixel_coord[2] = (int32_t)extents.width, pc.ray_debug_pixel_coord[3] = (int32_t)extents.height;
     pc.launch_id_size[0] = (uint32_t)tile_coord.x, pc.launch_id_size[1] = (uint32_t)tile_coord.y, pc.launch_id_size[2] = extents.width, pc.launch_id_size[3] = extents.height;
     pc.num_lights      = render_state.num_lights();
-    pc.num_frames      = m_num_accumulated_samples;
+    pc.num_frames      = m_bake.samples;
     pc.accumulation    = float(pc.num_frames) / float(pc.num_frames + 1);
     pc.debug_vis       = 0;
-    pc.max_ray_bounces = m_max_ray_bounces;
-    pc.shadow_ray_bias = m_shadow_ray_bias;
+    pc.max_ray_bounces = m_cfg.max_bounces;
+    pc.shadow_ray_bias = m_cfg.shadow_bias;
     pc.focal_length    = cam->focal_length();
     pc.aperture_radius = cam->aperture_radius();
     return pc;
@@ -120,18 +120,18 @@ void PathIntegrator::compute_tile_coords()
 {
     auto       backend = m_backend.lock();
     const auto extents = backend->swap_chain_extents();
-    m_tile_coords.clear();
-    if (m_tiled)
+    m_tiles.clear();
+    if (m_cfg.tiled)
     {
         const uint32_t nx = (uint32_t)ceilf(float(extents.width) / float(TILE_SIZE)), ny = (uint32_t)ceilf(float(extents.height) / float(TILE_SIZE));
         for (uint32_t x = 0; x < nx; x++)
-            for (uint32_t y = 0; y < ny; y++) m_tile_coords.push_back(glm::uvec2(x * TILE_SIZE, y * TILE_SIZE));
-        m_tile_size = glm::uvec2(TILE_SIZE, TILE_SIZE);
+            for (uint32_t y = 0; y < ny; y++) m_tiles.push_back(glm::uvec2(x * TILE_SIZE, y * TILE_SIZE));
+        m_tile_extent = glm::uvec2(TILE_SIZE, TILE_SIZE);
     }
     else
     {
-        m_tile_coords.push_back(glm::uvec2(0, 0));
-        m_tile_size = glm::uvec2(extents.width, extents.height);
+        m_tiles.push_back(glm::uvec2(0, 0));
+        m_tile_extent = glm::uvec2(extents.width, extents.height);
     }
 }
 } // namespace helios

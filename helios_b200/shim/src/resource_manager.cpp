@@ -150,7 +150,7 @@ Texture2D::Ptr ResourceManager::load_texture_2d(const std::string& path, bool sr
 {
     if (m_backend.expired()) return nullptr;
     vk::BatchUploader uploader(m_backend.lock());
-    auto              resource = load_texture_2d_internal(path, srgb, uploader);
+    auto              resource = fetch_texture_2d(path, srgb, uploader);
     uploader.submit();
     return resource;
 }
@@ -158,7 +158,7 @@ TextureCube::Ptr ResourceManager::load_texture_cube(const std::string& path, boo
 {
     if (m_backend.expired()) return nullptr;
     vk::BatchUploader uploader(m_backend.lock());
-    auto              resource = load_texture_cube_internal(path, srgb, uploader);
+    auto              resource = fetch_texture_cube(path, srgb, uploader);
     uploader.submit();
     return resource;
 }
@@ -166,7 +166,7 @@ Material::Ptr ResourceManager::load_material(const std::string& path)
 {
     if (m_backend.expired()) return nullptr;
     vk::BatchUploader uploader(m_backend.lock());
-    auto              resource = load_material_internal(path, uploader);
+    auto              resource = fetch_material(path, uploader);
     uploader.submit();
     return resource;
 }
@@ -174,7 +174,7 @@ Mesh::Ptr ResourceManager::load_mesh(const std::string& path)
 {
     if (m_backend.expired()) return nullptr;
     vk::BatchUploader uploader(m_backend.lock());
-    auto              resource = load_mesh_internal(path, uploader);
+    auto              resource = fetch_mesh(path, uploader);
     uploader.submit();
     return resource;
 }
@@ -186,15 +186,15 @@ Scene::Ptr ResourceManager::load_scene(const std::string& path)
     ast::Scene        ast_scene;
     const std::string full = full_path(path);
     if (!ast::load_scene(full, ast_scene)) return nullptr;
-    Node::Ptr root = ast_scene.scene_graph ? create_node(ast_scene.scene_graph, uploader) : nullptr;
+    Node::Ptr root = ast_scene.scene_graph ? node_from_description(ast_scene.scene_graph, uploader) : nullptr;
     uploader.submit();
     return root ? Scene::create(backend, ast_scene.name, root, full) : nullptr;
 }
 
-Texture2D::Ptr ResourceManager::load_texture_2d_internal(const std::string& path, bool srgb, vk::BatchUploader&)
+Texture2D::Ptr ResourceManager::fetch_texture_2d(const std::string& path, bool srgb, vk::BatchUploader&)
 {
-    auto it = m_textures_2d.find(path);
-    if (it != m_textures_2d.end()) return it->second;
+    auto it = m_cache_2d.find(path);
+    if (it != m_cache_2d.end()) return it->second;
     ast::Image        image;
     const std::string full = full_path(path);
     if (!ast::load_image(full, image))
@@ -211,13 +211,13 @@ Texture2D::Ptr ResourceManager::load_texture_2d_internal(const std::string& path
         return nullptr;
     }
     Texture2D::Ptr texture = Texture2D::create(m_backend.lock(), fmt, w, h, texels.data(), full);
-    if (texture) m_textures_2d[path] = texture;
+    if (texture) m_cache_2d[path] = texture;
     return texture;
 }
-TextureCube::Ptr ResourceManager::load_texture_cube_internal(const std::string& path, bool srgb, vk::BatchUploader&)
+TextureCube::Ptr ResourceManager::fetch_texture_cube(const std::string& path, bool srgb, vk::BatchUploader&)
 {
-    auto it = m_textures_cube.find(path);
-    if (it != m_textures_cube.end()) return it->second;
+    auto it = m_cache_cube.find(path);
+    if (it != m_cache_cube.end()) return it->second;
     ast::Image        image;
     const std::string full = full_path(path);
     if (!ast::load_image(full, image) || image.array_slices != 6)
@@ -256,10 +256,10 @@ TextureCube::Ptr ResourceManager::load_texture_cube_internal(const std::string& 
             }
     }
     TextureCube::Ptr texture = TextureCube::create(m_backend.lock(), size, faces.data(), full);
-    if (texture) m_textures_cube[path] = texture;
+    if (texture) m_cache_cube[path] = texture;
     return texture;
 }
-Material::Ptr ResourceManager::load_material_internal(const std::string& path, vk::BatchUploader& uploader)
+Material::Ptr ResourceManager::fetch_material(const std::string& path, vk::BatchUploader& uploader)
 {
     auto it = m_materials.find(path);
     if (it != m_materials.end()) return it->second;
@@ -282,7 +282,7 @@ Material::Ptr ResourceManager::load_material_internal(const std::string& path, v
         if (slot_of.find(t.path) == slot_of.end())
         {
             slot_of[t.path] = (uint32_t)textures.size();
-            textures.push_back(load_texture_2d_internal(t.path, t.srgb, uploader));
+            textures.push_back(fetch_texture_2d(t.path, t.srgb, uploader));
         }
         info->array_index   = (int32_t)slot_of[t.path];
         info->channel_index = (int32_t)t.channel_index;
@@ -308,7 +308,7 @@ Material::Ptr ResourceManager::load_material_internal(const std::string& path, v
     m_materials[path] = material;
     return material;
 }
-Mesh::Ptr ResourceManager::load_mesh_internal(const std::string& path, vk::BatchUploader& uploader)
+Mesh::Ptr ResourceManager::fetch_mesh(const std::string& path, vk::BatchUploader& uploader)
 {
     auto it = m_meshes.find(path);
     if (it != m_meshes.end()) return it->second;
@@ -364,7 +364,7 @@ Mesh::Ptr ResourceManager::load_mesh_internal(const std::string& path, vk::Batch
         }
     }
     std::vector<Material::Ptr> materials(am.material_paths.size());
-    for (size_t i = 0; i < materials.size(); i++) materials[i] = load_material_internal(am.material_paths[i], uploader);
+    for (size_t i = 0; i < materials.size(); i++) materials[i] = fetch_material(am.material_paths[i], uploader);
     for (const SubMesh& sm : submeshes)
         if (sm.mat_idx >= materials.size() || !materials[sm.mat_idx])
         {
@@ -376,7 +376,7 @@ Mesh::Ptr ResourceManager::load_mesh_internal(const std::string& path, vk::Batch
     return mesh;
 }
 
-Node::Ptr ResourceManager::create_node(std::shared_ptr<ast::SceneNode> n, vk::BatchUploader& uploader)
+Node::Ptr ResourceManager::node_from_description(std::shared_ptr<ast::SceneNode> n, vk::BatchUploader& uploader)
 {
     if (!n) return nullptr;
     switch (n->type)
@@ -386,20 +386,20 @@ Node::Ptr ResourceManager::create_node(std::shared_ptr<ast::SceneNode> n, vk::Ba
             MeshNode::Ptr node = std::shared_ptr<MeshNode>(new MeshNode(n->name));
             if (n->mesh != "")
             {
-                Mesh::Ptr mesh = load_mesh_internal(n->mesh, uploader);
+                Mesh::Ptr mesh = fetch_mesh(n->mesh, uploader);
                 if (mesh)
                     node->set_mesh(mesh);
                 else
                     HELIOS_LOG_ERROR("Failed to load mesh: " + n->mesh);
                 if (n->material_override != "")
                 {
-                    Material::Ptr material_override = load_material_internal(n->material_override, uploader);
+                    Material::Ptr material_override = fetch_material(n->material_override, uploader);
                     if (!material_override) HELIOS_LOG_ERROR("Failed to load material override: " + n->material_override);
                     node->set_material_override(material_override);
                 }
             }
-            populate_transform_node(node, n);
-            populate_scene_node(node, n, uploader);
+            fill_transform(node, n);
+            fill_node(node, n, uploader);
             return node;
         }
         case ast::SCENE_NODE_CAMERA:
@@ -408,8 +408,8 @@ Node::Ptr ResourceManager::create_node(std::shared_ptr<ast::SceneNode> n, vk::Ba
             node->set_near_plane(n->near_plane);
             node->set_far_plane(n->far_plane);
             node->set_fov(n->fov);
-            populate_transform_node(node, n);
-            populate_scene_node(node, n, uploader);
+            fill_transform(node, n);
+            fill_node(node, n, uploader);
             return node;
         }
         case ast::SCENE_NODE_DIRECTIONAL_LIGHT:
@@ -418,8 +418,8 @@ Node::Ptr ResourceManager::create_node(std::shared_ptr<ast::SceneNode> n, vk::Ba
             node->set_color(glm::vec3(n->color[0], n->color[1], n->color[2]));
             node->set_intensity(n->intensity);
             node->set_radius(n->radius);
-            populate_transform_node(node, n);
-            populate_scene_node(node, n, uploader);
+            fill_transform(node, n);
+            fill_node(node, n, uploader);
             return node;
         }
         case ast::SCENE_NODE_SPOT_LIGHT:
@@ -430,8 +430,8 @@ Node::Ptr ResourceManager::create_node(std::shared_ptr<ast::SceneNode> n, vk::Ba
             node->set_radius(n->radius);
             node->set_inner_cone_angle(n->inner_cone_angle);
             node->set_outer_cone_angle(n->inner_cone_angle); // sic: the reference passes the INNER angle twice (resource_manager.cpp:591)
-            populate_transform_node(node, n);
-            populate_scene_node(node, n, uploader);
+            fill_transform(node, n);
+            fill_node(node, n, uploader);
             return node;
         }
         case ast::SCENE_NODE_POINT_LIGHT:
@@ -440,8 +440,8 @@ Node::Ptr ResourceManager::create_node(std::shared_ptr<ast::SceneNode> n, vk::Ba
             node->set_color(glm::vec3(n->color[0], n->color[1], n->color[2]));
             node->set_intensity(n->intensity);
             node->set_radius(n->radius);
-            populate_transform_node(node, n);
-            populate_scene_node(node, n, uploader);
+            fill_transform(node, n);
+            fill_node(node, n, uploader);
             return node;
         }
         case ast::SCENE_NODE_IBL:
@@ -449,34 +449,34 @@ Node::Ptr ResourceManager::create_node(std::shared_ptr<ast::SceneNode> n, vk::Ba
             IBLNode::Ptr node = std::shared_ptr<IBLNode>(new IBLNode(n->name));
             if (n->image != "")
             {
-                TextureCube::Ptr cube = load_texture_cube_internal(n->image, false, uploader);
+                TextureCube::Ptr cube = fetch_texture_cube(n->image, false, uploader);
                 if (cube)
                     node->set_image(cube);
                 else
                     HELIOS_LOG_ERROR("Failed to load cubemap: " + n->image);
             }
-            populate_scene_node(node, n, uploader);
+            fill_node(node, n, uploader);
             return node;
         }
         case ast::SCENE_NODE_ROOT:
         {
             RootNode::Ptr node = std::shared_ptr<RootNode>(new RootNode(n->name));
-            populate_transform_node(node, n);
-            populate_scene_node(node, n, uploader);
+            fill_transform(node, n);
+            fill_node(node, n, uploader);
             return node;
         }
         default: return nullptr; // SCENE_NODE_CUSTOM has no engine node (resource_manager.cpp:513)
     }
 }
-void ResourceManager::populate_scene_node(Node::Ptr node, std::shared_ptr<ast::SceneNode> ast_node, vk::BatchUploader& uploader)
+void ResourceManager::fill_node(Node::Ptr node, std::shared_ptr<ast::SceneNode> ast_node, vk::BatchUploader& uploader)
 {
     for (auto& ast_child : ast_node->children)
     {
-        Node::Ptr child = create_node(ast_child, uploader);
+        Node::Ptr child = node_from_description(ast_child, uploader);
         if (child) node->add_child(child);
     }
 }
-void ResourceManager::populate_transform_node(TransformNode::Ptr node, std::shared_ptr<ast::SceneNode> ast_node)
+void ResourceManager::fill_transform(TransformNode::Ptr node, std::shared_ptr<ast::SceneNode> ast_node)
 {
     node->set_from_local_transform(recompose_matrix_from_components(ast_node->position, ast_node->rotation, ast_node->scale));
 }

@@ -216,7 +216,7 @@ void MeshNode::set_mesh(std::shared_ptr<Mesh> mesh)
 }
 void MeshNode::set_material_override(std::shared_ptr<Material> material_override) { m_material_override = material_override; }
 
-DirectionalLightNode::DirectionalLightNode(const std::string& name) : TransformNode(NODE_DIRECTIONAL_LIGHT, name) {}
+DirectionalLightNode::DirectionalLightNode(const std::string& name) : TransformNode(NODE_DIRECTIONAL_LIGHT, name), LightParameters(0.1f) {}
 DirectionalLightNode::~DirectionalLightNode() {}
 void DirectionalLightNode::update(RenderState& render_state)
 {
@@ -226,7 +226,7 @@ void DirectionalLightNode::update(RenderState& render_state)
     update_children(render_state);
 }
 
-SpotLightNode::SpotLightNode(const std::string& name) : TransformNode(NODE_SPOT_LIGHT, name) {}
+SpotLightNode::SpotLightNode(const std::string& name) : TransformNode(NODE_SPOT_LIGHT, name), LightParameters(5.0f) {}
 SpotLightNode::~SpotLightNode() {}
 void SpotLightNode::update(RenderState& render_state)
 {
@@ -236,7 +236,7 @@ void SpotLightNode::update(RenderState& render_state)
     update_children(render_state);
 }
 
-PointLightNode::PointLightNode(const std::string& name) : TransformNode(NODE_POINT_LIGHT, name) {}
+PointLightNode::PointLightNode(const std::string& name) : TransformNode(NODE_POINT_LIGHT, name), LightParameters(5.0f) {}
 PointLightNode::~PointLightNode() {}
 void PointLightNode::update(RenderState& render_state)
 {
