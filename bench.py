@@ -321,7 +321,7 @@ def main():
     }
 
     # ---------------- end to end through the C ABI with host buffers ----------------
-    host_ring = [torch.empty((scene.height, scene.width, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(3)]
+    host_ring = [torch.empty((scene.height, scene.width, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(8)]  # one per frame that can be in flight (HL_OPT_FRAMES_IN_FLIGHT <= 8)
     host_img = host_ring[0]
     ctx.accum_clear()
     ctx.reset_counters()
@@ -334,7 +334,7 @@ def main():
         if dist is None:
             # fused accumulate + tone-map resolve pass, RGBA8 image copied to pinned host memory on the frame's own stream
             # (every step's image reaches the host; the copy of step s overlaps the rendering of step s + 1)
-            ctx.render_frame_readback(pc, host_ring[s % 3], 1.0, abi.TONE_MAP_ACES)
+            ctx.render_frame_readback(pc, host_ring[s % 8], 1.0, abi.TONE_MAP_ACES)
         else:  # sum mode: separate tone-map pass (needs the sample scale)
             ctx.render_frame(pc)
             ctx._chk(ctx.lib.hl_tonemap(ctx.h, C.c_float(1.0), C.c_int(0), C.c_float(1.0 / (s + 1)), host_img.ctypes.data_as(C.c_void_p)))

@@ -224,8 +224,9 @@ HL_API hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_consta
 /* The same, plus an asynchronous device->host copy of the frame's RGBA8 image into rgba8_host (W*H*4 bytes, pinned memory
  * for a truly asynchronous copy) on the frame's own stream: the read-back of frame f overlaps the rendering of frame
  * f + 1 (the reference's save path also trails the frame, renderer.cpp:637-711).  The image is complete after
- * hl_synchronize(); the caller must not reuse rgba8_host before that (or before two later frames were issued and
- * synchronised).  Full-frame or tiled launches. */
+ * hl_synchronize(); the caller must not reuse rgba8_host before that: with N frames in flight (HL_OPT_FRAMES_IN_FLIGHT,
+ * default 4) a ring of N host buffers is safe, because frame f + N runs on frame f's stream, behind its copy.  Full-frame
+ * or tiled launches. */
 HL_API hl_status hl_render_frame_readback(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h,
                                           float exposure, int tone_map_operator, uint8_t* rgba8_host);
 /* copies the RGBA8 target written by the last hl_tonemap / hl_render_frame_tonemapped to host memory (synchronises) */

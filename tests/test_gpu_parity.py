@@ -196,8 +196,8 @@ def test_fused_resolve_equals_separate_tone_map():
 
 
 def test_pipelined_readback_and_tiles():
-    """hl_render_frame_readback: every frame's RGBA8 image lands in host memory asynchronously (frames alternate between
-    two wavefront slots / streams); the images equal the synchronous path's, also for tiled launches, and switching
+    """hl_render_frame_readback: every frame's RGBA8 image lands in host memory asynchronously (frames rotate through the
+    wavefront slots / streams); the images equal the synchronous path's, also for tiled launches, and switching
     the frame pipeline off (HL_OPT_PIPELINE = 0) changes nothing"""
     import torch
 
@@ -223,14 +223,18 @@ def test_pipelined_readback_and_tiles():
     for f in range(5):
         assert np.array_equal(host[f], ref_imgs[f]), f
     # tiled: four 80x64 launches per sample; the image after each sample's last tile equals the full-frame one
+    # (one host buffer per launch in flight: copies issued on different streams are not ordered among themselves)
+    tile_host = [torch.empty((s.height, s.width, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(8)]
     ctx.accum_clear()
+    k = 0
     for f in range(5):
         for ty in (0, 64):
             for tx in (0, 80):
-                ctx.render_frame_readback(s.push_constants(f, tile=(tx, ty)), host[f], launch=(80, 64))
+                ctx.render_frame_readback(s.push_constants(f, tile=(tx, ty)), tile_host[k % 8], launch=(80, 64))
+                k += 1
     ctx.synchronize()
     assert np.array_equal(ctx.read_accum(), ref_acc)
-    assert np.array_equal(host[4], ref_imgs[4])
+    assert np.array_equal(tile_host[(k - 1) % 8], ref_imgs[4])
     ctx.close()
 
 
