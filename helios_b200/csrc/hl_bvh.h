@@ -149,13 +149,19 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
     // 2.6e8 secondary rays of the city scene lost an edge hit, u + v = 0.99999, in one tree and not in another).
     // The slack is folded into the fma addend: near planes use org - s, far planes org + s.  (Scaled per axis
     // by |idir|, not a common maximum in t: an axis with a near-zero direction component has a huge |idir| and
-    // would otherwise open every box of the tree.)  2^-19 * 1536 |adj| = 2^-8.4 |adj| > 2^-9 |adj| (rounding of
+    // would otherwise open every box of the tree.)  2^-16 * 192 |adj| = 2^-8.4 |adj| > 2^-9 |adj| (rounding of
     // B) + the 2^-19 * 255 |adj| of the exact-byte formulation.
-    const float C  = 1.9073486e-6f; /* 2^-19 */
+    // The factor on D: the fp32 Moeller-Trumbore test places the hit with an in-plane error of about
+    // k / cos(theta) * 2^-24 * D (k a handful of roundings, theta the angle between ray and triangle normal), so a
+    // grazing ray can be accepted while passing the triangle's box at that distance.  2^-19 D covered k / cos(theta)
+    // <= 32 and lost one edge hit (u + v = 0.99995 on a wall seen at 107 units, grazing) of 5e7 rays of the 4K city
+    // frame in the LBVH tree but not in the SAH tree (tests/test_gpu_fullsize.py found it); 2^-16 D covers
+    // k / cos(theta) <= 256, i.e. rays within 0.5 degrees of the plane, and inflates a box by 1.5e-5 of its distance.
+    const float C  = 1.5258789e-5f; /* 2^-16 */
     const float D  = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-    const float sx = C * (fabsf(r.idir.x) * D + 1536.0f * fabsf(adjx));
-    const float sy = C * (fabsf(r.idir.y) * D + 1536.0f * fabsf(adjy));
-    const float sz = C * (fabsf(r.idir.z) * D + 1536.0f * fabsf(adjz));
+    const float sx = C * (fabsf(r.idir.x) * D + 192.0f * fabsf(adjx));
+    const float sy = C * (fabsf(r.idir.y) * D + 192.0f * fabsf(adjy));
+    const float sz = C * (fabsf(r.idir.z) * D + 192.0f * fabsf(adjz));
     const float Ax = adjx * 32768.0f, Ay = adjy * 32768.0f, Az = adjz * 32768.0f;
     const float Bnx = (orgx - sx) - Ax, Bfx = (orgx + sx) - Ax;
     const float Bny = (orgy - sy) - Ay, Bfy = (orgy + sy) - Ay;

@@ -412,12 +412,18 @@ static void mesh_build_bvh(Mesh& m)
 static inline bool box_test(const float* lo, const float* hi, vec3 o, vec3 d, float tmin, float tmax)
 {
     double t0 = tmin, t1 = tmax;
+    // distance over ALL axes: a ray that grazes an axis-aligned wall is close to the box in the wall's axis and far away
+    // in the others, and the triangle test's placement error scales with the far ones
+    double dist = 0.0, ext = 0.0;
+    for (int a = 0; a < 3; a++)
+    {
+        dist = std::max(dist, std::max(std::fabs((double)o[a] - lo[a]), std::fabs((double)o[a] - hi[a])));
+        ext  = std::max(ext, (double)hi[a] - (double)lo[a]);
+    }
+    const double margin = 1e-4 * (dist + ext) + 1e-30;
     for (int a = 0; a < 3; a++)
     {
         double oa = o[a], da = d[a];
-        double ext    = (double)hi[a] - (double)lo[a];
-        double dist   = std::max(std::fabs(oa - lo[a]), std::fabs(oa - hi[a]));
-        double margin = 1e-5 * (dist + ext) + 1e-30;
         double l = lo[a] - margin, h = hi[a] + margin;
         if (da == 0.0)
         {
