@@ -157,7 +157,10 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
     // <= 32 and lost one edge hit (u + v = 0.99995 on a wall seen at 107 units, grazing) of 5e7 rays of the 4K city
     // frame in the LBVH tree but not in the SAH tree (tests/test_gpu_fullsize.py found it); 2^-16 D covers
     // k / cos(theta) <= 256, i.e. rays within 0.5 degrees of the plane, and inflates a box by 1.5e-5 of its distance.
-    const float C  = 1.5258789e-5f; /* 2^-16 */
+#ifndef HL_NODE_SLACK
+#define HL_NODE_SLACK 1.5258789e-5f /* 2^-16 */
+#endif
+    const float C  = HL_NODE_SLACK;
     const float D  = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
     const float sx = C * (fabsf(r.idir.x) * D + 192.0f * fabsf(adjx));
     const float sy = C * (fabsf(r.idir.y) * D + 192.0f * fabsf(adjy));

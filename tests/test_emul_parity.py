@@ -207,3 +207,25 @@ def test_bounce_limits(bounces, oracle_mod, emul):
     o, e = pair(s, oracle_mod, emul)
     a, b = o.render(3, max_ray_bounces=bounces), e.render(3, max_ray_bounces=bounces)
     assert np.abs(a - b)[..., :3].max() < 2e-6 and a[..., :3].max() > 0
+
+
+def test_grazing_rays_never_lose_an_edge_hit(oracle_mod, emul):
+    """tests/graze.py: 300 000 adversarial grazing rays; the device traversal (both tree builds, one- and two-level) and the
+    oracle's BVH must return the brute-force closest hit for every one of them, bit for bit"""
+    import ctypes as C
+
+    from tests import graze
+
+    s, tris = graze.graze_scene()
+    rays = graze.graze_rays(tris, 300_000)
+    brute = oracle_mod.OracleScene(s, brute_force=True).trace_rays(rays, 0)
+    assert np.isfinite(brute[:, 0]).mean() > 0.9
+    assert np.array_equal(oracle_mod.OracleScene(s).trace_rays(rays, 0).view(np.uint32), brute.view(np.uint32))
+    try:
+        for top, two_level in ((0, False), (2, False), (2, True)):
+            emul.lib().em_set_sah_top(C.c_int(top))
+            h = emul.EmulScene(s, force_two_level=two_level).trace_rays(rays, 0)
+            bad = (h.view(np.uint32) != brute.view(np.uint32)).any(1)
+            assert not bad.any(), f"tree {top}, two-level {two_level}: {int(bad.sum())} of {len(rays)} grazing rays differ from brute force"
+    finally:
+        emul.lib().em_set_sah_top(C.c_int(2))  # HL_DEFAULT_SAH_CLUSTER

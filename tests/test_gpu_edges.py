@@ -221,3 +221,21 @@ def test_cuda_graph_replay_follows_every_setting(api):
     assert np.array_equal(run(g, a2, 9), run(p, a2, 9))
     assert g.kernel_launches() == p.kernel_launches()  # graph nodes are counted like plain launches
     g.close(), p.close()
+
+
+def test_grazing_rays_never_lose_an_edge_hit(api, oracle_mod):
+    """tests/graze.py on the GPU: 2e6 adversarial grazing rays through the LBVH tree and the SAH re-split tree; both must
+    return the oracle's hit (its BVH is checked against brute force in tests/test_emul_parity.py) bit for bit"""
+    from tests import graze
+
+    s, tris = graze.graze_scene()
+    rays = graze.graze_rays(tris, 2_000_000)
+    ref = oracle_mod.OracleScene(s).trace_rays(rays, 0)
+    for cluster in (0, 2):
+        ctx = api.Context(s.width, s.height)
+        ctx.set_option(abi.OPT_SAH_CLUSTER, cluster)
+        ctx.load_scene(s)
+        h = ctx.trace_rays(rays, 0)
+        bad = (h.view(np.uint32) != ref.view(np.uint32)).any(1)
+        assert not bad.any(), f"SAH cluster {cluster}: {int(bad.sum())} of {len(rays)} grazing rays differ"
+        ctx.close()
