@@ -229,3 +229,43 @@ def test_grazing_rays_never_lose_an_edge_hit(oracle_mod, emul):
             assert not bad.any(), f"tree {top}, two-level {two_level}: {int(bad.sum())} of {len(rays)} grazing rays differ from brute force"
     finally:
         emul.lib().em_set_sah_top(C.c_int(2))  # HL_DEFAULT_SAH_CLUSTER
+
+
+@pytest.mark.parametrize("tex_size", [1, 3, 5, 7])
+def test_odd_texture_extents(tex_size, oracle_mod, emul):
+    """REPEAT addressing without integer modulo (hl_tex.h texture_footprint) on 1x1 and non-power-of-two textures, through
+    the any-hit alpha fetch and the albedo fetch"""
+    s = scenes.foliage_scene(n_clusters=30, cards_per_cluster=8, width=48, height=27, ground_grid=4, tex_size=tex_size)
+    o, e = pair(s, oracle_mod, emul)
+    pc = s.push_constants(1)
+    assert_ids_equal(o.trace_primary_ids(pc), e.trace_primary_ids(pc))
+    assert np.abs(o.render(3) - e.render(3)).max() < 2e-6
+
+
+def hostile_rays(n=2000, seed=0):
+    """zero / NaN / denormal / huge directions, infinite and NaN origins and intervals: a traversal must terminate on them"""
+    rng = np.random.default_rng(seed)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.normal(size=(n, 3)) * 30
+    rays[:, 3] = 1e-3
+    rays[:, 4:7] = rng.normal(size=(n, 3))
+    rays[:, 7] = 1e4
+    rays[0::10, 4:7] = 0.0
+    rays[1::10, 4] = np.nan
+    rays[2::10, 0] = np.inf
+    rays[3::10, 4:7] *= 1e-30
+    with np.errstate(over="ignore"):
+        rays[4::10, 4:7] *= np.float32(1e30)
+        rays[7::10, 0:3] *= np.float32(1e20)
+    rays[5::10, 7] = np.inf
+    rays[6::10, 3] = np.nan
+    return rays
+
+
+@pytest.mark.timeout(120)
+def test_hostile_rays_terminate_and_match(oracle_mod, emul):
+    s = SCENES["city"]()
+    o, e = pair(s, oracle_mod, emul)
+    rays = hostile_rays()
+    a, b = o.trace_rays(rays, 0), e.trace_rays(rays, 0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

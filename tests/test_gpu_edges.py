@@ -239,3 +239,18 @@ def test_grazing_rays_never_lose_an_edge_hit(api, oracle_mod):
         bad = (h.view(np.uint32) != ref.view(np.uint32)).any(1)
         assert not bad.any(), f"SAH cluster {cluster}: {int(bad.sum())} of {len(rays)} grazing rays differ"
         ctx.close()
+
+
+@pytest.mark.timeout(120)
+def test_hostile_rays_terminate_and_match(api, oracle_mod):
+    """zero / NaN / denormal / huge directions, infinite origins, NaN intervals (checked on the CPU emulation first:
+    tests/test_emul_parity.py): the kernels terminate and return the oracle's answer"""
+    from tests.test_emul_parity import hostile_rays
+
+    s = scenes.city_scene(n_instances=30, n_meshes=3, width=96, height=54, floors=(2, 4), detail=(1, 3))
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    rays = hostile_rays(20000)
+    a, b = ctx.trace_rays(rays, 0), oracle_mod.OracleScene(s).trace_rays(rays, 0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    ctx.close()
