@@ -181,8 +181,11 @@ HL_HD void sah_node_costs(BinaryTree& t, uint32_t node, float area)
     const uint32_t P       = subtree_prims(t, node);
     const float    c_leaf  = P <= HL_MAX_LEAF_PRIMS ? area * (float)P * t.c_prim : inf;
     const float    c_inner = area * HL_SAH_C_NODE + D[8];
-    float          c       = c_leaf <= c_inner ? c_leaf : c_inner;
-    uint32_t       d       = c_leaf <= c_inner ? 0u : 15u;
+    // (the decision must be valid whatever the costs are: with coordinates around 1e20 the areas overflow to +inf, and
+    //  inf <= inf would make a leaf of a subtree that holds more than HL_MAX_LEAF_PRIMS primitives)
+    const bool     leaf    = P <= HL_MAX_LEAF_PRIMS && c_leaf <= c_inner;
+    float          c       = leaf ? c_leaf : c_inner;
+    uint32_t       d       = leaf ? 0u : 15u;
     uint32_t       packed  = d | (K[8] << 28);
     t.cost[(size_t)node * 7] = c;
     for (int i = 2; i <= 7; i++)

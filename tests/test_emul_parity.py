@@ -269,3 +269,44 @@ def test_hostile_rays_terminate_and_match(oracle_mod, emul):
     rays = hostile_rays()
     a, b = o.trace_rays(rays, 0), e.trace_rays(rays, 0)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def extreme_vertex_scenes():
+    """finite but absurd and non-finite vertex positions: the builder must stay structurally valid (areas overflow to +inf
+    from about 1e19 on) and every triangle that can be hit must still be found"""
+
+    def soup(mod):
+        s = scenes.triangle_soup(500, 64, 36, seed=1)
+        with np.errstate(all="ignore"):
+            mod(s.meshes[0].vertices["position"])
+        return s
+
+    def one(p):
+        p[90, :3] = 1e30
+
+    def tri(p):
+        p[90:93, :3] = 1e30
+
+    def neg(p):
+        p[120:123, :3] = -3e38
+
+    def mixed(p):
+        p[3, 0], p[30, 1], p[60, 2] = np.nan, np.inf, -np.inf
+        p[90:93, :3], p[120:123, :3] = 1e30, -3e38
+
+    return {"one_vertex_1e30": soup(one), "triangle_1e30": soup(tri), "triangle_-3e38": soup(neg), "nan_inf_huge_mixed": soup(mixed)}
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name", ["one_vertex_1e30", "triangle_1e30", "triangle_-3e38", "nan_inf_huge_mixed"])
+def test_extreme_vertices(name, oracle_mod, emul):
+    """(a triangle with one vertex at 1e30 used to make the collapse DP choose a leaf for a subtree of more than three
+    triangles — inf <= inf — and the leaf writer ran past its array)"""
+    s = extreme_vertex_scenes()[name]
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    e = emul.EmulScene(s)
+    pc = s.push_constants(1)
+    with np.errstate(all="ignore"):
+        a, b = o.trace_primary_ids(pc), e.trace_primary_ids(pc)
+    assert_ids_equal(a, b)
+    assert int((a[0] != abi.MISS_ID).sum()) > 100

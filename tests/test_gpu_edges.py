@@ -254,3 +254,22 @@ def test_hostile_rays_terminate_and_match(api, oracle_mod):
     a, b = ctx.trace_rays(rays, 0), oracle_mod.OracleScene(s).trace_rays(rays, 0)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     ctx.close()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name", ["one_vertex_1e30", "triangle_1e30", "triangle_-3e38", "nan_inf_huge_mixed"])
+def test_extreme_vertices(name, api, oracle_mod):
+    """finite but absurd (1e30, -3e38) and non-finite vertex positions: the GPU builder stays valid for both tree builds and
+    the hits equal the oracle's brute force (checked on the CPU emulation first, tests/test_emul_parity.py)"""
+    from tests.test_emul_parity import extreme_vertex_scenes
+
+    s = extreme_vertex_scenes()[name]
+    pc = s.push_constants(1)
+    with np.errstate(all="ignore"):
+        ref = oracle_mod.OracleScene(s, brute_force=True).trace_primary_ids(pc)
+    for cluster in (2, 0):
+        ctx = api.Context(s.width, s.height)
+        ctx.set_option(abi.OPT_SAH_CLUSTER, cluster)
+        ctx.load_scene(s)
+        assert ids_equal(ctx.trace_primary_ids(pc), ref), cluster
+        ctx.close()
