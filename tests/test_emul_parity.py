@@ -310,3 +310,63 @@ def test_extreme_vertices(name, oracle_mod, emul):
         a, b = o.trace_primary_ids(pc), e.trace_primary_ids(pc)
     assert_ids_equal(a, b)
     assert int((a[0] != abi.MISS_ID).sum()) > 100
+
+
+def _set_instance_matrix(s, k, M):
+    s.instances["model_matrix"][k] = M.T.reshape(16).astype(np.float32)  # column-major
+    N4 = np.eye(4)
+    N4[:3, :3] = np.linalg.inv(M[:3, :3]).T
+    s.instances["normal_matrix"][k] = N4.T.reshape(16).astype(np.float32)
+
+
+def instance_transform_scenes():
+    """instanced city variants for the two-level traversal: non-uniform scale / shear / mirror / arbitrary linear maps,
+    every instance at the same place (tie rule across instances), and the whole scene far from the origin"""
+    rng = np.random.default_rng(4)
+    base = lambda: scenes.city_scene(n_instances=12, n_meshes=3, width=96, height=54, floors=(1, 3), detail=(1, 2))  # noqa: E731
+    out = {}
+    s = base()
+    for k in range(1, len(s.instances)):
+        M = np.array(s.instances["model_matrix"][k], np.float64).reshape(4, 4).T
+        A = np.eye(4)
+        if k % 4 == 0:
+            A[:3, :3] = np.diag([1.7, 0.3, 0.9])
+        elif k % 4 == 1:
+            A[0, 1], A[2, 0] = 0.6, -0.4
+        elif k % 4 == 2:
+            A[:3, :3] = np.diag([-1.0, 1.0, 1.0])
+        else:
+            A[:3, :3] = rng.normal(size=(3, 3)) * 0.8
+        _set_instance_matrix(s, k, M @ A)
+    out["non_rigid"] = s
+    s = base()
+    for k in range(2, len(s.instances)):
+        for f in ("model_matrix", "normal_matrix", "mesh_index"):
+            s.instances[f][k] = s.instances[f][1]
+    s.submesh_info = [s.submesh_info[0]] + [s.submesh_info[1]] * (len(s.instances) - 1)
+    out["coincident"] = s
+    s = base()
+    off = np.array([3e5, -2e5, 1e5])
+    for k in range(len(s.instances)):
+        M = np.array(s.instances["model_matrix"][k], np.float64).reshape(4, 4).T
+        M[:3, 3] += off
+        _set_instance_matrix(s, k, M)
+    s.camera.position = (np.asarray(s.camera.position, np.float64) + off).astype(np.float32)
+    out["far_from_origin"] = s
+    return out
+
+
+@pytest.mark.parametrize("name", ["non_rigid", "coincident", "far_from_origin"])
+def test_instance_transform_edge_cases(name, oracle_mod, emul):
+    s = instance_transform_scenes()[name]
+    cf = sky_coefficients(s.sun_direction)
+    o = oracle_mod.OracleScene(s, brute_force=True, sky_coeffs_override=cf, sky_size=32)
+    e = emul.EmulScene(s, sky_faces=oracle_mod.sky_bake(cf, s.sun_direction, 32))
+    for f in (1, 2):
+        pc = s.push_constants(f)
+        a = o.trace_primary_ids(pc)
+        assert_ids_equal(a, e.trace_primary_ids(pc))
+        if name == "coincident":
+            hit = a[0] != abi.MISS_ID
+            assert not np.any(a[0][hit] > 1)  # of the coincident copies the smallest instance id wins
+    assert np.abs(o.render(3) - e.render(3)).max() < 2e-6

@@ -273,3 +273,22 @@ def test_extreme_vertices(name, api, oracle_mod):
         ctx.load_scene(s)
         assert ids_equal(ctx.trace_primary_ids(pc), ref), cluster
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["non_rigid", "coincident", "far_from_origin"])
+def test_instance_transform_edge_cases(name, api, oracle_mod):
+    """two-level traversal with non-uniform scale / shear / mirrored / arbitrary instance transforms, coincident instances
+    (tie rule across instances) and a scene 3e5 units from the origin: hits equal the oracle's brute force"""
+    from tests.test_emul_parity import instance_transform_scenes
+
+    s = instance_transform_scenes()[name]
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    for f in (1, 2):
+        pc = s.push_constants(f)
+        assert ids_equal(ctx.trace_primary_ids(pc), o.trace_primary_ids(pc))
+    rays = np.concatenate([np.random.default_rng(1).normal(size=(20000, 3)) * 20 + np.asarray(s.camera.position), np.full((20000, 1), 1e-3),
+                           np.random.default_rng(2).normal(size=(20000, 3)), np.full((20000, 1), 1e4)], 1).astype(np.float32)
+    assert np.array_equal(ctx.trace_rays(rays, 0).view(np.uint32), o.trace_rays(rays, 0).view(np.uint32))
+    ctx.close()
