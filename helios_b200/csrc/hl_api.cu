@@ -122,6 +122,9 @@ hl_status hl_context_destroy(hl_context ctx)
         if (w.stream) cudaStreamSynchronize(w.stream);
         if (w.graph_exec) cudaGraphExecDestroy(w.graph_exec);
         if (w.stream) cudaStreamDestroy(w.stream);
+        if (w.copy_stream) cudaStreamSynchronize(w.copy_stream), cudaStreamDestroy(w.copy_stream);
+        if (w.image_ready) cudaEventDestroy(w.image_ready);
+        if (w.copy_done) cudaEventDestroy(w.copy_done);
         if (w.resolved) cudaEventDestroy(w.resolved);
     }
     if (ctx->main_ev) cudaEventDestroy(ctx->main_ev);

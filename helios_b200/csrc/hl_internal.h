@@ -132,6 +132,11 @@ struct hl_wave_slot
     cudaStream_t stream   = nullptr;
     cudaEvent_t  resolved = nullptr; // recorded after the slot's last resolve pass
     bool         pending  = false;   // frames were issued on `stream` since the last join with the main stream
+    // asynchronous read-back (hl_render_frame_readback): the device->host copy of `rgba8` runs on its own stream, so the
+    // slot's next frame can start tracing behind it; only that frame's resolve pass (which overwrites rgba8) waits for it
+    cudaStream_t copy_stream  = nullptr;
+    cudaEvent_t  image_ready  = nullptr, copy_done = nullptr;
+    bool         copy_pending = false;
     // the bounce loop of a frame (tail / extend / shade / connect per bounce: ~30 launches with arguments that only change
     // with the scene tables or the integrator settings) as an instantiated CUDA graph; rebuilt when `graph_key` changes
     cudaGraphExec_t graph_exec     = nullptr;

@@ -474,7 +474,10 @@ static void slot_alloc(hl_context_t* ctx, hl_wave_slot& w, size_t n)
     }
     if (!w.stream) HL_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     if (!w.resolved) HL_CUDA(cudaEventCreateWithFlags(&w.resolved, cudaEventDisableTiming));
-    w.pending = false;
+    if (!w.copy_stream) HL_CUDA(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+    if (!w.image_ready) HL_CUDA(cudaEventCreateWithFlags(&w.image_ready, cudaEventDisableTiming));
+    if (!w.copy_done) HL_CUDA(cudaEventCreateWithFlags(&w.copy_done, cudaEventDisableTiming));
+    w.pending = false, w.copy_pending = false;
 }
 static void slot_drop_graph(hl_wave_slot& w)
 {
@@ -532,12 +535,19 @@ void wavefront_release(hl_context_t* ctx)
 void wavefront_join(hl_context_t* ctx)
 {
     for (hl_wave_slot& w : ctx->slot)
+    {
         if (w.pending)
         {
             HL_CUDA(cudaEventRecord(w.resolved, w.stream));
             HL_CUDA(cudaStreamWaitEvent(ctx->stream, w.resolved, 0));
             w.pending = false;
         }
+        if (w.copy_pending)
+        {
+            HL_CUDA(cudaStreamWaitEvent(ctx->stream, w.copy_done, 0));
+            w.copy_pending = false;
+        }
+    }
 }
 
 void film_clear(hl_context_t* ctx)
@@ -702,6 +712,12 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
     if (prof) HL_CUDA(cudaEventRecord(ctx->ev[last], st));
     // progressive blends are applied in frame order: wait for the previous frame's resolve pass
     if (piped && other.pending) HL_CUDA(cudaStreamWaitEvent(st, other.resolved, 0));
+    // ... and this slot's RGBA8 target may still be on its way to the host (read-back of the frame issued n_slots ago)
+    if (w.copy_pending && opt.tone_map)
+    {
+        HL_CUDA(cudaStreamWaitEvent(st, w.copy_done, 0));
+        w.copy_pending = false;
+    }
     const bool full  = lw == ctx->W && lh == ctx->H;
     const bool fused = opt.tone_map && full;
     k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, w.rgba8.as<uint32_t>(), fused ? 1 : 0, opt.exposure, opt.op);
@@ -714,12 +730,25 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
             ctx->launches++;
         }
         ctx->rgba8_cur = w.rgba8.p;
-        if (opt.host) HL_CUDA(cudaMemcpyAsync(opt.host, w.rgba8.p, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost, st));
     }
     if (piped)
     {
-        HL_CUDA(cudaEventRecord(w.resolved, st));
+        HL_CUDA(cudaEventRecord(w.resolved, st)); // the next frame's blend waits for this, not for the copy below
         w.pending = true;
+    }
+    if (opt.tone_map && opt.host)
+    {
+        const size_t bytes = (size_t)ctx->W * ctx->H * 4;
+        if (piped)
+        {
+            HL_CUDA(cudaEventRecord(w.image_ready, st));
+            HL_CUDA(cudaStreamWaitEvent(w.copy_stream, w.image_ready, 0));
+            HL_CUDA(cudaMemcpyAsync(opt.host, w.rgba8.p, bytes, cudaMemcpyDeviceToHost, w.copy_stream));
+            HL_CUDA(cudaEventRecord(w.copy_done, w.copy_stream));
+            w.copy_pending = true;
+        }
+        else
+            HL_CUDA(cudaMemcpyAsync(opt.host, w.rgba8.p, bytes, cudaMemcpyDeviceToHost, st));
     }
     k_totals<<<1, 32, 0, st>>>(ctr, (unsigned long long*)((char*)w.counters.p + CTR_TOTALS_OFFSET), bounces);
     ctx->launches += 2;
