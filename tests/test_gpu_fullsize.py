@@ -114,3 +114,39 @@ def test_configs2_and_3_full_size_invariances(name):
     acc, e, h = render(ctx2, s, frames)
     assert np.array_equal(acc, ref) and (e, h) == (ext, sh)
     ctx2.close()
+
+
+@pytest.mark.parametrize("name", ["terrain", "foliage", "city"])
+def test_full_size_scene_tile_against_oracle(name, oracle_mod):
+    """the full-size scenes of configs[1..3], one 480 x 270 launch rectangle in the middle of the frame (tile offsets as
+    PathIntegrator uses them), 3 launches: primary hit ids equal the oracle's on >= 99.99 % of the tile's rays (north_star
+    bar; thin-lens scenes differ by cosf / sinf ulps), radiance within 1e-4 on >= 99 % of the pixels, relMSE < 2e-3"""
+    from helios_b200 import api
+    from helios_b200.sky import sky_coefficients
+
+    s = {"terrain": scenes.terrain_scene, "foliage": scenes.foliage_scene, "city": scenes.city_scene}[name]()
+    cf = sky_coefficients(s.sun_direction) if s.sun_direction is not None else None
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s, sky_coeffs=cf)
+    o = oracle_mod.OracleScene(s, sky_coeffs_override=cf)
+    tw, th = 480, 270
+    tx, ty = (s.width - tw) // 2, (s.height - th) // 2
+    acc = np.zeros((s.height, s.width, 4), np.float32)
+    acc[..., 3] = 1.0
+    ctx.accum_clear()
+    for f in range(3):
+        pc = s.push_constants(f, tile=(tx, ty))
+        ctx.render_frame(pc, launch=(tw, th))
+        o.render_frame(pc, acc, launch=(tw, th))
+    g = ctx.read_accum()[ty:ty + th, tx:tx + tw, :3]
+    r = acc[ty:ty + th, tx:tx + tw, :3]
+    d = np.abs(g - r).max(-1)
+    assert (d > 1e-4).mean() < 0.01, f"{int((d > 1e-4).sum())} of {d.size} pixels differ by more than 1e-4"
+    mse = float(np.mean((g.astype(np.float64) - r) ** 2) / max(float(np.mean(r.astype(np.float64) ** 2)), 1e-12))
+    assert mse < 2e-3, mse
+    # primary hits of the whole frame through both (the oracle's BVH is conservative: tests/test_emul_parity.py)
+    pc = s.push_constants(1)
+    a, b = ctx.trace_primary_ids(pc), o.trace_primary_ids(pc)
+    same = (a[0] == b[0]) & (a[1] == b[1]) & (a[2] == b[2])
+    assert same.mean() >= 1.0 - 1e-4, f"{int((~same).sum())} of {same.size} primary hits differ"
+    ctx.close()
