@@ -236,7 +236,7 @@ hl_status hl_envmap_set(hl_context ctx, uint32_t size, const float* faces)
         c_->env_faces.upload(faces, (size_t)6 * size * size * 16, c_->stream);
         HL_CUDA(cudaStreamSynchronize(c_->stream));
     }
-    c_->view.env.faces = c_->env_faces.as<f4>(), c_->view.env.size = size;
+    env_pad(c_);
     HL_CATCH
 }
 
@@ -245,7 +245,7 @@ hl_status hl_sky_update(hl_context ctx, const float coeffs[40], const float sun_
     HL_TRY(ctx)
     if (!coeffs || !sun_direction) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_sky_update: null argument");
     sky_bake(c_, coeffs, sun_direction, 512); // SKY_CUBEMAP_SIZE, hosek_wilkie_sky_model.cpp:17
-    c_->view.env.faces = c_->env_faces.as<f4>(), c_->view.env.size = c_->env_size;
+    env_pad(c_);
     HL_CATCH
 }
 
@@ -351,7 +351,7 @@ hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint
     v.materials = c_->materials.as<hl_material>(), v.instances = c_->instances.as<hl_instance>(), v.inst_inv = c_->inst_inv.as<float>();
     v.submesh_info = c_->submesh_info.as<uint32_t>(), v.submesh_offset = c_->submesh_offset.as<uint32_t>(), v.lights = c_->lights.as<hl_light>();
     v.meshes = c_->mesh_views.as<MeshView>(), v.textures = c_->tex_views_dev.as<TexView>(), v.lut8 = c_->lut8.as<float>();
-    v.env.faces = c_->env_faces.as<f4>(), v.env.size = c_->env_size;
+    v.env.faces = c_->env_size ? c_->env_padded.as<f4>() : nullptr, v.env.size = c_->env_size;
     v.tlas_nodes = c_->tlas.nodes.as<WideNode>(), v.tlas_leaf = c_->tlas.leaves.as<uint32_t>();
     v.n_instances = n_instances, v.n_lights = n_lights, v.single_identity = identity ? 1u : 0u;
     c_->scene_ready = true;

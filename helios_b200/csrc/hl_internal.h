@@ -166,7 +166,8 @@ struct hl_context_t
     std::vector<hl_mesh_t*>  meshes;
     std::vector<hl::DevBuf*> textures;
     std::vector<hl::TexView> tex_views;
-    hl::DevBuf               env_faces;
+    hl::DevBuf               env_faces;  // 6 * size^2 texels as uploaded / baked (hl_envmap_read returns these)
+    hl::DevBuf               env_padded; // the same with the one-texel seamless border: what the kernels sample
     uint32_t                 env_size = 0;
     // scene tables
     hl::DevBuf      materials, instances, inst_inv, submesh_info, submesh_offset, lights, mesh_views, tex_views_dev, lut8;
@@ -200,6 +201,7 @@ void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes);
 // hl_wavefront.cu
 void wavefront_alloc(hl_context_t* ctx);
 void wavefront_release(hl_context_t* ctx);
+void env_pad(hl_context_t* ctx); // env_faces -> env_padded + ctx->view.env
 void wavefront_set_slots(hl_context_t* ctx, int n_slots); // HL_OPT_FRAMES_IN_FLIGHT
 void wavefront_join(hl_context_t* ctx); // main stream waits for every frame in flight
 struct ResolveOptions

@@ -57,8 +57,11 @@ struct TexView
 
 struct EnvView
 {
-    const f4* faces; // 6 * size * size
-    uint32_t  size;  // 0 = black default cube map
+    // 6 faces of (size + 2)^2 texels: every face carries a one-texel border holding the texels of the adjoining faces
+    // (corners: the mean of the three that exist), filled once per upload / sky bake (hl_tex.h cube_pad_texel), so that
+    // the seamless bilinear lookup Vulkan prescribes for cube maps is one branch-free 2 x 2 fetch
+    const f4* faces;
+    uint32_t  size; // 0 = black default cube map
 };
 
 struct SceneView

@@ -3,7 +3,7 @@
 // path_trace_rmiss.glsl:60, path_trace_rchit.glsl:370).  The reference leaves filtering to the Vulkan
 // driver (sampler state gfx/vk.cpp:3557-3587: LINEAR, REPEAT); this implementation fixes: level 0 only,
 // fp32 bilinear weights, texel centres at +0.5, 8-bit decode through a host-built LUT, cube faces
-// selected with the Vulkan major-axis table and filtered inside the face with clamp-to-edge.
+// selected with the Vulkan major-axis table and filtered seamlessly across face edges (cube_texel).
 #pragma once
 #include "hl_scene.h"
 
@@ -78,6 +78,60 @@ HL_HD float sample_texture_alpha_lod0(const SceneView& s, int index, float u, fl
     return a * (1.0f - f.fy) + b * f.fy;
 }
 
+// ---- seamless cube maps: the border texels ------------------------------------------------------------------
+// `faces` = 6 * N * N texels without border.  Exactly one of ix, iy is one texel outside face `face`: the texel centre
+// is placed on the extended face plane, folded over the shared edge onto the adjoining face (the coordinate along the
+// edge is kept, the other one becomes the first texel row) and mapped back with the face table of sample_environment().
+HL_HD f4 cube_texel_over_edge(const f4* faces, int N, int face, int ix, int iy)
+{
+    const float inv = 1.0f / (float)N;
+    const float sc = 2.0f * ((float)ix + 0.5f) * inv - 1.0f, tc = 2.0f * ((float)iy + 0.5f) * inv - 1.0f;
+    float       p[3];
+    switch (face)
+    {
+        case 0: p[0] = 1.0f, p[1] = -tc, p[2] = -sc; break;
+        case 1: p[0] = -1.0f, p[1] = -tc, p[2] = sc; break;
+        case 2: p[0] = sc, p[1] = 1.0f, p[2] = tc; break;
+        case 3: p[0] = sc, p[1] = -1.0f, p[2] = -tc; break;
+        case 4: p[0] = sc, p[1] = -tc, p[2] = 1.0f; break;
+        default: p[0] = -sc, p[1] = -tc, p[2] = -1.0f; break;
+    }
+    const int a = face >> 1; // axis of the face's normal
+    int       b = 0;         // axis the texel centre overshoots along
+    for (int k = 0; k < 3; k++)
+        if (k != a && fabsf(p[k]) > 1.0f) b = k;
+    p[a] = (p[a] < 0.0f ? -1.0f : 1.0f) * (1.0f - inv);
+    p[b] = p[b] < 0.0f ? -1.0f : 1.0f;
+    const int nf = 2 * b + (p[b] < 0.0f ? 1 : 0);
+    float     s2, t2;
+    switch (nf)
+    {
+        case 0: s2 = -p[2], t2 = -p[1]; break;
+        case 1: s2 = p[2], t2 = -p[1]; break;
+        case 2: s2 = p[0], t2 = p[2]; break;
+        case 3: s2 = p[0], t2 = -p[2]; break;
+        case 4: s2 = p[0], t2 = -p[1]; break;
+        default: s2 = -p[0], t2 = -p[1]; break;
+    }
+    int jx = (int)floorf(0.5f * (s2 + 1.0f) * (float)N), jy = (int)floorf(0.5f * (t2 + 1.0f) * (float)N);
+    jx = jx < 0 ? 0 : (jx > N - 1 ? N - 1 : jx), jy = jy < 0 ? 0 : (jy > N - 1 ? N - 1 : jy);
+    return faces[((size_t)nf * N + (size_t)jy) * N + (size_t)jx];
+}
+// Texel (ix, iy) of the bordered face, ix, iy in -1 .. N: Vulkan cube maps are always seamless ("Cube Map Edge Handling":
+// a footprint that reaches over an edge takes the texel of the adjoining face; at a corner the fourth texel does not
+// exist and the three existing ones are averaged).
+HL_HD f4 cube_pad_texel(const f4* faces, int N, int face, int ix, int iy)
+{
+    const bool ox = ix < 0 || ix >= N, oy = iy < 0 || iy >= N;
+    if (!ox && !oy) return faces[((size_t)face * N + (size_t)iy) * N + (size_t)ix];
+    if (ox && oy)
+    {
+        const int cx = ix < 0 ? 0 : N - 1, cy = iy < 0 ? 0 : N - 1;
+        const f4  a = faces[((size_t)face * N + (size_t)cy) * N + (size_t)cx], b = cube_texel_over_edge(faces, N, face, ix, cy), c = cube_texel_over_edge(faces, N, face, cx, iy);
+        return (a + b + c) * (1.0f / 3.0f);
+    }
+    return cube_texel_over_edge(faces, N, face, ix, iy);
+}
 HL_HD f3 sample_environment(const EnvView& e, f3 r)
 {
     if (e.size == 0) return mk3(0.0f);
@@ -106,14 +160,10 @@ HL_HD f3 sample_environment(const EnvView& e, f3 r)
     const float x = s * (float)N - 0.5f, y = t * (float)N - 0.5f;
     const float x0 = floorf(x), y0 = floorf(y);
     const float fx = x - x0, fy = y - y0;
-    int         ix0 = (int)x0, iy0 = (int)y0;
-    int         ix1 = ix0 + 1, iy1 = iy0 + 1;
-    ix0 = ix0 < 0 ? 0 : (ix0 > N - 1 ? N - 1 : ix0);
-    iy0 = iy0 < 0 ? 0 : (iy0 > N - 1 ? N - 1 : iy0);
-    ix1 = ix1 > N - 1 ? N - 1 : ix1;
-    iy1 = iy1 > N - 1 ? N - 1 : iy1;
-    const f4* base = e.faces + (size_t)face * N * N;
-    const f4  c    = bilinear(base[(size_t)iy0 * N + ix0], base[(size_t)iy0 * N + ix1], base[(size_t)iy1 * N + ix0], base[(size_t)iy1 * N + ix1], fx, fy);
+    const int   ix0 = (int)x0, iy0 = (int)y0; // -1 .. N - 1: the footprint may reach one texel over an edge
+    const int   P    = N + 2; // bordered face
+    const f4*   base = e.faces + ((size_t)face * P + (size_t)(iy0 + 1)) * P + (size_t)(ix0 + 1);
+    const f4    c    = bilinear(base[0], base[1], base[P], base[P + 1], fx, fy);
     return mk3(c.x, c.y, c.z);
 }
 } // namespace hl

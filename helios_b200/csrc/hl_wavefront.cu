@@ -581,6 +581,29 @@ void sky_bake(hl_context_t* ctx, const float* coeffs40, const float* sun3, uint3
     ctx->launches++;
 }
 
+__global__ void k_env_pad(const float4* __restrict__ faces, uint32_t size, float4* __restrict__ out)
+{
+    const uint32_t P = size + 2;
+    const size_t   i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)6 * P * P) return;
+    const int face = (int)(i / ((size_t)P * P));
+    const int iy = (int)((i / P) % P) - 1, ix = (int)(i % P) - 1;
+    const f4  c = cube_pad_texel((const f4*)faces, (int)size, face, ix, iy);
+    out[i]      = make_float4(c.x, c.y, c.z, c.w);
+}
+void env_pad(hl_context_t* ctx)
+{
+    const uint32_t size = ctx->env_size;
+    if (size)
+    {
+        const size_t n = (size_t)6 * (size + 2) * (size + 2);
+        ctx->env_padded.alloc(n * 16);
+        k_env_pad<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->env_faces.as<float4>(), size, ctx->env_padded.as<float4>());
+        ctx->launches++;
+    }
+    ctx->view.env.faces = ctx->env_padded.as<f4>(), ctx->view.env.size = size;
+}
+
 static void ensure_events(hl_context_t* ctx)
 {
     if (ctx->ev_ready) return;

@@ -206,6 +206,52 @@ struct EnvMap
     uint32_t           size = 0;
     std::vector<float> data; // 6 * size * size * 4
 };
+// Vulkan "Cube Map Edge Handling": cube maps are always seamless — a bilinear footprint that reaches over a face edge
+// takes the texel of the adjoining face, and at a corner (where the fourth texel does not exist) the three existing
+// texels are averaged.  (ix, iy) is at most one texel outside face `face`.
+static vec4 env_texel(const EnvMap& e, int face, int ix, int iy)
+{
+    const int N   = (int)e.size;
+    auto      raw = [&](int f, int x, int y) {
+        const float* p = e.data.data() + (((size_t)f * N + (size_t)y) * N + (size_t)x) * 4;
+        return vec4(p[0], p[1], p[2], p[3]);
+    };
+    const bool out_x = ix < 0 || ix >= N, out_y = iy < 0 || iy >= N;
+    if (!out_x && !out_y) return raw(face, ix, iy);
+    if (out_x && out_y)
+    {
+        const int cx = ix < 0 ? 0 : N - 1, cy = iy < 0 ? 0 : N - 1;
+        return (env_texel(e, face, cx, cy) + env_texel(e, face, ix, cy) + env_texel(e, face, cx, iy)) * (1.0f / 3.0f);
+    }
+    // centre of the texel on the extended plane of the face, in the cube's coordinates
+    const float rn = 1.0f / (float)N;
+    const float u = 2.0f * ((float)ix + 0.5f) * rn - 1.0f, v = 2.0f * ((float)iy + 0.5f) * rn - 1.0f;
+    float       q[3];
+    if (face == 0) q[0] = 1.0f, q[1] = -v, q[2] = -u;
+    else if (face == 1) q[0] = -1.0f, q[1] = -v, q[2] = u;
+    else if (face == 2) q[0] = u, q[1] = 1.0f, q[2] = v;
+    else if (face == 3) q[0] = u, q[1] = -1.0f, q[2] = -v;
+    else if (face == 4) q[0] = u, q[1] = -v, q[2] = 1.0f;
+    else q[0] = -u, q[1] = -v, q[2] = -1.0f;
+    // fold over the shared edge: the overshooting axis becomes the new face's normal, the old normal axis the first row
+    const int normal_axis = face / 2;
+    int       over_axis   = -1;
+    for (int k = 0; k < 3; k++)
+        if (k != normal_axis && std::fabs(q[k]) > 1.0f) over_axis = k;
+    q[normal_axis] = (q[normal_axis] < 0.0f ? -1.0f : 1.0f) * (1.0f - rn);
+    q[over_axis]   = q[over_axis] < 0.0f ? -1.0f : 1.0f;
+    const int nf   = 2 * over_axis + (q[over_axis] < 0.0f ? 1 : 0);
+    float     s, t;
+    if (nf == 0) s = -q[2], t = -q[1];
+    else if (nf == 1) s = q[2], t = -q[1];
+    else if (nf == 2) s = q[0], t = q[2];
+    else if (nf == 3) s = q[0], t = -q[2];
+    else if (nf == 4) s = q[0], t = -q[1];
+    else s = -q[0], t = -q[1];
+    int jx = (int)std::floor(0.5f * (s + 1.0f) * (float)N), jy = (int)std::floor(0.5f * (t + 1.0f) * (float)N);
+    jx = std::min(std::max(jx, 0), N - 1), jy = std::min(std::max(jy, 0), N - 1);
+    return raw(nf, jx, jy);
+}
 static vec3 env_sample(const EnvMap& e, vec3 r)
 {
     if (e.size == 0) return vec3(0.0f); // reference default cube map is black (gfx/vk.cpp:3589-3612)
@@ -242,16 +288,8 @@ static vec3 env_sample(const EnvMap& e, vec3 r)
     float y  = t * (float)N - 0.5f;
     float x0 = std::floor(x), y0 = std::floor(y);
     float fx = x - x0, fy = y - y0;
-    int   ix0 = std::max((int)x0, 0), iy0 = std::max((int)y0, 0);
-    int   ix1 = std::min((int)x0 + 1, N - 1), iy1 = std::min((int)y0 + 1, N - 1);
-    ix0 = std::min(ix0, N - 1);
-    iy0 = std::min(iy0, N - 1);
-    const float* base = e.data.data() + (size_t)face * N * N * 4;
-    auto         px   = [&](int xx, int yy) {
-        const float* p = base + ((size_t)yy * N + xx) * 4;
-        return vec4(p[0], p[1], p[2], p[3]);
-    };
-    vec4 c = bilerp(px(ix0, iy0), px(ix1, iy0), px(ix0, iy1), px(ix1, iy1), fx, fy);
+    int   ix0 = (int)x0, iy0 = (int)y0; // -1 .. N-1
+    vec4  c = bilerp(env_texel(e, face, ix0, iy0), env_texel(e, face, ix0 + 1, iy0), env_texel(e, face, ix0, iy0 + 1), env_texel(e, face, ix0 + 1, iy0 + 1), fx, fy);
     return c.xyz();
 }
 

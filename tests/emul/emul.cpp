@@ -238,8 +238,11 @@ EM_API int em_scene_add_texture(EmScene* s, int format, uint32_t w, uint32_t h, 
 EM_API void em_scene_set_envmap(EmScene* s, uint32_t size, const float* faces)
 {
     s->env_size = size;
-    s->env.resize((size_t)6 * size * size);
-    memcpy(s->env.data(), faces, s->env.size() * 16);
+    const uint32_t P = size + 2; // bordered faces (hl_tex.h cube_pad_texel), as env_pad() builds them on the device
+    s->env.resize((size_t)6 * P * P);
+    for (int face = 0; face < 6; face++)
+        for (uint32_t y = 0; y < P; y++)
+            for (uint32_t x = 0; x < P; x++) s->env[((size_t)face * P + y) * P + x] = cube_pad_texel((const f4*)faces, (int)size, face, (int)x - 1, (int)y - 1);
 }
 EM_API void em_sky_bake(const float* cf40, const float* sun, uint32_t size, float* out)
 {
