@@ -370,3 +370,37 @@ def test_instance_transform_edge_cases(name, oracle_mod, emul):
             hit = a[0] != abi.MISS_ID
             assert not np.any(a[0][hit] > 1)  # of the coincident copies the smallest instance id wins
     assert np.abs(o.render(3) - e.render(3)).max() < 2e-6
+
+
+def hostile_shading_scenes():
+    """out-of-range material parameters and degenerate punctual lights on the Cornell box (finite values only: with an
+    infinite light intensity the reference computes inf * 0 for an occluded sample, which is outside defined behaviour)"""
+    base = lambda: scenes.cornell_box(48, 48)  # noqa: E731
+    out = {}
+    for tag, rough, metal, alb in (("rough0_metal1", 0.0, 1.0, (1, 1, 1, 1)), ("albedo_gt_1", 1.0, 0.0, (3, 2, 5, 1)), ("albedo_0", 0.5, 0.5, (0, 0, 0, 1)),
+                                   ("albedo_negative", 0.3, 0.2, (-1, 0.5, 0.5, 1)), ("rough5_metal_neg", 5.0, -1.0, (0.5, 0.5, 0.5, 1))):
+        s = base()
+        s.materials["roughness_metallic"][:3, 0], s.materials["roughness_metallic"][:3, 1], s.materials["albedo"][:3] = rough, metal, alb
+        out[tag] = s
+    for tag, rows in (("point_radius_0", [scenes.point_light((0, 1.0, 0), intensity=5.0, radius=0.0)]), ("point_radius_50", [scenes.point_light((0, 1.0, 0), intensity=5.0, radius=50.0)]),
+                      ("spot_inner_eq_outer", [scenes.spot_light((0, 1.9, 0), forward=(0, 1, 0), intensity=50.0, radius=0.1, inner_deg=25.0, outer_deg=25.0)]),
+                      ("spot_zero_direction", [scenes.spot_light((0, 1.9, 0), forward=(0, 0, 0), intensity=50.0, radius=0.1, inner_deg=10.0, outer_deg=60.0)]),
+                      ("point_on_floor", [scenes.point_light((0.0, 0.0, 0.0), intensity=5.0)])):
+        s = base()
+        s.lights = scenes._stack(rows, abi.LIGHT)
+        out[tag] = s
+    return out
+
+
+HOSTILE_SHADING = ["rough0_metal1", "albedo_gt_1", "albedo_0", "albedo_negative", "rough5_metal_neg", "point_radius_0", "point_radius_50", "spot_inner_eq_outer", "spot_zero_direction", "point_on_floor"]
+
+
+@pytest.mark.parametrize("name", HOSTILE_SHADING)
+def test_hostile_materials_and_lights(name, oracle_mod, emul):
+    s = hostile_shading_scenes()[name]
+    o, e = oracle_mod.OracleScene(s, brute_force=True), emul.EmulScene(s)
+    with np.errstate(all="ignore"):
+        a, b = o.render(4), e.render(4)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.abs(np.nan_to_num(a) - np.nan_to_num(b)).max() < 2e-6
+    assert int(o.counters[0]) == int(e.counters[0])

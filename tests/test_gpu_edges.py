@@ -292,3 +292,20 @@ def test_instance_transform_edge_cases(name, api, oracle_mod):
                            np.random.default_rng(2).normal(size=(20000, 3)), np.full((20000, 1), 1e4)], 1).astype(np.float32)
     assert np.array_equal(ctx.trace_rays(rays, 0).view(np.uint32), o.trace_rays(rays, 0).view(np.uint32))
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["rough0_metal1", "albedo_gt_1", "albedo_negative", "rough5_metal_neg", "point_radius_50", "spot_inner_eq_outer", "spot_zero_direction", "point_on_floor"])
+def test_hostile_materials_and_lights(name, api, oracle_mod):
+    """out-of-range material parameters and degenerate punctual lights: same NaN pattern and radiance as the oracle"""
+    from tests.test_emul_parity import hostile_shading_scenes
+
+    s = hostile_shading_scenes()[name]
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    with np.errstate(all="ignore"):
+        a, b = ctx.render(s, 4), o.render(4)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    d = np.abs(np.nan_to_num(a) - np.nan_to_num(b))[..., :3].max(-1)
+    assert (d > 1e-4).mean() < 0.01 and d.max() < 0.2, (int((d > 1e-4).sum()), float(d.max()))
+    ctx.close()
