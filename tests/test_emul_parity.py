@@ -404,3 +404,41 @@ def test_hostile_materials_and_lights(name, oracle_mod, emul):
     assert np.array_equal(np.isnan(a), np.isnan(b))
     assert np.abs(np.nan_to_num(a) - np.nan_to_num(b)).max() < 2e-6
     assert int(o.counters[0]) == int(e.counters[0])
+
+
+def hostile_light_geometry_scenes():
+    out = {}
+    s = scenes.cornell_box(48, 48)
+    m = s.meshes[0]
+    i0 = int(m.submeshes[-1]["base_index"])  # the emissive quad; only its triangle 0 is ever sampled
+    m.vertices["position"][m.indices[i0 + 1], :3] = m.vertices["position"][m.indices[i0], :3]  # zero-area sampled triangle: pdf guard max(1e-4, cos * A)
+    out["area_light_degenerate"] = s
+    s = scenes.cornell_box(48, 48)
+    m = s.meshes[0]
+    sub = m.submeshes[-1]
+    for k in range(int(sub["index_count"])):
+        m.vertices["position"][m.indices[int(sub["base_index"]) + k], 1] = 0.0  # light quad in the floor plane
+    out["area_light_in_floor_plane"] = s
+    s = scenes.terrain_scene(grid=24, n_spheres=4, sphere_level=1, width=48, height=27)
+    faces = np.full((6, 8, 8, 4), 0.5, np.float32)
+    faces[0, :, :, :3], faces[4, 0, 0, :3], faces[3] = -1.0, 1e30, 0.0  # negative, huge and black texels (finite)
+    s.env_cube, s.sun_direction = (8, faces), None
+    out["env_map_hostile_finite"] = s
+    s = scenes.foliage_scene(n_clusters=30, cards_per_cluster=8, width=48, height=27, ground_grid=4, tex_size=4)
+    fmt, w, h, data = s.textures[0]
+    d = np.array(data).copy().reshape(h, w, 4)
+    d[..., 3] = np.array([[25, 26, 25, 26]] * 4, np.uint8)  # 25/255 = 0.098, 26/255 = 0.102: around the any-hit threshold 0.1
+    s.textures[0] = (fmt, w, h, d)
+    out["alpha_around_threshold"] = s
+    return out
+
+
+@pytest.mark.parametrize("name", ["area_light_degenerate", "area_light_in_floor_plane", "env_map_hostile_finite", "alpha_around_threshold"])
+def test_hostile_light_geometry_and_texels(name, oracle_mod, emul):
+    s = hostile_light_geometry_scenes()[name]
+    o, e = oracle_mod.OracleScene(s, brute_force=True), emul.EmulScene(s)
+    with np.errstate(all="ignore"):
+        a, b = o.render(4), e.render(4)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.abs(np.nan_to_num(a) - np.nan_to_num(b)).max() < 2e-6
+    assert int(o.counters[0]) == int(e.counters[0])
