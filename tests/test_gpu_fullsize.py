@@ -150,3 +150,29 @@ def test_full_size_scene_tile_against_oracle(name, oracle_mod):
     same = (a[0] == b[0]) & (a[1] == b[1]) & (a[2] == b[2])
     assert same.mean() >= 1.0 - 1e-4, f"{int((~same).sum())} of {same.size} primary hits differ"
     ctx.close()
+
+
+@pytest.mark.parametrize("aperture,bias", [(0.0, 0.0), (0.1, 1e-3)])
+def test_configs0_cornell_512_64spp(aperture, bias, oracle_mod):
+    """BASELINE configs[0] as specified: Cornell box, 512 x 512, 65 launches (num_frames 0..64 = 64 effective
+    samples, frame 0 is overwritten: A.8-1), depth 8; pinhole / bias 0 and aperture 0.1 / bias 1e-3.  Against the oracle:
+    primary hit ids bit-exact (pinhole), converged image within 1e-4 on >= 99 % of the pixels and relMSE < 2e-3"""
+    from helios_b200 import api
+
+    s = scenes.cornell_box(512, 512, aperture_radius=aperture, shadow_ray_bias=bias)
+    assert s.max_ray_bounces == 8 and len(s.lights) == 1
+    ctx = api.Context(s.width, s.height)
+    ctx.load_scene(s)
+    o = oracle_mod.OracleScene(s, brute_force=True)
+    if aperture == 0.0:
+        for f in (0, 1, 64):
+            pc = s.push_constants(f)
+            for a, b in zip(ctx.trace_primary_ids(pc), o.trace_primary_ids(pc)):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    g, r = ctx.render(s, 65), o.render(65)
+    d = np.abs(g - r)[..., :3].max(-1)
+    assert (d > 1e-4).mean() < 0.01, f"{int((d > 1e-4).sum())} of {d.size} pixels differ by more than 1e-4"
+    mse = float(np.mean((g[..., :3].astype(np.float64) - r[..., :3]) ** 2) / np.mean(r[..., :3].astype(np.float64) ** 2))
+    assert mse < 2e-3, mse
+    assert 0.005 < float(g[..., :3].mean()) < 0.5  # a lit box, not a black or saturated frame
+    ctx.close()
