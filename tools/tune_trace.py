@@ -37,6 +37,7 @@ VARIANT_SETS["shade"] = {
     "g16": ["-DHL_SHADE_GRID_MULT=16"], "g4": ["-DHL_SHADE_GRID_MULT=4"],
 }
 VARIANT_SETS["sah"] = {"c020": ["-DHL_SAH_C_PRIM_TRIANGLE=0.2f"], "c035": [], "c060": ["-DHL_SAH_C_PRIM_TRIANGLE=0.6f"], "c100": ["-DHL_SAH_C_PRIM_TRIANGLE=1.0f"], "c150": ["-DHL_SAH_C_PRIM_TRIANGLE=1.5f"], "c250": ["-DHL_SAH_C_PRIM_TRIANGLE=2.5f"]}
+VARIANT_SETS["defslots"] = {"d4": [], "d6": ["-DHL_DEFAULT_WAVE_SLOTS=6"], "d8": ["-DHL_DEFAULT_WAVE_SLOTS=8"]}
 VARIANT_SETS["slots"] = {"base": [], "slots3": ["-DHL_WAVE_SLOTS=3"], "slots2": ["-DHL_WAVE_SLOTS=2"], "slots4": ["-DHL_WAVE_SLOTS=4"], "slots6": ["-DHL_WAVE_SLOTS=6"], "mb7": ["-DHL_TRACE_MIN_BLOCKS=7"], "mb6": ["-DHL_TRACE_MIN_BLOCKS=6", "-DHL_TRACE_GRID_MULT=6"]}
 VARIANTS = VARIANT_SETS[os.environ.get("HL_TUNE_SET", "occ")]
 OUT = ROOT / "build" / "variants"
