@@ -221,6 +221,11 @@ def main():
         import torch.distributed as dist
 
         torch.cuda.set_device(local_rank)
+        # stdout carries exactly one JSON line: NCCL's logs go to stderr, and its version banner (a plain printf at
+        # NCCL_DEBUG=VERSION, which this image exports) is switched off; an explicit INFO / TRACE request is left alone
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from helios_b200 import abi, api
     from helios_b200.sky import sky_coefficients
