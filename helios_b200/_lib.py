@@ -20,6 +20,7 @@ SYMBOLS = [
     "hl_envmap_set", "hl_sky_update", "hl_envmap_read", "hl_scene_set_tables", "hl_render_frame", "hl_render_frame_tonemapped", "hl_render_frame_readback", "hl_read_rgba8", "hl_accum_clear",
     "hl_set_accum_mode", "hl_trace_primary_ids", "hl_render_output_buffer", "hl_gather_debug_rays", "hl_trace_rays", "hl_tonemap", "hl_read_accum", "hl_write_accum",
     "hl_accum_device_ptr", "hl_synchronize", "hl_get_counters", "hl_reset_counters", "hl_set_profiling", "hl_kernel_launches", "hl_event_record", "hl_event_elapsed_ms", "hl_set_option",
+    "hl_get_bounce_profile", "hl_comm_unique_id", "hl_comm_init_rank", "hl_comm_init_all", "hl_comm_destroy", "hl_comm_last_error", "hl_accum_all_reduce", "hl_accum_reduce", "hl_multi_gpu_reduce", "hl_multi_gpu_resolve",
 ]
 
 _lib = None
@@ -45,5 +46,6 @@ def load():
     lib.hl_last_error.restype = C.c_char_p
     lib.hl_last_error.argtypes = [C.c_void_p]
     lib.hl_version.restype = C.c_char_p
+    lib.hl_comm_last_error.restype = C.c_char_p
     _lib = lib
     return lib

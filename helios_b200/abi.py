@@ -82,3 +82,5 @@ OPT_TAIL_THRESHOLD, OPT_TAIL_START, OPT_PIPELINE, OPT_SAH_CLUSTER, OPT_FRAMES_IN
 DEBUG_RAY_VERTEX = np.dtype([("position", "<f4", 4), ("color", "<f4", 4)])  # common.glsl:54-58
 MAX_DEBUG_RAY_DRAW_COUNT = 1024  # include/gfx/renderer.h:9
 MISS_ID = 0xFFFFFFFF
+COMM_ID_BYTES = 128  # HL_COMM_ID_BYTES
+BOUNCE_PROFILE = np.dtype([("extension_rays", "<u4"), ("shadow_rays", "<u4"), ("ms_tail", "<f4"), ("ms_extend", "<f4"), ("ms_shade", "<f4"), ("ms_connect", "<f4")])  # hl_bounce_profile

@@ -177,8 +177,11 @@ class Context:
         self._chk(self.lib.hl_trace_rays(self.h, _p(rays), C.c_uint32(len(rays)), C.c_uint32(flags), _p(hits)))
         return hits
 
-    def tonemap(self, exposure=1.0, op=abi.TONE_MAP_ACES, sample_scale=1.0, download=True):
-        out = np.zeros((self.height, self.width, 4), np.uint8) if download else None
+    def tonemap(self, exposure=1.0, op=abi.TONE_MAP_ACES, sample_scale=1.0, download=True, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), np.uint8) if download else None
+        else:
+            assert out.dtype == np.uint8 and out.size == self.width * self.height * 4 and out.flags["C_CONTIGUOUS"]
         self._chk(self.lib.hl_tonemap(self.h, C.c_float(exposure), C.c_int(op), C.c_float(sample_scale), _p(out)))
         return out
 
@@ -205,6 +208,14 @@ class Context:
         self._chk(self.lib.hl_get_counters(self.h, _p(out)))
         return out
 
+    def bounce_profile(self):
+        """per-bounce breakdown of the last frame rendered under set_profiling(True): (array of abi.BOUNCE_PROFILE, rays traced by
+        the tail kernel: extension, shadow)"""
+        out = np.zeros(64, abi.BOUNCE_PROFILE)
+        n, te, ts = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.hl_get_bounce_profile(self.h, _p(out), C.c_uint32(64), C.byref(n), C.byref(te), C.byref(ts)))
+        return out[: n.value], te.value, ts.value
+
     def reset_counters(self):
         self._chk(self.lib.hl_reset_counters(self.h))
 
@@ -227,9 +238,58 @@ class Context:
         self._chk(self.lib.hl_event_elapsed_ms(self.h, C.c_int(a), C.c_int(b), C.byref(ms)))
         return ms.value
 
+    # ---- multi-GPU, one process per GPU (hl_comm_init_rank + NCCL on the context's stream)
+    def comm_init_rank(self, unique_id: bytes, n_ranks: int, rank: int):
+        assert len(unique_id) == abi.COMM_ID_BYTES
+        buf = (C.c_uint8 * abi.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._chk(self.lib.hl_comm_init_rank(self.h, buf, C.c_int(n_ranks), C.c_int(rank)))
+
+    def comm_destroy(self):
+        self._chk(self.lib.hl_comm_destroy(self.h))
+
+    def accum_all_reduce(self):
+        """accumulation image <- sum over ranks (asynchronous, behind the frames in flight)"""
+        self._chk(self.lib.hl_accum_all_reduce(self.h))
+
+    def accum_reduce(self, root: int = 0):
+        self._chk(self.lib.hl_accum_reduce(self.h, C.c_int(root)))
+
     def render(self, scene, n_launches, **kw):
         """Renderer::render loop: clear, then launches with num_frames = 0 .. n_launches-1"""
         self.accum_clear()
         for f in range(n_launches):
             self.render_frame(scene.push_constants(f, **kw))
         return self.read_accum()
+
+
+def comm_unique_id() -> bytes:
+    """rank 0: the NCCL unique id every rank passes to Context.comm_init_rank"""
+    lib = load()
+    buf = (C.c_uint8 * abi.COMM_ID_BYTES)()
+    st = lib.hl_comm_unique_id(buf)
+    if st != 0:
+        raise HeliosError(st, lib.hl_comm_last_error().decode())
+    return bytes(buf)
+
+
+class Group:
+    """all GPUs in one process (hl_comm_init_all): contexts[i] is rank i"""
+
+    def __init__(self, contexts):
+        self.ctxs = list(contexts)
+        self.lib = load()
+        self._arr = (C.c_void_p * len(self.ctxs))(*[c.h.value for c in self.ctxs])
+        self._chk(self.lib.hl_comm_init_all(self._arr, C.c_int(len(self.ctxs))))
+
+    def _chk(self, st):
+        if st != 0:
+            raise HeliosError(st, self.lib.hl_comm_last_error().decode())
+
+    def reduce(self, root: int = 0):
+        self._chk(self.lib.hl_multi_gpu_reduce(self._arr, C.c_int(len(self.ctxs)), C.c_int(root)))
+
+    def resolve(self, root=0, exposure=1.0, op=abi.TONE_MAP_ACES, sample_scale=1.0, download=True):
+        c = self.ctxs[root]
+        out = np.zeros((c.height, c.width, 4), np.uint8) if download else None
+        self._chk(self.lib.hl_multi_gpu_resolve(self._arr, C.c_int(len(self.ctxs)), C.c_int(root), C.c_float(exposure), C.c_int(op), C.c_float(sample_scale), _p(out)))
+        return out

@@ -14,13 +14,14 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "libhelios_b200.so"
-SOURCES = ["hl_builder.cu", "hl_wavefront.cu", "hl_api.cu"]
+SOURCES = ["hl_builder.cu", "hl_wavefront.cu", "hl_api.cu", "hl_comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-shared",
 ]
+LINK_FLAGS = ["-ldl"]  # hl_comm.cu opens libnccl.so.2 at run time
 
 
 def needs_build() -> bool:
@@ -32,13 +33,25 @@ def needs_build() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: Path | None = None) -> Path:
-    """`defines` / `out` build a tuning variant (e.g. ["-DHL_REFILL_MIN=4"]) next to the product library."""
+    """`defines` / `out` build a tuning variant (e.g. ["-DHL_REFILL_MIN=4"]) next to the product library.
+    The translation units are compiled side by side (one nvcc process each), then linked."""
     lib = Path(out) if out else LIB
     if not defines and not force and not needs_build():
         return lib
     lib.parent.mkdir(parents=True, exist_ok=True)
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, *(defines or []), *( ["-Xptxas", "-v"] if verbose else []), "-o", str(lib), *[str(CSRC / s) for s in SOURCES]]
+    objdir = ROOT.parent / "build" / ("obj_" + lib.stem)
+    objdir.mkdir(parents=True, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    procs = []
+    for src in SOURCES:
+        cmd = [nvcc, *cflags, *(defines or []), *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(objdir / (src + ".o")), str(CSRC / src)]
+        print("[helios_b200] " + " ".join(cmd), file=sys.stderr)
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(lib), *[str(objdir / (src + ".o")) for src in SOURCES], *LINK_FLAGS]
     print("[helios_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
     return lib

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 
 using namespace hl;
 
@@ -75,11 +76,16 @@ hl_status hl_context_create(int device_ordinal, uint32_t width, uint32_t height,
         HL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         HL_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal));
         {
-            // keep freed build scratch in the stream-ordered pool instead of returning it to the driver
-            cudaMemPool_t pool;
-            HL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
-            uint64_t keep = ~0ull;
-            HL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            // build scratch comes from a PRIVATE stream-ordered pool (ScratchBuf): freed scratch up to 1 GiB stays in it for
+            // the next build, the rest goes back to the driver; the device's default pool (other cudaMallocAsync users of
+            // the process: torch, NCCL) is left alone
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned, props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice, props.location.id = device_ordinal;
+            HL_CUDA(cudaMemPoolCreate(&c->scratch_pool, &props));
+            uint64_t keep = 1ull << 30;
+            HL_CUDA(cudaMemPoolSetAttribute(c->scratch_pool, cudaMemPoolAttrReleaseThreshold, &keep));
         }
         c->W = width, c->H = height;
         // 8-bit decode tables (unorm, srgb, snorm), computed in double like the oracle's
@@ -111,6 +117,7 @@ hl_status hl_context_destroy(hl_context ctx)
     if (!ctx) return HL_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    hl::comm_release(ctx);
     for (auto m : ctx->meshes) delete m;
     for (auto t : ctx->textures) delete t;
     if (ctx->ev_ready)
@@ -129,7 +136,9 @@ hl_status hl_context_destroy(hl_context ctx)
     }
     if (ctx->main_ev) cudaEventDestroy(ctx->main_ev);
     cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    cudaMemPool_t pool = ctx->scratch_pool;
+    delete ctx; // (frees the device buffers)
+    if (pool) cudaMemPoolDestroy(pool);
     return HL_OK;
 }
 
@@ -204,12 +213,16 @@ hl_status hl_texture2d_create(hl_context ctx, int format, uint32_t width, uint32
     HL_TRY(ctx)
     if (!texels || !out_index || width == 0 || height == 0 || format < 0 || format > 3) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_texture2d_create: invalid argument");
     if (c_->textures.size() >= HL_MAX_SCENE_MATERIAL_TEXTURE_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_texture2d_create: MAX_SCENE_MATERIAL_TEXTURE_COUNT exceeded");
-    DevBuf* b = new DevBuf();
-    c_->textures.push_back(b);
-    b->upload(texels, (size_t)width * height * (format == HL_TEX_RGBA32F ? 16 : 4), c_->stream);
+    const uint64_t bytes = (uint64_t)width * height * (format == HL_TEX_RGBA32F ? 16 : 4);
+    if (width > 65536u || height > 65536u || bytes > (1ull << 34)) HL_FAIL(HL_ERR_LIMIT, "hl_texture2d_create: extent above 65536 or level above 16 GiB");
+    std::unique_ptr<DevBuf> b(new DevBuf());
+    b->upload(texels, (size_t)bytes, c_->stream);
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     TexView v;
     v.texels = b->p, v.w = width, v.h = height, v.format = format, v.pad = 0;
+    c_->tex_views.reserve(c_->tex_views.size() + 1); // the two vectors change together or not at all
+    c_->textures.push_back(b.get());
+    b.release();
     c_->tex_views.push_back(v);
     *out_index      = (int32_t)c_->tex_views.size() - 1;
     c_->scene_ready = false;
@@ -286,6 +299,30 @@ hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint
     if (n_instances > HL_MAX_SCENE_MESH_INSTANCE_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_scene_set_tables: MAX_SCENE_MESH_INSTANCE_COUNT (1024) exceeded");
     if (n_materials > HL_MAX_SCENE_MATERIAL_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_scene_set_tables: MAX_SCENE_MATERIAL_COUNT (4096) exceeded");
     if (n_lights > HL_MAX_SCENE_LIGHT_COUNT) HL_FAIL(HL_ERR_LIMIT, "hl_scene_set_tables: MAX_SCENE_LIGHT_COUNT (100000) exceeded");
+    // every index a shader follows is checked here: a bad one would be a device out-of-bounds read, and the resulting
+    // cudaErrorIllegalAddress is sticky for the whole process (load_surface, any_hit_ignores, sample_light: hl_shade.h, hl_bvh.h)
+    const int32_t n_tex = (int32_t)c_->tex_views.size();
+    for (uint32_t m = 0; m < n_materials; m++)
+    {
+        const int32_t ti[5] = { materials[m].texture_indices0[0], materials[m].texture_indices0[1], materials[m].texture_indices0[2], materials[m].texture_indices0[3], materials[m].texture_indices1[0] };
+        for (int k = 0; k < 5; k++)
+            if (ti[k] < -1 || ti[k] >= n_tex) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: material " + std::to_string(m) + " refers to texture " + std::to_string(ti[k]) + " (" + std::to_string(n_tex) + " textures exist)");
+    }
+    for (uint32_t l = 0; l < n_lights; l++)
+    {
+        const hl_light& L = lights[l];
+        if (!(L.light_data0[0] == (float)HL_LIGHT_AREA)) continue;
+        // sample_light reads: instance = data0.y, material = data0.z, first primitive = data0.w, primitive count = data1.z
+        const float f[4] = { L.light_data0[1], L.light_data0[2], L.light_data0[3], L.light_data1[2] };
+        for (int k = 0; k < 4; k++)
+            if (!(f[k] >= 0.0f && f[k] < 2147483648.0f)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: area light " + std::to_string(l) + " has a negative or non-finite index field");
+        const uint32_t li = (uint32_t)f[0], lm = (uint32_t)f[1], lp = (uint32_t)f[2], lc = (uint32_t)f[3];
+        if (li >= n_instances) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: area light " + std::to_string(l) + " refers to instance " + std::to_string(li));
+        if (lm >= n_materials) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: area light " + std::to_string(l) + " refers to material " + std::to_string(lm));
+        auto it = std::find(c_->meshes.begin(), c_->meshes.end(), meshes[li]);
+        if (it == c_->meshes.end()) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: instance refers to an unknown mesh");
+        if ((uint64_t)lp + std::max(lc, 1u) > (uint64_t)(*it)->n_indices / 3) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: area light " + std::to_string(l) + " primitive range exceeds its mesh");
+    }
     cudaStream_t st = c_->stream;
     HL_CUDA(cudaStreamSynchronize(st)); // Scene::create_gpu_resources calls wait_idle (scene.cpp:929)
     // mesh table in context order; instance.mesh_index is rewritten to that order
@@ -387,10 +424,10 @@ hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_constants* pc
     HL_TRY_FRAME(ctx)
     if (!pc) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: null push constants");
     if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_frame_tonemapped: hl_scene_set_tables has not been called since the last resource change");
-    if (c_->accum_mode != HL_ACCUM_RUNNING_MEAN) HL_FAIL(HL_ERR_STATE, "hl_render_frame_tonemapped: needs HL_ACCUM_RUNNING_MEAN (use hl_tonemap with sample_scale for sums)");
     if (op != HL_TONE_MAP_ACES && op != HL_TONE_MAP_REINHARD) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: unknown tone map operator");
     if (!clip_launch(c_, pc, launch_w, launch_h)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_tonemapped: launch_id_size.zw differs from the context extent");
     if (pc->max_ray_bounces > HL_MAX_BOUNCES) HL_FAIL(HL_ERR_LIMIT, "hl_render_frame_tonemapped: max_ray_bounces > 64");
+    if (c_->accum_mode == HL_ACCUM_SUM && (launch_w != c_->W || launch_h != c_->H)) HL_FAIL(HL_ERR_STATE, "hl_render_frame_tonemapped: HL_ACCUM_SUM takes full-frame launches only (tiles: hl_render_frame + hl_tonemap)");
     ResolveOptions opt;
     opt.tone_map = true, opt.exposure = exposure, opt.op = op;
     wavefront_render_frame(c_, *pc, launch_w, launch_h, opt);
@@ -403,10 +440,10 @@ hl_status hl_render_frame_readback(hl_context ctx, const hl_push_constants* pc, 
     HL_TRY_FRAME(ctx)
     if (!pc || !rgba8_host) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_readback: null argument");
     if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_render_frame_readback: hl_scene_set_tables has not been called since the last resource change");
-    if (c_->accum_mode != HL_ACCUM_RUNNING_MEAN) HL_FAIL(HL_ERR_STATE, "hl_render_frame_readback: needs HL_ACCUM_RUNNING_MEAN");
     if (op != HL_TONE_MAP_ACES && op != HL_TONE_MAP_REINHARD) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_readback: unknown tone map operator");
     if (!clip_launch(c_, pc, launch_w, launch_h)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_render_frame_readback: launch_id_size.zw differs from the context extent");
     if (pc->max_ray_bounces > HL_MAX_BOUNCES) HL_FAIL(HL_ERR_LIMIT, "hl_render_frame_readback: max_ray_bounces > 64");
+    if (c_->accum_mode == HL_ACCUM_SUM && (launch_w != c_->W || launch_h != c_->H)) HL_FAIL(HL_ERR_STATE, "hl_render_frame_readback: HL_ACCUM_SUM takes full-frame launches only (tiles: hl_render_frame + hl_tonemap)");
     ResolveOptions opt;
     opt.tone_map = true, opt.exposure = exposure, opt.op = op, opt.host = rgba8_host;
     wavefront_render_frame(c_, *pc, launch_w, launch_h, opt);
@@ -573,6 +610,19 @@ hl_status hl_get_counters(hl_context ctx, hl_counters* out)
     *out                = c_->last;
     out->extension_rays = out->shadow_rays = 0, out->frames = c_->frames;
     for (int k = 0; k < c_->n_slots; k++) out->extension_rays += totals[k][0], out->shadow_rays += totals[k][1];
+    const uint64_t lost = trav_overflow_count(c_, false);
+    if (lost) HL_FAIL(HL_ERR_LIMIT, "hl_get_counters: " + std::to_string(lost) + " traversal-stack overflows since the last hl_reset_counters (BVH deeper than the 64-entry stack): results are incomplete");
+    HL_CATCH
+}
+
+hl_status hl_get_bounce_profile(hl_context ctx, hl_bounce_profile* out, uint32_t capacity, uint32_t* n_bounces, uint64_t* tail_ext, uint64_t* tail_sh)
+{
+    HL_TRY(ctx)
+    if (!n_bounces || (!out && capacity)) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_get_bounce_profile: null pointer");
+    *n_bounces = c_->bounce_prof_n;
+    for (uint32_t b = 0; b < c_->bounce_prof_n && b < capacity; b++) out[b] = c_->bounce_prof[b];
+    if (tail_ext) *tail_ext = c_->prof_tail_ext;
+    if (tail_sh) *tail_sh = c_->prof_tail_sh;
     HL_CATCH
 }
 
@@ -580,6 +630,7 @@ hl_status hl_reset_counters(hl_context ctx)
 {
     HL_TRY(ctx)
     for (int k = 0; k < c_->n_slots; k++) HL_CUDA(cudaMemsetAsync((char*)c_->slot[k].counters.p + CTR_TOTALS_OFFSET, 0, 16, c_->stream));
+    trav_overflow_count(c_, true);
     c_->frames = 0;
     HL_CATCH
 }

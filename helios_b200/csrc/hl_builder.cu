@@ -481,6 +481,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
 
 void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
 {
+    t_scratch_pool           = ctx->scratch_pool;
     cudaStream_t          st = ctx->stream;
     const uint32_t        ng = (uint32_t)mesh->subs.size();
     std::vector<uint32_t> tri_start(ng + 1, 0);
@@ -525,6 +526,7 @@ void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
 
 void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes)
 {
+    t_scratch_pool = ctx->scratch_pool;
     DevBuf boxes;
     boxes.upload(instance_boxes.data(), sizeof(Box) * instance_boxes.size(), ctx->stream);
     build_wide_device(ctx, boxes.as<Box>(), (uint32_t)instance_boxes.size(), sizeof(uint32_t), ctx->tlas, [](const uint32_t* sorted, void* leaves) {

@@ -52,8 +52,31 @@ inline bool& emul_force_postpone()
 #ifndef HL_STACK_FAST
 #define HL_STACK_FAST 12 /* entries kept in fast (shared) memory per ray */
 #endif
+#ifndef HL_STACK_SPILL
 #define HL_STACK_SPILL 52 /* further entries in thread-local memory; total depth 64 */
+#endif
 
+// Stack overflow is counted, never silent: hl_get_counters fails loudly while the count is non-zero.  An entry that
+// does not fit is dropped (that subtree is lost for this ray — the result is flagged as untrustworthy, but nothing
+// dropped is ever popped, so the instance sentinel cannot be confused with a lost entry and no index leaves its array).
+#if defined(__CUDACC__)
+static __device__ unsigned long long g_trav_overflow; // per translation unit; hl_wavefront.cu owns the trace kernels
+#endif
+#if !defined(__CUDA_ARCH__)
+inline unsigned long long& emul_trav_overflow()
+{
+    static unsigned long long n = 0;
+    return n;
+}
+#endif
+HL_HD void note_stack_overflow()
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(&g_trav_overflow, 1ull);
+#else
+    emul_trav_overflow()++;
+#endif
+}
 // traversal stack: the first HL_STACK_FAST entries live in `fast` (shared memory on the GPU,
 // interleaved with `stride` so that a warp's accesses are conflict-free), deeper entries spill.
 struct TravStack
@@ -62,22 +85,25 @@ struct TravStack
     int stride;
     int sp;
     u2  spill[HL_STACK_SPILL];
+    HL_HD bool has_room(int n) const { return sp + n <= HL_STACK_FAST + HL_STACK_SPILL; }
     HL_HD void push(u2 e)
     {
         if (sp < HL_STACK_FAST)
             fast[sp * stride] = e;
         else if (sp - HL_STACK_FAST < HL_STACK_SPILL)
             spill[sp - HL_STACK_FAST] = e;
+        else
+        {
+            note_stack_overflow();
+            return;
+        }
         sp++;
     }
     HL_HD u2 pop()
     {
         sp--;
         if (sp < HL_STACK_FAST) return fast[sp * stride];
-        if (sp - HL_STACK_FAST < HL_STACK_SPILL) return spill[sp - HL_STACK_FAST];
-        u2 z;
-        z.x = 0, z.y = 0;
-        return z;
+        return spill[sp - HL_STACK_FAST];
     }
 };
 
@@ -383,7 +409,9 @@ HL_HD void trav_step_leaves(const SceneView& s, Trav& t, TravStack& st)
         HL_STAT_LEAF();
         const uint32_t  id   = s.tlas_leaf[t.tgroup.x + (uint32_t)i];
         const MeshView& mesh = s.meshes[s.instances[id].mesh_index];
-        if (mesh.n_tris != 0)
+        if (mesh.n_tris != 0 && !st.has_room(3))
+            note_stack_overflow(); // the instance is skipped: its sentinel must never be the entry that gets dropped
+        else if (mesh.n_tris != 0)
         {
             if (t.tgroup.y) st.push(t.tgroup);
             if (t.ngroup.y > 0x00FFFFFFu) st.push(t.ngroup);

@@ -53,8 +53,10 @@ struct DevBuf
     T* as() const { return (T*)p; }
 };
 
-// build scratch: stream-ordered allocation from the device's default memory pool (cudaMallocAsync); the
-// context raises the pool's release threshold so a second build reuses the first build's memory
+// build scratch: stream-ordered allocation from the context's PRIVATE memory pool (hl_context_create; the builder entry
+// points select it for the calling thread), so a second build reuses the first build's memory and no other
+// cudaMallocAsync user of the process is affected
+inline thread_local cudaMemPool_t t_scratch_pool = nullptr;
 struct ScratchBuf
 {
     void*        p = nullptr;
@@ -70,7 +72,10 @@ struct ScratchBuf
     {
         if (p) cudaFreeAsync(p, s), p = nullptr;
         s = stream;
-        HL_CUDA(cudaMallocAsync(&p, n ? n : 16, stream));
+        if (t_scratch_pool)
+            HL_CUDA(cudaMallocFromPoolAsync(&p, n ? n : 16, t_scratch_pool, stream));
+        else
+            HL_CUDA(cudaMallocAsync(&p, n ? n : 16, stream));
     }
     template <class T>
     T* as() const { return (T*)p; }
@@ -137,6 +142,7 @@ struct hl_wave_slot
     cudaStream_t copy_stream  = nullptr;
     cudaEvent_t  image_ready  = nullptr, copy_done = nullptr;
     bool         copy_pending = false;
+    uint8_t*     copy_host    = nullptr; // destination of that copy: a later read-back into the same memory is ordered behind it
     // the bounce loop of a frame (tail / extend / shade / connect per bounce: ~30 launches with arguments that only change
     // with the scene tables or the integrator settings) as an instantiated CUDA graph; rebuilt when `graph_key` changes
     cudaGraphExec_t graph_exec     = nullptr;
@@ -155,6 +161,7 @@ struct hl_context_t
     cudaStream_t stream = nullptr;
     uint32_t     W = 0, H = 0;
     int          sm_count = 148;
+    cudaMemPool_t scratch_pool = nullptr; // private pool of the builder's scratch (ScratchBuf)
     std::string  err;
     uint64_t     launches = 0;
     bool         profiling = false;
@@ -185,12 +192,21 @@ struct hl_context_t
     cudaEvent_t  main_ev     = nullptr; // orders work enqueued on the main stream before the next frame
     size_t       queue_capacity = 0;
     // profiling
-    cudaEvent_t ev[2 + 4 * HL_MAX_BOUNCES + 4] {};
+    cudaEvent_t ev[2 + 5 * HL_MAX_BOUNCES + 4] {};
+    hl_bounce_profile bounce_prof[HL_MAX_BOUNCES] {};
+    uint32_t    bounce_prof_n = 0;
+    uint64_t    prof_tail_ext = 0, prof_tail_sh = 0;
     bool        ev_ready = false;
     hl_counters last {};
     cudaEvent_t user_ev[8] {};
     bool        user_ev_ready = false;
     uint64_t    frames = 0;
+    // multi-GPU (hl_comm.cu): NCCL communicator (opaque) and / or the peer-memory group this context belongs to
+    void*       comm = nullptr;
+    int         comm_nranks = 1, comm_rank = 0;
+    bool        comm_p2p = false;                               // bound by hl_comm_init_all with peer access between all members
+    cudaEvent_t comm_ready_ev = nullptr, comm_done_ev = nullptr; // "my image is complete" / "my slice is written"
+    uint64_t    sum_samples = 0;                                // HL_ACCUM_SUM: full-frame launches since the last clear
 };
 
 namespace hl
@@ -216,7 +232,10 @@ void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc);
 void wavefront_output_buffer(hl_context_t* ctx, const hl_push_constants& pc, int which, float4* d_out); // debug output buffers
 void wavefront_debug_rays(hl_context_t* ctx, const hl_push_constants& pc, uint32_t n, float4* d_verts, uint32_t capacity, uint32_t* d_count); // ray debug view
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits);
+uint64_t trav_overflow_count(hl_context_t* ctx, bool reset);
 void film_clear(hl_context_t* ctx);
 void film_tonemap(hl_context_t* ctx, float exposure, int op, float scale);
 void sky_bake(hl_context_t* ctx, const float* coeffs40, const float* sun3, uint32_t size);
+// hl_comm.cu
+void comm_release(hl_context_t* ctx);
 } // namespace hl

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_tail(SceneView s, ShadeParam
 }
 
 // ---- resolve ---------------------------------------------------------------------------------------
-__global__ void k_resolve(FrameParams fp, const float4* __restrict__ state_b, float4* accum, int accum_mode, uint32_t* rgba8, int fused, float exposure, int op)
+__global__ void k_resolve(FrameParams fp, const float4* __restrict__ state_b, float4* accum, int accum_mode, uint32_t* rgba8, int fused, float exposure, int op, float scale)
 {
     const uint32_t n = fp.lw * fp.lh;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,7 +352,8 @@ __global__ void k_resolve(FrameParams fp, const float4* __restrict__ state_b, fl
     const f3       L = mk3(sb.x, sb.y, sb.z), prev = mk3(pv.x, pv.y, pv.z);
     const f3       c = accum_mode == HL_ACCUM_SUM ? accumulate_sum(L, prev) : accumulate_running_mean(L, prev, fp.pc.num_frames);
     accum[pix]       = make_float4(c.x, c.y, c.z, 1.0f);
-    if (fused) rgba8[(size_t)(H - 1 - py) * W + px] = tone_map_rgba8(c, exposure, op);
+    // scale = 1 for the running mean (x * 1.0f is exact); 1 / samples for a per-GPU sum image (HL_ACCUM_SUM preview)
+    if (fused) rgba8[(size_t)(H - 1 - py) * W + px] = tone_map_rgba8(mk3(c.x * scale, c.y * scale, c.z * scale), exposure, op);
 }
 
 __global__ void k_totals(uint32_t* counters, unsigned long long* totals, uint32_t bounces)
@@ -559,6 +560,7 @@ void film_clear(hl_context_t* ctx)
     for (hl_wave_slot& w : ctx->slot)
         if (w.rgba8.p) HL_CUDA(cudaMemsetAsync(w.rgba8.p, 0, n * 4, ctx->stream));
     ctx->rgba8_cur = ctx->rgba8.p;
+    ctx->sum_samples = 0;
 }
 
 void film_tonemap(hl_context_t* ctx, float exposure, int op, float scale)
@@ -625,7 +627,7 @@ static void run_bounces(hl_context_t* ctx, hl_wave_slot& w, cudaStream_t st, con
         // ray parameters per SURVEY A.5: primary tmin 0.001 flags 0; indirect tmin 0.0001 Opaque
         const float    ext_tmin  = b == 0 ? 0.001f : 0.0001f;
         const uint32_t ext_flags = b == 0 ? 0u : HL_RAY_OPAQUE;
-        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 0], st));
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 5 * b + 0], st));
         if (shade && b >= ctx->tail_start && ctx->tail_threshold > 0)
         {
             // sparse late bounces: finish the surviving paths in one launch when the queue is small (see k_tail)
@@ -633,16 +635,17 @@ static void run_bounces(hl_context_t* ctx, hl_wave_slot& w, cudaStream_t st, con
                                                      w.state_b.as<float4>());
             ctx->launches++;
         }
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 5 * b + 1], st));
         k_extend<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, w.ext_o[cur].as<float4>(), w.ext_d[cur].as<float4>(), ctr + CTR_EXT_COUNT + b, ctr + CTR_EXT_FETCH + b, ext_tmin,
                                                    10000.0f, ext_flags, w.hit_a.as<float4>(), w.hit_b.as<uint2>());
         ctx->launches++;
         if (!shade) break;
-        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 1], st));
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 5 * b + 2], st));
         k_shade<<<sgrid, HL_SHADE_BLOCK, 0, st>>>(ctx->view, prm, b, ctr + CTR_EXT_COUNT + b, w.ext_o[cur].as<float4>(), w.ext_d[cur].as<float4>(), w.hit_a.as<float4>(),
                                                   w.hit_b.as<uint2>(), w.state_a.as<float4>(), w.state_b.as<float4>(), w.ext_o[nxt].as<float4>(), w.ext_d[nxt].as<float4>(),
                                                   ctr + CTR_EXT_COUNT + b + 1, w.sh_o.as<float4>(), w.sh_d.as<float4>(), w.sh_c.as<float4>(), ctr + CTR_SH_COUNT + b);
         ctx->launches++;
-        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 2], st));
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 5 * b + 3], st));
         // shadow rays: depth 0 -> flags 0 (any-hit runs); deeper -> Opaque | TerminateOnFirstHit (rchit:286-290).
         // Visibility only asks whether ANY accepted intersection exists in (tmin, tmax) — acceptance is a
         // per-candidate test (alpha), independent of order — so the depth-0 query may also stop at its first
@@ -651,7 +654,7 @@ static void run_bounces(hl_context_t* ctx, hl_wave_slot& w, cudaStream_t st, con
         k_connect<<<tgrid, HL_TRACE_BLOCK, 0, st>>>(ctx->view, w.sh_o.as<float4>(), w.sh_d.as<float4>(), w.sh_c.as<float4>(), ctr + CTR_SH_COUNT + b, ctr + CTR_SH_FETCH + b, 0.0001f,
                                                     sh_flags, w.state_b.as<float4>());
         ctx->launches++;
-        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 4 * b + 3], st));
+        if (prof) HL_CUDA(cudaEventRecord(ctx->ev[2 + 5 * b + 4], st));
     }
 }
 
@@ -731,7 +734,7 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
         replay_bounces(ctx, w, st, fp, bounces);
     else
         run_bounces(ctx, w, st, fp, bounces, true);
-    const size_t last = 2 + 4 * (size_t)bounces;
+    const size_t last = 2 + 5 * (size_t)bounces;
     if (prof) HL_CUDA(cudaEventRecord(ctx->ev[last], st));
     // progressive blends are applied in frame order: wait for the previous frame's resolve pass
     if (piped && other.pending) HL_CUDA(cudaStreamWaitEvent(st, other.resolved, 0));
@@ -743,7 +746,9 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
     }
     const bool full  = lw == ctx->W && lh == ctx->H;
     const bool fused = opt.tone_map && full;
-    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, w.rgba8.as<uint32_t>(), fused ? 1 : 0, opt.exposure, opt.op);
+    if (ctx->accum_mode == HL_ACCUM_SUM && full) ctx->sum_samples++;
+    const float scale = ctx->accum_mode == HL_ACCUM_SUM ? 1.0f / (float)std::max<uint64_t>(ctx->sum_samples, 1) : 1.0f;
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(fp, w.state_b.as<float4>(), ctx->accum.as<float4>(), ctx->accum_mode, w.rgba8.as<uint32_t>(), fused ? 1 : 0, opt.exposure, opt.op, scale);
     if (opt.tone_map)
     {
         if (!fused) // a tile launch resolves only its own pixels: tone map the whole image, as the reference's full-screen pass does
@@ -766,9 +771,13 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
         {
             HL_CUDA(cudaEventRecord(w.image_ready, st));
             HL_CUDA(cudaStreamWaitEvent(w.copy_stream, w.image_ready, 0));
+            // copies of different slots run on different streams: two read-backs into the SAME host memory (a caller without
+            // the ring of n_slots buffers the header asks for) are ordered, the later frame's image lands last
+            for (hl_wave_slot& o : ctx->slot)
+                if (&o != &w && o.copy_pending && o.copy_host == opt.host) HL_CUDA(cudaStreamWaitEvent(w.copy_stream, o.copy_done, 0));
             HL_CUDA(cudaMemcpyAsync(opt.host, w.rgba8.p, bytes, cudaMemcpyDeviceToHost, w.copy_stream));
             HL_CUDA(cudaEventRecord(w.copy_done, w.copy_stream));
-            w.copy_pending = true;
+            w.copy_pending = true, w.copy_host = opt.host;
         }
         else
             HL_CUDA(cudaMemcpyAsync(opt.host, w.rgba8.p, bytes, cudaMemcpyDeviceToHost, st));
@@ -784,14 +793,20 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
         float ms;
         HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]));
         c.ms_generate = ms;
+        std::vector<uint32_t> hc(CTR_U32_TOTAL);
+        HL_CUDA(cudaMemcpy(hc.data(), ctr, CTR_U32_TOTAL * 4, cudaMemcpyDeviceToHost));
+        ctx->bounce_prof_n = bounces, ctx->prof_tail_ext = hc[CTR_TAIL_EXT], ctx->prof_tail_sh = hc[CTR_TAIL_SH];
         for (uint32_t b = 0; b < bounces; b++)
         {
-            HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 + 4 * b], ctx->ev[2 + 4 * b + 1]));
-            c.ms_extend += ms;
-            HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 + 4 * b + 1], ctx->ev[2 + 4 * b + 2]));
-            c.ms_shade += ms;
-            HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 + 4 * b + 2], ctx->ev[2 + 4 * b + 3]));
-            c.ms_connect += ms;
+            hl_bounce_profile& bp = ctx->bounce_prof[b];
+            bp.extension_rays = hc[CTR_EXT_COUNT + b], bp.shadow_rays = hc[CTR_SH_COUNT + b];
+            HL_CUDA(cudaEventElapsedTime(&bp.ms_tail, ctx->ev[2 + 5 * b], ctx->ev[2 + 5 * b + 1]));
+            HL_CUDA(cudaEventElapsedTime(&bp.ms_extend, ctx->ev[2 + 5 * b + 1], ctx->ev[2 + 5 * b + 2]));
+            HL_CUDA(cudaEventElapsedTime(&bp.ms_shade, ctx->ev[2 + 5 * b + 2], ctx->ev[2 + 5 * b + 3]));
+            HL_CUDA(cudaEventElapsedTime(&bp.ms_connect, ctx->ev[2 + 5 * b + 3], ctx->ev[2 + 5 * b + 4]));
+            // hl_counters: the tail kernel's time is booked under the extend stage as before (it replaces the three stages of the
+            // bounces it finishes); hl_get_bounce_profile separates it
+            c.ms_extend += bp.ms_tail + bp.ms_extend, c.ms_shade += bp.ms_shade, c.ms_connect += bp.ms_connect;
         }
         HL_CUDA(cudaEventElapsedTime(&ms, ctx->ev[last], ctx->ev[1]));
         c.ms_resolve = ms;
@@ -835,6 +850,20 @@ void wavefront_debug_rays(hl_context_t* ctx, const hl_push_constants& pc, uint32
     const uint32_t blocks = std::min<uint32_t>((n + HL_TRACE_BLOCK - 1) / HL_TRACE_BLOCK, (uint32_t)ctx->sm_count * 8u);
     k_debug_rays<<<blocks, HL_TRACE_BLOCK, 0, ctx->stream>>>(ctx->view, pc, n, out);
     ctx->launches++;
+}
+
+// traversals that ran out of stack since the last reset (hl_bvh.h note_stack_overflow)
+uint64_t trav_overflow_count(hl_context_t* ctx, bool reset)
+{
+    unsigned long long n = 0;
+    HL_CUDA(cudaMemcpyFromSymbolAsync(&n, g_trav_overflow, sizeof(n), 0, cudaMemcpyDeviceToHost, ctx->stream));
+    HL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (reset && n)
+    {
+        const unsigned long long z = 0;
+        HL_CUDA(cudaMemcpyToSymbolAsync(g_trav_overflow, &z, sizeof(z), 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return n;
 }
 
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits)

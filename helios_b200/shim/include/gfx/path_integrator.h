@@ -40,6 +40,13 @@ public:
                            std::vector<hl_debug_ray_vertex>& vertices, uint32_t max_vertices);
     void on_window_resize();
     void set_tiled(bool tiled);
+    // samples-per-pixel sharding across GPUs (no counterpart in the reference): this integrator is rank
+    // `rank` of `world` and renders frame indices rank + 1, rank + 1 + world, ... (frame 0 is discarded by the reference's
+    // blend, path_trace_rgen.glsl:219-247, so it is skipped) into a per-GPU SUM image; MultiGpuRenderer combines the images.
+    // world = 1 restores the reference's counting.  Full-frame launches only.
+    void set_sample_sharding(uint32_t rank, uint32_t world);
+    uint32_t shard_rank() const { return m_shard_rank; }
+    uint32_t shard_world() const { return m_shard_world; }
 
     // Renderer::render hands the tone-map settings down so that the launch can resolve accumulation and tone map
     // in one fused pass (hl_render_frame_tonemapped); launched_last_render() tells it whether a launch happened
@@ -70,6 +77,7 @@ private:
     std::vector<glm::uvec2> m_tiles;
     std::weak_ptr<vk::Backend> m_backend;
     hl_push_constants m_last_push_constants {};
+    uint32_t m_shard_rank = 0, m_shard_world = 1;
     bool m_fuse_tone_map = false, m_launched = false;
     float m_fuse_exposure = 1.0f;
     int m_fuse_operator = HL_TONE_MAP_ACES;

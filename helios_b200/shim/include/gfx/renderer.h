@@ -86,4 +86,23 @@ private:
     float m_exposure = 1.0f;
     OutputBuffer m_current_output_buffer = OUTPUT_BUFFER_FINAL;
 };
+
+// Samples-per-pixel sharding across the GPUs of ONE process (the reference renders on one GPU): one
+// Backend / Scene / Renderer per GPU, the scene replicated, renderer g set to shard (g, n) — its frame loop is the
+// reference's own (scene->update, renderer->render) — and ONE reduction per finished picture: hl_multi_gpu_resolve sums the
+// per-GPU images over peer memory (or NCCL), applies 1 / samples, exposure and the tone map, and hands back the image.
+class MultiGpuRenderer
+{
+public:
+    MultiGpuRenderer(const std::vector<vk::Backend::Ptr>& backends); // hl_comm_init_all; creates one Renderer per backend
+    size_t size() const { return m_renderers.size(); }
+    Renderer* renderer(size_t rank) { return m_renderers[rank].get(); }
+    // RGBA8 image (row 0 = top) of sum / samples_total with renderer(0)'s exposure and tone map operator; the sum stays
+    // in rank 0's accumulation image (renderer(0)->read_accumulation())
+    std::vector<uint8_t> resolve(uint32_t samples_total);
+
+private:
+    std::vector<vk::Backend::Ptr> m_backends;
+    std::vector<std::unique_ptr<Renderer>> m_renderers;
+};
 } // namespace helios

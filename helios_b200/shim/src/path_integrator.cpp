@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <stdexcept>
 
 namespace helios
 {
@@ -48,8 +49,20 @@ void PathIntegrator::on_window_resize()
     compute_tile_coords();
 }
 
+void PathIntegrator::set_sample_sharding(uint32_t rank, uint32_t world)
+{
+    if (world == 0 || rank >= world) throw std::runtime_error("PathIntegrator::set_sample_sharding: rank outside the world");
+    if (world > 1 && m_cfg.tiled) throw std::runtime_error("PathIntegrator::set_sample_sharding: sharded bakes use full-frame launches");
+    auto backend  = m_backend.lock();
+    m_shard_rank  = rank;
+    m_shard_world = world;
+    backend->check(hl_set_accum_mode(backend->require_device("PathIntegrator::set_sample_sharding"), world > 1 ? HL_ACCUM_SUM : HL_ACCUM_RUNNING_MEAN), "hl_set_accum_mode");
+    restart_bake();
+}
+
 void PathIntegrator::set_tiled(bool tiled)
 {
+    if (tiled && m_shard_world > 1) throw std::runtime_error("PathIntegrator::set_tiled: sharded bakes use full-frame launches");
     m_cfg.tiled = tiled;
     compute_tile_coords();
 }
@@ -91,7 +104,7 @@ hl_push_constants PathIntegrator::make_push_constants(RenderState& render_state,
     pc.ray_debug_pixel_coord[2] = (int32_t)extents.width, pc.ray_debug_pixel_coord[3] = (int32_t)extents.height;
     pc.launch_id_size[0] = (uint32_t)tile_coord.x, pc.launch_id_size[1] = (uint32_t)tile_coord.y, pc.launch_id_size[2] = extents.width, pc.launch_id_size[3] = extents.height;
     pc.num_lights      = render_state.num_lights();
-    pc.num_frames      = m_bake.samples;
+    pc.num_frames      = m_shard_world > 1 ? 1u + m_shard_rank + m_bake.samples * m_shard_world : m_bake.samples;
     pc.accumulation    = float(pc.num_frames) / float(pc.num_frames + 1);
     pc.debug_vis       = 0;
     pc.max_ray_bounces = m_cfg.max_bounces;

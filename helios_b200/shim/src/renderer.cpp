@@ -141,6 +141,41 @@ std::vector<float> Renderer::read_output_buffer(RenderState& render_state)
     return out;
 }
 
+MultiGpuRenderer::MultiGpuRenderer(const std::vector<vk::Backend::Ptr>& backends) : m_backends(backends)
+{
+    if (backends.empty()) throw std::runtime_error("MultiGpuRenderer: no backend");
+    std::vector<hl_context> ctxs;
+    for (auto& b : m_backends) ctxs.push_back(b->require_device("MultiGpuRenderer"));
+    if (hl_comm_init_all(ctxs.data(), (int)ctxs.size()) != HL_OK)
+    {
+        const std::string msg = std::string("hl_comm_init_all: ") + hl_comm_last_error();
+        HELIOS_LOG_FATAL(msg);
+        throw std::runtime_error(msg);
+    }
+    for (size_t g = 0; g < m_backends.size(); g++)
+    {
+        m_renderers.emplace_back(new Renderer(m_backends[g]));
+        m_renderers.back()->path_integrator()->set_sample_sharding((uint32_t)g, (uint32_t)m_backends.size());
+    }
+}
+
+std::vector<uint8_t> MultiGpuRenderer::resolve(uint32_t samples_total)
+{
+    std::vector<hl_context> ctxs;
+    for (auto& b : m_backends) ctxs.push_back(b->require_device("MultiGpuRenderer::resolve"));
+    const auto           ext = m_backends[0]->swap_chain_extents();
+    std::vector<uint8_t> img((size_t)ext.width * ext.height * 4);
+    Renderer*            r0 = m_renderers[0].get();
+    const int            op = r0->tone_map_operator() == TONE_MAP_OPERATOR_ACES ? HL_TONE_MAP_ACES : HL_TONE_MAP_REINHARD;
+    if (hl_multi_gpu_resolve(ctxs.data(), (int)ctxs.size(), 0, r0->exposure(), op, 1.0f / float(samples_total ? samples_total : 1u), img.data()) != HL_OK)
+    {
+        const std::string msg = std::string("hl_multi_gpu_resolve: ") + hl_comm_last_error();
+        HELIOS_LOG_FATAL(msg);
+        throw std::runtime_error(msg);
+    }
+    return img;
+}
+
 std::vector<float> Renderer::read_accumulation()
 {
     auto               backend = m_backend.lock();

@@ -13,6 +13,7 @@
 // --no-device builds the scene graph and the tables on the host only (for inspection); rendering needs a GPU.
 #include <core/resource_manager.h>
 #include <gfx/renderer.h>
+#include <utility/png_writer.h>
 #include <resource/material.h>
 #include <resource/mesh.h>
 #include <resource/scene.h>
@@ -78,6 +79,7 @@ int main(int argc, char** argv)
     uint32_t    spp = 16, bounces = 0, arg_width = 1280, arg_height = 720;
     float       focal_length = -1.0f, aperture = -1.0f;
     int         device = 0;
+    std::vector<int> devices; // --gpus N / --devices a,b,...: one rank per entry (entries may repeat: ranks sharing a GPU)
     bool        tiled = false, no_device = false;
     float       exposure = 1.0f;
     for (int i = 1; i < argc; i++)
@@ -98,6 +100,23 @@ int main(int argc, char** argv)
             else if (a == "--aperture") aperture = std::stof(next());
             else if (a == "--spp") spp = (uint32_t)std::stoul(next());
             else if (a == "--device") device = std::stoi(next());
+            else if (a == "--gpus") // samples sharded over GPUs 0..N-1 of this process, one reduction at the end
+            {
+                const int n = std::stoi(next());
+                devices.clear();
+                for (int g = 0; g < n; g++) devices.push_back(g);
+            }
+            else if (a == "--devices")
+            {
+                devices.clear();
+                const std::string list = next();
+                for (size_t b = 0; b < list.size();)
+                {
+                    const size_t e = list.find(',', b) == std::string::npos ? list.size() : list.find(',', b);
+                    devices.push_back(std::stoi(list.substr(b, e - b)));
+                    b = e + 1;
+                }
+            }
             else if (a == "--bounces") bounces = (uint32_t)std::stoul(next());
             else if (a == "--exposure") exposure = std::stof(next());
             else if (a == "--out") out_path = next();
@@ -135,6 +154,8 @@ int main(int argc, char** argv)
       float            bias  = 0.0f;
       vk::Backend::Ptr backend;
       Scene::Ptr       scene;
+      // builds backend + scene on GPU `device` (called once per rank for --gpus / --devices: the scene is replicated)
+      auto make_scene = [&](int device) {
       if (!ast_scene_path.empty())
       {
         // the reference's own asset route: ResourceManager::load_scene on an AssetCore scene description
@@ -149,7 +170,6 @@ int main(int argc, char** argv)
             if (focal_length >= 0.0f) camera->set_focal_length(focal_length);
             if (aperture >= 0.0f) camera->set_aperture_radius(aperture);
         }
-        scene_path = ast_scene_path;
       }
       else
       {
@@ -267,6 +287,82 @@ int main(int argc, char** argv)
 
         scene = Scene::create(backend, "scene", root, scene_path);
       }
+      };
+      if (devices.size() > 1)
+      {
+        // ---- samples-per-pixel sharding: one Backend / Scene / Renderer per rank, the reference's frame loop on each, one reduction
+        if (no_device || tiled) throw std::runtime_error("--gpus / --devices needs a device and full-frame launches");
+        std::vector<vk::Backend::Ptr> backends;
+        std::vector<Scene::Ptr>       scenes;
+        for (int d : devices)
+        {
+            make_scene(d);
+            backends.push_back(backend), scenes.push_back(scene);
+        }
+        backend.reset(), scene.reset();
+        const uint32_t G = (uint32_t)devices.size();
+        if (spp % G != 0) throw std::runtime_error("--spp must be divisible by the number of ranks");
+        {
+            MultiGpuRenderer         group(backends);
+            std::vector<RenderState> states(G);
+            auto                     cmd = std::make_shared<vk::CommandBuffer>();
+            for (uint32_t g = 0; g < G; g++)
+            {
+                auto pi = group.renderer(g)->path_integrator();
+                pi->set_max_ray_bounces(bounces ? bounces : file_bounces);
+                pi->set_shadow_ray_bias(bias);
+                group.renderer(g)->set_exposure(exposure);
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            for (uint32_t k = 0; k < spp / G; k++)
+                for (uint32_t g = 0; g < G; g++) // asynchronous launches: one host thread keeps every GPU busy
+                {
+                    states[g].setup(width, height, cmd);
+                    scenes[g]->update(states[g]);
+                    group.renderer(g)->render(states[g]);
+                }
+            const std::vector<uint8_t> img = group.resolve(spp);
+            const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (!out_path.empty())
+            {
+                const std::string& p = out_path;
+                const bool ppm = p.size() > 4 && p.compare(p.size() - 4, 4, ".ppm") == 0;
+                if (ppm)
+                {
+                    if (FILE* f = std::fopen(p.c_str(), "wb"))
+                    {
+                        std::fprintf(f, "P6\n%u %u\n255\n", width, height);
+                        for (size_t i = 0; i < (size_t)width * height; i++) std::fwrite(&img[i * 4], 1, 3, f);
+                        std::fclose(f);
+                    }
+                }
+                else if (!write_png_rgba8(p, width, height, img.data(), (size_t)width * 4))
+                    throw std::runtime_error("cannot write " + p);
+            }
+            if (!accum_path.empty())
+            {
+                const auto acc = group.renderer(0)->read_accumulation(); // the reduced SUM (divide by --spp for radiance)
+                if (FILE* f = std::fopen(accum_path.c_str(), "wb"))
+                {
+                    std::fwrite(acc.data(), 4, acc.size(), f);
+                    std::fclose(f);
+                }
+            }
+            unsigned long long ext = 0, sh = 0;
+            for (uint32_t g = 0; g < G; g++)
+            {
+                hl_counters c {};
+                backends[g]->check(hl_get_counters(backends[g]->context(), &c), "hl_get_counters");
+                ext += c.extension_rays, sh += c.shadow_rays;
+            }
+            std::printf("{\"scene\": \"%s\", \"width\": %u, \"height\": %u, \"ranks\": %u, \"launches\": %u, \"seconds\": %.6f, \"extension_rays\": %llu, \"shadow_rays\": %llu, \"mrays_per_s\": %.1f}\n",
+                        (ast_scene_path.empty() ? scene_path : ast_scene_path).c_str(), width, height, G, spp, seconds, ext, sh, seconds > 0 ? double(ext + sh) / seconds / 1e6 : 0.0);
+        }
+        scenes.clear();
+        return 0;
+      }
+      make_scene(devices.empty() ? device : devices[0]);
+      if (scene_path.empty()) scene_path = ast_scene_path;
         RenderState render_state;
         auto        cmd = std::make_shared<vk::CommandBuffer>();
 

@@ -217,8 +217,9 @@ HL_API hl_status hl_scene_set_tables(hl_context ctx, const hl_material* material
 HL_API hl_status hl_render_frame(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h);
 /* The same frame with the progressive blend and the tone map fused into ONE resolve pass (reads the frame's radiance
  * and the previous accumulation, writes RGBA32F + RGBA8): Renderer::render = PathIntegrator::render + tone_map
- * (renderer.cpp:225-330, :369-428) in a single call.  Running-mean mode only (HL_ACCUM_SUM needs the sample
- * count of the final reduction: use hl_tonemap with sample_scale there).  Asynchronous. */
+ * (renderer.cpp:225-330, :369-428) in a single call.  In HL_ACCUM_SUM mode (full-frame launches only) the image shown
+ * is this GPU's own sum / n, n = full-frame launches since hl_accum_clear — the rank-local progressive preview; the
+ * final picture of a sharded render comes from the reduction + hl_tonemap(sample_scale = 1 / total).  Asynchronous. */
 HL_API hl_status hl_render_frame_tonemapped(hl_context ctx, const hl_push_constants* pc, uint32_t launch_w, uint32_t launch_h,
                                             float exposure, int tone_map_operator);
 /* The same, plus an asynchronous device->host copy of the frame's RGBA8 image into rgba8_host (W*H*4 bytes, pinned memory
@@ -277,7 +278,20 @@ HL_API hl_status hl_write_accum(hl_context ctx, const float* rgba32f_host);
 /* device pointer of the accumulation image (W*H*4 floats) for NCCL reduction by the host layer */
 HL_API hl_status hl_accum_device_ptr(hl_context ctx, void** out_ptr);
 HL_API hl_status hl_synchronize(hl_context ctx);
+/* fails with HL_ERR_LIMIT when a traversal ran out of stack since the last hl_reset_counters (hl_counters is still filled):
+ * results of such rays are not trustworthy (hl_bvh.h TravStack; depth 64 entries) */
 HL_API hl_status hl_get_counters(hl_context ctx, hl_counters* out);
+/* per-bounce breakdown of the last frame rendered with hl_set_profiling(1): queue sizes and CUDA-event times of each
+ * stage launch.  ms_extend brackets k_extend alone (the tail kernel has its own column).  tail_* = rays traced by the
+ * tail kernel (all bounces it finished).  Returns the number of bounces in *n_bounces (<= capacity are written). */
+typedef struct hl_bounce_profile
+{
+    uint32_t extension_rays; /* size of the extension queue this bounce's k_extend launch found (0: empty launch) */
+    uint32_t shadow_rays;
+    float    ms_tail, ms_extend, ms_shade, ms_connect;
+} hl_bounce_profile;
+HL_API hl_status hl_get_bounce_profile(hl_context ctx, hl_bounce_profile* out, uint32_t capacity, uint32_t* n_bounces,
+                                       uint64_t* tail_extension_rays, uint64_t* tail_shadow_rays);
 HL_API hl_status hl_reset_counters(hl_context ctx);
 /* per-stage CUDA-event timing on/off (off by default: no events inside the frame) */
 HL_API hl_status hl_set_profiling(hl_context ctx, int enabled);
@@ -301,6 +315,38 @@ HL_API hl_status hl_event_elapsed_ms(hl_context ctx, int slot_begin, int slot_en
 HL_API hl_status hl_set_option(hl_context ctx, int option, int64_t value);
 /* number of kernels launched by this library on this context since creation */
 HL_API hl_status hl_kernel_launches(hl_context ctx, uint64_t* out);
+
+/* ------------------------------------------------------------------ multi-GPU (SURVEY.md 8e / 8b hl_multi_gpu_reduce)
+ * Samples per pixel are sharded across the GPUs of one box: the scene is replicated, rank g renders frame indices
+ * g+1, g+1+G, ... into its own HL_ACCUM_SUM image, and ONE reduction of the W*H*4-float accumulation images combines
+ * them; 1 / samples goes into the tone-map pass (sample_scale).  The reference has no multi-GPU path: what is kept is
+ * its blend (path_trace_rgen.glsl:219-247) — sum / count equals that running mean up to fp32 rounding.
+ *
+ * (1) one process per GPU (torchrun / MPI style): rank 0 calls hl_comm_unique_id and hands the HL_COMM_ID_BYTES bytes to
+ *     the other ranks by any means; every rank calls hl_comm_init_rank (collective, blocking), then hl_accum_all_reduce /
+ *     hl_accum_reduce — NCCL on the context's stream, asynchronous like hl_render_frame, ordered behind the frames in
+ *     flight.  libnccl.so.2 is opened at run time (no link-time dependency); HL_ERR_STATE when it cannot be loaded.
+ * (2) all GPUs in one process (helios_headless --gpus N): hl_comm_init_all binds n contexts (rank = position in the
+ *     array; contexts may also share a device), hl_multi_gpu_reduce sums their images into the root's, and
+ *     hl_multi_gpu_resolve does that plus tone map plus read-back.  With peer access between all members both run as ONE
+ *     kernel per GPU over peer memory (each GPU reduces 1/n of the image in rank order and writes the fp32 sum and the
+ *     tone-mapped RGBA8 pixels straight into the root's images; CUDA events order it, nothing blocks the host);
+ *     otherwise they fall back to ncclReduce + the root's tone-map pass. */
+#define HL_COMM_ID_BYTES 128
+HL_API hl_status hl_comm_unique_id(uint8_t* id /* HL_COMM_ID_BYTES */);
+HL_API hl_status hl_comm_init_rank(hl_context ctx, const uint8_t* id, int n_ranks, int rank);
+HL_API hl_status hl_comm_init_all(hl_context* ctxs, int n);
+HL_API hl_status hl_comm_destroy(hl_context ctx);
+HL_API const char* hl_comm_last_error(void); /* message of the last failed hl_comm_* / hl_multi_gpu_* call of this thread */
+/* accumulation image <- sum over ranks, on every rank / on `root` only (other ranks keep their own image) */
+HL_API hl_status hl_accum_all_reduce(hl_context ctx);
+HL_API hl_status hl_accum_reduce(hl_context ctx, int root);
+/* single-process form: root's accumulation image <- sum over the n contexts; asynchronous on the contexts' streams */
+HL_API hl_status hl_multi_gpu_reduce(hl_context* ctxs, int n, int root);
+/* the same, fused with Renderer::tone_map (tone_map.frag) of sum * sample_scale into the root's RGBA8 image; rgba8_host may be
+ * NULL (device only: hl_read_rgba8(root) fetches it later), otherwise the call copies the image there and synchronises */
+HL_API hl_status hl_multi_gpu_resolve(hl_context* ctxs, int n, int root, float exposure, int tone_map_operator, float sample_scale,
+                                      uint8_t* rgba8_host);
 
 #ifdef __cplusplus
 }

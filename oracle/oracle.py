@@ -24,6 +24,15 @@ def build(force: bool = False) -> Path:
     return _LIB_PATH
 
 
+def set_threads(n: int):
+    """OpenMP thread count of the oracle libraries (torchrun exports OMP_NUM_THREADS=1 to its workers; libgomp reads the
+    variable once, so it is set through the runtime call)"""
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(C.c_int(int(n)))
+    except OSError:
+        pass
+
+
 def lib():
     global _lib
     if _lib is None:

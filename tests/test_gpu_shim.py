@@ -133,3 +133,20 @@ def test_ray_debug_view_through_renderer(tmp_path):
         starts, ends = seg[:, 0, :3], seg[:, 1, :3]
         linked = [(np.abs(ends - st).max(-1) < 1e-4).any() for st in starts]
         assert sum(linked) >= len(seg) - 1
+
+
+def test_headless_sharded_over_ranks_matches_one_rank(tmp_path):
+    """SURVEY 8e through the C++ host: helios_headless --devices 0,0 runs MultiGpuRenderer — two Backend / Scene / Renderer
+    sets (here on the same GPU, so the driver's one-GPU box runs it), renderer g takes frames g+1, g+3, ... into a SUM image,
+    hl_multi_gpu_resolve combines them over peer memory.  sum / spp must equal the running mean one renderer builds over
+    launches 0..spp (frame 0 is discarded by the blend, path_trace_rgen.glsl:219-247) up to fp32 summation order."""
+    s = scenes.cornell_box(128, 96)
+    spp = 8
+    one, _, _ = headless_render(s, tmp_path, spp + 1)  # launches num_frames = 0..spp: the mean of frames 1..spp
+    acc, stats, img = headless_render(s, tmp_path, spp, extra=("--devices", "0,0"), out="multi.ppm")
+    assert stats["ranks"] == 2 and stats["launches"] == spp
+    d = np.abs(acc[..., :3] / spp - one[..., :3])
+    assert d.max() < 2e-6 * spp, d.max()
+    raw = img.read_bytes()
+    rgb = np.frombuffer(raw[len(raw) - s.width * s.height * 3 :], np.uint8)
+    assert rgb.max() > 0
