@@ -309,3 +309,54 @@ def test_hostile_materials_and_lights(name, api, oracle_mod):
     d = np.abs(np.nan_to_num(a) - np.nan_to_num(b))[..., :3].max(-1)
     assert (d > 1e-4).mean() < 0.01 and d.max() < 0.2, (int((d > 1e-4).sum()), float(d.max()))
     ctx.close()
+
+
+def test_scene_tables_reject_indices_a_shader_would_follow_out_of_bounds(api):
+    """hl_scene_set_tables validates every index the kernels dereference: material texture slots, and the
+    instance / material / primitive range of area-light rows (sample_light, path_trace_rchit.glsl:376-451 reads them from
+    LightData).  A bad one must come back as HL_ERR_INVALID_ARGUMENT — not as a sticky cudaErrorIllegalAddress — and the
+    context must keep working afterwards."""
+    from helios_b200._lib import HeliosError
+
+    s = scenes.cornell_box(64, 64)
+    ctx = api.Context(s.width, s.height)
+    handles = ctx.load_scene(s)
+    good = ctx.render(s, 2)
+    meshes = [handles[int(i["mesh_index"])] for i in s.instances]
+
+    def attempt(materials=None, lights=None):
+        with pytest.raises(HeliosError) as e:
+            ctx.set_tables(s.materials if materials is None else materials, s.instances, meshes, s.submesh_info, s.lights if lights is None else lights)
+        assert e.value.status == 1, e.value  # HL_ERR_INVALID_ARGUMENT
+
+    for slot, field in [(0, "texture_indices0"), (1, "texture_indices0"), (2, "texture_indices0"), (3, "texture_indices0"), (0, "texture_indices1")]:
+        for bad in (0, 7, -2):  # the scene has no textures: any index but -1 is stale
+            m = s.materials.copy()
+            m[field][1, slot] = bad
+            attempt(materials=m)
+    area = [k for k, l in enumerate(s.lights) if int(l["light_data0"][0]) == abi.LIGHT_AREA]
+    assert area
+    k = area[0]
+    n_tris = len(s.meshes[0].indices) // 3
+    for field, comp, bad in [("light_data0", 1, 5.0), ("light_data0", 1, -1.0), ("light_data0", 2, 4096.0), ("light_data0", 3, float(n_tris)), ("light_data1", 2, float(n_tris + 1)),
+                             ("light_data0", 3, float("nan")), ("light_data1", 2, 3e9)]:
+        l = s.lights.copy()
+        l[field][k, comp] = bad
+        attempt(lights=l)
+    # the failed calls changed nothing a frame depends on: the old tables are still installed and render the same image
+    ctx.set_tables(s.materials, s.instances, meshes, s.submesh_info, s.lights)
+    assert np.array_equal(ctx.render(s, 2), good)
+    ctx.close()
+
+
+def test_textures_clear_makes_material_indices_stale(api):
+    from helios_b200._lib import HeliosError
+
+    s = scenes.terrain_scene(grid=24, n_spheres=2, sphere_level=1, width=64, height=36, textured=True)
+    ctx = api.Context(s.width, s.height)
+    handles = ctx.load_scene(s)
+    ctx.render(s, 1)
+    ctx._chk(ctx.lib.hl_textures_clear(ctx.h))
+    with pytest.raises(HeliosError):
+        ctx.set_tables(s.materials, s.instances, [handles[int(i["mesh_index"])] for i in s.instances], s.submesh_info, s.lights)
+    ctx.close()

@@ -97,6 +97,38 @@ def test_soup_primary_ids_bit_exact(api, oracle_mod, n_tris):
     ctx.close()
 
 
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("n_tris", [1_000_000, 10_000_000])
+def test_config5_soup_full_size_primary_ids_bit_exact(api, oracle_mod, n_tris):
+    """BASELINE configs[4] ("config 5") at full size, where the driver sees it: uniform triangle soup of 1M / 10M triangles
+    (seed = N), the fixed 1920x1080 pinhole primary-ray set, GPU builder + traversal against the oracle's own BVH (median
+    split, 0.7 s / ~11 s to build on the host).  Bar (north_star): hit IDs (instance, geometry, primitive) bit-exact
+    except FP-ambiguous edge hits, which are counted and must stay below 0.01 % of the rays; (t, u, v) bit-exact on
+    the rays whose IDs agree.  Round-1 sweep: 0 and 0 at every size (profiles/r01f_config5_sweep.jsonl)."""
+    s = scenes.triangle_soup(n_tris)
+    assert (s.width, s.height) == (1920, 1080)
+    ctx = api.Context(s.width, s.height)
+    handles = ctx.load_scene(s)
+    st = ctx.mesh_build_stats(handles[0])
+    assert st["triangles"] == n_tris
+    pc = s.push_constants(1)
+    g = ctx.trace_primary_ids(pc)
+    ctx.counters()  # fails loudly on a traversal-stack overflow
+    ctx.close()
+    o = oracle_mod.OracleScene(s)
+    r = o.trace_primary_ids(pc)
+    ids_bad = (g[0] != r[0]) | (g[1] != r[1]) | (g[2] != r[2])
+    tuv_bad = np.zeros_like(ids_bad)
+    for k in (3, 4, 5):
+        tuv_bad |= g[k].view(np.uint32) != r[k].view(np.uint32)
+    n = ids_bad.size
+    ambiguous = int(ids_bad.sum())
+    print(f"config 5, {n_tris} triangles: build {float(st['ms_build']):.2f} ms, {ambiguous} of {n} ids differ (FP-ambiguous), {int((tuv_bad & ~ids_bad).sum())} (t,u,v) bit mismatches")
+    assert ambiguous <= 1e-4 * n, f"{ambiguous} of {n} primary hit ids differ"
+    assert int((tuv_bad & ~ids_bad).sum()) == 0
+    assert (g[0] != abi.MISS_ID).mean() > 0.2  # a quarter of the 1080p view looks at the unit cube
+
+
 @pytest.mark.parametrize("scene", ["soup", "city"])
 def test_builder_sah_cluster_never_changes_a_result(api, oracle_mod, scene):
     """HL_OPT_SAH_CLUSTER (binned-SAH re-split of the upper BVH levels, hl_build.h top_*): every setting builds a
