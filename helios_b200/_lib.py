@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("HELIOS_B200_LIB") or Path(__file__).resolve().pa
 SYMBOLS = [
     "hl_context_create", "hl_context_destroy", "hl_context_resize", "hl_last_error", "hl_version",
     "hl_mesh_create", "hl_mesh_destroy", "hl_mesh_build_stats", "hl_texture2d_create", "hl_textures_clear",
-    "hl_envmap_set", "hl_sky_update", "hl_envmap_read", "hl_scene_set_tables", "hl_render_frame", "hl_render_frame_tonemapped", "hl_render_frame_readback", "hl_read_rgba8", "hl_accum_clear",
+    "hl_envmap_set", "hl_sky_update", "hl_envmap_read", "hl_scene_set_tables", "hl_scene_update_instances", "hl_render_frame", "hl_render_frame_tonemapped", "hl_render_frame_readback", "hl_read_rgba8", "hl_accum_clear",
     "hl_set_accum_mode", "hl_trace_primary_ids", "hl_render_output_buffer", "hl_gather_debug_rays", "hl_trace_rays", "hl_tonemap", "hl_read_accum", "hl_write_accum",
     "hl_accum_device_ptr", "hl_synchronize", "hl_get_counters", "hl_reset_counters", "hl_set_profiling", "hl_kernel_launches", "hl_event_record", "hl_event_elapsed_ms", "hl_set_option",
     "hl_get_bounce_profile", "hl_comm_unique_id", "hl_comm_init_rank", "hl_comm_init_all", "hl_comm_destroy", "hl_comm_last_error", "hl_accum_all_reduce", "hl_accum_reduce", "hl_multi_gpu_reduce", "hl_multi_gpu_resolve",

@@ -98,6 +98,11 @@ class Context:
         mh = (C.c_void_p * max(len(meshes), 1))(*[m.value for m in meshes])
         self._chk(self.lib.hl_scene_set_tables(self.h, _p(mats), C.c_uint32(len(mats)), _p(inst), mh, ptrs, C.c_uint32(len(inst)), _p(lts), C.c_uint32(len(lts))))
 
+    def update_instances(self, instances):
+        """new transforms for the installed instances: instance-tree REFIT instead of a rebuild (hl_scene_update_instances)"""
+        inst = np.ascontiguousarray(instances, abi.INSTANCE)
+        self._chk(self.lib.hl_scene_update_instances(self.h, _p(inst), C.c_uint32(len(inst))))
+
     def load_scene(self, scene, sky_coeffs=None):
         """uploads a helios_b200.scenes.SceneData: meshes (+BLAS build), textures, environment, tables (+TLAS)"""
         handles = [self.create_mesh(m.vertices, m.indices, m.submeshes) for m in scene.meshes]

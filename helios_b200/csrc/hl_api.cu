@@ -291,6 +291,29 @@ static void affine_inverse(const float* m, float* out)
     out[8] = (float)i20, out[9] = (float)i21, out[10] = (float)i22, out[11] = (float)(-(i20 * t0 + i21 * t1 + i22 * t2));
 }
 
+// world box of an instance: the 8 corners of the mesh's object-space root box through the model matrix, in double, padded
+static Box instance_world_box(const float* M, const Box& rb)
+{
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (int cidx = 0; cidx < 8; cidx++)
+    {
+        const double x = (cidx & 1) ? rb.hi[0] : rb.lo[0], y = (cidx & 2) ? rb.hi[1] : rb.lo[1], z = (cidx & 4) ? rb.hi[2] : rb.lo[2];
+        for (int a = 0; a < 3; a++)
+        {
+            const double w = (double)M[a] * x + (double)M[4 + a] * y + (double)M[8 + a] * z + (double)M[12 + a];
+            lo[a] = std::min(lo[a], w), hi[a] = std::max(hi[a], w);
+        }
+    }
+    Box out;
+    for (int a = 0; a < 3; a++)
+    {
+        const double pad = 1e-5 * (std::fabs(lo[a]) + std::fabs(hi[a]) + (hi[a] - lo[a]));
+        out.lo[a] = (float)(lo[a] - pad), out.hi[a] = (float)(hi[a] + pad);
+    }
+    return out;
+}
+static const float kIdentity16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+
 hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint32_t n_materials, const hl_instance* instances, const hl_mesh* meshes,
                               const uint32_t* const* submesh_info, uint32_t n_instances, const hl_light* lights, uint32_t n_lights)
 {
@@ -338,9 +361,11 @@ hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint
     std::vector<hl_instance> inst(instances, instances + n_instances);
     std::vector<float>       inv((size_t)n_instances * 12);
     std::vector<uint32_t>    info, offset(n_instances);
+    std::vector<InstAlpha>   ialpha(n_instances);
+    std::vector<GeomAlpha>   galpha;
     std::vector<Box>         boxes(n_instances);
     bool                     identity = n_instances == 1;
-    static const float       I16[16]  = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    const float*             I16      = kIdentity16;
     for (uint32_t i = 0; i < n_instances; i++)
     {
         auto it = std::find(c_->meshes.begin(), c_->meshes.end(), meshes[i]);
@@ -352,34 +377,27 @@ hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint
         {
             if (submesh_info[i][2 * g + 1] >= n_materials) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_set_tables: material index out of range");
             info.push_back(submesh_info[i][2 * g]), info.push_back(submesh_info[i][2 * g + 1]);
+            const hl_material& mat = materials[submesh_info[i][2 * g + 1]];
+            GeomAlpha          ga;
+            ga.texture = mat.texture_indices0[0], ga.alpha = mat.albedo[3];
+            galpha.push_back(ga);
         }
+        ialpha[i].alpha = m->alpha.p && m->bvh.n_leaves ? m->alpha.as<AlphaTri>() : nullptr, ialpha[i].tris = m->bvh.leaves.as<LeafTri>(), ialpha[i].info_base = offset[i];
         affine_inverse(inst[i].model_matrix, &inv[(size_t)i * 12]);
         if (memcmp(inst[i].model_matrix, I16, 64) != 0) identity = false;
-        // world box of the transformed object-space root box (8 corners in double, padded)
-        double       lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-        const float* M     = inst[i].model_matrix;
-        const Box&   rb    = m->bvh.root;
-        for (int cidx = 0; cidx < 8; cidx++)
-        {
-            const double x = (cidx & 1) ? rb.hi[0] : rb.lo[0], y = (cidx & 2) ? rb.hi[1] : rb.lo[1], z = (cidx & 4) ? rb.hi[2] : rb.lo[2];
-            for (int a = 0; a < 3; a++)
-            {
-                const double w = (double)M[a] * x + (double)M[4 + a] * y + (double)M[8 + a] * z + (double)M[12 + a];
-                lo[a] = std::min(lo[a], w), hi[a] = std::max(hi[a], w);
-            }
-        }
-        for (int a = 0; a < 3; a++)
-        {
-            const double pad = 1e-5 * (std::fabs(lo[a]) + std::fabs(hi[a]) + (hi[a] - lo[a]));
-            boxes[i].lo[a] = (float)(lo[a] - pad), boxes[i].hi[a] = (float)(hi[a] + pad);
-        }
+        boxes[i] = instance_world_box(inst[i].model_matrix, m->bvh.root);
     }
+    c_->h_instances = inst;
+    c_->h_inst_mesh.resize(n_instances);
+    for (uint32_t i = 0; i < n_instances; i++) c_->h_inst_mesh[i] = c_->meshes[inst[i].mesh_index];
     c_->materials.upload(materials, sizeof(hl_material) * (size_t)n_materials, st);
     c_->instances.upload(inst.data(), sizeof(hl_instance) * (size_t)n_instances, st);
     c_->inst_inv.upload(inv.data(), 4 * inv.size(), st);
     c_->submesh_info.upload(info.data(), 4 * info.size(), st);
     c_->submesh_offset.upload(offset.data(), 4 * offset.size(), st);
     c_->lights.upload(lights, sizeof(hl_light) * (size_t)n_lights, st);
+    c_->inst_alpha.upload(ialpha.data(), sizeof(InstAlpha) * ialpha.size(), st);
+    c_->geom_alpha.upload(galpha.data(), sizeof(GeomAlpha) * galpha.size(), st);
     c_->mesh_views.upload(views.data(), sizeof(MeshView) * views.size(), st);
     c_->tex_views_dev.upload(c_->tex_views.data(), sizeof(TexView) * c_->tex_views.size(), st);
     HL_CUDA(cudaStreamSynchronize(st));
@@ -391,7 +409,39 @@ hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint
     v.env.faces = c_->env_size ? c_->env_padded.as<f4>() : nullptr, v.env.size = c_->env_size;
     v.tlas_nodes = c_->tlas.nodes.as<WideNode>(), v.tlas_leaf = c_->tlas.leaves.as<uint32_t>();
     v.n_instances = n_instances, v.n_lights = n_lights, v.single_identity = identity ? 1u : 0u;
+    v.inst_alpha = c_->inst_alpha.as<InstAlpha>(), v.geom_alpha = c_->geom_alpha.as<GeomAlpha>();
     c_->scene_ready = true;
+    HL_CATCH
+}
+
+hl_status hl_scene_update_instances(hl_context ctx, const hl_instance* instances, uint32_t n_instances)
+{
+    HL_TRY(ctx)
+    if (!instances && n_instances) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_update_instances: null argument");
+    if (!c_->scene_ready) HL_FAIL(HL_ERR_STATE, "hl_scene_update_instances: hl_scene_set_tables has not been called since the last resource change");
+    if (n_instances != c_->h_instances.size()) HL_FAIL(HL_ERR_INVALID_ARGUMENT, "hl_scene_update_instances: the instance count differs from the installed tables (use hl_scene_set_tables)");
+    if (n_instances == 0) return HL_OK;
+    cudaStream_t       st = c_->stream;
+    std::vector<float> inv((size_t)n_instances * 12);
+    std::vector<Box>   boxes(n_instances);
+    bool               identity = n_instances == 1;
+    for (uint32_t i = 0; i < n_instances; i++)
+    {
+        hl_instance& I = c_->h_instances[i];
+        memcpy(I.model_matrix, instances[i].model_matrix, 64), memcpy(I.normal_matrix, instances[i].normal_matrix, 64); // the instance keeps its mesh
+        affine_inverse(I.model_matrix, &inv[(size_t)i * 12]);
+        if (memcmp(I.model_matrix, kIdentity16, 64) != 0) identity = false;
+        boxes[i] = instance_world_box(I.model_matrix, c_->h_inst_mesh[i]->bvh.root);
+    }
+    c_->instances.upload(c_->h_instances.data(), sizeof(hl_instance) * (size_t)n_instances, st);
+    c_->inst_inv.upload(inv.data(), 4 * inv.size(), st);
+    HL_CUDA(cudaStreamSynchronize(st)); // (the staging vectors go out of scope)
+    if (n_instances == 1 || c_->tlas.n_nodes > 1024u)
+        build_tlas(c_, boxes); // nothing to keep / larger than the one-block refit handles
+    else
+        refit_tlas(c_, boxes);
+    c_->view.tlas_nodes = c_->tlas.nodes.as<WideNode>(), c_->view.tlas_leaf = c_->tlas.leaves.as<uint32_t>();
+    c_->view.single_identity = identity ? 1u : 0u;
     HL_CATCH
 }
 

@@ -6,6 +6,10 @@
 // thin loops over thread ids (and the tests/emul harness can run the same logic sequentially).
 #pragma once
 #include "hl_scene.h"
+#if defined(__CUDACC__)
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+#endif
 
 namespace hl
 {
@@ -199,13 +203,17 @@ HL_HD void sah_node_costs(BinaryTree& t, uint32_t node, float area)
 
 // bottom-up fit: called once per leaf (after its box is written); the second arrival at a node continues.
 // On the GPU the caller issues __threadfence() between the writes and the counter increment.
+// `stop_above` != 0: nodes that cover more than stop_above primitives are left alone — when the upper levels are going to be
+// re-split (top_* below), everything above the cut is re-linked and re-fitted by top_refit_from_cluster anyway, so the
+// first fit only has to produce the boxes and cost tables of the cluster subtrees.
 template <class Fence>
-HL_HD void fit_from_leaf(BinaryTree& t, uint32_t leaf, Fence fence)
+HL_HD void fit_from_leaf(BinaryTree& t, uint32_t leaf, Fence fence, uint32_t stop_above = 0u)
 {
     sah_leaf_costs(t, (t.n - 1) + leaf, box_half_area(t.box[(t.n - 1) + leaf]));
     uint32_t node = t.parent[(t.n - 1) + leaf];
     while (node != 0xFFFFFFFFu)
     {
+        if (stop_above && subtree_prims(t, node) > stop_above) return;
         fence();
         if (hl_atomic_add(&t.visits[node], 1u) == 0u) return;
         fence();
@@ -246,7 +254,9 @@ HL_HD void fit_from_leaf(BinaryTree& t, uint32_t leaf, Fence fence)
 #define HL_TOP_MODE_ARRIVAL 1u
 #define HL_TOP_MODE_SINGLE 2u
 #define HL_TOP_MODE_SMALL 3u
-#define HL_TOP_SMALL 16u
+#ifndef HL_TOP_SMALL
+#define HL_TOP_SMALL 8u /* nodes with at most this many clusters are finished by one thread each with exact SAH sweeps (16: that kernel alone took 0.8 of 5.3 ms at 1M triangles, one level fewer in the level loop) */
+#endif
 #define HL_ORD_POS_INF 0xFF800000u /* f2ord(+inf) */
 #define HL_ORD_NEG_INF 0x007FFFFFu /* f2ord(-inf) */
 
@@ -300,6 +310,24 @@ HL_HD uint32_t hl_alloc(uint32_t* counter, uint32_t amount)
     }
 #endif
     return hl_atomic_add(counter, amount);
+}
+
+// counter += amount (amounts differ per lane, 0 allowed), returns the old value.  On the GPU the lanes that arrive here
+// together are served by ONE atomic (prefix sum over the coalesced group): the collapse hands out wide-node, leaf and queue
+// slots from three global counters, and one atomic per lane on the same address is what bounded that kernel.
+HL_HD uint32_t hl_alloc_var(uint32_t* counter, uint32_t amount)
+{
+#if defined(__CUDA_ARCH__)
+    namespace cg = cooperative_groups;
+    const cg::coalesced_group g    = cg::coalesced_threads();
+    const uint32_t            incl = cg::inclusive_scan(g, amount);
+    uint32_t                  base = 0;
+    if (g.thread_rank() == g.size() - 1 && incl) base = atomicAdd(counter, incl);
+    base = g.shfl(base, g.size() - 1);
+    return base + incl - amount;
+#else
+    return hl_atomic_add(counter, amount);
+#endif
 }
 
 struct TopBin
@@ -838,10 +866,13 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
             n_leafprims += subtree_prims(t, c);
     }
     w.imask      = (uint8_t)imask;
-    w.child_base = n_inner ? hl_atomic_add(out.node_counter, n_inner) : 0u;
-    w.leaf_base  = n_leafprims ? hl_atomic_add(out.leaf_counter, n_leafprims) : 0u;
+    // (every lane allocates, also with amount 0: the lanes of a warp that build a node together share one atomic per counter)
+    w.child_base = hl_alloc_var(out.node_counter, n_inner);
+    w.leaf_base  = hl_alloc_var(out.leaf_counter, n_leafprims);
     uint32_t inner_rank = 0, leaf_off = 0;
-    uint32_t first_task = n_inner ? hl_atomic_add(next_count, n_inner) : 0u;
+    uint32_t first_task = hl_alloc_var(next_count, n_inner);
+    if (!n_inner) w.child_base = 0u;
+    if (!n_leafprims) w.leaf_base = 0u;
     for (int s = 0; s < 8; s++)
     {
         if (slot_child[s] < 0)
@@ -876,6 +907,52 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
     return n_inner;
 }
 
+// ---- instance-tree refit (moving instances) ---------------------------------------------------------------------------
+// The reference creates its top-level structure with ALLOW_UPDATE (src/engine/resource/scene.cpp:797) and re-issues the build
+// whenever a transform changes (src/engine/gfx/renderer.cpp:147-168).  Here the instance tree keeps its topology and only
+// the boxes move: refit_node_box() recomputes the box of one wide node from its children (instance boxes for leaf slots,
+// the children's boxes — from the previous sweep — for inner slots), refit_requantize() rewrites the node's origin,
+// exponents and the 8-bit child planes from those boxes with the builder's own conservative rounding.  Slot assignment
+// (the octant order chosen at build time) stays: it affects visit order only, never a result.
+HL_HD Box box_empty()
+{
+    Box b;
+    for (int k = 0; k < 3; k++) b.lo[k] = 3.0e38f, b.hi[k] = -3.0e38f;
+    return b;
+}
+HL_HD uint32_t wide_inner_rank(const WideNode& w, int s) { return (uint32_t)hl_popc((uint32_t)w.imask & ((1u << s) - 1u)); }
+// box of child slot s of an instance-tree node (slot must not be empty)
+HL_HD Box refit_child_box(const WideNode& w, int s, const uint32_t* inst_leaf, const Box* inst_boxes, const Box* node_box)
+{
+    if (w.imask & (1u << s)) return load_box_coherent(&node_box[w.child_base + wide_inner_rank(w, s)]);
+    const uint32_t meta = w.meta[s], off = meta & 31u;
+    Box            b    = box_empty();
+    for (uint32_t k = 0; k < 3u; k++)
+        if ((meta >> 5) & (1u << k)) b = box_union(b, inst_boxes[inst_leaf[w.leaf_base + off + k]]);
+    return b;
+}
+HL_HD Box refit_node_box(const WideNode& w, const uint32_t* inst_leaf, const Box* inst_boxes, const Box* node_box)
+{
+    Box b = box_empty();
+    for (int s = 0; s < 8; s++)
+        if (w.meta[s]) b = box_union(b, refit_child_box(w, s, inst_leaf, inst_boxes, node_box));
+    return b;
+}
+HL_HD void refit_requantize(WideNode& w, const Box& nb, const uint32_t* inst_leaf, const Box* inst_boxes, const Box* node_box)
+{
+    w.px = nb.lo[0], w.py = nb.lo[1], w.pz = nb.lo[2];
+    const uint32_t ex = quant_exponent(nb.hi[0] - nb.lo[0]), ey = quant_exponent(nb.hi[1] - nb.lo[1]), ez = quant_exponent(nb.hi[2] - nb.lo[2]);
+    w.ex = (uint8_t)ex, w.ey = (uint8_t)ey, w.ez = (uint8_t)ez;
+    for (int s = 0; s < 8; s++)
+    {
+        if (!w.meta[s]) continue;
+        const Box b = refit_child_box(w, s, inst_leaf, inst_boxes, node_box);
+        quantize_axis(w.px, ex, b.lo[0], b.hi[0], w.qlox[s], w.qhix[s]);
+        quantize_axis(w.py, ey, b.lo[1], b.hi[1], w.qloy[s], w.qhiy[s]);
+        quantize_axis(w.pz, ez, b.lo[2], b.hi[2], w.qloz[s], w.qhiz[s]);
+    }
+}
+
 // geometry lookup for a flat triangle index: tri_start[g] <= f < tri_start[g+1]
 HL_HD uint32_t find_geometry(const uint32_t* tri_start, uint32_t n_geom, uint32_t f)
 {
@@ -899,6 +976,7 @@ struct TriLeafWriter
     uint32_t          n_geom;
     const uint32_t*   sorted_prim; // flat triangle index per sorted leaf position
     LeafTri*          tris;
+    AlphaTri*         alpha = nullptr; // any-hit records beside the leaves (meshes with a non-opaque submesh), or nullptr
     HL_HD void        operator()(uint32_t dst, uint32_t sorted_pos) const
     {
         const uint32_t f = sorted_prim[sorted_pos];
@@ -916,6 +994,15 @@ struct TriLeafWriter
         r.geom_flags = g | (submeshes[g].opaque ? 0x80000000u : 0u);
         r.pad        = 0;
         tris[dst]    = r;
+        if (alpha)
+        {
+            const float* t0 = vertices[indices[b + 0]].tex_coord;
+            const float* t1 = vertices[indices[b + 1]].tex_coord;
+            const float* t2 = vertices[indices[b + 2]].tex_coord;
+            AlphaTri     q;
+            q.u0 = t0[0], q.v0 = t0[1], q.u1 = t1[0], q.v1 = t1[1], q.u2 = t2[0], q.v2 = t2[1], q.pad[0] = q.pad[1] = 0.0f;
+            alpha[dst] = q;
+        }
     }
 };
 HL_HD Box triangle_box(const hl_vertex* vertices, const uint32_t* indices, const hl_submesh* submeshes, const uint32_t* tri_start, uint32_t n_geom, uint32_t f)

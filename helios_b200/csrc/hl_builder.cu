@@ -15,6 +15,7 @@
 //   collapse       ~48 read (boxes) + 8 decisions + 0.12 x 80 node + 48 leaf + 48 src + 2 x 8 queue   ~180
 //   total                                                              ~ 930 B / triangle
 #include "hl_internal.h"
+#include <cooperative_groups/reduce.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -60,12 +61,12 @@ struct DeviceFence
 {
     __device__ void operator()() const { __threadfence(); }
 };
-__global__ void k_fit(BinaryTree t, const Box* prim_boxes, const uint32_t* sorted)
+__global__ void k_fit(BinaryTree t, const Box* prim_boxes, const uint32_t* sorted, uint32_t stop_above)
 {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < t.n; j += gridDim.x * blockDim.x)
     {
         t.box[(t.n - 1) + j] = prim_boxes[sorted[j]];
-        fit_from_leaf(t, j, DeviceFence());
+        fit_from_leaf(t, j, DeviceFence(), stop_above);
     }
 }
 
@@ -181,9 +182,95 @@ __device__ __forceinline__ void top_choose_node_warp(TopBuild& tb, uint32_t leve
             N.mode = HL_TOP_MODE_ARRIVAL;
     }
 }
+// The first levels hold a handful of nodes, and every cluster of the tree adds itself to their bins: with global atomics
+// the BIN and ASSIGN phases of those levels serialise on a few hundred addresses (traced at 1M triangles: 60-180 us per
+// level for work that moves 18 MB).  While a level has at most HL_TOP_SMEM_NODES nodes every block accumulates into its own
+// copy of the bins / of the children's centroid bounds in shared memory and flushes each non-empty entry once.
+#define HL_TOP_SMEM_NODES 16u
+__device__ __forceinline__ void top_bin_level_private(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t K, uint32_t nodes, TopBin* sb, uint32_t tid, uint32_t nthr)
+{
+    const uint32_t nb = nodes * 3u * HL_TOP_BINS;
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) top_clear_bin(sb + b);
+    __syncthreads();
+    for (uint32_t i = tid; i < K; i += nthr)
+    {
+        const uint32_t nd = tb.cnode[i];
+        if (nd == HL_TOP_DONE) continue;
+        TopNode& N = tb.level[level & 1u][nd];
+        if (__ldcg(&N.mode) != HL_TOP_MODE_BINNED)
+        {
+            top_bin_cluster(t, tb, level, i); // SINGLE / SMALL / ARRIVAL: the generic path (no bins involved)
+            continue;
+        }
+        const uint32_t m = tb.cluster[i];
+        float          c[3];
+        top_cluster_centroid(t, m, c);
+        const Box&     b     = t.box[m];
+        const uint32_t prims = subtree_prims(t, m);
+        TopBin*        bins  = sb + nd * (3u * HL_TOP_BINS);
+        for (int ax = 0; ax < 3; ax++)
+        {
+            const int bi = top_bin_of(c[ax], ord2f(__ldcg(&N.cb_lo[ax])), ord2f(__ldcg(&N.cb_hi[ax])));
+            if (bi < 0) continue;
+            TopBin& B = bins[ax * HL_TOP_BINS + bi];
+            for (int k = 0; k < 3; k++) atomicMin(&B.lo[k], f2ord(b.lo[k])), atomicMax(&B.hi[k], f2ord(b.hi[k]));
+            atomicAdd(&B.prims, prims), atomicAdd(&B.clusters, 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
+    {
+        const TopBin& S = sb[b];
+        if (S.clusters == 0u) continue;
+        const TopNode& N = tb.level[level & 1u][b / (3u * HL_TOP_BINS)];
+        TopBin&        G = tb.bins[level & 1u][(size_t)__ldcg(&N.bins) * (3u * HL_TOP_BINS) + b % (3u * HL_TOP_BINS)];
+        for (int k = 0; k < 3; k++) atomicMin(&G.lo[k], S.lo[k]), atomicMax(&G.hi[k], S.hi[k]);
+        atomicAdd(&G.prims, S.prims), atomicAdd(&G.clusters, S.clusters);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void top_assign_level_private(const BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t K, uint32_t next_nodes, uint32_t* scb, uint32_t tid, uint32_t nthr)
+{
+    for (uint32_t k = threadIdx.x; k < next_nodes * 6u; k += blockDim.x) scb[k] = (k % 6u) < 3u ? HL_ORD_POS_INF : HL_ORD_NEG_INF;
+    __syncthreads();
+    for (uint32_t i = tid; i < K; i += nthr)
+    {
+        const uint32_t nd = tb.cnode[i];
+        if (nd == HL_TOP_DONE) continue;
+        TopNode& N = tb.level[level & 1u][nd];
+        float    c[3];
+        top_cluster_centroid(t, tb.cluster[i], c);
+        uint32_t side;
+        if (__ldcg(&N.mode) == HL_TOP_MODE_BINNED)
+        {
+            const uint32_t split = __ldcg(&N.split);
+            const int      ax    = (int)(split & 3u);
+            side                 = top_bin_of(c[ax], ord2f(__ldcg(&N.cb_lo[ax])), ord2f(__ldcg(&N.cb_hi[ax]))) > (int)(split >> 2) ? 1u : 0u;
+        }
+        else
+            side = atomicAdd(&N.arrivals, 1u) >= __ldcg(&N.n_left) ? 1u : 0u;
+        const uint32_t child = __ldcg(&N.child) + side;
+        tb.cnode[i]          = child;
+        for (int k = 0; k < 3; k++) atomicMin(&scb[child * 6u + k], f2ord(c[k])), atomicMax(&scb[child * 6u + 3u + k], f2ord(c[k]));
+    }
+    __syncthreads();
+    TopNode* next = tb.level[(level + 1u) & 1u];
+    for (uint32_t k = threadIdx.x; k < next_nodes * 6u; k += blockDim.x)
+    {
+        const uint32_t v = scb[k], child = k / 6u, a = k % 6u;
+        if (a < 3u)
+        {
+            if (v != HL_ORD_POS_INF) atomicMin(&next[child].cb_lo[a], v);
+        }
+        else if (v != HL_ORD_NEG_INF)
+            atomicMax(&next[child].cb_hi[a - 3u], v);
+    }
+    __syncthreads();
+}
 // `trace` (debug, HL_TOP_TRACE=1): global timer after every phase, read back and printed by the host
 __global__ void __launch_bounds__(256, 4) k_top_build(BinaryTree t, TopBuild tb, uint32_t* bar, unsigned long long* trace)
 {
+    __shared__ TopBin s_bins[HL_TOP_SMEM_NODES * 3u * HL_TOP_BINS]; // 24 KB; the ASSIGN phase reuses it for 2 x 16 x 6 words
     uint32_t       ntrace = 1;
     const uint32_t K      = *tb.n_clusters;
     if (K < 2u || K > tb.k_cap) return; // (uniform) cut too fine for the scratch arrays: keep the radix tree
@@ -197,10 +284,13 @@ __global__ void __launch_bounds__(256, 4) k_top_build(BinaryTree t, TopBuild tb,
     top_trace(trace, ntrace);
     for (uint32_t level = 0; level + 1u < HL_TOP_MAX_LEVELS; level++)
     {
-        for (uint32_t i = tid; i < K; i += nthr) top_bin_cluster(t, tb, level, i);
+        const uint32_t nodes = __ldcg(tb.level_count + level);
+        if (nodes <= HL_TOP_SMEM_NODES)
+            top_bin_level_private(t, tb, level, K, nodes, s_bins, tid, nthr);
+        else
+            for (uint32_t i = tid; i < K; i += nthr) top_bin_cluster(t, tb, level, i);
         grid_barrier(bar);
         top_trace(trace, ntrace);
-        const uint32_t nodes = __ldcg(tb.level_count + level);
         for (uint32_t j = warp; j < nodes; j += nwarps) top_choose_node_warp(tb, level, j, lane);
         grid_barrier(bar);
         top_trace(trace, ntrace);
@@ -210,7 +300,11 @@ __global__ void __launch_bounds__(256, 4) k_top_build(BinaryTree t, TopBuild tb,
         if (__ldcg(tb.level_count + level + 1u) == 0u) break; // only single / small nodes were left
         TopBin* next_bins = tb.bins[(level + 1u) & 1u];
         for (uint32_t b = tid, nb = top_bins_to_clear(tb, level + 1u); b < nb; b += nthr) top_clear_bin(next_bins + b);
-        for (uint32_t i = tid; i < K; i += nthr) top_assign_cluster(t, tb, level, i);
+        const uint32_t next_nodes = __ldcg(tb.level_count + level + 1u);
+        if (next_nodes <= 2u * HL_TOP_SMEM_NODES)
+            top_assign_level_private(t, tb, level, K, next_nodes, (uint32_t*)s_bins, tid, nthr);
+        else
+            for (uint32_t i = tid; i < K; i += nthr) top_assign_cluster(t, tb, level, i);
         grid_barrier(bar);
         top_trace(trace, ntrace);
     }
@@ -244,8 +338,9 @@ __global__ void __launch_bounds__(128) k_top_small(BinaryTree t, TopBuild tb)
 }
 __global__ void k_top_refit(BinaryTree t, TopBuild tb)
 {
+    // (no bail-out here: k_fit stopped at the cut, so the nodes above it are fitted by this pass whether k_top_build re-linked
+    //  them or — cut too fine for the scratch arrays — left the radix tree's topology in place)
     const uint32_t K = *tb.n_clusters;
-    if (K < 2u || K > tb.k_cap) return;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) top_refit_from_cluster(t, tb.cluster[i], DeviceFence());
 }
 
@@ -267,7 +362,7 @@ __global__ void __launch_bounds__(128) k_collapse(BinaryTree t, WideOut out, Col
     bool               have  = false;
     for (;;)
     {
-        if (!have) idx = atomicAdd(ctl + 3, 1u), have = true;
+        if (!have) idx = hl_alloc_var(ctl + 3, 1u), have = true; // one atomic per group of lanes that need a new queue index
         bool ready = false;
         CollapseTask task;
         task.wide = task.bnode = 0xFFFFFFFFu;
@@ -281,11 +376,17 @@ __global__ void __launch_bounds__(128) k_collapse(BinaryTree t, WideOut out, Col
         {
             const uint32_t spawned = collapse_one(t, task, out, queue, ctl + 2, writer);
             have                   = false;
-            // outstanding += spawned - 1; the thread that brings it to zero ends the launch
-            if (atomicAdd(ctl + 4, spawned - 1u) + spawned - 1u == 0u)
+            // outstanding += spawned - 1 (summed over the lanes that finished a task together: one atomic); the update that brings
+            // it to zero ends the launch.  Every finished task was published before, so zero is only reached at the very end.
             {
-                __threadfence();
-                *vdone = 1u;
+                namespace cg = cooperative_groups;
+                const cg::coalesced_group g     = cg::coalesced_threads();
+                const uint32_t            delta = cg::reduce(g, spawned - 1u, cg::plus<uint32_t>());
+                if (g.thread_rank() == 0 && atomicAdd(ctl + 4, delta) + delta == 0u)
+                {
+                    __threadfence();
+                    *vdone = 1u;
+                }
             }
         }
         else if (*vdone)
@@ -406,7 +507,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         k_radix_tree<<<grid_for(n - 1, 256, cap), 256, 0, st>>>(keys, t);
         ctx->launches++;
     }
-    k_fit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted);
+    k_fit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted, resplit ? C : 0u); // with a re-split: cluster subtrees only, k_top_refit fits the rest
     ctx->launches++;
     if (resplit)
     {
@@ -426,8 +527,8 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         unsigned long long* trace  = top_trace_buf.p ? top_trace_buf.as<unsigned long long>() : nullptr;
         void*               args[] = { (void*)&t, (void*)&tb, (void*)&bar, (void*)&trace };
         HL_CUDA(cudaLaunchCooperativeKernel((const void*)k_top_build, dim3((unsigned)top_grid), dim3(256), args, 0, st));
-        k_top_small<<<ctx->sm_count * 2, 128, 0, st>>>(t, tb);
-        k_top_refit<<<grid_for(k_cap, 256, cap), 256, 0, st>>>(t, tb);
+        k_top_small<<<grid_for(k_cap / 2 + 1, 128, ctx->sm_count * 16), 128, 0, st>>>(t, tb);
+        k_top_refit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, tb);
         ctx->launches += 9;
         if (trace)
         {
@@ -505,9 +606,13 @@ void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
     const uint32_t*   di  = mesh->indices.as<uint32_t>();
     const hl_submesh* dsm = mesh->submeshes.as<hl_submesh>();
     const uint32_t*   dts = mesh->tri_start.as<uint32_t>();
+    bool              any_hit = false; // a geometry without VK_GEOMETRY_OPAQUE_BIT runs the any-hit stage: give its triangles alpha records
+    for (const hl_submesh& sm : mesh->subs) any_hit = any_hit || !sm.opaque;
+    if (any_hit && n) mesh->alpha.alloc(sizeof(AlphaTri) * (size_t)n);
+    AlphaTri* da = any_hit && n ? mesh->alpha.as<AlphaTri>() : nullptr;
     build_wide_device(ctx, boxes.as<Box>(), n, sizeof(LeafTri), mesh->bvh, [=](const uint32_t* sorted, void* leaves) {
         TriLeafWriter w;
-        w.vertices = dv, w.indices = di, w.submeshes = dsm, w.tri_start = dts, w.n_geom = ng, w.sorted_prim = sorted, w.tris = (LeafTri*)leaves;
+        w.vertices = dv, w.indices = di, w.submeshes = dsm, w.tri_start = dts, w.n_geom = ng, w.sorted_prim = sorted, w.tris = (LeafTri*)leaves, w.alpha = da;
         return w;
     });
     float ms0 = 0.0f;
@@ -522,6 +627,63 @@ void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh)
     mesh->stats.sah_cost        = mesh->bvh.sah_cost;
     mesh->stats.bytes_nodes     = sizeof(WideNode) * (uint64_t)mesh->bvh.n_nodes;
     mesh->stats.bytes_triangles = sizeof(LeafTri) * (uint64_t)mesh->bvh.n_leaves;
+}
+
+// Instance-tree refit in ONE block (at most 1024 instances -> at most ~1024 wide nodes): sweeps "box of every node from its
+// children's boxes of the previous sweep" until nothing changes — the number of sweeps is the depth of the tree — then
+// requantises every node.  node_box = scratch, one Box per wide node.
+__global__ void __launch_bounds__(256) k_tlas_refit(WideNode* nodes, uint32_t n_nodes, const uint32_t* inst_leaf, const Box* inst_boxes, Box* node_box)
+{
+    __shared__ int changed;
+    for (uint32_t i = threadIdx.x; i < n_nodes; i += blockDim.x) node_box[i] = box_empty();
+    __syncthreads();
+    for (int sweep = 0; sweep < 64; sweep++)
+    {
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        Box      mine[4]; // up to 4 nodes per thread (1024 / 256)
+        uint32_t k = 0;
+        for (uint32_t i = threadIdx.x; i < n_nodes && k < 4u; i += blockDim.x, k++) mine[k] = refit_node_box(nodes[i], inst_leaf, inst_boxes, node_box);
+        __syncthreads();
+        k = 0;
+        for (uint32_t i = threadIdx.x; i < n_nodes && k < 4u; i += blockDim.x, k++)
+        {
+            bool diff = false;
+            for (int a = 0; a < 3; a++) diff = diff || mine[k].lo[a] != node_box[i].lo[a] || mine[k].hi[a] != node_box[i].hi[a];
+            if (diff) node_box[i] = mine[k], changed = 1;
+        }
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < n_nodes; i += blockDim.x)
+    {
+        WideNode w = nodes[i];
+        refit_requantize(w, node_box[i], inst_leaf, inst_boxes, node_box);
+        nodes[i] = w;
+    }
+}
+
+void refit_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes)
+{
+    cudaStream_t st = ctx->stream;
+    t_scratch_pool  = ctx->scratch_pool;
+    if (ctx->tlas.n_nodes == 0 || ctx->tlas.n_nodes > 4u * 256u) throw CudaError(HL_ERR_STATE, "refit_tlas: no instance tree (or one larger than the refit kernel handles)");
+    ScratchBuf boxes, node_box;
+    boxes.alloc(sizeof(Box) * instance_boxes.size(), st);
+    node_box.alloc(sizeof(Box) * (size_t)ctx->tlas.n_nodes, st);
+    HL_CUDA(cudaMemcpyAsync(boxes.p, instance_boxes.data(), sizeof(Box) * instance_boxes.size(), cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1;
+    HL_CUDA(cudaEventCreate(&e0));
+    HL_CUDA(cudaEventCreate(&e1));
+    HL_CUDA(cudaEventRecord(e0, st));
+    k_tlas_refit<<<1, 256, 0, st>>>(ctx->tlas.nodes.as<WideNode>(), ctx->tlas.n_nodes, ctx->tlas.leaves.as<uint32_t>(), boxes.as<Box>(), node_box.as<Box>());
+    ctx->launches++;
+    HL_CUDA(cudaEventRecord(e1, st));
+    HL_CUDA(cudaMemcpyAsync(&ctx->tlas.root, node_box.p, sizeof(Box), cudaMemcpyDeviceToHost, st));
+    HL_CUDA(cudaStreamSynchronize(st)); // (the host vector must outlive the copy)
+    HL_CUDA(cudaEventElapsedTime(&ctx->tlas.ms_build, e0, e1));
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
 }
 
 void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes)

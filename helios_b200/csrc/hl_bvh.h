@@ -84,6 +84,7 @@ struct TravStack
     u2* fast;
     int stride;
     int sp;
+    uint8_t* pairs; // GPU: HL_COOP_TABLE bytes of shared memory per WARP (cooperative triangle phase, coop_triangles below)
     u2  spill[HL_STACK_SPILL];
     HL_HD bool has_room(int n) const { return sp + n <= HL_STACK_FAST + HL_STACK_SPILL; }
     HL_HD void push(u2 e)
@@ -228,9 +229,26 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
     return hitmask;
 }
 
-// path_trace_rahit.glsl:174-188: true when the candidate intersection is ignored (albedo alpha < 0.1)
-HL_HD bool any_hit_ignores(const SceneView& s, uint32_t inst, uint32_t geom, uint32_t prim, float bu, float bv)
+// path_trace_rahit.glsl:174-188: true when the candidate intersection is ignored (albedo alpha < 0.1).  `tri` = the leaf
+// record of the candidate.  With any-hit records (SceneView::inst_alpha, built by hl_scene_set_tables) the texture coordinates
+// come from the AlphaTri beside the leaf and the material's alpha source from the per-geometry table: the same values the
+// walk instance -> mesh -> index -> vertex -> tex_coord and submesh_info -> material reads, in two loads instead of nine.
+HL_HD bool any_hit_ignores(const SceneView& s, uint32_t inst, uint32_t geom, uint32_t prim, float bu, float bv, const LeafTri* tri)
 {
+    const float b0 = 1.0f - bu - bv;
+    if (s.inst_alpha)
+    {
+        const InstAlpha ia = s.inst_alpha[inst];
+        if (ia.alpha)
+        {
+            const GeomAlpha ga = s.geom_alpha[ia.info_base + geom];
+            if (ga.texture == -1) return ga.alpha < 0.1f;
+            const AlphaTri& a  = ia.alpha[tri - ia.tris];
+            const float     tu = a.u0 * b0 + a.u1 * bu + a.u2 * bv;
+            const float     tv = a.v0 * b0 + a.v1 * bu + a.v2 * bv;
+            return sample_texture_alpha_lod0(s, ga.texture, tu, tv) < 0.1f;
+        }
+    }
     const hl_instance& I    = s.instances[inst];
     const MeshView&    m    = s.meshes[I.mesh_index];
     const uint32_t*    info = s.submesh_info + 2 * (size_t)(s.submesh_offset[inst] + geom); // fetch_hit_info
@@ -240,7 +258,6 @@ HL_HD bool any_hit_ignores(const SceneView& s, uint32_t inst, uint32_t geom, uin
     const float* t0 = m.vertices[m.indices[3 * (size_t)pid + 0]].tex_coord;
     const float* t1 = m.vertices[m.indices[3 * (size_t)pid + 1]].tex_coord;
     const float* t2 = m.vertices[m.indices[3 * (size_t)pid + 2]].tex_coord;
-    const float  b0 = 1.0f - bu - bv;
     const float  tu = t0[0] * b0 + t1[0] * bu + t2[0] * bv;
     const float  tv = t0[1] * b0 + t1[1] * bu + t2[1] * bv;
     return sample_texture_alpha_lod0(s, mat.texture_indices0[0], tu, tv) < 0.1f;
@@ -281,7 +298,7 @@ HL_HD bool test_leaf_triangle(const SceneView& s, const LeafTri* tri, f3 o, f3 d
         else if (prim >= b.primitive)
             return false;
     }
-    if (!(flags & HL_RAY_OPAQUE) && !(e1w.w >> 31) && any_hit_ignores(s, inst, geom, prim, u, v)) return false;
+    if (!(flags & HL_RAY_OPAQUE) && !(e1w.w >> 31) && any_hit_ignores(s, inst, geom, prim, u, v, tri)) return false;
     b.t = t, b.u = u, b.v = v, b.instance = inst, b.geometry = geom, b.primitive = prim;
     return true;
 }
@@ -433,6 +450,151 @@ HL_HD void trav_step_leaves(const SceneView& s, Trav& t, TravStack& st)
     }
 }
 
+// ---- warp-cooperative triangle phase (GPU) ---------------------------------------------------------------------
+// After a node visit a few lanes of the warp hold a handful of leaf triangles each while the others hold none: run
+// lane by lane, the ~90-instruction triangle test issues at 5-6 of 32 lanes (ncu, round 1: 20 % of k_extend's warp
+// instructions).  Here the warp pools its pending (ray, triangle) pairs instead — every owner lane contributes up to
+// HL_COOP_K triangles of its current leaf group — and lane p of the warp tests pair p with the OWNER's ray, fetched
+// through shuffles; the owner then takes the closest accepted result of its own pairs.  Same arithmetic on the same
+// operands (test_leaf_candidate is the code test_leaf_triangle runs), closest hit + tie rule are order independent and
+// the any-hit decision is per candidate, so the result is bit-identical to the lane-by-lane phase.
+// Pair order: round j holds the j-th triangle of every owner that has one, owners in lane order; slot of (owner, j) =
+// (pairs in rounds < j) + rank of the owner in round j.  Owners publish "lane | j << 5" at their slots in a small
+// per-warp table in shared memory; results travel back through shuffles.
+#ifndef HL_COOP_LEAVES
+#define HL_COOP_LEAVES 0 /* measured (tools/tune_trace.py set "coop", round 2): images bit-identical, but 1.55 -> 1.76 ms/frame on configs[1], 6.2 -> 7.0 on configs[2], 9.2 -> 10.8 on configs[3]: the 13 shuffles + merge cost as much as the two lane-by-lane tests they replace and the kernel goes from 72 to 96 registers */
+#endif
+#ifndef HL_COOP_K
+#define HL_COOP_K 4
+#endif
+#define HL_COOP_TABLE (32 * HL_COOP_K)
+#if defined(__CUDA_ARCH__)
+// the candidate half of test_leaf_triangle: Moeller-Trumbore + range test; no comparison with the best hit so far
+__device__ __forceinline__ bool test_leaf_candidate(const LeafTri* tri, f3 o, f3 d, float tmin, float tmax, float& t, float& u, float& v, uint32_t& prim, uint32_t& geom_flags)
+{
+    const U4    a = load_u4((const char*)tri + 0), e1w = load_u4((const char*)tri + 16), e2w = load_u4((const char*)tri + 32);
+    const f3    e1   = mk3(u2f(e1w.x), u2f(e1w.y), u2f(e1w.z));
+    const f3    e2   = mk3(u2f(e2w.x), u2f(e2w.y), u2f(e2w.z));
+    const f3    pvec = cross(d, e2);
+    const float det  = dot(e1, pvec);
+    prim = a.w, geom_flags = e1w.w;
+    if (det == 0.0f || det != det) return false;
+    const float inv  = 1.0f / det;
+    const f3    tvec = o - mk3(u2f(a.x), u2f(a.y), u2f(a.z));
+    u                = dot(tvec, pvec) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const f3 qvec = cross(tvec, e1);
+    v             = dot(d, qvec) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    t = dot(e2, qvec) * inv;
+    return t > tmin && t < tmax;
+}
+// `mine`: this lane holds a bottom-level leaf group (all 32 lanes call; at least one has mine == true)
+__device__ __forceinline__ void coop_triangles(const SceneView& s, Trav& t, TravStack& st, bool mine)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    unsigned       lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const uint32_t lt = (1u << lane) - 1u;
+    // up to HL_COOP_K triangles of my leaf group: their bit indices, one byte each (nearest-first order = highest bit first)
+    uint32_t rem = mine ? t.tgroup.y : 0u, bits = 0u;
+    int      cnt = 0;
+#pragma unroll
+    for (int k = 0; k < HL_COOP_K; k++)
+        if (rem)
+        {
+            const int i = hl_bfind(rem);
+            rem &= ~(1u << i), bits |= (uint32_t)i << (8 * k), cnt++;
+        }
+    uint32_t slot[HL_COOP_K];
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < HL_COOP_K; k++)
+    {
+        const uint32_t m = __ballot_sync(FULL, cnt > k);
+        slot[k]          = total + (uint32_t)__popc(m & lt);
+        if (cnt > k) st.pairs[slot[k]] = (uint8_t)(lane | ((uint32_t)k << 5));
+        total += (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    float    bt = hl_inf(); // closest accepted candidate among my pairs so far, and where its record sits
+    uint32_t bsrc = 0, bbase = 0xFFFFFFFFu;
+    bool     tie = false;
+    for (uint32_t base = 0; base < total; base += 32u)
+    {
+        const uint32_t p   = base + lane;
+        const bool     act = p < total;
+        const uint32_t e = act ? (uint32_t)st.pairs[p] : 0u, owner = e & 31u, k = e >> 5;
+        // the owner's query
+        const uint32_t obits = __shfl_sync(FULL, bits, owner), obase = __shfl_sync(FULL, t.tgroup.x, owner), oinst = __shfl_sync(FULL, t.inst, owner), oflags = __shfl_sync(FULL, t.flags, owner);
+        const unsigned long long otris = __shfl_sync(FULL, (unsigned long long)t.tris, owner);
+        const f3 oo = mk3(__shfl_sync(FULL, t.r.o.x, owner), __shfl_sync(FULL, t.r.o.y, owner), __shfl_sync(FULL, t.r.o.z, owner));
+        const f3 od = mk3(__shfl_sync(FULL, t.r.d.x, owner), __shfl_sync(FULL, t.r.d.y, owner), __shfl_sync(FULL, t.r.d.z, owner));
+        const float otmin = __shfl_sync(FULL, t.tmin, owner), otmax = __shfl_sync(FULL, t.tmax, owner), obest = __shfl_sync(FULL, t.best.t, owner);
+        float    ct = hl_inf(), cu = 0.0f, cv = 0.0f;
+        uint32_t cprim = 0, cgf = 0;
+        if (act)
+        {
+            const uint32_t i = (obits >> (8 * k)) & 0xFFu;
+            HL_STAT_LEAF();
+            float tt, uu, vv;
+            bool  ok = test_leaf_candidate((const LeafTri*)otris + (obase + i), oo, od, otmin, otmax, tt, uu, vv, cprim, cgf);
+            // a candidate behind the owner's best hit cannot win (equal t: the owner applies the tie rule)
+            ok = ok && !(tt > obest);
+            if (ok && !(oflags & HL_RAY_OPAQUE) && !(cgf >> 31) && any_hit_ignores(s, oinst, cgf & 0x7FFFFFFFu, cprim, uu, vv, (const LeafTri*)otris + (obase + i))) ok = false;
+            if (ok) ct = tt, cu = uu, cv = vv;
+        }
+        // owners: the closest accepted candidate of my pairs that sit in this batch
+#pragma unroll
+        for (int j = 0; j < HL_COOP_K; j++)
+        {
+            const float tj = __shfl_sync(FULL, ct, slot[j] & 31u);
+            if (j < cnt && slot[j] - base < 32u)
+            {
+                if (tj == bt && tj < hl_inf()) tie = true;
+                if (tj < bt) bt = tj, bsrc = slot[j] & 31u, bbase = base;
+            }
+        }
+        // fetch the winner's record while this batch's registers are live (lanes whose winner sits in an earlier batch keep theirs)
+        const bool     fresh = bbase == base;
+        const float    wu = __shfl_sync(FULL, cu, bsrc), wv = __shfl_sync(FULL, cv, bsrc);
+        const uint32_t wp = __shfl_sync(FULL, cprim, bsrc), wg = __shfl_sync(FULL, cgf, bsrc) & 0x7FFFFFFFu;
+        if (__any_sync(FULL, tie))
+        {
+            // two of an owner's candidates at the same distance (coincident triangles): resolve by the tie rule over all of them
+#pragma unroll
+            for (int j = 0; j < HL_COOP_K; j++)
+            {
+                const uint32_t src = slot[j] & 31u;
+                const float    tj = __shfl_sync(FULL, ct, src), uj = __shfl_sync(FULL, cu, src), vj = __shfl_sync(FULL, cv, src);
+                const uint32_t pj = __shfl_sync(FULL, cprim, src), gj = __shfl_sync(FULL, cgf, src) & 0x7FFFFFFFu;
+                if (tie && j < cnt && slot[j] - base < 32u && tj < hl_inf())
+                {
+                    Hit& b = t.best;
+                    bool take = tj < b.t;
+                    if (!take && tj == b.t) take = t.inst != b.instance ? t.inst < b.instance : (gj != b.geometry ? gj < b.geometry : pj < b.primitive);
+                    if (take) b.t = tj, b.u = uj, b.v = vj, b.instance = t.inst, b.geometry = gj, b.primitive = pj;
+                }
+            }
+        }
+        if (fresh && !tie)
+        {
+            Hit& b = t.best;
+            bool take = bt < b.t;
+            if (!take && bt == b.t) take = t.inst != b.instance ? t.inst < b.instance : (wg != b.geometry ? wg < b.geometry : wp < b.primitive);
+            if (take) b.t = bt, b.u = wu, b.v = wv, b.instance = t.inst, b.geometry = wg, b.primitive = wp;
+        }
+        if (tie) bt = t.best.t, tie = false, bbase = 0xFFFFFFFFu; // (the slow path folded everything into best)
+    }
+    if (mine)
+    {
+        t.tgroup.y = rem;
+        if ((t.flags & HL_RAY_TERMINATE) && bt < hl_inf()) t.ngroup.y = 0, t.tgroup.y = 0, st.sp = 0; // gl_RayFlagsTerminateOnFirstHitEXT
+    }
+    __syncwarp(); // the table is rewritten by the next call
+}
+#endif
+
 // One step of every lane of the warp; `busy_mask` = ballot of the lanes that hold an unfinished query (all
 // 32 lanes must call this).  The leaf phase runs when at least HL_TRI_MIN_LANES lanes (or every busy lane)
 // have a leaf group; otherwise lanes that can postpone do so and the others keep theirs for the next step
@@ -445,6 +607,14 @@ HL_HD void trav_step_warp(const SceneView& s, Trav& t, TravStack& st, bool busy,
 {
     if (busy) trav_step_nodes(s, t, st);
     const bool want = busy && t.tgroup.y != 0;
+#if defined(__CUDA_ARCH__) && HL_COOP_LEAVES
+    (void)busy_mask;
+    // top level: one instance entry per lane and step, as before; bottom level: the warp's triangles pooled
+    const bool top = want && t.inst == HL_MISS;
+    if (top) trav_step_leaves(s, t, st);
+    const bool mine = want && !top;
+    if (__ballot_sync(0xFFFFFFFFu, mine)) coop_triangles(s, t, st, mine);
+#else
 #if defined(__CUDA_ARCH__)
     const uint32_t wm = __ballot_sync(0xFFFFFFFFu, want);
     if (wm == 0) return;
@@ -465,6 +635,7 @@ HL_HD void trav_step_warp(const SceneView& s, Trav& t, TravStack& st, bool busy,
 #if !defined(__CUDA_ARCH__)
     else
         trav_step_leaves(s, t, st); // a single host lane cannot wait for company
+#endif
 #endif
 }
 

@@ -110,6 +110,7 @@ struct WideBVHDev
 struct hl_mesh_t
 {
     hl::DevBuf              vertices, indices, submeshes, tri_start;
+    hl::DevBuf              alpha; // AlphaTri per leaf (only when a submesh is not opaque)
     std::vector<hl_submesh> subs;
     uint32_t                n_vertices = 0, n_indices = 0;
     hl::WideBVHDev          bvh;
@@ -177,8 +178,10 @@ struct hl_context_t
     hl::DevBuf               env_padded; // the same with the one-texel seamless border: what the kernels sample
     uint32_t                 env_size = 0;
     // scene tables
-    hl::DevBuf      materials, instances, inst_inv, submesh_info, submesh_offset, lights, mesh_views, tex_views_dev, lut8;
+    hl::DevBuf      materials, instances, inst_inv, submesh_info, submesh_offset, lights, mesh_views, tex_views_dev, lut8, inst_alpha, geom_alpha;
     hl::WideBVHDev  tlas;
+    std::vector<hl_instance> h_instances; // the table as uploaded (mesh_index in context order): hl_scene_update_instances edits transforms in place
+    std::vector<hl_mesh_t*>  h_inst_mesh; // mesh of every instance
     hl::SceneView   view {};
     bool            scene_ready = false;
     // film + wavefront state
@@ -214,6 +217,7 @@ namespace hl
 // hl_builder.cu
 void build_mesh_bvh(hl_context_t* ctx, hl_mesh_t* mesh);
 void build_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes);
+void refit_tlas(hl_context_t* ctx, const std::vector<Box>& instance_boxes); // same topology, new boxes (hl_scene_update_instances)
 // hl_wavefront.cu
 void wavefront_alloc(hl_context_t* ctx);
 void wavefront_release(hl_context_t* ctx);

@@ -37,6 +37,31 @@ struct LeafTri
 };
 static_assert(sizeof(LeafTri) == 48, "LeafTri must be 48 bytes");
 
+// Any-hit record of one leaf triangle (same index as its LeafTri; only meshes that have a non-opaque submesh carry them):
+// the three texture coordinates the any-hit shader interpolates (path_trace_rahit.glsl:121-160 fetches index -> vertex ->
+// tex_coord for that), copied bit for bit at build time so that the alpha test is one 32-byte load instead of six gathers.
+struct AlphaTri
+{
+    float u0, v0, u1, v1, u2, v2;
+    float pad[2];
+};
+static_assert(sizeof(AlphaTri) == 32, "AlphaTri must be 32 bytes");
+// per instance: where the any-hit stage finds its data
+struct InstAlpha
+{
+    const AlphaTri* alpha = nullptr; // the instance's mesh's records (nullptr: every geometry of the mesh is opaque)
+    const LeafTri*  tris  = nullptr; // that mesh's leaf array (record index = leaf pointer - tris)
+    uint32_t        info_base = 0;   // first entry of the instance in SceneView::geom_alpha (= submesh_offset[instance])
+    uint32_t        pad[3] = { 0, 0, 0 };
+};
+static_assert(sizeof(InstAlpha) == 32, "InstAlpha must be 32 bytes");
+// per (instance, geometry): what fetch_albedo(...).a needs (path_trace_rahit.glsl:162-172): albedo texture or the constant alpha
+struct GeomAlpha
+{
+    int32_t texture; // material.texture_indices0.x; -1 = none
+    float   alpha;   // material.albedo.a
+};
+
 struct MeshView
 {
     const hl_vertex* vertices;
@@ -81,6 +106,9 @@ struct SceneView
     uint32_t           n_instances;
     uint32_t           n_lights;
     uint32_t           single_identity; // 1: one instance with an identity transform -> BLAS traversed directly
+    uint32_t           pad0 = 0;
+    const InstAlpha*   inst_alpha = nullptr; // [n_instances] any-hit records (nullptr: the any-hit stage walks the vertex tables)
+    const GeomAlpha*   geom_alpha = nullptr; // [sum of submesh counts] parallel to submesh_info
 };
 
 struct Hit

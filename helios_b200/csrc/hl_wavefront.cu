@@ -53,6 +53,14 @@ struct FrameParams
 
 __device__ __forceinline__ float4 ld4(const float4* p) { return *p; }
 
+// shared memory of a kernel that traces: HL_STACK_FAST stack entries per thread + the pair table of the warp-cooperative
+// triangle phase (hl_bvh.h coop_triangles) per warp
+#define HL_TRACE_SHARED(st)                                                                   \
+    __shared__ u2      stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];                             \
+    __shared__ uint8_t pair_mem[HL_COOP_TABLE * (HL_TRACE_BLOCK / 32)];                       \
+    TravStack          st;                                                                    \
+    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0, st.pairs = pair_mem + HL_COOP_TABLE * (threadIdx.x >> 5)
+
 // ---- generate --------------------------------------------------------------------------------------
 __global__ void k_generate(FrameParams fp, float4* state_a, float4* state_b, float4* ext_o, float4* ext_d, uint32_t* counters)
 {
@@ -142,9 +150,7 @@ struct ExtendQueue
 __global__ void HL_TRACE_BOUNDS k_extend(SceneView s, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const uint32_t* __restrict__ count_ptr,
                                                            uint32_t* fetch, float tmin, float tmax, uint32_t flags, float4* __restrict__ hit_a, uint2* __restrict__ hit_b)
 {
-    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
-    TravStack     st;
-    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    HL_TRACE_SHARED(st);
     ExtendQueue q;
     q.ray_o = ray_o, q.ray_d = ray_d, q.hit_a = hit_a, q.hit_b = hit_b, q.tmin = tmin, q.tmax = tmax;
     trace_queue(s, q, *count_ptr, fetch, flags, st);
@@ -250,9 +256,7 @@ struct ConnectQueue
 __global__ void HL_TRACE_BOUNDS k_connect(SceneView s, const float4* __restrict__ sh_o, const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                             const uint32_t* __restrict__ count_ptr, uint32_t* fetch, float tmin, uint32_t flags, float4* state_b)
 {
-    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
-    TravStack     st;
-    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    HL_TRACE_SHARED(st);
     ConnectQueue q;
     q.sh_o = sh_o, q.sh_d = sh_d, q.sh_c = sh_c, q.state_b = state_b, q.tmin = tmin;
     trace_queue(s, q, *count_ptr, fetch, flags, st);
@@ -267,9 +271,7 @@ __global__ void HL_TRACE_BOUNDS k_connect(SceneView s, const float4* __restrict_
 __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_tail(SceneView s, ShadeParams prm, uint32_t depth0, uint32_t threshold, uint32_t* counters, const float4* __restrict__ ray_o,
                                                          const float4* __restrict__ ray_d, const float4* __restrict__ state_a, float4* state_b)
 {
-    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
-    TravStack     st;
-    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    HL_TRACE_SHARED(st);
     const uint32_t count = counters[CTR_EXT_COUNT + depth0];
     if (count == 0 || count > threshold) return;
     const uint32_t lane = threadIdx.x & 31u;
@@ -398,9 +400,7 @@ __global__ void k_sky(SkyCoeffs c, uint32_t size, float4* out)
 }
 __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_trace_generic(SceneView s, const float* __restrict__ rays, uint32_t n, uint32_t flags, float* __restrict__ hits)
 {
-    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
-    TravStack     st;
-    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    HL_TRACE_SHARED(st);
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x)
     {
@@ -449,9 +449,7 @@ struct DebugRayOut
 };
 __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_debug_rays(SceneView s, hl_push_constants pc, uint32_t n, DebugRayOut out)
 {
-    __shared__ u2 stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];
-    TravStack     st;
-    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0;
+    HL_TRACE_SHARED(st);
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x)
         debug_ray_path(s, pc, base + lane, base + lane < n, st, out);

@@ -543,12 +543,18 @@ def checker_texture(size, seed, base_rgb, alpha_disc=False):
 # config 3: alpha-tested foliage, 64 area + 16 punctual lights
 # ----------------------------------------------------------------------------------------------
 def foliage_scene(n_clusters=50_000, cards_per_cluster=50, width=1920, height=1080, seed=2, ground_grid=64, tex_size=256) -> SceneData:
-    """config 3: leaf-card clusters (alpha-masked albedo texture, geometry NOT opaque -> any-hit) over a ground mesh;
-    64 area lights = ONE untranslated mesh node with 64 emissive 2-triangle submeshes (lights are registered per emissive
-    submesh; only triangle 0 of each quad is sampled, A.8-2) + 8 point + 8 spot lights; no directional
-    light and no IBL -> no environment light: num_lights = 80.  Defaults give 2*64^2 + 50,000*50*2 + 128 = 5,008,320 tris."""
+    """config 3: a stand of trees made of leaf-card clusters (alpha-masked albedo texture, geometry NOT opaque -> any-hit)
+    over a ground mesh; 64 area lights = ONE untranslated mesh node with 64 emissive 2-triangle submeshes (lights are
+    registered per emissive submesh, SURVEY A.8-4; only triangle 0 of each quad is sampled, A.8-2) + 8 point + 8 spot lights;
+    no directional light and no IBL -> no environment light: num_lights = 80.
+    Defaults give 2*64^2 + 50,000*50*2 + 128 = 5,008,320 triangles.
+    Layout (round 2: the round-1 layout was one uniform 3 m slab of cards with the camera inside it — 1 % of the pixels were
+    lit): clusters of cards (sigma 0.25) are grouped into tree crowns (ellipsoids on a jittered grid, ~125 clusters each)
+    with gaps between them, the area lights hang above the crowns, and the camera looks down on the stand from outside, so
+    most pixels see lit foliage or lit ground and nearly every shading point draws a non-black light sample (NEE stress)."""
     rng = np.random.default_rng(seed)
     extent = 60.0
+    ground_extent = 3.0 * extent
     textures = [checker_texture(tex_size, seed, (0.25, 0.6, 0.2), alpha_disc=True)]
     GROUND, LEAF, EMIT = 0, 1, 2
     mats = _stack(
@@ -561,7 +567,7 @@ def foliage_scene(n_clusters=50_000, cards_per_cluster=50, width=1920, height=10
     )
     # ground
     n = ground_grid + 1
-    gx, gz = np.meshgrid(np.linspace(-extent / 2, extent / 2, n), np.linspace(-extent / 2, extent / 2, n), indexing="xy")
+    gx, gz = np.meshgrid(np.linspace(-ground_extent / 2, ground_extent / 2, n), np.linspace(-ground_extent / 2, ground_extent / 2, n), indexing="xy")
     gy = 1.5 * (_fbm(gx * 0.1 + 50.0, gz * 0.1 + 50.0, seed) - 0.5)
     pos = np.stack([gx, gy, gz], -1).reshape(-1, 3)
     qi, qj = np.meshgrid(np.arange(ground_grid), np.arange(ground_grid), indexing="xy")
@@ -573,16 +579,26 @@ def foliage_scene(n_clusters=50_000, cards_per_cluster=50, width=1920, height=10
     gs = np.zeros(1, abi.SUBMESH)
     gs[0] = (0, tris.size, len(pos), 1)
     ground = MeshData(gv, tris, gs, [GROUND])
-    # foliage: clusters of randomly oriented quads ("leaf cards")
+    # foliage: tree crowns = ellipsoids of clusters, clusters = randomly oriented quads ("leaf cards")
     ncards = n_clusters * cards_per_cluster
-    cc = (rng.random((n_clusters, 3)) - 0.5) * np.array([extent * 0.9, 0.0, extent * 0.9]) + np.array([0.0, 2.5, 0.0])
-    cc[:, 1] += rng.random(n_clusters) * 3.0
-    centre = np.repeat(cc, cards_per_cluster, axis=0) + rng.normal(scale=0.6, size=(ncards, 3))
+    n_trees = max(4, int(round(n_clusters / 125.0)))
+    side = int(math.ceil(math.sqrt(n_trees)))
+    cell = extent * 0.9 / side
+    tk = np.arange(n_trees)
+    tree = np.stack([((tk % side) + 0.5) * cell - extent * 0.45, np.zeros(n_trees), ((tk // side) + 0.5) * cell - extent * 0.45], -1)
+    tree[:, [0, 2]] += (rng.random((n_trees, 2)) - 0.5) * 0.5 * cell
+    tree[:, 1] = 3.0 + rng.random(n_trees) * 1.5
+    crown = np.stack([0.42 * cell * (0.8 + 0.4 * rng.random(n_trees)), 1.1 + 0.6 * rng.random(n_trees), 0.42 * cell * (0.8 + 0.4 * rng.random(n_trees))], -1)
+    d = rng.normal(size=(n_clusters, 3))
+    d *= (rng.random((n_clusters, 1)) ** (1.0 / 3.0)) / np.linalg.norm(d, axis=1, keepdims=True)  # uniform in the unit ball
+    owner = np.arange(n_clusters) % n_trees
+    cc = tree[owner] + d * crown[owner]
+    centre = np.repeat(cc, cards_per_cluster, axis=0) + rng.normal(scale=0.25, size=(ncards, 3))
     a = rng.normal(size=(ncards, 3))
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     b = np.cross(a, rng.normal(size=(ncards, 3)))
     b /= np.linalg.norm(b, axis=1, keepdims=True)
-    size = 0.12 + rng.random((ncards, 1)) * 0.1
+    size = 0.06 + rng.random((ncards, 1)) * 0.05
     a *= size
     b *= size
     quad = np.stack([centre - a - b, centre + a - b, centre + a + b, centre - a + b], 1).reshape(-1, 3)
@@ -594,11 +610,11 @@ def foliage_scene(n_clusters=50_000, cards_per_cluster=50, width=1920, height=10
     fs = np.zeros(1, abi.SUBMESH)
     fs[0] = (0, fidx.size, len(quad), 0)  # alpha tested -> no VK_GEOMETRY_OPAQUE_BIT (mesh.cpp:73-76)
     foliage = MeshData(fv, fidx, fs, [LEAF])
-    # 64 emissive quads (8 x 8 grid above the canopy), one submesh each, facing down
+    # 64 emissive quads (8 x 8 grid above the crowns), one submesh each, facing down
     lb = _MeshBuilder()
     for k in range(64):
-        lx, lz = ((k % 8) - 3.5) * extent / 9.0, ((k // 8) - 3.5) * extent / 9.0
-        h, y = 0.4, 9.0
+        lx, lz = ((k % 8) - 3.5) * extent / 6.5, ((k // 8) - 3.5) * extent / 6.5
+        h, y = 1.0, 13.0
         lb.begin_submesh(EMIT)
         p, i, nn = _quad((lx - h, y, lz - h), (lx + h, y, lz - h), (lx + h, y, lz + h), (lx - h, y, lz + h))
         lb.add(p, i, nn, uv=[[0, 0], [1, 0], [1, 1], [0, 1]])
@@ -609,11 +625,11 @@ def foliage_scene(n_clusters=50_000, cards_per_cluster=50, width=1920, height=10
     light_rows = area_lights_for(lights_mesh, 2, mats)
     for k in range(8):
         ang = 2 * math.pi * k / 8
-        light_rows.append(point_light((18 * math.cos(ang), 6.0, 18 * math.sin(ang)), color=(1.0, 0.9, 0.8), intensity=60.0, radius=0.2))
+        light_rows.append(point_light((20 * math.cos(ang), 8.0, 20 * math.sin(ang)), color=(1.0, 0.9, 0.8), intensity=90.0, radius=0.2))
     for k in range(8):
         ang = 2 * math.pi * (k + 0.5) / 8
-        light_rows.append(spot_light((8 * math.cos(ang), 8.0, 8 * math.sin(ang)), forward=(0.0, 1.0, 0.0), color=(0.8, 0.9, 1.0), intensity=120.0, radius=0.1, inner_deg=25.0, outer_deg=25.0))
-    cam = Camera.look_at((0.0, 5.0, 26.0), (0.0, 2.5, 0.0), fov=60.0, near=1.0, far=1000.0, focal_length=24.0, aperture_radius=0.0)
+        light_rows.append(spot_light((10 * math.cos(ang), 9.0, 10 * math.sin(ang)), forward=(0.0, 1.0, 0.0), color=(0.8, 0.9, 1.0), intensity=160.0, radius=0.1, inner_deg=25.0, outer_deg=25.0))
+    cam = Camera.look_at((0.0, 40.0, 36.0), (0.0, 0.0, 3.0), fov=60.0, near=1.0, far=1000.0, focal_length=50.0, aperture_radius=0.0)
     return SceneData(f"foliage{n_clusters}x{cards_per_cluster}", width, height, meshes, mats, instances, [submesh_table(m) for m in meshes], _stack(light_rows, abi.LIGHT), cam, textures=textures)
 
 

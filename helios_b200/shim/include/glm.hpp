@@ -136,37 +136,39 @@ inline mat4 scale(const mat4& m, const vec3& v)
     r[0] = m[0] * v.x, r[1] = m[1] * v.y, r[2] = m[2] * v.z;
     return r;
 }
-// general 4x4 inverse by cofactors (2x2 sub-determinants of the lower two rows, then of the upper two)
+inline vec4 operator*(const vec4& a, const vec4& b) { return vec4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+inline vec4 operator-(const vec4& a, const vec4& b) { return vec4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+// 4x4 inverse and determinant with GLM 0.9.9's operation order (detail/func_matrix.inl, compute_inverse<4,4> /
+// compute_determinant<4,4>; the reference vendors GLM at b3f8772 under external/AssetCore/external/glm): the path's
+// view_proj_inverse (path_integrator.cpp:152) and the parent-relative transforms (scene.cpp:319-321) go through it, and
+// the tables must come out bit for bit (tests/test_ref_scene.py runs the same inputs through the reference's GLM)
 inline mat4 inverse(const mat4& m)
 {
-    const float a00 = m[0][0], a01 = m[0][1], a02 = m[0][2], a03 = m[0][3];
-    const float a10 = m[1][0], a11 = m[1][1], a12 = m[1][2], a13 = m[1][3];
-    const float a20 = m[2][0], a21 = m[2][1], a22 = m[2][2], a23 = m[2][3];
-    const float a30 = m[3][0], a31 = m[3][1], a32 = m[3][2], a33 = m[3][3];
-    const float b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10;
-    const float b03 = a01 * a12 - a02 * a11, b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12;
-    const float b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30, b08 = a20 * a33 - a23 * a30;
-    const float b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
-    const float det = b00 * b11 - b01 * b10 + b02 * b09 + b03 * b08 - b04 * b07 + b05 * b06;
-    const float id  = 1.0f / det;
-    mat4        r(0.0f);
-    r[0][0] = (a11 * b11 - a12 * b10 + a13 * b09) * id;
-    r[0][1] = (a02 * b10 - a01 * b11 - a03 * b09) * id;
-    r[0][2] = (a31 * b05 - a32 * b04 + a33 * b03) * id;
-    r[0][3] = (a22 * b04 - a21 * b05 - a23 * b03) * id;
-    r[1][0] = (a12 * b08 - a10 * b11 - a13 * b07) * id;
-    r[1][1] = (a00 * b11 - a02 * b08 + a03 * b07) * id;
-    r[1][2] = (a32 * b02 - a30 * b05 - a33 * b01) * id;
-    r[1][3] = (a20 * b05 - a22 * b02 + a23 * b01) * id;
-    r[2][0] = (a10 * b10 - a11 * b08 + a13 * b06) * id;
-    r[2][1] = (a01 * b08 - a00 * b10 - a03 * b06) * id;
-    r[2][2] = (a30 * b04 - a31 * b02 + a33 * b00) * id;
-    r[2][3] = (a21 * b02 - a20 * b04 - a23 * b00) * id;
-    r[3][0] = (a11 * b07 - a10 * b09 - a12 * b06) * id;
-    r[3][1] = (a00 * b09 - a01 * b07 + a02 * b06) * id;
-    r[3][2] = (a31 * b01 - a30 * b03 - a32 * b00) * id;
-    r[3][3] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
-    return r;
+    const float Coef00 = m[2][2] * m[3][3] - m[3][2] * m[2][3], Coef02 = m[1][2] * m[3][3] - m[3][2] * m[1][3], Coef03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+    const float Coef04 = m[2][1] * m[3][3] - m[3][1] * m[2][3], Coef06 = m[1][1] * m[3][3] - m[3][1] * m[1][3], Coef07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+    const float Coef08 = m[2][1] * m[3][2] - m[3][1] * m[2][2], Coef10 = m[1][1] * m[3][2] - m[3][1] * m[1][2], Coef11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+    const float Coef12 = m[2][0] * m[3][3] - m[3][0] * m[2][3], Coef14 = m[1][0] * m[3][3] - m[3][0] * m[1][3], Coef15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+    const float Coef16 = m[2][0] * m[3][2] - m[3][0] * m[2][2], Coef18 = m[1][0] * m[3][2] - m[3][0] * m[1][2], Coef19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+    const float Coef20 = m[2][0] * m[3][1] - m[3][0] * m[2][1], Coef22 = m[1][0] * m[3][1] - m[3][0] * m[1][1], Coef23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+    const vec4  Fac0(Coef00, Coef00, Coef02, Coef03), Fac1(Coef04, Coef04, Coef06, Coef07), Fac2(Coef08, Coef08, Coef10, Coef11);
+    const vec4  Fac3(Coef12, Coef12, Coef14, Coef15), Fac4(Coef16, Coef16, Coef18, Coef19), Fac5(Coef20, Coef20, Coef22, Coef23);
+    const vec4  Vec0(m[1][0], m[0][0], m[0][0], m[0][0]), Vec1(m[1][1], m[0][1], m[0][1], m[0][1]), Vec2(m[1][2], m[0][2], m[0][2], m[0][2]), Vec3(m[1][3], m[0][3], m[0][3], m[0][3]);
+    const vec4  Inv0(Vec1 * Fac0 - Vec2 * Fac1 + Vec3 * Fac2), Inv1(Vec0 * Fac0 - Vec2 * Fac3 + Vec3 * Fac4), Inv2(Vec0 * Fac1 - Vec1 * Fac3 + Vec3 * Fac5), Inv3(Vec0 * Fac2 - Vec1 * Fac4 + Vec2 * Fac5);
+    const vec4  SignA(+1.0f, -1.0f, +1.0f, -1.0f), SignB(-1.0f, +1.0f, -1.0f, +1.0f);
+    const mat4  Inverse(Inv0 * SignA, Inv1 * SignB, Inv2 * SignA, Inv3 * SignB);
+    const vec4  Row0(Inverse[0][0], Inverse[1][0], Inverse[2][0], Inverse[3][0]);
+    const vec4  Dot0(m[0] * Row0);
+    const float Dot1 = (Dot0.x + Dot0.y) + (Dot0.z + Dot0.w);
+    const float OneOverDeterminant = 1.0f / Dot1;
+    return mat4(Inverse[0] * OneOverDeterminant, Inverse[1] * OneOverDeterminant, Inverse[2] * OneOverDeterminant, Inverse[3] * OneOverDeterminant);
+}
+inline float determinant(const mat4& m)
+{
+    const float SubFactor00 = m[2][2] * m[3][3] - m[3][2] * m[2][3], SubFactor01 = m[2][1] * m[3][3] - m[3][1] * m[2][3], SubFactor02 = m[2][1] * m[3][2] - m[3][1] * m[2][2];
+    const float SubFactor03 = m[2][0] * m[3][3] - m[3][0] * m[2][3], SubFactor04 = m[2][0] * m[3][2] - m[3][0] * m[2][2], SubFactor05 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
+    const vec4  DetCof(+(m[1][1] * SubFactor00 - m[1][2] * SubFactor01 + m[1][3] * SubFactor02), -(m[1][0] * SubFactor00 - m[1][2] * SubFactor03 + m[1][3] * SubFactor04),
+                      +(m[1][0] * SubFactor01 - m[1][1] * SubFactor03 + m[1][3] * SubFactor05), -(m[1][0] * SubFactor02 - m[1][1] * SubFactor04 + m[1][2] * SubFactor05));
+    return m[0][0] * DetCof[0] + m[0][1] * DetCof[1] + m[0][2] * DetCof[2] + m[0][3] * DetCof[3];
 }
 // right-handed, clip z in [-1, 1] (no GLM_FORCE_* is defined by the reference's build)
 inline mat4 perspective(float fovy, float aspect, float z_near, float z_far)

@@ -66,21 +66,76 @@ inline quat quat_cast(const mat4& m)
         default: return quat((m[0][1] - m[1][0]) * mult, (m[2][0] + m[0][2]) * mult, (m[1][2] + m[2][1]) * mult, v);
     }
 }
-// affine TRS decomposition (no skew / perspective): what TransformNode::set_from_*_transform needs
-// (scene.cpp:298-323 calls glm::decompose and discards skew and perspective)
-inline bool decompose(const mat4& m, vec3& scale, quat& orientation, vec3& translation, vec3& skew, vec4& perspective)
+// glm::decompose (gtx/matrix_decompose.inl of GLM 0.9.9, the version the reference vendors; itself after WebCore's
+// TransformationMatrix) with its operation order: normalise by m[3][3], Gram-Schmidt over the three basis rows with the
+// shear factors, flip check, then the quaternion straight from the orthonormal rows.  TransformNode::set_from_*_transform
+// (scene.cpp:298-323) feeds every mesh node's matrix through it, so the instance table only comes out bit for bit with the
+// same arithmetic.  The perspective partition is solved as GLM does when the bottom row is not (0, 0, 0, w).
+inline bool decompose(const mat4& model, vec3& scale, quat& orientation, vec3& translation, vec3& skew, vec4& perspective)
 {
-    translation = vec3(m[3][0], m[3][1], m[3][2]);
-    vec3 c0(m[0][0], m[0][1], m[0][2]), c1(m[1][0], m[1][1], m[1][2]), c2(m[2][0], m[2][1], m[2][2]);
-    scale = vec3(length(c0), length(c1), length(c2));
-    if (scale.x == 0.0f || scale.y == 0.0f || scale.z == 0.0f) return false;
-    if (dot(c0, cross(c1, c2)) < 0.0f) scale = vec3(-scale.x, -scale.y, -scale.z); // mirrored basis
-    c0 = c0 / scale.x, c1 = c1 / scale.y, c2 = c2 / scale.z;
-    mat4 r(1.0f);
-    r[0] = vec4(c0, 0.0f), r[1] = vec4(c1, 0.0f), r[2] = vec4(c2, 0.0f);
-    orientation = quat_cast(r);
-    skew        = vec3(0.0f);
-    perspective = vec4(0.0f, 0.0f, 0.0f, 1.0f);
+    const float eps = 1.1920928955078125e-7f; // epsilon<float>()
+    mat4        L   = model;
+    if (std::fabs(L[3][3]) < eps) return false;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) L[i][j] /= L[3][3];
+    mat4 P = L;
+    for (int i = 0; i < 3; i++) P[i][3] = 0.0f;
+    P[3][3] = 1.0f;
+    if (std::fabs(determinant(P)) < eps) return false;
+    if (!(std::fabs(L[0][3]) < eps) || !(std::fabs(L[1][3]) < eps) || !(std::fabs(L[2][3]) < eps))
+    {
+        const vec4 rhs(L[0][3], L[1][3], L[2][3], L[3][3]);
+        perspective = transpose(inverse(P)) * rhs;
+        L[0][3] = L[1][3] = L[2][3] = 0.0f;
+        L[3][3]                     = 1.0f;
+    }
+    else
+        perspective = vec4(0.0f, 0.0f, 0.0f, 1.0f);
+    translation = vec3(L[3][0], L[3][1], L[3][2]);
+    vec3 row[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) row[i][j] = L[i][j];
+    auto unit    = [](const vec3& v) { return v * 1.0f / length(v); };                                     // detail::scale(v, 1)
+    auto combine = [](const vec3& a, const vec3& b, float as, float bs) { return (a * as) + (b * bs); }; // detail::combine
+    scale.x = length(row[0]);
+    row[0]  = unit(row[0]);
+    skew.z  = dot(row[0], row[1]);
+    row[1]  = combine(row[1], row[0], 1.0f, -skew.z);
+    scale.y = length(row[1]);
+    row[1]  = unit(row[1]);
+    skew.z /= scale.y;
+    skew.y = dot(row[0], row[2]);
+    row[2] = combine(row[2], row[0], 1.0f, -skew.y);
+    skew.x = dot(row[1], row[2]);
+    row[2] = combine(row[2], row[1], 1.0f, -skew.x);
+    scale.z = length(row[2]);
+    row[2]  = unit(row[2]);
+    skew.y /= scale.z;
+    skew.x /= scale.z;
+    if (dot(row[0], cross(row[1], row[2])) < 0.0f)
+        for (int i = 0; i < 3; i++) scale[i] *= -1.0f, row[i] = row[i] * -1.0f;
+    float       o[4]; // x, y, z, w
+    const float trace = row[0].x + row[1].y + row[2].z;
+    if (trace > 0.0f)
+    {
+        float root = std::sqrt(trace + 1.0f);
+        o[3]       = 0.5f * root;
+        root       = 0.5f / root;
+        o[0] = root * (row[1].z - row[2].y), o[1] = root * (row[2].x - row[0].z), o[2] = root * (row[0].y - row[1].x);
+    }
+    else
+    {
+        static const int next[3] = { 1, 2, 0 };
+        int              i       = 0;
+        if (row[1].y > row[0].x) i = 1;
+        if (row[2].z > row[i][i]) i = 2;
+        const int j = next[i], k = next[j];
+        float     root = std::sqrt(row[i][i] - row[j][j] - row[k][k] + 1.0f);
+        o[i]           = 0.5f * root;
+        root           = 0.5f / root;
+        o[j] = root * (row[i][j] + row[j][i]), o[k] = root * (row[i][k] + row[k][i]), o[3] = root * (row[j][k] - row[k][j]);
+    }
+    orientation = quat(o[3], o[0], o[1], o[2]);
     return true;
 }
 } // namespace glm

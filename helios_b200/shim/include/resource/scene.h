@@ -339,6 +339,8 @@ public:
     void force_update() { m_force_update = true; }
     HosekWilkieSkyModel* sky_model() { return m_sky_model.get(); }
     const SceneTables& tables() const { return m_tables; }
+    // Texture2D ids in the order of the device texture array (descriptor set 4 of the reference), as of the last table build
+    const std::vector<uint32_t>& texture_array_ids() const { return m_texture_array_ids; }
 
 private:
     Scene(vk::Backend::Ptr backend, const std::string& name, Node::Ptr root = nullptr, const std::string& path = "");
@@ -354,6 +356,12 @@ private:
     std::string m_path;
     bool m_force_update = false;
     SceneTables m_tables;
+    // what hl_scene_set_tables installed last (create_gpu_resources turns a transform-only change into hl_scene_update_instances)
+    SceneTables m_previous_tables;
+    bool m_tables_installed = false, m_black_env_installed = false;
+    std::vector<hl_mesh> m_installed_meshes;
+    std::vector<uint32_t> m_installed_textures;
+    std::vector<uint32_t> m_texture_array_ids;
     // state of the device-side copy
     glm::vec3 m_last_sun_direction = glm::vec3(0.0f);
     bool m_sky_valid = false;

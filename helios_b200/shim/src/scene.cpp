@@ -376,6 +376,7 @@ void Scene::create_gpu_resources(RenderState& render_state)
         throw std::runtime_error("Scene::update: more than MAX_SCENE_MESH_INSTANCE_COUNT mesh instances");
     }
     SceneTables& T = m_tables;
+    m_previous_tables = T; // what the device holds (when m_tables_installed): a change of transforms only becomes a refit
     T.materials.clear(), T.instances.clear(), T.lights.clear(), T.submesh_info.clear();
     m_num_area_lights = 0;
     m_global_mesh_indices.clear();
@@ -514,9 +515,41 @@ void Scene::create_gpu_resources(RenderState& render_state)
     }
     if (T.lights.size() > MAX_SCENE_LIGHT_COUNT) throw std::runtime_error("Scene::update: more than MAX_SCENE_LIGHT_COUNT lights");
     T.num_textures = (uint32_t)texture_array.size();
+    m_texture_array_ids.clear();
+    for (auto& tex : texture_array) m_texture_array_ids.push_back(tex->id());
 
     if (!backend->has_device()) return; // host-only inspection of the tables
     hl_context ctx = backend->context();
+    std::vector<hl_mesh> handles(T.instances.size());
+    for (size_t i = 0; i < T.instances.size(); i++) handles[i] = render_state.m_meshes[i]->mesh()->acceleration_structure();
+    std::vector<uint32_t> texture_ids;
+    for (auto& tex : texture_array) texture_ids.push_back(tex->id());
+    m_texture_array_ids = texture_ids;
+    // Moving mesh nodes (the common interactive edit): same materials, lights, textures, meshes and submesh tables, only the
+    // instances' matrices differ -> hl_scene_update_instances refits the instance tree instead of rebuilding everything.
+    // (the reference rebuilds its TLAS here although it was created ALLOW_UPDATE, scene.cpp:797, renderer.cpp:147-168)
+    {
+        const SceneTables& P    = m_previous_tables;
+        auto               same = [](const void* a, const void* b, size_t n) { return n == 0 || std::memcmp(a, b, n) == 0; };
+        auto               same_info = [&](const std::vector<std::vector<glm::uvec2>>& a, const std::vector<std::vector<glm::uvec2>>& b) {
+            if (a.size() != b.size()) return false;
+            for (size_t i = 0; i < a.size(); i++)
+                if (a[i].size() != b[i].size() || !same(a[i].data(), b[i].data(), sizeof(glm::uvec2) * a[i].size())) return false;
+            return true;
+        };
+        bool               only_transforms = m_tables_installed && !T.instances.empty() && P.instances.size() == T.instances.size() && P.materials.size() == T.materials.size() &&
+                               P.lights.size() == T.lights.size() && same_info(P.submesh_info, T.submesh_info) && handles == m_installed_meshes && texture_ids == m_installed_textures &&
+                               same(P.materials.data(), T.materials.data(), sizeof(hl_material) * T.materials.size()) && same(P.lights.data(), T.lights.data(), sizeof(hl_light) * T.lights.size());
+        const bool env_unchanged = (has_ibl && m_env_source_id == render_state.ibl_environment_map()->image()->id()) || (!has_ibl && !render_state.m_directional_lights.empty() && m_sky_valid) ||
+                                   (!has_ibl && render_state.m_directional_lights.empty() && m_env_source_id == 0xFFFFFFFFu && !m_sky_valid && m_black_env_installed);
+        for (size_t i = 0; only_transforms && i < T.instances.size(); i++) only_transforms = P.instances[i].mesh_index == T.instances[i].mesh_index;
+        if (only_transforms && env_unchanged)
+        {
+            backend->check(hl_scene_update_instances(ctx, T.instances.data(), (uint32_t)T.instances.size()), "hl_scene_update_instances");
+            return;
+        }
+    }
+    m_tables_installed = false;
     // textures: slot i of the device array = texture_array[i]
     backend->check(hl_textures_clear(ctx), "hl_textures_clear");
     for (auto& tex : texture_array)
@@ -537,17 +570,14 @@ void Scene::create_gpu_resources(RenderState& render_state)
     else if (render_state.m_directional_lights.empty())
     {
         backend->check(hl_envmap_set(ctx, 0, nullptr), "hl_envmap_set");
-        m_env_source_id = 0xFFFFFFFFu, m_sky_valid = false;
+        m_env_source_id = 0xFFFFFFFFu, m_sky_valid = false, m_black_env_installed = true;
     }
-    std::vector<hl_mesh>         handles(T.instances.size());
+    if (has_ibl || !render_state.m_directional_lights.empty()) m_black_env_installed = false;
     std::vector<const uint32_t*> info(T.instances.size());
-    for (size_t i = 0; i < T.instances.size(); i++)
-    {
-        handles[i] = render_state.m_meshes[i]->mesh()->acceleration_structure();
-        info[i]    = reinterpret_cast<const uint32_t*>(T.submesh_info[i].data());
-    }
+    for (size_t i = 0; i < T.instances.size(); i++) info[i] = reinterpret_cast<const uint32_t*>(T.submesh_info[i].data());
     backend->check(hl_scene_set_tables(ctx, T.materials.data(), (uint32_t)T.materials.size(), T.instances.data(), handles.data(), info.data(), (uint32_t)T.instances.size(), T.lights.data(),
                                        (uint32_t)T.lights.size()),
                    "hl_scene_set_tables");
+    m_tables_installed = true, m_installed_meshes = handles, m_installed_textures = texture_ids;
 }
 } // namespace helios

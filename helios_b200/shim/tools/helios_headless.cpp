@@ -81,6 +81,7 @@ int main(int argc, char** argv)
     int         device = 0;
     std::vector<int> devices; // --gpus N / --devices a,b,...: one rank per entry (entries may repeat: ranks sharing a GPU)
     bool        tiled = false, no_device = false;
+    int         jitter_seed = -1, jitter_after = 0; // --jitter-nodes SEED [--jitter-after K]: move every second mesh node after K frames
     float       exposure = 1.0f;
     for (int i = 1; i < argc; i++)
     {
@@ -129,6 +130,8 @@ int main(int argc, char** argv)
                 ray_debug[0] = std::atoi(next().c_str()), ray_debug[1] = std::atoi(next().c_str()), ray_debug[2] = std::atoi(next().c_str());
             }
             else if (a == "--dump-ray-debug") ray_debug_path = next(); // raw vertices, 8 floats each
+            else if (a == "--jitter-nodes") jitter_seed = std::stoi(next()); // moves mesh nodes (seeded offsets): Scene::update turns a transform-only change into an instance-tree refit
+            else if (a == "--jitter-after") jitter_after = std::stoi(next()); // ... after this many frames (0 = before the first one); the bake restarts, --spp frames follow
             else if (a == "--tiled") tiled = true;
             else if (a == "--no-device") no_device = true;
             else
@@ -154,6 +157,7 @@ int main(int argc, char** argv)
       float            bias  = 0.0f;
       vk::Backend::Ptr backend;
       Scene::Ptr       scene;
+      std::vector<uint32_t> file_texture_ids; // Texture2D id of the k-th texture of the scene file (--dump-tables trailer)
       // builds backend + scene on GPU `device` (called once per rank for --gpus / --devices: the scene is replicated)
       auto make_scene = [&](int device) {
       if (!ast_scene_path.empty())
@@ -191,6 +195,7 @@ int main(int argc, char** argv)
             std::vector<uint8_t> texels((size_t)w * h * (fmt == HL_TEX_RGBA32F ? 16 : 4));
             r.raw(texels.data(), texels.size());
             t = Texture2D::create(backend, fmt, w, h, texels.data(), "texture");
+            file_texture_ids.push_back(t->id());
         }
         std::vector<Material::Ptr> materials(r.get<uint32_t>());
         for (size_t k = 0; k < materials.size(); k++)
@@ -385,8 +390,25 @@ int main(int argc, char** argv)
             uint32_t   done = 0;
             const auto t0   = std::chrono::steady_clock::now();
             auto finished   = [&]() { return tiled ? (done > 0 && pi->tile_idx() * pi->max_samples() >= pi->num_target_samples()) : done == spp; };
+            int  frames_before_jitter = jitter_seed >= 0 ? jitter_after : -1;
             while (!finished())
             {
+                if (frames_before_jitter == 0)
+                {
+                    // seeded offsets for every second mesh node; set_position marks the transforms dirty, the next Scene::update
+                    // reports a hierarchy change (the bake restarts) and only the instance matrices differ
+                    uint32_t k = 0, state = 0x9E3779B9u * (uint32_t)(jitter_seed + 1);
+                    auto     rnd = [&]() { state = state * 1664525u + 1013904223u; return float(state >> 8) / 16777216.0f - 0.5f; };
+                    if (scene->root_node())
+                        for (auto& child : scene->root_node()->children())
+                            if (child->type() == NODE_MESH && (k++ & 1u))
+                            {
+                                auto node = std::static_pointer_cast<MeshNode>(child);
+                                node->set_position(node->local_position() + glm::vec3(rnd() * 3.0f, rnd() * 0.5f, rnd() * 3.0f));
+                            }
+                    done = 0;
+                }
+                frames_before_jitter--;
                 if (!tiled && !out_path.empty() && done + 1 == spp) renderer->save_image_to_disk(out_path);
                 render_state.setup(width, height, cmd);
                 scene->update(render_state);
@@ -472,6 +494,17 @@ int main(int argc, char** argv)
             }
             std::fwrite(&pc, sizeof(pc), 1, f);
             std::fwrite(scene->sky_model()->coefficients(), 4, 40, f);
+            // trailer: the texture array as indices into the scene file's texture list (file order = creation order = ascending id)
+            std::vector<uint32_t> ids = scene->texture_array_ids(), sorted_ids = file_texture_ids;
+            const uint32_t        nt  = (uint32_t)ids.size();
+            std::fwrite(&nt, 4, 1, f);
+            for (uint32_t id : ids)
+            {
+                uint32_t idx = 0xFFFFFFFFu;
+                for (size_t k = 0; k < sorted_ids.size(); k++)
+                    if (sorted_ids[k] == id) idx = (uint32_t)k;
+                std::fwrite(&idx, 4, 1, f);
+            }
             std::fclose(f);
         }
         // release in dependency order: scene graph and resources before the backend

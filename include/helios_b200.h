@@ -209,6 +209,14 @@ HL_API hl_status hl_scene_set_tables(hl_context ctx, const hl_material* material
                                      const uint32_t* const* submesh_info, uint32_t n_instances,
                                      const hl_light* lights, uint32_t n_lights);
 
+/* Moving instances: new model / normal matrices for the n_instances instances of the installed tables (same order; each
+ * instance keeps its mesh and submesh table — mesh_index is ignored; materials, lights and textures stay).  Replaces the
+ * reference's per-change top-level rebuild (the structure is created ALLOW_UPDATE, src/engine/resource/scene.cpp:797, and
+ * rebuilt in src/engine/gfx/renderer.cpp:147-168) by a REFIT of the instance tree: topology kept, node boxes recomputed
+ * and requantised on the GPU in one launch; world->object transforms are recomputed.  Results are those of a rebuild
+ * (closest hit + tie rule do not depend on the tree).  Returns HL_ERR_INVALID_ARGUMENT when the count differs. */
+HL_API hl_status hl_scene_update_instances(hl_context ctx, const hl_instance* instances, uint32_t n_instances);
+
 /* ------------------------------------------------------------------ the hot path */
 /* replaces PathIntegrator::launch_rays -> vkCmdTraceRaysKHR (path_integrator.cpp:125-200): one sample
  * per pixel over the launch rectangle [tile, tile + (launch_w, launch_h)) clipped to (W, H), blended

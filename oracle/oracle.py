@@ -72,6 +72,19 @@ def build_ref_ast(force: bool = False):
     return _REF_AST_TOOL if _REF_AST_TOOL.exists() else None
 
 
+_REF_SCENE_TOOL = _HERE / "_ref" / "ref_scene_tool"
+_REF_GLM_PIN = _HERE / "_ref" / "glm_pin_ref"
+
+
+def build_ref_scene(force: bool = False):
+    """(Re)build oracle/_ref/ref_scene_tool (the reference's own scene.cpp + material.cpp behind a stand-in device layer,
+    oracle/ref_scene/) and oracle/_ref/glm_pin_ref (oracle/ref_scene/glm_pin.cpp against the GLM the reference vendors) where
+    the reference checkout is mounted; elsewhere the prebuilt files are used.  Returns (tool, glm_pin) paths, None where absent."""
+    if Path("/root/reference/src/engine/resource/scene.cpp").is_file():
+        subprocess.check_call(["make", "-C", str(_HERE), "-s", "ref_scene"] + (["-B"] if force else []))
+    return (_REF_SCENE_TOOL if _REF_SCENE_TOOL.exists() else None, _REF_GLM_PIN if _REF_GLM_PIN.exists() else None)
+
+
 def ref_lib():
     """ctypes handle of the reference-GLSL library (contains the restatement's or_* entry points as well), or None"""
     global _ref_lib

@@ -143,6 +143,7 @@ struct EmMesh
     std::vector<uint32_t>   idx;
     std::vector<hl_submesh> subs;
     std::vector<uint32_t>   tri_start;
+    std::vector<AlphaTri>   alpha; // any-hit records beside the leaves (meshes with a non-opaque submesh), as hl_builder.cu allocates them
     WideBVH                 bvh;
 };
 struct EmTexture
@@ -162,6 +163,8 @@ struct EmScene
     std::vector<hl_light>    lights;
     std::vector<uint32_t>    submesh_info, submesh_offset;
     std::vector<float>       inst_inv;
+    std::vector<InstAlpha>   inst_alpha;
+    std::vector<GeomAlpha>   geom_alpha;
     std::vector<MeshView>    mesh_views;
     std::vector<TexView>     tex_views;
     std::vector<float>       lut8;
@@ -217,10 +220,13 @@ EM_API int  em_scene_add_mesh(EmScene* s, const hl_vertex* v, uint32_t nv, const
     const uint32_t   ntri = m->tri_start[ns];
     std::vector<Box> prim(ntri);
     for (uint32_t f = 0; f < ntri; f++) prim[f] = triangle_box(m->v.data(), m->idx.data(), m->subs.data(), m->tri_start.data(), ns, f);
+    bool any_hit = false;
+    for (const hl_submesh& sm : m->subs) any_hit = any_hit || !sm.opaque;
+    if (any_hit) m->alpha.resize(ntri);
     build_wide(prim, m->bvh, [&](const uint32_t* order) {
         TriLeafWriter w;
         w.vertices = m->v.data(), w.indices = m->idx.data(), w.submeshes = m->subs.data(), w.tri_start = m->tri_start.data();
-        w.n_geom = ns, w.sorted_prim = order, w.tris = m->bvh.tris.data();
+        w.n_geom = ns, w.sorted_prim = order, w.tris = m->bvh.tris.data(), w.alpha = any_hit && ntri ? m->alpha.data() : nullptr;
         return w;
     }, true);
     s->meshes.push_back(m);
@@ -317,8 +323,70 @@ EM_API void em_scene_set_tables(EmScene* s, const hl_material* mats, uint32_t nm
     v.env.faces = s->env.data(), v.env.size = s->env_size;
     v.tlas_nodes = s->tlas.nodes.data(), v.tlas_leaf = s->tlas.inst_leaf.data();
     v.n_instances = ni, v.n_lights = nl, v.single_identity = identity ? 1u : 0u;
+    // any-hit records, as hl_scene_set_tables builds them
+    s->inst_alpha.assign(ni, InstAlpha());
+    s->geom_alpha.clear();
+    for (uint32_t i = 0; i < ni; i++)
+    {
+        const EmMesh& m = *s->meshes[inst[i].mesh_index];
+        for (size_t g = 0; g < m.subs.size(); g++)
+        {
+            const hl_material& mat = mats[submesh_info[i][2 * g + 1]];
+            GeomAlpha          ga;
+            ga.texture = mat.texture_indices0[0], ga.alpha = mat.albedo[3];
+            s->geom_alpha.push_back(ga);
+        }
+        s->inst_alpha[i].alpha = m.alpha.empty() ? nullptr : m.alpha.data(), s->inst_alpha[i].tris = m.bvh.tris.data(), s->inst_alpha[i].info_base = s->submesh_offset[i];
+    }
+    v.inst_alpha = s->inst_alpha.data(), v.geom_alpha = s->geom_alpha.data();
 }
 EM_API void em_scene_force_two_level(EmScene* s) { s->view.single_identity = 0; }
+// hl_scene_update_instances on the host: new transforms, instance tree REFITTED with the product's per-node functions
+// (hl_build.h refit_node_box / refit_requantize; the CUDA kernel k_tlas_refit runs the same sweeps in one block)
+EM_API int em_scene_update_instances(EmScene* s, const hl_instance* inst, uint32_t ni)
+{
+    if (ni != s->instances.size() || s->tlas.nodes.empty()) return 1;
+    std::vector<Box> iboxes(ni);
+    bool             identity = ni == 1;
+    for (uint32_t i = 0; i < ni; i++)
+    {
+        memcpy(s->instances[i].model_matrix, inst[i].model_matrix, 64), memcpy(s->instances[i].normal_matrix, inst[i].normal_matrix, 64);
+        affine_inverse(inst[i].model_matrix, &s->inst_inv[(size_t)i * 12]);
+        static const float I[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+        if (memcmp(inst[i].model_matrix, I, 64) != 0) identity = false;
+        const EmMesh& m     = *s->meshes[s->instances[i].mesh_index];
+        double        lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+        const float*  M     = inst[i].model_matrix;
+        const Box&    rb    = m.bvh.root;
+        for (int c = 0; c < 8; c++)
+        {
+            double x = (c & 1) ? rb.hi[0] : rb.lo[0], y = (c & 2) ? rb.hi[1] : rb.lo[1], z = (c & 4) ? rb.hi[2] : rb.lo[2];
+            for (int a = 0; a < 3; a++)
+            {
+                double w = (double)M[a] * x + (double)M[4 + a] * y + (double)M[8 + a] * z + (double)M[12 + a];
+                lo[a] = std::min(lo[a], w), hi[a] = std::max(hi[a], w);
+            }
+        }
+        for (int a = 0; a < 3; a++)
+        {
+            double pad      = 1e-5 * (std::fabs(lo[a]) + std::fabs(hi[a]) + (hi[a] - lo[a]));
+            iboxes[i].lo[a] = (float)(lo[a] - pad), iboxes[i].hi[a] = (float)(hi[a] + pad);
+        }
+    }
+    std::vector<WideNode>& nodes = s->tlas.nodes;
+    std::vector<Box>       nb(nodes.size(), box_empty());
+    int                    sweeps = 0;
+    for (; sweeps < 64; sweeps++)
+    {
+        std::vector<Box> next(nodes.size());
+        for (size_t i = 0; i < nodes.size(); i++) next[i] = refit_node_box(nodes[i], s->tlas.inst_leaf.data(), iboxes.data(), nb.data());
+        if (memcmp(next.data(), nb.data(), sizeof(Box) * nb.size()) == 0) break;
+        nb = next;
+    }
+    for (size_t i = 0; i < nodes.size(); i++) refit_requantize(nodes[i], nb[i], s->tlas.inst_leaf.data(), iboxes.data(), nb.data());
+    s->view.single_identity = identity ? 1u : 0u;
+    return 0;
+}
 
 static void trace_one(const SceneView& s, f3 o, float tmin, f3 d, float tmax, uint32_t flags, Hit& h)
 {

@@ -76,6 +76,11 @@ class EmulScene:
         except Exception:
             pass
 
+    def update_instances(self, instances):
+        """hl_scene_update_instances on the emulator: new transforms, instance tree refitted (not rebuilt)"""
+        inst = np.ascontiguousarray(instances)
+        assert lib().em_scene_update_instances(self.h, _p(inst), C.c_uint32(len(inst))) == 0
+
     def render_frame(self, pc, accum, launch=(0, 0), accum_mode=0):
         pcb = np.ascontiguousarray(pc)
         lib().em_render_frame(self.h, _p(pcb), C.c_uint32(launch[0]), C.c_uint32(launch[1]), _p(accum), _p(self.counters), C.c_int(accum_mode))

@@ -150,3 +150,15 @@ def test_headless_sharded_over_ranks_matches_one_rank(tmp_path):
     raw = img.read_bytes()
     rgb = np.frombuffer(raw[len(raw) - s.width * s.height * 3 :], np.uint8)
     assert rgb.max() > 0
+
+
+def test_moving_nodes_refit_the_instance_tree(tmp_path):
+    """SURVEY 8 f2: a transform-only change goes through hl_scene_update_instances (instance-tree refit) in Scene::update.
+    Run A moves the mesh nodes before the first frame (everything is built for the moved scene); run B renders one frame,
+    then moves the same nodes by the same offsets — the shim refits — and the restarted bake must give A's image bit for bit."""
+    s = scenes.city_scene(n_instances=30, n_meshes=3, width=128, height=72, floors=(2, 4), detail=(1, 3))
+    a, sa, _ = headless_render(s, tmp_path, 4, extra=("--jitter-nodes", "5", "--jitter-after", "0"))
+    b, sb, _ = headless_render(s, tmp_path, 4, extra=("--jitter-nodes", "5", "--jitter-after", "1"))
+    still, _, _ = headless_render(s, tmp_path, 4)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, still)  # the nodes really moved

@@ -39,6 +39,10 @@ VARIANT_SETS["shade"] = {
 VARIANT_SETS["sah"] = {"c020": ["-DHL_SAH_C_PRIM_TRIANGLE=0.2f"], "c035": [], "c060": ["-DHL_SAH_C_PRIM_TRIANGLE=0.6f"], "c100": ["-DHL_SAH_C_PRIM_TRIANGLE=1.0f"], "c150": ["-DHL_SAH_C_PRIM_TRIANGLE=1.5f"], "c250": ["-DHL_SAH_C_PRIM_TRIANGLE=2.5f"]}
 VARIANT_SETS["defslots"] = {"d4": [], "d6": ["-DHL_DEFAULT_WAVE_SLOTS=6"], "d8": ["-DHL_DEFAULT_WAVE_SLOTS=8"]}
 VARIANT_SETS["slots"] = {"base": [], "slots3": ["-DHL_WAVE_SLOTS=3"], "slots2": ["-DHL_WAVE_SLOTS=2"], "slots4": ["-DHL_WAVE_SLOTS=4"], "slots6": ["-DHL_WAVE_SLOTS=6"], "mb7": ["-DHL_TRACE_MIN_BLOCKS=7"], "mb6": ["-DHL_TRACE_MIN_BLOCKS=6", "-DHL_TRACE_GRID_MULT=6"]}
+VARIANT_SETS["coop"] = {
+    "base0": ["-DHL_COOP_LEAVES=0"], "coop4": [], "coop4_mb6": ["-DHL_TRACE_MIN_BLOCKS=6"], "coop4_mb7": ["-DHL_TRACE_MIN_BLOCKS=7"],
+    "coop2": ["-DHL_COOP_K=2"], "coop2_mb7": ["-DHL_COOP_K=2", "-DHL_TRACE_MIN_BLOCKS=7"], "coop3_mb6": ["-DHL_COOP_K=3", "-DHL_TRACE_MIN_BLOCKS=6"],
+}
 VARIANTS = VARIANT_SETS[os.environ.get("HL_TUNE_SET", "occ")]
 OUT = ROOT / "build" / "variants"
 if sys.argv[1] == "build":
