@@ -314,6 +314,17 @@ static Box instance_world_box(const float* M, const Box& rb)
 }
 static const float kIdentity16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
 
+// bit i set: instance i's model matrix is the identity (hl_bvh.h skips the ray transform for it)
+static void upload_identity_bits(hl_context_t* c, const std::vector<hl_instance>& inst)
+{
+    std::vector<uint32_t> bits((inst.size() + 31) / 32 + 1, 0u);
+    for (size_t i = 0; i < inst.size(); i++)
+        if (memcmp(inst[i].model_matrix, kIdentity16, 64) == 0) bits[i >> 5] |= 1u << (i & 31);
+    c->inst_identity.upload(bits.data(), 4 * bits.size(), c->stream);
+    HL_CUDA(cudaStreamSynchronize(c->stream));
+    c->view.inst_identity = c->inst_identity.as<uint32_t>();
+}
+
 hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint32_t n_materials, const hl_instance* instances, const hl_mesh* meshes,
                               const uint32_t* const* submesh_info, uint32_t n_instances, const hl_light* lights, uint32_t n_lights)
 {
@@ -410,6 +421,7 @@ hl_status hl_scene_set_tables(hl_context ctx, const hl_material* materials, uint
     v.tlas_nodes = c_->tlas.nodes.as<WideNode>(), v.tlas_leaf = c_->tlas.leaves.as<uint32_t>();
     v.n_instances = n_instances, v.n_lights = n_lights, v.single_identity = identity ? 1u : 0u;
     v.inst_alpha = c_->inst_alpha.as<InstAlpha>(), v.geom_alpha = c_->geom_alpha.as<GeomAlpha>();
+    upload_identity_bits(c_, inst);
     c_->scene_ready = true;
     HL_CATCH
 }
@@ -442,6 +454,7 @@ hl_status hl_scene_update_instances(hl_context ctx, const hl_instance* instances
         refit_tlas(c_, boxes);
     c_->view.tlas_nodes = c_->tlas.nodes.as<WideNode>(), c_->view.tlas_leaf = c_->tlas.leaves.as<uint32_t>();
     c_->view.single_identity = identity ? 1u : 0u;
+    upload_identity_bits(c_, c_->h_instances);
     HL_CATCH
 }
 
@@ -541,13 +554,14 @@ hl_status hl_trace_primary_ids(hl_context ctx, const hl_push_constants* pc, uint
     HL_CUDA(cudaStreamSynchronize(c_->stream));
     for (size_t i = 0; i < n; i++)
     {
-        const bool hit = hb[2 * i] != HL_MISS;
-        if (instance) instance[i] = hb[2 * i];
-        if (geometry) geometry[i] = hb[2 * i + 1];
-        if (primitive) memcpy(&primitive[i], &ha[4 * i + 3], 4);
-        if (t) t[i] = hit ? ha[4 * i] : INFINITY;
-        if (u) u[i] = hit ? ha[4 * i + 1] : 0.0f;
-        if (v) v[i] = hit ? ha[4 * i + 2] : 0.0f;
+        const bool   hit = hb[2 * i] != HL_MISS;
+        const size_t p   = wavefront_path_pixel(c_, (uint32_t)i); // the hit buffers are in path order (8 x 4 pixel tiles per warp)
+        if (instance) instance[p] = hb[2 * i];
+        if (geometry) geometry[p] = hb[2 * i + 1];
+        if (primitive) memcpy(&primitive[p], &ha[4 * i + 3], 4);
+        if (t) t[p] = hit ? ha[4 * i] : INFINITY;
+        if (u) u[p] = hit ? ha[4 * i + 1] : 0.0f;
+        if (v) v[p] = hit ? ha[4 * i + 2] : 0.0f;
     }
     HL_CATCH
 }

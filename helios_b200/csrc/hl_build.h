@@ -352,6 +352,13 @@ struct TopSmall
 {
     uint32_t count, link, list_base, arrivals; // arrivals: ticket counter of the registering clusters
 }; // 16 B
+// what the per-level passes need of a cluster, in cluster order (written once by top_seed_cluster): the BIN and ASSIGN
+// phases stream 32-byte records instead of gathering box + range of a scattered radix-tree node per cluster and level
+struct TopCluster
+{
+    float    lo[3], hi[3];
+    uint32_t prims, pad;
+};
 struct TopBuild
 {
     uint32_t        cluster_prims; // C
@@ -361,6 +368,7 @@ struct TopBuild
     const uint32_t* cluster;       // [K] binary node id of each cluster root
     const uint32_t* free_nodes;    // [K - 1] internal nodes above the cut, the root (id 0) first
     uint32_t*       cnode;         // [K] index of the level node each cluster sits in, HL_TOP_DONE once linked
+    TopCluster*     crec;          // [K] box + primitive count of each cluster
     TopNode*        level[2];      // node arrays of the even / odd levels
     TopBin*         bins[2];       // bin arrays of the even / odd levels, 3 * HL_TOP_BINS per slot
     TopSmall*       small;         // [K / 2 + 1] nodes with 2..HL_TOP_SMALL clusters, finished after the level loop
@@ -376,10 +384,9 @@ HL_HD uint32_t subtree_prims_cg(const BinaryTree& t, uint32_t node) { return nod
 HL_HD bool top_is_cluster_root(const BinaryTree& t, uint32_t m, uint32_t C) { return m != 0u && subtree_prims(t, m) <= C && subtree_prims(t, t.parent[m]) > C; }
 HL_HD bool top_is_upper_node(const BinaryTree& t, uint32_t m, uint32_t C) { return m < t.n - 1 && subtree_prims(t, m) > C; }
 
-HL_HD void top_cluster_centroid(const BinaryTree& t, uint32_t m, float c[3])
+HL_HD void top_cluster_centroid(const TopCluster& r, float c[3])
 {
-    const Box& b = t.box[m];
-    for (int k = 0; k < 3; k++) c[k] = 0.5f * (b.lo[k] + b.hi[k]);
+    for (int k = 0; k < 3; k++) c[k] = 0.5f * (r.lo[k] + r.hi[k]);
 }
 // bin of centroid coordinate c inside [lo, hi]; -1 when the axis has no extent
 HL_HD int top_bin_of(float c, float lo, float hi)
@@ -470,8 +477,13 @@ HL_HD void top_begin(TopBuild& tb, uint32_t K)
 HL_HD void top_seed_cluster(const BinaryTree& t, TopBuild& tb, uint32_t i)
 {
     tb.cnode[i] = 0u;
+    TopCluster     r;
+    const uint32_t m0 = tb.cluster[i];
+    for (int k = 0; k < 3; k++) r.lo[k] = t.box[m0].lo[k], r.hi[k] = t.box[m0].hi[k];
+    r.prims = subtree_prims(t, m0), r.pad = 0u;
+    tb.crec[i] = r;
     float c[3];
-    top_cluster_centroid(t, tb.cluster[i], c);
+    top_cluster_centroid(r, c);
     uint32_t oc[3];
     for (int k = 0; k < 3; k++) oc[k] = f2ord(c[k]);
     TopNode& root = tb.level[0][0];
@@ -514,12 +526,12 @@ HL_HD void top_bin_cluster(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t
         return;
     }
     if (mode != HL_TOP_MODE_BINNED) return;
-    float c[3];
-    top_cluster_centroid(t, m, c);
-    const Box& b = t.box[m];
-    uint32_t   olo[3], ohi[3];
+    const TopCluster b = tb.crec[i];
+    float            c[3];
+    top_cluster_centroid(b, c);
+    uint32_t olo[3], ohi[3];
     for (int k = 0; k < 3; k++) olo[k] = f2ord(b.lo[k]), ohi[k] = f2ord(b.hi[k]);
-    const uint32_t prims = subtree_prims(t, m);
+    const uint32_t prims = b.prims;
     TopBin*        bins  = tb.bins[level & 1u] + (size_t)hl_load_cg(&N.bins) * (3 * HL_TOP_BINS);
     for (int ax = 0; ax < 3; ax++)
     {
@@ -682,7 +694,7 @@ HL_HD void top_assign_cluster(const BinaryTree& t, TopBuild& tb, uint32_t level,
     if (nd == HL_TOP_DONE) return;
     TopNode& N = tb.level[level & 1u][nd];
     float    c[3];
-    top_cluster_centroid(t, tb.cluster[i], c);
+    top_cluster_centroid(tb.crec[i], c);
     uint32_t side;
     if (hl_load_cg(&N.mode) == HL_TOP_MODE_BINNED)
     {

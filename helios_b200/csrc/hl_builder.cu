@@ -202,11 +202,10 @@ __device__ __forceinline__ void top_bin_level_private(BinaryTree& t, TopBuild& t
             top_bin_cluster(t, tb, level, i); // SINGLE / SMALL / ARRIVAL: the generic path (no bins involved)
             continue;
         }
-        const uint32_t m = tb.cluster[i];
-        float          c[3];
-        top_cluster_centroid(t, m, c);
-        const Box&     b     = t.box[m];
-        const uint32_t prims = subtree_prims(t, m);
+        const TopCluster b = tb.crec[i];
+        float            c[3];
+        top_cluster_centroid(b, c);
+        const uint32_t prims = b.prims;
         TopBin*        bins  = sb + nd * (3u * HL_TOP_BINS);
         for (int ax = 0; ax < 3; ax++)
         {
@@ -239,7 +238,7 @@ __device__ __forceinline__ void top_assign_level_private(const BinaryTree& t, To
         if (nd == HL_TOP_DONE) continue;
         TopNode& N = tb.level[level & 1u][nd];
         float    c[3];
-        top_cluster_centroid(t, tb.cluster[i], c);
+        top_cluster_centroid(tb.crec[i], c);
         uint32_t side;
         if (__ldcg(&N.mode) == HL_TOP_MODE_BINNED)
         {
@@ -444,12 +443,13 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     const uint32_t k_cap    = resplit ? (uint32_t)std::min<uint64_t>(n, 4ull * n / C + 1024) : 0u;
     const uint32_t bins_cap = k_cap / (HL_TOP_SMALL + 1u) + 2u;
     const size_t   top_ctl_words = 8 + 2 * (HL_TOP_MAX_LEVELS + 1);
+    ScratchBuf     top_crec;
     ScratchBuf     top_clusters, top_free, top_cnode, top_level[2], top_bins[2], top_list, top_small, top_ctl, top_tmp, top_trace_buf;
     size_t         top_tmp_bytes = 0;
     int            top_grid      = 0;
     if (resplit)
     {
-        top_clusters.alloc(4ull * n, st), top_free.alloc(4ull * n, st), top_cnode.alloc(4ull * k_cap, st);
+        top_clusters.alloc(4ull * n, st), top_free.alloc(4ull * n, st), top_cnode.alloc(4ull * k_cap, st), top_crec.alloc(sizeof(TopCluster) * (size_t)k_cap, st);
         for (int p = 0; p < 2; p++)
         {
             top_level[p].alloc(sizeof(TopNode) * ((size_t)k_cap + 2), st);
@@ -518,7 +518,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         HL_CUDA(cub::DeviceSelect::If(top_tmp.p, top_tmp_bytes, ids, top_free.as<uint32_t>(), ctl + 1, (int)(n - 1), IsUpperNode { t, C }, st));
         TopBuild tb;
         tb.cluster_prims = C, tb.k_cap = k_cap, tb.bins_cap = bins_cap;
-        tb.n_clusters = ctl, tb.cluster = top_clusters.as<uint32_t>(), tb.free_nodes = top_free.as<uint32_t>(), tb.cnode = top_cnode.as<uint32_t>();
+        tb.n_clusters = ctl, tb.cluster = top_clusters.as<uint32_t>(), tb.free_nodes = top_free.as<uint32_t>(), tb.cnode = top_cnode.as<uint32_t>(), tb.crec = top_crec.as<TopCluster>();
         for (int p = 0; p < 2; p++) tb.level[p] = top_level[p].as<TopNode>(), tb.bins[p] = top_bins[p].as<TopBin>();
         tb.free_next   = ctl + 2;
         tb.list = top_list.as<uint32_t>(), tb.small = top_small.as<TopSmall>(), tb.small_count = ctl + 6;

@@ -178,7 +178,7 @@ struct hl_context_t
     hl::DevBuf               env_padded; // the same with the one-texel seamless border: what the kernels sample
     uint32_t                 env_size = 0;
     // scene tables
-    hl::DevBuf      materials, instances, inst_inv, submesh_info, submesh_offset, lights, mesh_views, tex_views_dev, lut8, inst_alpha, geom_alpha;
+    hl::DevBuf      materials, instances, inst_inv, submesh_info, submesh_offset, lights, mesh_views, tex_views_dev, lut8, inst_alpha, geom_alpha, inst_identity;
     hl::WideBVHDev  tlas;
     std::vector<hl_instance> h_instances; // the table as uploaded (mesh_index in context order): hl_scene_update_instances edits transforms in place
     std::vector<hl_mesh_t*>  h_inst_mesh; // mesh of every instance
@@ -235,6 +235,7 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
 void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc);
 void wavefront_output_buffer(hl_context_t* ctx, const hl_push_constants& pc, int which, float4* d_out); // debug output buffers
 void wavefront_debug_rays(hl_context_t* ctx, const hl_push_constants& pc, uint32_t n, float4* d_verts, uint32_t capacity, uint32_t* d_count); // ray debug view
+uint32_t wavefront_path_pixel(hl_context_t* ctx, uint32_t i); // path index -> row-major pixel index of a full-frame launch
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits);
 uint64_t trav_overflow_count(hl_context_t* ctx, bool reset);
 void film_clear(hl_context_t* ctx);

@@ -107,6 +107,8 @@ struct SceneView
     uint32_t           n_lights;
     uint32_t           single_identity; // 1: one instance with an identity transform -> BLAS traversed directly
     uint32_t           pad0 = 0;
+    const uint32_t*    inst_identity = nullptr; // bit i: instance i has an identity model matrix (object space = world space: entering and
+                                                // leaving it needs no ray transform and no new reciprocal direction); nullptr = none
     const InstAlpha*   inst_alpha = nullptr; // [n_instances] any-hit records (nullptr: the any-hit stage walks the vertex tables)
     const GeomAlpha*   geom_alpha = nullptr; // [sum of submesh counts] parallel to submesh_info
 };

@@ -49,7 +49,26 @@ struct FrameParams
 {
     hl_push_constants pc;
     uint32_t          lw, lh; // launch rectangle (already clipped to the image)
+    uint32_t          tiled;  // 1: path i covers pixel launch_pixel(i) in 8 x 4 tiles (lw % 8 == 0 and lh % 4 == 0), 0: row-major
 };
+// Path index -> pixel of the launch rectangle.  A warp's 32 consecutive paths cover an 8 x 4 pixel tile instead of a 32 x 1
+// strip whenever the rectangle allows it: the primary rays of a warp (and, because the queues are compacted in order, the
+// rays their paths spawn) stay close in BOTH image dimensions, so they visit the same nodes and the same materials.
+// The image does not depend on the mapping: every pixel's sample is a function of (pixel, frame index) alone.
+#ifndef HL_TILE_PATHS
+#define HL_TILE_PATHS 1
+#endif
+__host__ __device__ __forceinline__ void launch_pixel(uint32_t lw, uint32_t tiled, uint32_t i, uint32_t& x, uint32_t& y)
+{
+    if (tiled)
+    {
+        const uint32_t tile = i >> 5, w = i & 31u, tiles_x = lw >> 3;
+        x = (tile % tiles_x) * 8u + (w & 7u), y = (tile / tiles_x) * 4u + (w >> 3);
+    }
+    else
+        x = i % lw, y = i / lw;
+}
+static inline uint32_t launch_is_tiled(uint32_t lw, uint32_t lh) { return HL_TILE_PATHS && lw % 8u == 0u && lh % 4u == 0u ? 1u : 0u; }
 
 __device__ __forceinline__ float4 ld4(const float4* p) { return *p; }
 
@@ -68,7 +87,9 @@ __global__ void k_generate(FrameParams fp, float4* state_a, float4* state_b, flo
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) counters[CTR_EXT_COUNT] = n;
     if (i >= n) return;
-    const uint32_t px = fp.pc.launch_id_size[0] + i % fp.lw, py = fp.pc.launch_id_size[1] + i / fp.lw;
+    uint32_t lx, ly;
+    launch_pixel(fp.lw, fp.tiled, i, lx, ly);
+    const uint32_t px = fp.pc.launch_id_size[0] + lx, py = fp.pc.launch_id_size[1] + ly;
     Rng            rng = rng_seed(px, py, fp.pc.num_frames);
     f3             o, d;
     primary_ray(fp.pc, px, py, rng, o, d);
@@ -347,7 +368,9 @@ __global__ void k_resolve(FrameParams fp, const float4* __restrict__ state_b, fl
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t W = fp.pc.launch_id_size[2], H = fp.pc.launch_id_size[3];
-    const uint32_t px = fp.pc.launch_id_size[0] + i % fp.lw, py = fp.pc.launch_id_size[1] + i / fp.lw;
+    uint32_t       lx, ly;
+    launch_pixel(fp.lw, fp.tiled, i, lx, ly);
+    const uint32_t px = fp.pc.launch_id_size[0] + lx, py = fp.pc.launch_id_size[1] + ly;
     const size_t   pix = (size_t)py * W + px;
     const float4   sb  = state_b[i];
     const float4   pv  = accum[pix];
@@ -421,16 +444,18 @@ __global__ void __launch_bounds__(HL_TRACE_BLOCK) k_trace_generic(SceneView s, c
 // rasterises with debug_visualization.frag:144-161 — albedo, shading normal * 0.5 + 0.5, roughness, metallic,
 // emissive of the surface seen through each pixel — evaluated here on the primary hits with the path's own
 // surface fetch (path_trace_rchit.glsl:206-252 and debug_visualization.frag:74-135 are the same fetch_* functions).
-__global__ void k_output_buffer(SceneView s, const float4* __restrict__ hit_a, const uint2* __restrict__ hit_b, uint32_t n, int which, float4* __restrict__ out)
+__global__ void k_output_buffer(SceneView s, const float4* __restrict__ hit_a, const uint2* __restrict__ hit_b, uint32_t n, uint32_t W, uint32_t tiled, int which, float4* __restrict__ out)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
+        uint32_t x, y;
+        launch_pixel(W, tiled, i, x, y);
         const float4 ha = hit_a[i];
         const uint2  hb = hit_b[i];
         Hit          h;
         h.t = ha.x, h.u = ha.y, h.v = ha.z, h.primitive = __float_as_uint(ha.w), h.instance = hb.x, h.geometry = hb.y;
         const f4 c = output_buffer_value(s, h, which);
-        out[i] = make_float4(c.x, c.y, c.z, c.w);
+        out[(size_t)y * W + x] = make_float4(c.x, c.y, c.z, c.w);
     }
 }
 
@@ -704,7 +729,7 @@ void wavefront_render_frame(hl_context_t* ctx, const hl_push_constants& pc, uint
 {
     FrameParams fp;
     fp.pc = pc;
-    fp.lw = lw, fp.lh = lh;
+    fp.lw = lw, fp.lh = lh, fp.tiled = launch_is_tiled(lw, lh);
     const uint32_t n = lw * lh;
     if (n == 0) return;
     // max_ray_bounces = 0 still traces and shades the primary ray (rgen:205; the closest-hit shader only skips the indirect ray)
@@ -823,7 +848,7 @@ void wavefront_primary_hits(hl_context_t* ctx, const hl_push_constants& pc)
     FrameParams   fp;
     fp.pc = pc;
     fp.pc.launch_id_size[0] = fp.pc.launch_id_size[1] = 0;
-    fp.lw = ctx->W, fp.lh = ctx->H;
+    fp.lw = ctx->W, fp.lh = ctx->H, fp.tiled = launch_is_tiled(ctx->W, ctx->H);
     const uint32_t n   = fp.lw * fp.lh;
     uint32_t*      ctr = w.counters.as<uint32_t>();
     HL_CUDA(cudaMemsetAsync(ctr, 0, CTR_U32_TOTAL * 4, st));
@@ -836,7 +861,7 @@ void wavefront_output_buffer(hl_context_t* ctx, const hl_push_constants& pc, int
 {
     wavefront_primary_hits(ctx, pc);
     const uint32_t n = ctx->W * ctx->H;
-    k_output_buffer<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->view, ctx->slot[0].hit_a.as<float4>(), ctx->slot[0].hit_b.as<uint2>(), n, which, d_out);
+    k_output_buffer<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->view, ctx->slot[0].hit_a.as<float4>(), ctx->slot[0].hit_b.as<uint2>(), n, ctx->W, launch_is_tiled(ctx->W, ctx->H), which, d_out);
     ctx->launches++;
 }
 
@@ -862,6 +887,14 @@ uint64_t trav_overflow_count(hl_context_t* ctx, bool reset)
         HL_CUDA(cudaMemcpyToSymbolAsync(g_trav_overflow, &z, sizeof(z), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
     return n;
+}
+
+// pixel (row-major index) of path i of a full-frame launch: hl_trace_primary_ids reorders the hit records with it
+uint32_t wavefront_path_pixel(hl_context_t* ctx, uint32_t i)
+{
+    uint32_t x, y;
+    launch_pixel(ctx->W, launch_is_tiled(ctx->W, ctx->H), i, x, y);
+    return y * ctx->W + x;
 }
 
 void wavefront_trace_rays(hl_context_t* ctx, const float* d_rays, uint32_t n, uint32_t flags, void* d_hits)

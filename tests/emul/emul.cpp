@@ -50,6 +50,7 @@ static void refine_top(BinaryTree& t, uint32_t C)
         if (top_is_upper_node(t, m, C)) upper.push_back(m);
     const uint32_t K = (uint32_t)clusters.size();
     if (K < 2 || upper.size() != K - 1 || upper[0] != 0u) abort();
+    std::vector<TopCluster> crec(K);
     std::vector<uint32_t> cnode(K), level_count(HL_TOP_MAX_LEVELS + 1, 0), bins_used(HL_TOP_MAX_LEVELS + 1, 0);
     std::vector<TopNode>  lv[2] = { std::vector<TopNode>(K + 2), std::vector<TopNode>(K + 2) };
     const uint32_t        bins_cap = K / (HL_TOP_SMALL + 1) + 2;
@@ -60,7 +61,7 @@ static void refine_top(BinaryTree& t, uint32_t C)
     uint32_t free_next = 0, kdev = K;
     TopBuild tb;
     tb.cluster_prims = C, tb.k_cap = K, tb.bins_cap = bins_cap, tb.n_clusters = &kdev, tb.cluster = clusters.data(), tb.free_nodes = upper.data();
-    tb.cnode = cnode.data(), tb.level[0] = lv[0].data(), tb.level[1] = lv[1].data(), tb.bins[0] = bins[0].data(), tb.bins[1] = bins[1].data();
+    tb.cnode = cnode.data(), tb.crec = crec.data(), tb.level[0] = lv[0].data(), tb.level[1] = lv[1].data(), tb.bins[0] = bins[0].data(), tb.bins[1] = bins[1].data();
     tb.list = list.data(), tb.small = small.data(), tb.small_count = &small_count;
     tb.level_count = level_count.data(), tb.bins_used = bins_used.data(), tb.free_next = &free_next;
     top_begin(tb, K);
@@ -163,6 +164,7 @@ struct EmScene
     std::vector<hl_light>    lights;
     std::vector<uint32_t>    submesh_info, submesh_offset;
     std::vector<float>       inst_inv;
+    std::vector<uint32_t>    inst_identity;
     std::vector<InstAlpha>   inst_alpha;
     std::vector<GeomAlpha>   geom_alpha;
     std::vector<MeshView>    mesh_views;
@@ -339,6 +341,13 @@ EM_API void em_scene_set_tables(EmScene* s, const hl_material* mats, uint32_t nm
         s->inst_alpha[i].alpha = m.alpha.empty() ? nullptr : m.alpha.data(), s->inst_alpha[i].tris = m.bvh.tris.data(), s->inst_alpha[i].info_base = s->submesh_offset[i];
     }
     v.inst_alpha = s->inst_alpha.data(), v.geom_alpha = s->geom_alpha.data();
+    s->inst_identity.assign((ni + 31) / 32 + 1, 0u);
+    for (uint32_t i = 0; i < ni; i++)
+    {
+        static const float I[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+        if (memcmp(inst[i].model_matrix, I, 64) == 0) s->inst_identity[i >> 5] |= 1u << (i & 31);
+    }
+    v.inst_identity = s->inst_identity.data();
 }
 EM_API void em_scene_force_two_level(EmScene* s) { s->view.single_identity = 0; }
 // hl_scene_update_instances on the host: new transforms, instance tree REFITTED with the product's per-node functions
@@ -385,6 +394,13 @@ EM_API int em_scene_update_instances(EmScene* s, const hl_instance* inst, uint32
     }
     for (size_t i = 0; i < nodes.size(); i++) refit_requantize(nodes[i], nb[i], s->tlas.inst_leaf.data(), iboxes.data(), nb.data());
     s->view.single_identity = identity ? 1u : 0u;
+    s->inst_identity.assign((ni + 31) / 32 + 1, 0u);
+    for (uint32_t i = 0; i < ni; i++)
+    {
+        static const float I[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+        if (memcmp(inst[i].model_matrix, I, 64) == 0) s->inst_identity[i >> 5] |= 1u << (i & 31);
+    }
+    s->view.inst_identity = s->inst_identity.data();
     return 0;
 }
 

@@ -22,7 +22,12 @@ for l in dis:
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         addr2line[int(m.group(1), 16)] = (cur, m.group(2))
-rows = list(csv.reader(open(sass_csv)))
+_lines = open(sass_csv).read().splitlines()
+import os
+_starts = [i for i, l in enumerate(_lines) if l.startswith('"Address"')] + [len(_lines) + 1]
+_sec = int(os.environ.get("NCU_SECTION", "0"))  # an export can hold several launches: NCU_SECTION picks one
+_lines = _lines[_starts[_sec]:_starts[_sec + 1] - 1]  # (the kernel-name line may be cut mid-quote by a column filter)
+rows = list(csv.reader(_lines))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]
 iA, iE, iT, iS = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
@@ -30,7 +35,7 @@ base = None
 agg = defaultdict(lambda: [0, 0, 0])
 tot = 0
 for r in rows[h + 1:]:
-    if len(r) != len(hdr) or r[0] == "Address":
+    if len(r) <= max(iA, iE, iT, iS) or r[0] == "Address":
         continue
     a = int(r[iA], 16)
     if base is None:

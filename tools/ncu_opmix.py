@@ -7,14 +7,19 @@ from collections import defaultdict
 
 f = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 28
-rows = list(csv.reader(open(f)))
+_lines = open(f).read().splitlines()
+import os
+_starts = [i for i, l in enumerate(_lines) if l.startswith('"Address"')] + [len(_lines) + 1]
+_sec = int(os.environ.get("NCU_SECTION", "0"))  # an export can hold several launches: NCU_SECTION picks one
+_lines = _lines[_starts[_sec]:_starts[_sec + 1] - 1]
+rows = list(csv.reader(_lines))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]
 iS, iE, iT = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
 agg = defaultdict(lambda: [0, 0])
 tot = tt = 0
 for r in rows[h + 1:]:
-    if len(r) != len(hdr) or r[0] == "Address":
+    if len(r) <= max(iS, iE, iT) or r[0] == "Address":
         continue
     m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[iS].strip())
     op = m.group(2) if m else r[iS].strip()[:10]
