@@ -95,6 +95,21 @@ bool convert_image_level0(const ast::Image& image, int array_slice, bool srgb, i
     {
         // kCompressedFormats: BC4 / BC5 / BC6H have no sRGB variant (VK_FORMAT_UNDEFINED)
         if (srgb && (image.compression == ast::COMPRESSION_BC4 || image.compression == ast::COMPRESSION_BC5 || image.compression == ast::COMPRESSION_BC6)) return false;
+        if (image.compression == ast::COMPRESSION_BC6)
+        {
+            // VK_FORMAT_BC6H_UFLOAT_BLOCK (kCompressedFormats): HDR, expanded to RGBA32F texels (alpha 1)
+            std::vector<uint16_t> half;
+            if (!decode_bc6h(L.bytes.data(), L.bytes.size(), w, h, false, half)) return false;
+            fmt = HL_TEX_RGBA32F;
+            out.resize(n * 16);
+            float* dst = (float*)out.data();
+            for (size_t i = 0; i < n; i++)
+            {
+                for (int k = 0; k < 3; k++) dst[i * 4 + (size_t)k] = half_to_float(half[i * 3 + (size_t)k]);
+                dst[i * 4 + 3] = 1.0f;
+            }
+            return true;
+        }
         if (!decode_bc((int)image.compression, L.bytes.data(), L.bytes.size(), w, h, out)) return false;
         fmt = srgb ? HL_TEX_RGBA8_SRGB : HL_TEX_RGBA8_UNORM;
         return true;

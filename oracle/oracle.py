@@ -85,6 +85,17 @@ def build_ref_scene(force: bool = False):
     return (_REF_SCENE_TOOL if _REF_SCENE_TOOL.exists() else None, _REF_GLM_PIN if _REF_GLM_PIN.exists() else None)
 
 
+_REF_BC_TOOL = _HERE / "_ref" / "ref_bc_tool"
+
+
+def build_ref_bc(force: bool = False):
+    """(Re)build oracle/_ref/ref_bc_tool (BC7 / BC6H decoding by the nvidia-texture-tools sources AssetCore vendors, compiled
+    where they lie) where the reference checkout is mounted; elsewhere the prebuilt file is used.  Path, or None."""
+    if Path("/root/reference/external/AssetCore/external/nvidia-texture-tools/src/bc7/avpcl.cpp").is_file():
+        subprocess.check_call(["make", "-C", str(_HERE), "-s", "ref_bc"] + (["-B"] if force else []))
+    return _REF_BC_TOOL if _REF_BC_TOOL.exists() else None
+
+
 def ref_lib():
     """ctypes handle of the reference-GLSL library (contains the restatement's or_* entry points as well), or None"""
     global _ref_lib
