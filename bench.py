@@ -64,11 +64,16 @@ class ClockSampler:
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_indices):
+        """one nvidia-smi poller for all the GPUs of the job (started by rank 0 only: N pollers at 10 Hz were N processes
+        taking driver locks while N ranks enqueue ~700 launches per second each)"""
         self.proc = None
         self.lines = []
+        if not gpu_indices:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(g) for g in gpu_indices), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -329,6 +334,7 @@ def main():
         # ranks), then the collective timed ALONE: barrier first, so the number is the reduction, not straggler wait
         for _ in range(W):
             ctx.accum_all_reduce()
+            ctx.accum_reduce(0)  # (ncclReduce connects its own channels on first use: ~1 s at 8 ranks when left inside the e2e region)
         ms_coll = []
         for _ in range(5):
             barrier()
@@ -344,15 +350,23 @@ def main():
     ctx.reset_counters()
     launches0 = ctx.kernel_launches()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])
+    if rank == 0:
+        time.sleep(0.3)  # (the poller's NVML start-up stays outside the timed region)
+    barrier()
     t0 = time.time()
     ctx.event_record(0)
     for s in range(K):
         ctx.render_frame(pcs[s])
+    t_enq = time.time() - t0
+    ctx.event_record(6)
     if dist is not None:
         ctx.accum_all_reduce()  # asynchronous, on the library's stream behind the frames in flight
     ctx.event_record(1)
     ms_total = ctx.event_elapsed_ms(0, 1)
+    if os.environ.get("HL_BENCH_DEBUG"):
+        print(f"[rank {rank}] device leg: {K} frames enqueued in {t_enq * 1e3:.2f} ms host time, frames {ctx.event_elapsed_ms(0, 6):.2f} ms + reduce {ctx.event_elapsed_ms(6, 1):.3f} ms on the device; "
+              f"cpus {host_threads()} of {os.cpu_count()}", file=sys.stderr, flush=True)
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
@@ -413,12 +427,15 @@ def main():
         # (every step's image reaches the host; the copy of step s overlaps the rendering of step s + 1).  N > 1: the image is
         # the rank's own progressive preview (sum / frames so far)
         ctx.render_frame_readback(pc, host_ring[s % 8], 1.0, abi.TONE_MAP_ACES)
+    t_e2e_enq = time.time() - te0
     if dist is not None:
         ctx.accum_reduce(0)  # the one collective, asynchronous on the library's stream
         if rank == 0:
             ctx.tonemap(1.0, abi.TONE_MAP_ACES, sample_scale=1.0 / (world * K), out=final_img)  # final picture on the host (synchronises)
     barrier()
     te = time.time() - te0
+    if os.environ.get("HL_BENCH_DEBUG"):
+        print(f"[rank {rank}] e2e leg: {K} steps enqueued in {t_e2e_enq * 1e3:.2f} ms host time, whole region {te * 1e3:.2f} ms", file=sys.stderr, flush=True)
     ce = ctx.counters()
     rays_e = float(ce["extension_rays"] + ce["shadow_rays"])
     (te,), (rays_e,) = max_sum([te], [rays_e])
@@ -455,7 +472,8 @@ def main():
         ctx.accum_clear()
         ctx.reset_counters()
         barrier()
-        samp2 = ClockSampler(local_rank)
+        samp2 = ClockSampler([local_rank])
+        time.sleep(0.3)
         ts0 = time.time()
         ctx.event_record(4)
         for s in range(n_sus):
