@@ -57,6 +57,25 @@ def build_library(force: bool = False, verbose: bool = False, defines: list[str]
     return lib
 
 
+TEST_VARIANTS = {
+    # a 3-entry traversal stack: tests/test_gpu_edges.py checks that overflows are counted and hl_get_counters fails loudly
+    "stack3": ["-DHL_STACK_FAST=2", "-DHL_STACK_SPILL=1"],
+}
+
+
+def build_test_variants(force: bool = False) -> dict:
+    """test-only builds of the library with other compile-time constants, in-tree (tests/_variants/, git-ignored) so that
+    they travel to the GPU box with the snapshot"""
+    out = {}
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + [ROOT.parent / "include" / "helios_b200.h"]
+    for name, defines in TEST_VARIANTS.items():
+        lib = ROOT.parent / "tests" / "_variants" / f"libhelios_b200_{name}.so"
+        if force or not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
+            build_library(force=True, defines=defines, out=lib)
+        out[name] = lib
+    return out
+
+
 SHIM = ROOT / "shim"
 ENGINE_LIB = ROOT / "libhelios_engine.so"
 HEADLESS = ROOT / "helios_headless"

@@ -396,6 +396,21 @@ HL_HD int top_bin_of(float c, float lo, float hi)
     int b = (int)((c - lo) / ext * (float)HL_TOP_BINS);
     return b < 0 ? 0 : (b >= HL_TOP_BINS ? HL_TOP_BINS - 1 : b);
 }
+// HL_TOP_ONE_AXIS_BELOW: nodes with fewer clusters than this are binned along the longest axis of their centroid bounds
+// only (a third of the atomics of the BIN phase); 0 = every node sweeps all three axes.  Default: every node.  Measured
+// (profiles/r02h_one_axis_binning.log): build 4.04 -> 3.45 ms at 1M triangles, 20.2 -> 17.4 ms at 10M; SAH cost of the
+// terrain 11.20 -> 11.35 with the frame time inside the run-to-run noise (1.52-1.56 ms), and the city's frame 8.65 ->
+// 7.98 ms (its box-shaped building meshes get more regular trees from longest-axis planes than from the 3-axis SAH pick).
+#ifndef HL_TOP_ONE_AXIS_BELOW
+#define HL_TOP_ONE_AXIS_BELOW 0xFFFFFFFFu
+#endif
+HL_HD int top_bin_axis(const TopNode& N)
+{
+    if (HL_TOP_ONE_AXIS_BELOW == 0u || hl_load_cg(&N.count) >= HL_TOP_ONE_AXIS_BELOW) return -1;
+    float e[3];
+    for (int k = 0; k < 3; k++) e[k] = ord2f(hl_load_cg(&N.cb_hi[k])) - ord2f(hl_load_cg(&N.cb_lo[k]));
+    return e[0] >= e[1] && e[0] >= e[2] ? 0 : (e[1] >= e[2] ? 1 : 2);
+}
 // dst.lo = min(dst.lo, vlo), dst.hi = max(dst.hi, vhi), optional counters += (prims, 1).  On the GPU the lanes
 // of a warp that arrive here together with the same destination (the common case near the root: clusters are
 // in Morton order, so neighbours share node and bin) are combined with warp reductions into one set of atomics
@@ -533,8 +548,10 @@ HL_HD void top_bin_cluster(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t
     for (int k = 0; k < 3; k++) olo[k] = f2ord(b.lo[k]), ohi[k] = f2ord(b.hi[k]);
     const uint32_t prims = b.prims;
     TopBin*        bins  = tb.bins[level & 1u] + (size_t)hl_load_cg(&N.bins) * (3 * HL_TOP_BINS);
+    const int      only  = top_bin_axis(N);
     for (int ax = 0; ax < 3; ax++)
     {
+        if (only >= 0 && ax != only) continue;
         const int bi = top_bin_of(c[ax], ord2f(hl_load_cg(&N.cb_lo[ax])), ord2f(hl_load_cg(&N.cb_hi[ax])));
         if (bi < 0) continue;
         TopBin& B = bins[ax * HL_TOP_BINS + bi];
@@ -551,9 +568,19 @@ HL_HD void top_small_node(BinaryTree& t, TopBuild& tb, uint32_t record, uint32_t
     uint32_t       ids[HL_TOP_SMALL], pr[HL_TOP_SMALL];
     Box            bx[HL_TOP_SMALL];
     uint8_t        ord[HL_TOP_SMALL]; // permutation of the clusters; sub-ranges of it are the nodes being built
+    // the clusters registered in arrival order (an atomic ticket): sort them by cluster index first, so that the subtree —
+    // ties between equal centroids included — is a function of the SET of clusters, not of the scheduling of one run
+    uint32_t idx[HL_TOP_SMALL];
     for (uint32_t k = 0; k < count; k++)
     {
-        ids[k] = tb.cluster[hl_load_cg(tb.list + list_base + k)];
+        const uint32_t v = hl_load_cg(tb.list + list_base + k);
+        int            j = (int)k - 1;
+        while (j >= 0 && idx[j] > v) idx[j + 1] = idx[j], j--;
+        idx[j + 1] = v;
+    }
+    for (uint32_t k = 0; k < count; k++)
+    {
+        ids[k] = tb.cluster[idx[k]];
         bx[k] = t.box[ids[k]], pr[k] = subtree_prims(t, ids[k]), ord[k] = (uint8_t)k;
     }
     uint32_t       used = 0;

@@ -207,8 +207,10 @@ __device__ __forceinline__ void top_bin_level_private(BinaryTree& t, TopBuild& t
         top_cluster_centroid(b, c);
         const uint32_t prims = b.prims;
         TopBin*        bins  = sb + nd * (3u * HL_TOP_BINS);
+        const int      only  = top_bin_axis(N);
         for (int ax = 0; ax < 3; ax++)
         {
+            if (only >= 0 && ax != only) continue;
             const int bi = top_bin_of(c[ax], ord2f(__ldcg(&N.cb_lo[ax])), ord2f(__ldcg(&N.cb_hi[ax])));
             if (bi < 0) continue;
             TopBin& B = bins[ax * HL_TOP_BINS + bi];

@@ -632,6 +632,13 @@ EM_API void em_traversal_stats(const EmScene* s, const float* rays, uint32_t n, 
     }
     out[0] = nodes, out[1] = leaves, out[2] = worst;
 }
+// traversal-stack overflows counted so far (hl_bvh.h note_stack_overflow; the counter is not thread safe on the host: use with one thread)
+EM_API uint64_t em_stack_overflows(int reset)
+{
+    const uint64_t n = emul_trav_overflow();
+    if (reset) emul_trav_overflow() = 0;
+    return n;
+}
 EM_API void em_tonemap(const float* accum, uint32_t W, uint32_t H, float exposure, int op, float scale, uint8_t* out)
 {
     for (uint32_t r = 0; r < H; r++)

@@ -492,3 +492,50 @@ def test_instance_tree_refit_equals_rebuild(emul):
             assert np.array_equal(x, y)
         assert np.array_equal(e.render(3), fresh.render(3))
     assert (a[0] != 0xFFFFFFFF).mean() > 0.3
+
+
+def test_traversal_stack_overflow_is_counted_and_memory_safe(tmp_path):
+    """hl_bvh.h TravStack: an entry that does not fit is dropped and COUNTED (hl_get_counters fails loudly on the GPU while the
+    count is non-zero), an instance whose sentinel would not fit is skipped — nothing dropped is ever popped.  Forced here by
+    compiling the device headers with a 3- and a 2-entry stack in a subprocess: the render must
+    finish, report overflows, and with the normal 64-entry stack the same scene must report none."""
+    import subprocess
+    import sys
+    import textwrap
+    from pathlib import Path
+
+    prog = textwrap.dedent(
+        """
+        import sys, ctypes as C
+        sys.path.insert(0, %r)
+        import numpy as np
+        from helios_b200 import scenes
+        from tests.emul import emul
+        s = scenes.city_scene(n_instances=30, n_meshes=3, width=48, height=27, floors=(2, 5), detail=(2, 3))
+        e = emul.EmulScene(s)
+        L = emul.lib()
+        L.em_stack_overflows.restype = C.c_uint64
+        L.em_stack_overflows(C.c_int(1))
+        a = e.render(2)
+        print(int(L.em_stack_overflows(C.c_int(0))), int(np.isfinite(a).all()))
+        """
+        % str(Path(__file__).resolve().parent.parent)
+    )
+    import os
+
+    def run(flags):
+        env = dict(os.environ, OMP_NUM_THREADS="1")
+        if flags:
+            env["HL_EMUL_CXXFLAGS"] = flags
+        else:
+            env.pop("HL_EMUL_CXXFLAGS", None)
+        r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [int(x) for x in r.stdout.split()]
+
+    lost, finite = run("-DHL_STACK_FAST=2 -DHL_STACK_SPILL=1")  # 3 entries: an instance fits (sentinel + 2), deeper pushes are dropped
+    assert lost > 0 and finite == 1
+    lost, finite = run("-DHL_STACK_FAST=1 -DHL_STACK_SPILL=1")  # 2 entries: no instance can be entered (its sentinel would not fit)
+    assert lost > 0 and finite == 1
+    lost, finite = run("")
+    assert lost == 0 and finite == 1
