@@ -77,20 +77,50 @@ HL_HD void note_stack_overflow()
     emul_trav_overflow()++;
 #endif
 }
-// traversal stack: the first HL_STACK_FAST entries live in `fast` (shared memory on the GPU,
-// interleaved with `stride` so that a warp's accesses are conflict-free), deeper entries spill.
+// traversal stack: the first HL_STACK_FAST entries live in fast memory, deeper entries spill to thread-local memory.
+// GPU: the fast part is ONE block-wide array in shared memory (entry k of thread t at [k * HL_TRACE_BLOCK + t]: a warp's
+// accesses are conflict-free), named directly so that every access is one LDS.64 / STS.64, and the struct holds nothing but
+// scalars and a pointer to the caller's spill array — it stays in registers.  (Round 2, from the SASS: with the spill array
+// INSIDE the struct the whole struct lived in local memory, and every push / pop re-loaded the stack pointer, the base
+// pointer and the stride from there and went through generic 32-bit loads.)
+#ifndef HL_TRACE_BLOCK
+#define HL_TRACE_BLOCK 128 /* threads per block of every kernel that traces */
+#endif
+#if defined(__CUDACC__)
+static __shared__ u2 g_trav_fast[HL_STACK_FAST * HL_TRACE_BLOCK];
+#endif
 struct TravStack
 {
-    u2* fast;
-    int stride;
-    int sp;
+#if defined(__CUDA_ARCH__)
+    uint32_t fast; // shared-space byte address of this thread's entry 0 (entries HL_TRACE_BLOCK * 8 bytes apart)
+#else
+    u2* fast; // host (emulator): HL_STACK_FAST entries
+#endif
+    int      sp;
     uint8_t* pairs; // GPU: HL_COOP_TABLE bytes of shared memory per WARP (cooperative triangle phase, coop_triangles below)
-    u2  spill[HL_STACK_SPILL];
+    u2*      spill; // HL_STACK_SPILL entries of the caller's thread-local memory
+    HL_HD void init(u2* spill_mem, u2* host_fast)
+    {
+#if defined(__CUDA_ARCH__)
+        fast = (uint32_t)__cvta_generic_to_shared(&g_trav_fast[threadIdx.x]);
+        (void)host_fast;
+#else
+        fast = host_fast;
+#endif
+        sp = 0, spill = spill_mem, pairs = nullptr;
+    }
     HL_HD bool has_room(int n) const { return sp + n <= HL_STACK_FAST + HL_STACK_SPILL; }
     HL_HD void push(u2 e)
     {
         if (sp < HL_STACK_FAST)
-            fast[sp * stride] = e;
+        {
+#if defined(__CUDA_ARCH__)
+            // (volatile keeps the stack's accesses in program order among themselves; nothing else touches this memory)
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(fast + (uint32_t)sp * (HL_TRACE_BLOCK * 8u)), "r"(e.x), "r"(e.y));
+#else
+            fast[sp] = e;
+#endif
+        }
         else if (sp - HL_STACK_FAST < HL_STACK_SPILL)
             spill[sp - HL_STACK_FAST] = e;
         else
@@ -103,7 +133,16 @@ struct TravStack
     HL_HD u2 pop()
     {
         sp--;
-        if (sp < HL_STACK_FAST) return fast[sp * stride];
+        if (sp < HL_STACK_FAST)
+        {
+#if defined(__CUDA_ARCH__)
+            u2 e;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(fast + (uint32_t)sp * (HL_TRACE_BLOCK * 8u)));
+            return e;
+#else
+            return fast[sp];
+#endif
+        }
         return spill[sp - HL_STACK_FAST];
     }
 };
@@ -156,11 +195,15 @@ HL_HD U4 load_u4(const void* p)
     return r;
 #endif
 }
-// Quantised plane byte -> t in two instructions: one PRMT drops byte i of `word` into mantissa bits 8..15
-// of 1.0f, giving F = 1 + b * 2^-15 exactly, and one FMA evaluates F * A + B with A = adj * 2^15 and
-// B = (org -+ slack) - A, i.e. b * adj + org -+ slack.  The only new error is the rounding of B
-// (<= 2^-24 |org| + 2^-9 |adj|), which the slack below absorbs.
-HL_HD float plane_t(uint32_t word, int i, float A, float B) { return hl_fma(u2f(hl_prmt(word, 0x3F800000u, 0x7604u | ((uint32_t)i << 4))), A, B); }
+// Quantised plane byte -> t in two instructions: one PRMT drops byte i of `word` into mantissa bits 8..15 of the axis'
+// scale 2^(e-127) (`E` = e << 23, the node's exponent byte in place), giving F = 2^(e-127) * (1 + b * 2^-15) exactly, and
+// one FMA evaluates F * A + B with A = idir * 2^15 and B = (org -+ slack) - 2^(e-127) * A, i.e. b * 2^(e-127) * idir + org
+// -+ slack.  The only new error is the rounding of B (<= 2^-24 |org| + 2^-9 |adj|), which the slack below absorbs.  A flat
+// axis (e = 0, all bytes 0) gives F = 0 and t = B = org -+ slack.  (Round 2: the PRMT used to merge the byte into the
+// CONSTANT 1.0f; with two immediates — selector and constant — ptxas kept the selector in a register and re-materialised it
+// before nearly every PRMT: 43 of the 311 instructions of a node visit were such moves.  With the exponent word as the
+// second source the selector is the only immediate.)
+HL_HD float plane_t(uint32_t word, int i, uint32_t E, float A, float B) { return hl_fma(u2f(hl_prmt(word, E, 0x7604u | ((uint32_t)i << 4))), A, B); }
 
 // Tests the 8 quantised child boxes of one node (five 16-byte loads); returns the hit mask: bits 24..31 =
 // internal children in octant-permuted order (highest bit = visit first), bits 0..23 = leaf primitives.
@@ -172,9 +215,8 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
     const U4 n3 = load_u4((const char*)node + 48);
     const U4 n4 = load_u4((const char*)node + 64);
     child_base  = n1.x, leaf_base = n1.y, imask = n0.w >> 24;
-    const float adjx = u2f((n0.w & 0xFFu) << 23) * r.idir.x;
-    const float adjy = u2f(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
-    const float adjz = u2f(((n0.w >> 16) & 0xFFu) << 23) * r.idir.z;
+    const uint32_t Ex = (n0.w << 23) & 0x7F800000u, Ey = (n0.w << 15) & 0x7F800000u, Ez = (n0.w << 7) & 0x7F800000u;
+    const float    adjx = u2f(Ex) * r.idir.x, adjy = u2f(Ey) * r.idir.y, adjz = u2f(Ez) * r.idir.z;
     const float dx = u2f(n0.x) - r.o.x, dy = u2f(n0.y) - r.o.y, dz = u2f(n0.z) - r.o.z;
     const float orgx = dx * r.idir.x, orgy = dy * r.idir.y, orgz = dz * r.idir.z;
     // conservative per-axis slack (in t): covers the rounding of org/adj/B/fma and the fact that the fp32
@@ -201,7 +243,8 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
     const float sx = C * (fabsf(r.idir.x) * D + 192.0f * fabsf(adjx));
     const float sy = C * (fabsf(r.idir.y) * D + 192.0f * fabsf(adjy));
     const float sz = C * (fabsf(r.idir.z) * D + 192.0f * fabsf(adjz));
-    const float Ax = adjx * 32768.0f, Ay = adjy * 32768.0f, Az = adjz * 32768.0f;
+    const float Ax = adjx * 32768.0f, Ay = adjy * 32768.0f, Az = adjz * 32768.0f;             // 2^(e-127) * A of plane_t
+    const float Rx = r.idir.x * 32768.0f, Ry = r.idir.y * 32768.0f, Rz = r.idir.z * 32768.0f; // A of plane_t
     const float Bnx = (orgx - sx) - Ax, Bfx = (orgx + sx) - Ax;
     const float Bny = (orgy - sy) - Ay, Bfy = (orgy + sy) - Ay;
     const float Bnz = (orgz - sz) - Az, Bfz = (orgz + sz) - Az;
@@ -230,8 +273,8 @@ HL_HD uint32_t intersect_children(const WideNode* node, const RayCtx& r, float t
 #endif
         for (int j = 0; j < 4; j++)
         {
-            const float tnear = fmaxf(fmaxf(plane_t(nearx, j, Ax, Bnx), plane_t(neary, j, Ay, Bny)), fmaxf(plane_t(nearz, j, Az, Bnz), tmin));
-            const float tfar  = fminf(fminf(plane_t(farx, j, Ax, Bfx), plane_t(fary, j, Ay, Bfy)), fminf(plane_t(farz, j, Az, Bfz), tbest));
+            const float tnear = fmaxf(fmaxf(plane_t(nearx, j, Ex, Rx, Bnx), plane_t(neary, j, Ey, Ry, Bny)), fmaxf(plane_t(nearz, j, Ez, Rz, Bnz), tmin));
+            const float tfar  = fminf(fminf(plane_t(farx, j, Ex, Rx, Bfx), plane_t(fary, j, Ey, Ry, Bfy)), fminf(plane_t(farz, j, Ez, Rz, Bfz), tbest));
             if (tnear <= tfar) hitmask |= hl_prmt(cnt4, 0u, 0x4440u | (uint32_t)j) << hl_prmt(bit4, 0u, 0x4440u | (uint32_t)j);
         }
     }
@@ -344,25 +387,43 @@ struct Trav
     Hit             best; // instance == HL_MISS when nothing was hit
 };
 
-HL_HD void trav_begin(const SceneView& s, Trav& t, TravStack& st, bool active, f3 o, float tmin, f3 d, float tmax, uint32_t flags)
+// where every query of a scene starts: the top-level tree, or — a scene of one identity instance — that instance's mesh.
+// Scene-wide, so the persistent kernels look it up once per thread instead of once per ray (three dependent loads).
+struct TravStart
 {
-    t.best.t = tmax, t.best.u = 0.0f, t.best.v = 0.0f;
-    t.best.instance = t.best.geometry = t.best.primitive = HL_MISS;
-    st.sp = 0;
-    t.ngroup.x = 0, t.ngroup.y = 0, t.tgroup.x = 0, t.tgroup.y = 0;
-    t.o = o, t.d = d, t.tmin = tmin, t.tmax = tmax, t.flags = flags;
-    t.r     = make_ray_ctx(o, d);
-    t.nodes = s.tlas_nodes, t.tris = nullptr, t.inst = HL_MISS;
-    if (active && s.n_instances != 0)
+    const WideNode* nodes;
+    const LeafTri*  tris;
+    uint32_t        inst, ngroup_y; // ngroup_y == 0: nothing to traverse
+};
+HL_HD TravStart trav_start(const SceneView& s)
+{
+    TravStart b;
+    b.nodes = s.tlas_nodes, b.tris = nullptr, b.inst = HL_MISS, b.ngroup_y = 0;
+    if (s.n_instances != 0)
     {
         if (s.single_identity)
         {
             const MeshView& mesh = s.meshes[s.instances[0].mesh_index];
-            if (mesh.n_tris != 0) t.nodes = mesh.nodes, t.tris = mesh.tris, t.inst = 0, t.ngroup.y = 0x80000000u;
+            if (mesh.n_tris != 0) b.nodes = mesh.nodes, b.tris = mesh.tris, b.inst = 0, b.ngroup_y = 0x80000000u;
         }
         else
-            t.ngroup.y = 0x80000000u;
+            b.ngroup_y = 0x80000000u;
     }
+    return b;
+}
+HL_HD void trav_begin(const TravStart& b, Trav& t, TravStack& st, bool active, f3 o, float tmin, f3 d, float tmax, uint32_t flags)
+{
+    t.best.t = tmax, t.best.u = 0.0f, t.best.v = 0.0f;
+    t.best.instance = t.best.geometry = t.best.primitive = HL_MISS;
+    st.sp = 0;
+    t.ngroup.x = 0, t.ngroup.y = active ? b.ngroup_y : 0u, t.tgroup.x = 0, t.tgroup.y = 0;
+    t.o = o, t.d = d, t.tmin = tmin, t.tmax = tmax, t.flags = flags;
+    t.r     = make_ray_ctx(o, d);
+    t.nodes = b.nodes, t.tris = b.tris, t.inst = b.inst;
+}
+HL_HD void trav_begin(const SceneView& s, Trav& t, TravStack& st, bool active, f3 o, float tmin, f3 d, float tmax, uint32_t flags)
+{
+    trav_begin(trav_start(s), t, st, active, o, tmin, d, tmax, flags);
 }
 HL_HD bool trav_busy(const Trav& t, const TravStack& st) { return t.ngroup.y > 0x00FFFFFFu || t.tgroup.y != 0 || st.sp > 0; }
 

@@ -37,7 +37,7 @@ struct f4
 {
     float x, y, z, w;
 };
-struct u2
+struct alignas(8) u2 // (8-byte aligned: one 64-bit shared / local memory access per traversal stack entry)
 {
     uint32_t x, y;
 };

@@ -19,9 +19,6 @@
 
 namespace hl
 {
-#ifndef HL_TRACE_BLOCK
-#define HL_TRACE_BLOCK 128
-#endif
 // register cap of the persistent trace kernels.  Measured on configs[1] (tools/tune_trace.py, set "occ"): the
 // compiler's own choice under __launch_bounds__(128) — 72 registers, 7 CTAs/SM — 1.81 ms/frame; capped to 64
 // (8 CTAs/SM, spills) 1.89 ms; uncapped (113 registers, 4 CTAs/SM) 2.21 ms.
@@ -75,10 +72,10 @@ __device__ __forceinline__ float4 ld4(const float4* p) { return *p; }
 // shared memory of a kernel that traces: HL_STACK_FAST stack entries per thread + the pair table of the warp-cooperative
 // triangle phase (hl_bvh.h coop_triangles) per warp
 #define HL_TRACE_SHARED(st)                                                                   \
-    __shared__ u2      stack_mem[HL_STACK_FAST * HL_TRACE_BLOCK];                             \
     __shared__ uint8_t pair_mem[HL_COOP_TABLE * (HL_TRACE_BLOCK / 32)];                       \
+    u2                 spill_mem[HL_STACK_SPILL];                                             \
     TravStack          st;                                                                    \
-    st.fast = stack_mem + threadIdx.x, st.stride = HL_TRACE_BLOCK, st.sp = 0, st.pairs = pair_mem + HL_COOP_TABLE * (threadIdx.x >> 5)
+    st.init(spill_mem, nullptr), st.pairs = pair_mem + HL_COOP_TABLE * (threadIdx.x >> 5)
 
 // ---- generate --------------------------------------------------------------------------------------
 __global__ void k_generate(FrameParams fp, float4* state_a, float4* state_b, float4* ext_o, float4* ext_d, uint32_t* counters)
@@ -113,7 +110,8 @@ __device__ __forceinline__ void trace_queue(const SceneView& s, const Q& q, uint
 {
     const uint32_t lane = threadIdx.x & 31u;
     Trav           t;
-    trav_begin(s, t, st, false, mk3(0.0f), 0.0f, mk3(0.0f), 0.0f, flags);
+    const TravStart start = trav_start(s);
+    trav_begin(start, t, st, false, mk3(0.0f), 0.0f, mk3(0.0f), 0.0f, flags);
     uint32_t mine      = 0xFFFFFFFFu; // index of the ray this lane is tracing
     bool     exhausted = false;       // warp-uniform: the cursor ran past the end of the queue
     for (;;)
@@ -135,7 +133,7 @@ __device__ __forceinline__ void trace_queue(const SceneView& s, const Q& q, uint
                 f3    o, d;
                 float tmin, tmax;
                 q.load(i, o, tmin, d, tmax);
-                trav_begin(s, t, st, true, o, tmin, d, tmax, flags);
+                trav_begin(start, t, st, true, o, tmin, d, tmax, flags);
                 mine = i, busy = true; // (a query that starts with nothing to do is retired on the next pass)
             }
             bm = __ballot_sync(0xFFFFFFFFu, busy);

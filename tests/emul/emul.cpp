@@ -406,9 +406,9 @@ EM_API int em_scene_update_instances(EmScene* s, const hl_instance* inst, uint32
 
 static void trace_one(const SceneView& s, f3 o, float tmin, f3 d, float tmax, uint32_t flags, Hit& h)
 {
-    u2        fast[HL_STACK_FAST];
+    u2        fast[HL_STACK_FAST], spill[HL_STACK_SPILL];
     TravStack st;
-    st.fast = fast, st.stride = 1, st.sp = 0;
+    st.init(spill, fast);
     trace_ray(s, true, o, tmin, d, tmax, flags, h, st);
 }
 
@@ -453,9 +453,9 @@ EM_API uint32_t em_gather_debug_rays(const EmScene* s, const hl_push_constants* 
     o.verts = out, o.capacity = max_vertices;
     for (uint32_t i = 0; i < n; i++)
     {
-        u2        fast[HL_STACK_FAST];
+        u2        fast[HL_STACK_FAST], spill[HL_STACK_SPILL];
         TravStack st;
-        st.fast = fast, st.stride = 1, st.sp = 0;
+        st.init(spill, fast);
         debug_ray_path(s->view, *pc, i, true, st, o);
     }
     return o.count;
