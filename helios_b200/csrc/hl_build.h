@@ -254,6 +254,7 @@ HL_HD void fit_from_leaf(BinaryTree& t, uint32_t leaf, Fence fence, uint32_t sto
 #define HL_TOP_MODE_ARRIVAL 1u
 #define HL_TOP_MODE_SINGLE 2u
 #define HL_TOP_MODE_SMALL 3u
+#define HL_TOP_MODE_TREELET 4u
 #ifndef HL_TOP_SMALL
 #define HL_TOP_SMALL 8u /* nodes with at most this many clusters are finished by one thread each with exact SAH sweeps (16: that kernel alone took 0.8 of 5.3 ms at 1M triangles, one level fewer in the level loop) */
 #endif
@@ -346,12 +347,20 @@ struct TopNode
     uint32_t n_left;   // clusters that go left
     uint32_t child;    // index of the left child in the next level's node array (right = + 1)
     uint32_t arrivals; // ARRIVAL: ticket counter
-    uint32_t pad[2];
+    uint32_t prims;    // primitives in the node (an upper bound below an ARRIVAL node); only kept when treelets are on
+    uint32_t p_left;   // BINNED, after SPLIT: primitives left of the plane
 }; // 64 B
 struct TopSmall
 {
     uint32_t count, link, list_base, arrivals; // arrivals: ticket counter of the registering clusters
 }; // 16 B
+// two-level re-split (hl_builder.cu k_treelets): a node of at most `treelet_prims` primitives leaves the level loop as a
+// TREELET — its clusters register in `tlist` during the next BIN phase, and one thread block re-splits the fine clusters below
+// them in shared memory.  A treelet of `count` clusters owns count - 1 ids of the free list (what the level loop would have used).
+struct TopTreelet
+{
+    uint32_t count, link, list_base, id_base, arrivals, root; // root: binary node id of the finished treelet (written by k_treelets)
+}; // 24 B
 // what the per-level passes need of a cluster, in cluster order (written once by top_seed_cluster): the BIN and ASSIGN
 // phases stream 32-byte records instead of gathering box + range of a scattered radix-tree node per cluster and level
 struct TopCluster
@@ -377,6 +386,11 @@ struct TopBuild
     uint32_t*       level_count;   // [HL_TOP_MAX_LEVELS + 1] nodes per level
     uint32_t*       bins_used;     // [HL_TOP_MAX_LEVELS + 1] bin slots handed out per level
     uint32_t*       free_next;     // next unused entry of free_nodes
+    uint32_t        treelet_prims = 0; // 0: no treelets (the level loop runs down to SMALL / SINGLE nodes)
+    TopTreelet*     treelet       = nullptr; // [K]
+    uint32_t*       treelet_count = nullptr;
+    uint32_t*       tlist         = nullptr; // [K] cluster indices, `count` entries per treelet
+    uint32_t*       tlist_used    = nullptr;
 };
 
 HL_HD uint32_t subtree_prims_cg(const BinaryTree& t, uint32_t node) { return node >= t.n - 1 ? 1u : hl_load_cg(t.last + node) - hl_load_cg(t.first + node) + 1u; }
@@ -460,11 +474,20 @@ HL_HD void top_clear_bin(TopBin* b)
 #endif
 }
 // mode of a node that holds `count` clusters at `level`; BINNED nodes get a bin slot (or fall back when none is left)
-HL_HD void top_init_node(TopBuild& tb, uint32_t level, TopNode& n, uint32_t count, uint32_t link)
+HL_HD void top_init_node(TopBuild& tb, uint32_t level, TopNode& n, uint32_t count, uint32_t link, uint32_t prims = 0xFFFFFFFFu)
 {
     for (int k = 0; k < 3; k++) n.cb_lo[k] = HL_ORD_POS_INF, n.cb_hi[k] = HL_ORD_NEG_INF;
     n.count = count, n.link = link, n.bins = 0, n.split = 0, n.n_left = 0, n.child = 0, n.arrivals = 0;
-    n.pad[0] = n.pad[1] = 0;
+    n.prims = prims, n.p_left = 0;
+    if (tb.treelet_prims && (prims <= tb.treelet_prims || (uint64_t)count * tb.cluster_prims <= tb.treelet_prims))
+    {
+        // (prims is exact below BINNED nodes and an upper bound below ARRIVAL nodes; count * cluster size bounds it as well)
+        n.mode = HL_TOP_MODE_TREELET, n.bins = hl_alloc(tb.treelet_count, 1u);
+        TopTreelet& r = tb.treelet[n.bins];
+        r.count = count, r.link = link, r.list_base = hl_alloc(tb.tlist_used, count), r.id_base = count > 1u ? hl_alloc(tb.free_next, count - 1u) : 0u;
+        r.arrivals = 0u, r.root = 0xFFFFFFFFu;
+        return;
+    }
     n.mode = count == 1u ? HL_TOP_MODE_SINGLE : HL_TOP_MODE_ARRIVAL;
     if (count >= 2u && count <= HL_TOP_SMALL)
     {
@@ -482,10 +505,10 @@ HL_HD void top_init_node(TopBuild& tb, uint32_t level, TopNode& n, uint32_t coun
     }
 }
 // level 0: one node over all K clusters (run by ONE thread before top_seed_cluster)
-HL_HD void top_begin(TopBuild& tb, uint32_t K)
+HL_HD void top_begin(TopBuild& tb, uint32_t K, uint32_t prims = 0xFFFFFFFFu)
 {
     tb.level_count[0] = 1u;
-    top_init_node(tb, 0u, tb.level[0][0], K, 0xFFFFFFFFu);
+    top_init_node(tb, 0u, tb.level[0][0], K, 0xFFFFFFFFu, prims);
     for (uint32_t b = 0; b < 3u * HL_TOP_BINS; b++) top_clear_bin(tb.bins[0] + b);
 }
 // every cluster starts in the root node and contributes its centroid to the root's centroid bounds
@@ -537,6 +560,13 @@ HL_HD void top_bin_cluster(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t
         // register with the node's record; top_small_node() links the cluster after the level loop
         TopSmall& r = tb.small[hl_load_cg(&N.bins)];
         tb.list[hl_load_cg(&r.list_base) + hl_atomic_add(&r.arrivals, 1u)] = i;
+        tb.cnode[i] = HL_TOP_DONE;
+        return;
+    }
+    if (mode == HL_TOP_MODE_TREELET)
+    {
+        TopTreelet& r = tb.treelet[hl_load_cg(&N.bins)];
+        tb.tlist[hl_load_cg(&r.list_base) + hl_atomic_add(&r.arrivals, 1u)] = i;
         tb.cnode[i] = HL_TOP_DONE;
         return;
     }
@@ -650,7 +680,7 @@ HL_HD void top_choose_node(TopBuild& tb, uint32_t level, uint32_t j)
     if (hl_load_cg(&N.mode) != HL_TOP_MODE_BINNED) return;
     const TopBin* bins = tb.bins[level & 1u] + (size_t)hl_load_cg(&N.bins) * (3 * HL_TOP_BINS);
     float         best = hl_inf();
-    uint32_t      split = 0u, n_left = 0u;
+    uint32_t      split = 0u, n_left = 0u, p_left = 0u;
     for (int ax = 0; ax < 3; ax++)
     {
         // suffix unions, then a prefix sweep over the 15 candidate planes (an empty bin is the identity of the union)
@@ -679,13 +709,13 @@ HL_HD void top_choose_node(TopBuild& tb, uint32_t level, uint32_t j)
             if (c != 0u && rc[b + 1] != 0u)
             {
                 const float cost = box_half_area(acc) * (float)p + rarea[b + 1] * (float)rp[b + 1];
-                if (cost < best) best = cost, split = (uint32_t)ax | ((uint32_t)b << 2), n_left = c;
+                if (cost < best) best = cost, split = (uint32_t)ax | ((uint32_t)b << 2), n_left = c, p_left = p;
             }
             acc = box_union(acc, bb[b + 1]), p += bp[b + 1], c += bc[b + 1];
         }
     }
     if (best < hl_inf())
-        N.split = split, N.n_left = n_left;
+        N.split = split, N.n_left = n_left, N.p_left = p_left;
     else
         N.mode = HL_TOP_MODE_ARRIVAL;
 }
@@ -697,7 +727,7 @@ HL_HD void top_commit_node(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t
     // (fields written by other thread blocks are read past the L1)
     TopNode&       N    = tb.level[level & 1u][j];
     const uint32_t mode = hl_load_cg(&N.mode), count = hl_load_cg(&N.count);
-    if (mode == HL_TOP_MODE_SINGLE || mode == HL_TOP_MODE_SMALL) return;
+    if (mode == HL_TOP_MODE_SINGLE || mode == HL_TOP_MODE_SMALL || mode == HL_TOP_MODE_TREELET) return;
     const uint32_t self = tb.free_nodes[hl_alloc(tb.free_next, 1u)];
     top_link(t, hl_load_cg(&N.link), self);
     t.visits[self]       = 0u;
@@ -705,8 +735,10 @@ HL_HD void top_commit_node(BinaryTree& t, TopBuild& tb, uint32_t level, uint32_t
     const uint32_t child  = hl_alloc(tb.level_count + (level + 1u), 2u);
     N.n_left = n_left, N.child = child, N.arrivals = 0u;
     TopNode* next = tb.level[(level + 1u) & 1u];
-    top_init_node(tb, level + 1u, next[child], n_left, self << 1);
-    top_init_node(tb, level + 1u, next[child + 1u], count - n_left, (self << 1) | 1u);
+    const uint32_t prims = hl_load_cg(&N.prims), p_left = hl_load_cg(&N.p_left);
+    const bool     exact = mode == HL_TOP_MODE_BINNED && prims != 0xFFFFFFFFu && p_left <= prims;
+    top_init_node(tb, level + 1u, next[child], n_left, self << 1, exact ? p_left : prims);
+    top_init_node(tb, level + 1u, next[child + 1u], count - n_left, (self << 1) | 1u, exact ? prims - p_left : prims);
 }
 // bin entries of `level` that must be empty before its BIN phase
 HL_HD uint32_t top_bins_to_clear(const TopBuild& tb, uint32_t level)

@@ -124,7 +124,7 @@ __device__ __forceinline__ void top_choose_node_warp(TopBuild& tb, uint32_t leve
     if (__ldcg(&N.mode) != HL_TOP_MODE_BINNED) return; // warp-uniform
     const TopBin* bins = tb.bins[level & 1u] + (size_t)__ldcg(&N.bins) * (3 * HL_TOP_BINS);
     float         best = hl_inf();
-    uint32_t      split = 0xFFFFFFFFu, n_left = 0u;
+    uint32_t      split = 0xFFFFFFFFu, n_left = 0u, p_left = 0u;
     for (int ax = 0; ax < 3; ax++)
     {
         float    lo[3], hi[3];
@@ -164,20 +164,20 @@ __device__ __forceinline__ void top_choose_node_warp(TopBuild& tb, uint32_t leve
         {
             const float parea = (phi[0] - plo[0]) * (phi[1] - plo[1]) + (phi[1] - plo[1]) * (phi[2] - plo[2]) + (phi[2] - plo[2]) * (phi[0] - plo[0]);
             const float cost  = parea * (float)pp + rarea * (float)rp;
-            if (cost < best) best = cost, split = (uint32_t)ax | (lane << 2), n_left = pc;
+            if (cost < best) best = cost, split = (uint32_t)ax | (lane << 2), n_left = pc, p_left = pp;
         }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
     {
         const float    ob = __shfl_xor_sync(FULL, best, d);
-        const uint32_t os = __shfl_xor_sync(FULL, split, d), on = __shfl_xor_sync(FULL, n_left, d);
-        if (ob < best || (ob == best && os < split)) best = ob, split = os, n_left = on;
+        const uint32_t os = __shfl_xor_sync(FULL, split, d), on = __shfl_xor_sync(FULL, n_left, d), op = __shfl_xor_sync(FULL, p_left, d);
+        if (ob < best || (ob == best && os < split)) best = ob, split = os, n_left = on, p_left = op;
     }
     if (lane == 0u)
     {
         if (best < hl_inf())
-            N.split = split, N.n_left = n_left;
+            N.split = split, N.n_left = n_left, N.p_left = p_left;
         else
             N.mode = HL_TOP_MODE_ARRIVAL;
     }
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256, 4) k_top_build(BinaryTree t, TopBuild tb,
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u, warp = tid >> 5, nwarps = nthr >> 5;
     top_trace(trace, ntrace);
-    if (tid == 0) top_begin(tb, K);
+    if (tid == 0) top_begin(tb, K, t.n);
     grid_barrier(bar);
     for (uint32_t i = tid; i < K; i += nthr) top_seed_cluster(t, tb, i);
     grid_barrier(bar);
@@ -343,6 +343,541 @@ __global__ void k_top_refit(BinaryTree t, TopBuild tb)
     //  them or — cut too fine for the scratch arrays — left the radix tree's topology in place)
     const uint32_t K = *tb.n_clusters;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) top_refit_from_cluster(t, tb.cluster[i], DeviceFence());
+}
+
+// ---- two-level re-split (round 2): treelets built inside one thread block ---------------------------------------------
+// The level-synchronous re-split above moves every cluster through global memory once per level and phase (BIN / ASSIGN:
+// ~8 L2 atomics per cluster, 4 grid barriers per level, ~20 levels): 2.2 of the 3.5 ms of a 1M-triangle build.  Here the
+// radix tree is cut TWICE.  The level loop runs over the COARSE cut (subtrees of <= C_A primitives, a few ten thousand of
+// them) and stops at nodes of <= HL_TREELET_PRIMS primitives ("treelets", hl_build.h TopTreelet).  Every treelet is then
+// re-split down to the FINE cut (clusters of <= C primitives) by ONE block entirely in shared memory: the fine clusters below
+// the treelet's coarse subtrees are loaded once (boxes, primitive counts, node ids), the binned-SAH recursion runs level by
+// level over index ranges of a permutation — one warp per range: centroid bounds by warp reductions, 16 bins along the longest
+// axis in shared memory, plane choice by the shuffle scans of top_choose_node_warp, stable partition by ballot prefix —,
+// ranges of <= HL_TOP_SMALL clusters are finished by one thread each with exact SAH sweeps (as top_small_node does), the
+// re-linked nodes reuse the treelet's own node ids (the free-list ids the level loop did not use + the radix-tree nodes
+// between the two cuts) and are fitted (box, primitive count, collapse cost table) bottom-up by the same block, level by
+// level, without atomics or fences.  Same planes as the one-level re-split except that, above the treelets, a plane cannot cut
+// through a coarse subtree.  Everything is a function of the input: items in (cluster index, Morton) order, node ids by
+// (level, range index), ties by (axis, bin) — the tree is the same run to run.
+#ifndef HL_TREELET_PRIMS
+#define HL_TREELET_PRIMS 1024u
+#endif
+#define HL_TREELET_THREADS 256
+#define HL_TREELET_WARPS (HL_TREELET_THREADS / 32)
+#define HL_TREELET_PER_THREAD (HL_TREELET_PRIMS / HL_TREELET_THREADS)
+// first fit, fine clusters only: the thread of a cluster root walks its subtree in post-order (stackless: parent links) and
+// writes leaf boxes, boxes and cost tables — no arrival counters, no fences (the atomic bottom-up pass took 46 of the 80 ms of
+// a 50M-triangle build)
+__global__ void k_fit_fine(BinaryTree t, const Box* prim_boxes, const uint32_t* sorted, uint32_t C)
+{
+    const uint32_t leaf0 = t.n - 1;
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < 2u * t.n - 1u; m += gridDim.x * blockDim.x)
+    {
+        if (!top_is_cluster_root(t, m, C)) continue;
+        uint32_t node = m;
+        while (node < leaf0) node = t.left[node];
+        for (;;)
+        {
+            if (node >= leaf0)
+            {
+                const Box b = prim_boxes[sorted[node - leaf0]];
+                t.box[node] = b;
+                sah_leaf_costs(t, node, box_half_area(b));
+            }
+            if (node == m) break;
+            const uint32_t p = t.parent[node];
+            if (t.left[p] == node)
+            {
+                node = t.right[p];
+                while (node < leaf0) node = t.left[node];
+                continue;
+            }
+            const Box b = box_union(t.box[t.left[p]], t.box[t.right[p]]);
+            t.box[p]    = b;
+            sah_node_costs(t, p, box_half_area(b));
+            node = p;
+        }
+    }
+}
+
+// boxes of the coarse subtrees' roots (what the level loop bins): union of the leaf boxes k_fit_fine wrote.  The nodes between
+// the two cuts are not fitted here — the treelets re-link them.
+__global__ void k_coarse_boxes(BinaryTree t, const uint32_t* cluster, const uint32_t* n_clusters, uint32_t C)
+{
+    const uint32_t K = *n_clusters, leaf0 = t.n - 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t R = cluster[i];
+        if (R >= leaf0 || subtree_prims(t, R) <= C) continue; // fitted by k_fit_fine
+        const uint32_t f = t.first[R], l = t.last[R];
+        Box            b = t.box[leaf0 + f];
+        for (uint32_t j = f + 1u; j <= l; j++) b = box_union(b, t.box[leaf0 + j]);
+        t.box[R] = b;
+    }
+}
+struct TreeletSmem
+{
+    float    lo[3][HL_TREELET_PRIMS], hi[3][HL_TREELET_PRIMS]; // item boxes
+    uint32_t prims[HL_TREELET_PRIMS];                          // item primitive counts
+    uint32_t node[HL_TREELET_PRIMS];                           // item = fine cluster: its binary node id
+    uint32_t ids[HL_TREELET_PRIMS];                            // node ids the treelet may use; [0] becomes its root
+    uint32_t sub_root[HL_TREELET_PRIMS];                       // coarse subtrees of the treelet (sorted by cluster index): root node,
+    uint32_t sub_off[HL_TREELET_PRIMS + 1];                    //   first position in the concatenated leaf ranges
+    uint16_t perm[2][HL_TREELET_PRIMS];
+    uint16_t seg_start[2][HL_TREELET_PRIMS / 2 + 2], seg_cnt[2][HL_TREELET_PRIMS / 2 + 2];
+    uint32_t seg_link[2][HL_TREELET_PRIMS / 2 + 2];
+    uint16_t seg_left[HL_TREELET_PRIMS / 2 + 2];   // items that go left, per range of the current level
+    uint16_t level_base[HL_TREELET_PRIMS + 2];     // ids[level_base[L] ...] = the nodes created at level L
+    uint16_t small_start[HL_TREELET_PRIMS / 2 + 2], small_cnt[HL_TREELET_PRIMS / 2 + 2], small_id[HL_TREELET_PRIMS / 2 + 2]; // ranges finished by one thread
+    uint32_t small_link[HL_TREELET_PRIMS / 2 + 2]; // bit 31 of small_start's companion: see small_buf
+    uint8_t  small_buf[HL_TREELET_PRIMS / 2 + 2];  // which perm buffer holds the range
+    alignas(16) TopBin bins[HL_TREELET_WARPS][HL_TOP_BINS]; // (top_clear_bin stores 16 bytes at a time)
+    uint32_t scan[HL_TREELET_WARPS + 1];
+    uint32_t n_items, n_ids, n_sub;
+};
+// exclusive prefix sum over one value per thread of the block (blockDim.x == HL_TREELET_THREADS); returns the total in `total`
+__device__ __forceinline__ uint32_t treelet_block_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t       incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += o;
+    }
+    __syncthreads(); // (warp_sums may still be read by the previous call)
+    if (lane == 31u) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, sum = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < HL_TREELET_WARPS; w++)
+    {
+        const uint32_t x = warp_sums[w];
+        if (w < warp) base += x;
+        sum += x;
+    }
+    total = sum;
+    return base + incl - v;
+}
+// plane choice of one range by one warp from the 16 bins of ONE axis in shared memory: same selection as top_choose_node_warp
+__device__ __forceinline__ bool treelet_choose(const TopBin* bins, uint32_t lane, uint32_t& split_bin, uint32_t& n_left)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    float          best = hl_inf();
+    split_bin = 0xFFFFFFFFu, n_left = 0u;
+    float    lo[3], hi[3];
+    uint32_t p = 0u, c = 0u;
+    for (int k = 0; k < 3; k++) lo[k] = hl_inf(), hi[k] = -hl_inf();
+    if (lane < HL_TOP_BINS)
+    {
+        const TopBin B = bins[lane];
+        for (int k = 0; k < 3; k++) lo[k] = ord2f(B.lo[k]), hi[k] = ord2f(B.hi[k]);
+        p = B.prims, c = B.clusters;
+    }
+    float    plo[3] = { lo[0], lo[1], lo[2] }, phi[3] = { hi[0], hi[1], hi[2] }, slo[3] = { lo[0], lo[1], lo[2] }, shi[3] = { hi[0], hi[1], hi[2] };
+    uint32_t pp = p, pc = c, sp = p, sc = c;
+#pragma unroll
+    for (int d = 1; d < HL_TOP_BINS; d <<= 1)
+    {
+        const bool up = (int)lane >= d, dn = lane + d < 32u; // (lanes >= 16 hold the identity)
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            const float a = __shfl_up_sync(FULL, plo[k], d), b = __shfl_up_sync(FULL, phi[k], d);
+            const float e = __shfl_down_sync(FULL, slo[k], d), f = __shfl_down_sync(FULL, shi[k], d);
+            if (up) plo[k] = fminf(plo[k], a), phi[k] = fmaxf(phi[k], b);
+            if (dn) slo[k] = fminf(slo[k], e), shi[k] = fmaxf(shi[k], f);
+        }
+        const uint32_t a = __shfl_up_sync(FULL, pp, d), b = __shfl_up_sync(FULL, pc, d);
+        const uint32_t e = __shfl_down_sync(FULL, sp, d), f = __shfl_down_sync(FULL, sc, d);
+        if (up) pp += a, pc += b;
+        if (dn) sp += e, sc += f;
+    }
+    const float    sarea = (shi[0] - slo[0]) * (shi[1] - slo[1]) + (shi[1] - slo[1]) * (shi[2] - slo[2]) + (shi[2] - slo[2]) * (shi[0] - slo[0]);
+    const float    rarea = __shfl_down_sync(FULL, sarea, 1);
+    const uint32_t rp = __shfl_down_sync(FULL, sp, 1), rc = __shfl_down_sync(FULL, sc, 1);
+    if (lane < HL_TOP_BINS - 1u && pc != 0u && rc != 0u)
+    {
+        const float parea = (phi[0] - plo[0]) * (phi[1] - plo[1]) + (phi[1] - plo[1]) * (phi[2] - plo[2]) + (phi[2] - plo[2]) * (phi[0] - plo[0]);
+        best = parea * (float)pp + rarea * (float)rp, split_bin = lane, n_left = pc;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const float    ob = __shfl_xor_sync(FULL, best, d);
+        const uint32_t os = __shfl_xor_sync(FULL, split_bin, d), on = __shfl_xor_sync(FULL, n_left, d);
+        if (ob < best || (ob == best && os < split_bin)) best = ob, split_bin = os, n_left = on;
+    }
+    return best < hl_inf();
+}
+// a range of 2..HL_TOP_SMALL items, by ONE thread: the whole subtree with exact SAH splits (items sorted along each axis, every
+// position between two neighbours is a candidate; the rule of top_small_node), then its boxes / counts / cost tables bottom-up
+__device__ void treelet_small(BinaryTree& t, const TreeletSmem& S, const uint16_t* pin, uint32_t count, uint32_t link, uint32_t id0)
+{
+    uint8_t  ord[HL_TOP_SMALL];
+    uint32_t created[HL_TOP_SMALL];
+    uint32_t used = 0;
+    for (uint32_t k = 0; k < count; k++) ord[k] = (uint8_t)k;
+    uint8_t  slo[HL_TOP_SMALL], shi[HL_TOP_SMALL];
+    uint32_t slink[HL_TOP_SMALL];
+    int      sp = 0;
+    slo[0] = 0, shi[0] = (uint8_t)count, slink[0] = link, sp = 1;
+    while (sp > 0)
+    {
+        sp--;
+        const int      lo = slo[sp], hi = shi[sp];
+        const uint32_t lk = slink[sp];
+        if (hi - lo == 1)
+        {
+            top_link(t, lk, S.node[pin[ord[lo]]]);
+            continue;
+        }
+        const uint32_t self = S.ids[id0 + used];
+        created[used++]     = self;
+        top_link(t, lk, self);
+        float best = hl_inf();
+        int   bax = 2, bk = (lo + hi) / 2;
+        for (int pass = 0; pass < 4; pass++)
+        {
+            // passes 0..2 evaluate the axes; pass 3 restores the order of the winning axis (unless it was sorted last)
+            const int ax = pass < 3 ? pass : bax;
+            if (pass == 3 && bax == 2) break;
+            for (int a = lo + 1; a < hi; a++)
+            {
+                const uint8_t m  = ord[a];
+                const float   cm = S.lo[ax][pin[m]] + S.hi[ax][pin[m]];
+                int           b  = a - 1;
+                while (b >= lo && S.lo[ax][pin[ord[b]]] + S.hi[ax][pin[ord[b]]] > cm) ord[b + 1] = ord[b], b--;
+                ord[b + 1] = m;
+            }
+            if (pass == 3) break;
+            float    rarea[HL_TOP_SMALL];
+            uint32_t rprims[HL_TOP_SMALL];
+            float    alo[3], ahi[3];
+            uint32_t p = 0;
+            for (int q = 0; q < 3; q++) alo[q] = hl_inf(), ahi[q] = -hl_inf();
+            for (int k = hi - 1; k > lo; k--)
+            {
+                const uint32_t it = pin[ord[k]];
+                for (int q = 0; q < 3; q++) alo[q] = fminf(alo[q], S.lo[q][it]), ahi[q] = fmaxf(ahi[q], S.hi[q][it]);
+                p += S.prims[it];
+                rarea[k] = (ahi[0] - alo[0]) * (ahi[1] - alo[1]) + (ahi[1] - alo[1]) * (ahi[2] - alo[2]) + (ahi[2] - alo[2]) * (ahi[0] - alo[0]), rprims[k] = p;
+            }
+            for (int q = 0; q < 3; q++) alo[q] = hl_inf(), ahi[q] = -hl_inf();
+            p = 0;
+            for (int k = lo + 1; k < hi; k++)
+            {
+                // left = [lo, k), right = [k, hi)
+                const uint32_t it = pin[ord[k - 1]];
+                for (int q = 0; q < 3; q++) alo[q] = fminf(alo[q], S.lo[q][it]), ahi[q] = fmaxf(ahi[q], S.hi[q][it]);
+                p += S.prims[it];
+                const float larea = (ahi[0] - alo[0]) * (ahi[1] - alo[1]) + (ahi[1] - alo[1]) * (ahi[2] - alo[2]) + (ahi[2] - alo[2]) * (ahi[0] - alo[0]);
+                const float cost  = larea * (float)p + rarea[k] * (float)rprims[k];
+                if (cost < best) best = cost, bax = ax, bk = k;
+            }
+        }
+        slo[sp] = (uint8_t)bk, shi[sp] = (uint8_t)hi, slink[sp] = (self << 1) | 1u, sp++;
+        slo[sp] = (uint8_t)lo, shi[sp] = (uint8_t)bk, slink[sp] = self << 1, sp++;
+    }
+    // children were created after their parents: the reverse order is bottom-up (all reads are of this thread's own writes or
+    // of the fine clusters fitted by k_fit_fine)
+    for (uint32_t k = used; k-- > 0u;)
+    {
+        const uint32_t node = created[k];
+        const uint32_t lc = t.left[node], rc = t.right[node];
+        const Box      b  = box_union(t.box[lc], t.box[rc]);
+        t.box[node]       = b;
+        const uint32_t p  = subtree_prims(t, lc) + subtree_prims(t, rc);
+        t.first[node] = 0u, t.last[node] = (p > HL_MAX_LEAF_PRIMS ? p : HL_MAX_LEAF_PRIMS + 1u) - 1u;
+        sah_node_costs(t, node, box_half_area(b));
+    }
+}
+// err: set to 1 when a treelet does not fit the shared arrays (cannot happen while the primitive counts of the level loop are
+// upper bounds; checked by the host)
+__global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, TopBuild tb, uint32_t C, uint32_t* err)
+{
+    extern __shared__ __align__(16) unsigned char treelet_raw[];
+    TreeletSmem&   S     = *(TreeletSmem*)treelet_raw;
+    const uint32_t tid   = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t leaf0 = t.n - 1;
+    const uint32_t count = *tb.treelet_count;
+    for (uint32_t ti = blockIdx.x; ti < count; ti += gridDim.x)
+    {
+        TopTreelet&    rec = tb.treelet[ti];
+        const uint32_t m   = rec.count, link = rec.link;
+        __syncthreads(); // the previous treelet is finished with the shared arrays
+        // ---- the treelet's coarse subtrees, sorted by cluster index (they registered in arrival order)
+        {
+            const uint32_t* list = tb.tlist + rec.list_base;
+            uint32_t        sizes = 0; // (this thread's subtrees: the sum of their sizes)
+            for (uint32_t k = tid; k < m; k += HL_TREELET_THREADS)
+            {
+                const uint32_t v = list[k];
+                uint32_t       rank = 0;
+                for (uint32_t j = 0; j < m; j++) rank += list[j] < v ? 1u : 0u;
+                S.sub_root[rank] = tb.cluster[v];
+            }
+            __syncthreads();
+            // exclusive scan of the subtree sizes, blocked: thread tid owns entries [tid * per, tid * per + per)
+            const uint32_t per = (m + HL_TREELET_THREADS - 1u) / HL_TREELET_THREADS;
+            for (uint32_t k = tid * per; k < min(m, tid * per + per); k++) sizes += subtree_prims(t, S.sub_root[k]);
+            uint32_t total;
+            uint32_t at = treelet_block_scan(sizes, S.scan, total);
+            for (uint32_t k = tid * per; k < min(m, tid * per + per); k++) S.sub_off[k] = at, at += subtree_prims(t, S.sub_root[k]);
+            if (tid == 0) S.sub_off[m] = total, S.n_sub = m;
+            __syncthreads();
+        }
+        const uint32_t P = S.sub_off[m];
+        if (P > HL_TREELET_PRIMS)
+        {
+            if (tid == 0) *err = 1u;
+            continue; // (uniform)
+        }
+        // ---- collect, in (subtree, Morton) order: the fine clusters (items) and the node ids between the two cuts
+        {
+            uint32_t root_of[HL_TREELET_PER_THREAD], flag[HL_TREELET_PER_THREAD], idf[HL_TREELET_PER_THREAD];
+            uint32_t mine = 0, mine_ids = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < HL_TREELET_PER_THREAD; k++)
+            {
+                // (thread tid owns positions 4 tid .. 4 tid + 3: a blocked arrangement keeps the scan order = position order)
+                const uint32_t j = tid * HL_TREELET_PER_THREAD + k;
+                flag[k] = 0u, root_of[k] = 0u, idf[k] = 0xFFFFFFFFu;
+                if (j < P)
+                {
+                    uint32_t a = 0, b = m; // subtree s with sub_off[s] <= j < sub_off[s + 1]
+                    while (b - a > 1u)
+                    {
+                        const uint32_t c = (a + b) >> 1;
+                        if (S.sub_off[c] <= j) a = c; else b = c;
+                    }
+                    const uint32_t Rs = S.sub_root[a], off = j - S.sub_off[a];
+                    const uint32_t fs = subtree_first(t, Rs), ls = fs + subtree_prims(t, Rs) - 1u;
+                    uint32_t       mm = leaf0 + fs + off;
+                    while (mm != Rs) // (never above the subtree's root: the nodes up there may be re-linked by another block right now)
+                    {
+                        const uint32_t pm = t.parent[mm];
+                        if (subtree_prims(t, pm) > C) break;
+                        mm = pm;
+                    }
+                    if (subtree_first(t, mm) == fs + off)
+                    {
+                        flag[k] = 1u, root_of[k] = mm;
+                        // the node ids between the two cuts: one per pair of adjacent clusters of a subtree — their lowest common
+                        // ancestor, i.e. the first ancestor of the left one that reaches further right (all inside the subtree:
+                        // radix-tree ranges nobody else touches)
+                        const uint32_t last_m = fs + off + subtree_prims(t, mm) - 1u;
+                        uint32_t       x = mm;
+                        while (x != Rs)
+                        {
+                            x = t.parent[x];
+                            if (t.last[x] > last_m)
+                            {
+                                idf[k] = x;
+                                break;
+                            }
+                        }
+                    }
+                    (void)ls;
+                }
+                mine += flag[k], mine_ids += idf[k] != 0xFFFFFFFFu ? 1u : 0u;
+            }
+            uint32_t total;
+            uint32_t at = treelet_block_scan(mine, S.scan, total);
+#pragma unroll
+            for (uint32_t k = 0; k < HL_TREELET_PER_THREAD; k++)
+                if (flag[k])
+                {
+                    const uint32_t mm = root_of[k];
+                    const Box      b  = t.box[mm];
+                    for (int a = 0; a < 3; a++) S.lo[a][at] = b.lo[a], S.hi[a][at] = b.hi[a];
+                    S.prims[at] = subtree_prims(t, mm), S.node[at] = mm, S.perm[0][at] = (uint16_t)at;
+                    at++;
+                }
+            if (tid == 0) S.n_items = total;
+            const uint32_t own = m - 1u; // ids of the free list
+            at = own + treelet_block_scan(mine_ids, S.scan, total);
+#pragma unroll
+            for (uint32_t k = 0; k < HL_TREELET_PER_THREAD; k++)
+                if (idf[k] != 0xFFFFFFFFu) S.ids[at++] = idf[k];
+            for (uint32_t k = tid; k < own; k += HL_TREELET_THREADS) S.ids[k] = tb.free_nodes[rec.id_base + k];
+            if (tid == 0) S.n_ids = own + total, S.seg_start[0][0] = 0, S.seg_link[0][0] = link, S.level_base[0] = 0;
+            __syncthreads();
+            // a treelet of ONE coarse subtree keeps that subtree's root as its root (the whole tree's root is node 0)
+            if (own == 0u)
+                for (uint32_t k = tid; k < total; k += HL_TREELET_THREADS)
+                    if (S.ids[k] == S.sub_root[0] && k != 0u) S.ids[k] = S.ids[0], S.ids[0] = S.sub_root[0]; // (at most one k matches)
+        }
+        __syncthreads();
+        const uint32_t n_items = S.n_items;
+        if (S.n_ids + 1u != n_items)
+        {
+            if (tid == 0) *err = 2u;
+            continue; // (uniform)
+        }
+        if (n_items == 1u)
+        {
+            if (tid == 0) top_link(t, link, S.node[0]), rec.root = S.node[0];
+            continue; // (uniform)
+        }
+        if (tid == 0) rec.root = S.ids[0];
+        // ---- top-down: one level per iteration, one warp per range; ranges of <= HL_TOP_SMALL items are set aside
+        uint32_t nseg = 0u, nsmall = 0u, level = 0u, base = 0u; // base = ids consumed by the levels above
+        uint32_t cur  = 0u;
+        if (n_items <= HL_TOP_SMALL)
+        {
+            if (tid == 0) S.small_start[0] = 0, S.small_cnt[0] = (uint16_t)n_items, S.small_link[0] = link, S.small_buf[0] = 0;
+            nsmall = 1u;
+        }
+        else
+        {
+            if (tid == 0) S.seg_cnt[0][0] = (uint16_t)n_items;
+            nseg = 1u;
+        }
+        __syncthreads();
+        while (nseg)
+        {
+            for (uint32_t k = warp; k < nseg; k += HL_TREELET_WARPS)
+            {
+                const uint32_t  s0 = S.seg_start[cur][k], cnt = S.seg_cnt[cur][k];
+                const uint16_t* pin = S.perm[cur] + s0;
+                uint16_t*       pout = S.perm[cur ^ 1u] + s0;
+                // centroid bounds
+                uint32_t clo[3] = { HL_ORD_POS_INF, HL_ORD_POS_INF, HL_ORD_POS_INF }, chi[3] = { HL_ORD_NEG_INF, HL_ORD_NEG_INF, HL_ORD_NEG_INF };
+                for (uint32_t i = lane; i < cnt; i += 32u)
+                {
+                    const uint32_t it = pin[i];
+                    for (int a = 0; a < 3; a++)
+                    {
+                        const uint32_t c = f2ord(0.5f * (S.lo[a][it] + S.hi[a][it]));
+                        clo[a] = min(clo[a], c), chi[a] = max(chi[a], c);
+                    }
+                }
+                float cbl[3], cbh[3];
+                for (int a = 0; a < 3; a++) cbl[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, clo[a])), cbh[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, chi[a]));
+                const float e0 = cbh[0] - cbl[0], e1 = cbh[1] - cbl[1], e2 = cbh[2] - cbl[2];
+                const int   ax = e0 >= e1 && e0 >= e2 ? 0 : (e1 >= e2 ? 1 : 2); // longest axis of the centroid bounds (top_bin_axis)
+                const float al = ax == 0 ? cbl[0] : (ax == 1 ? cbl[1] : cbl[2]), ah = ax == 0 ? cbh[0] : (ax == 1 ? cbh[1] : cbh[2]);
+                TopBin*     bins = S.bins[warp];
+                if (lane < HL_TOP_BINS) top_clear_bin(bins + lane);
+                __syncwarp();
+                for (uint32_t i = lane; i < cnt; i += 32u)
+                {
+                    const uint32_t it = pin[i];
+                    const int      bi = top_bin_of(0.5f * (S.lo[ax][it] + S.hi[ax][it]), al, ah);
+                    if (bi < 0) continue;
+                    TopBin& B = bins[bi];
+                    for (int q = 0; q < 3; q++) atomicMin(&B.lo[q], f2ord(S.lo[q][it])), atomicMax(&B.hi[q], f2ord(S.hi[q][it]));
+                    atomicAdd(&B.prims, S.prims[it]), atomicAdd(&B.clusters, 1u);
+                }
+                __syncwarp();
+                uint32_t   sbin, n_left;
+                const bool planar = treelet_choose(bins, lane, sbin, n_left);
+                __syncwarp();
+                if (!planar) n_left = cnt / 2u; // all centroids equal: first half left
+                uint32_t nl = 0u, nr = 0u;
+                for (uint32_t i0 = 0; i0 < cnt; i0 += 32u)
+                {
+                    const uint32_t i  = i0 + lane;
+                    const bool     in = i < cnt;
+                    uint32_t       it = 0u;
+                    bool           right = false;
+                    if (in)
+                    {
+                        it    = pin[i];
+                        right = planar ? top_bin_of(0.5f * (S.lo[ax][it] + S.hi[ax][it]), al, ah) > (int)sbin : i >= n_left;
+                    }
+                    const uint32_t mr = __ballot_sync(0xFFFFFFFFu, in && right), ml = __ballot_sync(0xFFFFFFFFu, in && !right);
+                    const uint32_t lt = (1u << lane) - 1u;
+                    if (in) pout[right ? n_left + nr + (uint32_t)__popc(mr & lt) : nl + (uint32_t)__popc(ml & lt)] = (uint16_t)it;
+                    nl += (uint32_t)__popc(ml), nr += (uint32_t)__popc(mr);
+                }
+                if (lane == 0u)
+                {
+                    S.seg_left[k] = (uint16_t)n_left;
+                    top_link(t, S.seg_link[cur][k], S.ids[base + k]);
+                }
+            }
+            __syncthreads();
+            // the ranges of the next level and the small ranges (exclusive scans over the ranges of this one); single items link themselves
+            uint32_t total_next = 0u;
+            for (uint32_t k0 = 0; k0 < nseg; k0 += HL_TREELET_THREADS)
+            {
+                const uint32_t k = k0 + tid;
+                uint32_t       s0 = 0, cnt = 0, nl = 0, self = 0, need = 0, need_small = 0;
+                if (k < nseg)
+                {
+                    s0 = S.seg_start[cur][k], cnt = S.seg_cnt[cur][k], nl = S.seg_left[k], self = S.ids[base + k];
+                    need       = (nl > HL_TOP_SMALL ? 1u : 0u) + (cnt - nl > HL_TOP_SMALL ? 1u : 0u);
+                    need_small = (nl >= 2u && nl <= HL_TOP_SMALL ? 1u : 0u) + (cnt - nl >= 2u && cnt - nl <= HL_TOP_SMALL ? 1u : 0u);
+                }
+                uint32_t tot, tot_small;
+                uint32_t at  = total_next + treelet_block_scan(need, S.scan, tot);
+                uint32_t ats = nsmall + treelet_block_scan(need_small, S.scan, tot_small);
+                if (k < nseg)
+                {
+                    const uint16_t* pnew = S.perm[cur ^ 1u];
+                    for (uint32_t side = 0; side < 2u; side++)
+                    {
+                        const uint32_t cs = side ? s0 + nl : s0, cc = side ? cnt - nl : nl, lk = (self << 1) | side;
+                        if (cc == 1u)
+                            top_link(t, lk, S.node[pnew[cs]]);
+                        else if (cc <= HL_TOP_SMALL)
+                            S.small_start[ats] = (uint16_t)cs, S.small_cnt[ats] = (uint16_t)cc, S.small_link[ats] = lk, S.small_buf[ats] = (uint8_t)(cur ^ 1u), ats++;
+                        else
+                            S.seg_start[cur ^ 1u][at] = (uint16_t)cs, S.seg_cnt[cur ^ 1u][at] = (uint16_t)cc, S.seg_link[cur ^ 1u][at] = lk, at++;
+                    }
+                }
+                total_next += tot, nsmall += tot_small;
+            }
+            base += nseg, level++;
+            if (tid == 0) S.level_base[level] = (uint16_t)base;
+            nseg = total_next, cur ^= 1u;
+            __syncthreads();
+        }
+        // ---- the small ranges: ids by an exclusive scan over (count - 1), one thread per range (build + fit)
+        {
+            uint32_t run = base;
+            for (uint32_t k0 = 0; k0 < nsmall; k0 += HL_TREELET_THREADS)
+            {
+                const uint32_t k    = k0 + tid;
+                const uint32_t need = k < nsmall ? (uint32_t)S.small_cnt[k] - 1u : 0u;
+                uint32_t       tot;
+                const uint32_t at = run + treelet_block_scan(need, S.scan, tot);
+                if (k < nsmall) treelet_small(t, S, S.perm[S.small_buf[k]] + S.small_start[k], S.small_cnt[k], S.small_link[k], at);
+                run += tot;
+            }
+        }
+        __syncthreads();
+        // ---- bottom-up over the levels: box, primitive count, collapse cost table of every node the warps created
+        for (uint32_t L = level; L-- > 0u;)
+        {
+            const uint32_t b0 = S.level_base[L], b1 = S.level_base[L + 1u];
+            for (uint32_t k = b0 + tid; k < b1; k += HL_TREELET_THREADS)
+            {
+                const uint32_t node = S.ids[k];
+                const uint32_t lc = __ldcg(t.left + node), rc = __ldcg(t.right + node);
+                const Box      b  = box_union(load_box_coherent(&t.box[lc]), load_box_coherent(&t.box[rc]));
+                t.box[node]       = b;
+                const uint32_t p  = subtree_prims_cg(t, lc) + subtree_prims_cg(t, rc);
+                t.first[node] = 0u, t.last[node] = (p > HL_MAX_LEAF_PRIMS ? p : HL_MAX_LEAF_PRIMS + 1u) - 1u;
+                sah_node_costs(t, node, box_half_area(b));
+            }
+            __syncthreads();
+        }
+    }
+}
+// the nodes of the level loop above the treelets: bottom-up from every treelet root
+__global__ void k_top_refit_treelets(BinaryTree t, TopBuild tb)
+{
+    const uint32_t count = *tb.treelet_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t root = tb.treelet[i].root;
+        if (root != 0xFFFFFFFFu) top_refit_from_cluster(t, root, DeviceFence());
+    }
 }
 
 // Collapse as ONE persistent launch over a device-side work queue (no host round trip per tree level):
@@ -440,36 +975,56 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     // cut has at most ~4M clusters; instance trees: single instances), scratch sized for k_cap clusters
     const bool tri_tree = leaf_bytes == sizeof(LeafTri);
     uint32_t   C        = ctx->sah_cluster == 0 ? 0u : (tri_tree ? ctx->sah_cluster : 1u);
-    while (C && tri_tree && n / C > (4u << 20)) C *= 2;
+    // two-level re-split (k_treelets): the fine cut stays at C whatever the size — nothing is kept per fine cluster —, the
+    // level loop runs over the coarse cut C_A and stops at treelets.  HL_NO_TREELETS=1 (debug / A-B runs): the one-level re-split.
+    const bool two_level = C != 0 && C <= 8u && n >= 2 && n > C && getenv("HL_NO_TREELETS") == nullptr;
+    while (!two_level && C && tri_tree && n / C > (4u << 20)) C *= 2;
     const bool     resplit  = C != 0 && n >= 2 && n > C;
-    const uint32_t k_cap    = resplit ? (uint32_t)std::min<uint64_t>(n, 4ull * n / C + 1024) : 0u;
+    const uint32_t C_A      = n > (16u << 20) ? 128u : (n > (4u << 20) ? 64u : 32u); // coarse cut of the two-level re-split
+    const uint32_t C_top    = two_level ? C_A : C;                    // cluster size of the level-synchronous kernels
+    const bool     resplit_top = resplit && n > C_top;                // (a tree of at most C_A primitives is one treelet)
+    const uint32_t k_cap    = resplit_top ? (uint32_t)std::min<uint64_t>(n, 4ull * n / C_top + 1024) : (two_level ? 1u : 0u);
     const uint32_t bins_cap = k_cap / (HL_TOP_SMALL + 1u) + 2u;
     const size_t   top_ctl_words = 8 + 2 * (HL_TOP_MAX_LEVELS + 1);
     ScratchBuf     top_crec;
-    ScratchBuf     top_clusters, top_free, top_cnode, top_level[2], top_bins[2], top_list, top_small, top_ctl, top_tmp, top_trace_buf;
+    ScratchBuf     top_clusters, top_free, top_cnode, top_level[2], top_bins[2], top_list, top_small, top_ctl, top_tmp, top_trace_buf, top_treelets, top_tlist;
     size_t         top_tmp_bytes = 0;
     int            top_grid      = 0;
     if (resplit)
     {
-        top_clusters.alloc(4ull * n, st), top_free.alloc(4ull * n, st), top_cnode.alloc(4ull * k_cap, st), top_crec.alloc(sizeof(TopCluster) * (size_t)k_cap, st);
-        for (int p = 0; p < 2; p++)
-        {
-            top_level[p].alloc(sizeof(TopNode) * ((size_t)k_cap + 2), st);
-            top_bins[p].alloc(sizeof(TopBin) * (size_t)bins_cap * (3 * HL_TOP_BINS), st);
-        }
-        top_list.alloc(4ull * ((size_t)k_cap / 2 + 1) * HL_TOP_SMALL, st), top_small.alloc(sizeof(TopSmall) * ((size_t)k_cap / 2 + 1), st);
         top_ctl.alloc(4ull * top_ctl_words, st);
-        if (getenv("HL_TOP_TRACE")) top_trace_buf.alloc(8000, st);
         size_t a = 0, b = 0;
         thrust::counting_iterator<uint32_t> ids(0u);
-        HL_CUDA(cub::DeviceSelect::If(nullptr, a, ids, top_clusters.as<uint32_t>(), top_ctl.as<uint32_t>(), (int)(2 * n - 1), IsClusterRoot { BinaryTree(), C }, st));
-        HL_CUDA(cub::DeviceSelect::If(nullptr, b, ids, top_free.as<uint32_t>(), top_ctl.as<uint32_t>() + 1, (int)(n - 1), IsUpperNode { BinaryTree(), C }, st));
+        top_clusters.alloc(4ull * n, st), top_free.alloc(4ull * n, st);
+        if (resplit_top)
+        {
+            top_cnode.alloc(4ull * k_cap, st), top_crec.alloc(sizeof(TopCluster) * (size_t)k_cap, st);
+            for (int p = 0; p < 2; p++)
+            {
+                top_level[p].alloc(sizeof(TopNode) * ((size_t)k_cap + 2), st);
+                top_bins[p].alloc(sizeof(TopBin) * (size_t)bins_cap * (3 * HL_TOP_BINS), st);
+            }
+            top_list.alloc(4ull * ((size_t)k_cap / 2 + 1) * HL_TOP_SMALL, st), top_small.alloc(sizeof(TopSmall) * ((size_t)k_cap / 2 + 1), st);
+            if (getenv("HL_TOP_TRACE")) top_trace_buf.alloc(8000, st);
+            HL_CUDA(cub::DeviceSelect::If(nullptr, a, ids, top_clusters.as<uint32_t>(), top_ctl.as<uint32_t>(), (int)(2 * n - 1), IsClusterRoot { BinaryTree(), C_top }, st));
+            HL_CUDA(cub::DeviceSelect::If(nullptr, b, ids, top_free.as<uint32_t>(), top_ctl.as<uint32_t>() + 1, (int)(n - 1), IsUpperNode { BinaryTree(), C_top }, st));
+            int per_sm = 0;
+            HL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_top_build, 256, 0));
+            top_grid = ctx->sm_count * std::max(1, std::min(per_sm, 4));
+            top_grid = std::max(1, std::min<int>(top_grid, (int)((k_cap + 255u) / 256u)));
+        }
+        if (two_level)
+        {
+            top_treelets.alloc(sizeof(TopTreelet) * ((size_t)k_cap + 1), st), top_tlist.alloc(4ull * ((size_t)k_cap + 1), st);
+            static bool attr_set = false;
+            if (!attr_set)
+            {
+                HL_CUDA(cudaFuncSetAttribute(k_treelets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeletSmem)));
+                attr_set = true;
+            }
+        }
         top_tmp_bytes = std::max(a, b);
-        top_tmp.alloc(top_tmp_bytes, st);
-        int per_sm = 0;
-        HL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_top_build, 256, 0));
-        top_grid = ctx->sm_count * std::max(1, std::min(per_sm, 4));
-        top_grid = std::max(1, std::min<int>(top_grid, (int)((k_cap + 255u) / 256u)));
+        top_tmp.alloc(std::max<size_t>(top_tmp_bytes, 16), st);
     }
 
     cudaEvent_t e0, e1, e2, e3;
@@ -509,41 +1064,86 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         k_radix_tree<<<grid_for(n - 1, 256, cap), 256, 0, st>>>(keys, t);
         ctx->launches++;
     }
-    k_fit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted, resplit ? C : 0u); // with a re-split: cluster subtrees only, k_top_refit fits the rest
-    ctx->launches++;
+    if (two_level)
+    {
+        k_fit_fine<<<grid_for(2 * n - 1, 256, cap), 256, 0, st>>>(t, d_boxes, sorted, C); // boxes + cost tables inside the fine clusters
+        ctx->launches++;
+    }
+    else
+    {
+        k_fit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted, resplit ? C : 0u); // with a re-split: cluster subtrees only, k_top_refit fits the rest
+        ctx->launches++;
+    }
     if (resplit)
     {
-        uint32_t* ctl = top_ctl.as<uint32_t>(); // [0] K, [1] upper nodes, [2] next free node, [4..5] barrier, [6] small nodes, [8..] per-level counters
+        uint32_t* ctl = top_ctl.as<uint32_t>(); // [0] K, [1] upper nodes, [2] next free node, [3] treelets, [4..5] barrier, [6] small nodes, [7] treelet error, [8..] per-level counters; behind them: tlist entries used
         HL_CUDA(cudaMemsetAsync(ctl, 0, 4ull * top_ctl_words, st));
-        thrust::counting_iterator<uint32_t> ids(0u);
-        HL_CUDA(cub::DeviceSelect::If(top_tmp.p, top_tmp_bytes, ids, top_clusters.as<uint32_t>(), ctl, (int)(2 * n - 1), IsClusterRoot { t, C }, st));
-        HL_CUDA(cub::DeviceSelect::If(top_tmp.p, top_tmp_bytes, ids, top_free.as<uint32_t>(), ctl + 1, (int)(n - 1), IsUpperNode { t, C }, st));
         TopBuild tb;
-        tb.cluster_prims = C, tb.k_cap = k_cap, tb.bins_cap = bins_cap;
+        tb.cluster_prims = C_top, tb.k_cap = k_cap, tb.bins_cap = bins_cap;
         tb.n_clusters = ctl, tb.cluster = top_clusters.as<uint32_t>(), tb.free_nodes = top_free.as<uint32_t>(), tb.cnode = top_cnode.as<uint32_t>(), tb.crec = top_crec.as<TopCluster>();
         for (int p = 0; p < 2; p++) tb.level[p] = top_level[p].as<TopNode>(), tb.bins[p] = top_bins[p].as<TopBin>();
         tb.free_next   = ctl + 2;
         tb.list = top_list.as<uint32_t>(), tb.small = top_small.as<TopSmall>(), tb.small_count = ctl + 6;
         tb.level_count = ctl + 8, tb.bins_used = tb.level_count + (HL_TOP_MAX_LEVELS + 1);
-        uint32_t*           bar    = ctl + 4;
-        unsigned long long* trace  = top_trace_buf.p ? top_trace_buf.as<unsigned long long>() : nullptr;
-        void*               args[] = { (void*)&t, (void*)&tb, (void*)&bar, (void*)&trace };
-        HL_CUDA(cudaLaunchCooperativeKernel((const void*)k_top_build, dim3((unsigned)top_grid), dim3(256), args, 0, st));
-        k_top_small<<<grid_for(k_cap / 2 + 1, 128, ctx->sm_count * 16), 128, 0, st>>>(t, tb);
-        k_top_refit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, tb);
-        ctx->launches += 9;
-        if (trace)
+        if (two_level)
         {
-            std::vector<unsigned long long> h(1000);
-            std::vector<uint32_t>           hc(top_ctl_words);
-            HL_CUDA(cudaMemcpyAsync(h.data(), trace, 8000, cudaMemcpyDeviceToHost, st));
-            HL_CUDA(cudaMemcpyAsync(hc.data(), ctl, 4 * top_ctl_words, cudaMemcpyDeviceToHost, st));
-            HL_CUDA(cudaStreamSynchronize(st));
-            fprintf(stderr, "[top re-split] n %u C %u K %u small %u grid %d: phase us:", n, C, hc[0], hc[6], top_grid);
-            for (uint32_t k = 2; k < h[0] && k < 1000; k++) fprintf(stderr, " %.1f", (double)(h[k] - h[k - 1]) * 1e-3);
-            fprintf(stderr, "\n  nodes per level:");
-            for (uint32_t k = 0; k < HL_TOP_MAX_LEVELS && hc[8 + k]; k++) fprintf(stderr, " %u", hc[8 + k]);
-            fprintf(stderr, "\n");
+            tb.treelet_prims = HL_TREELET_PRIMS, tb.treelet = top_treelets.as<TopTreelet>(), tb.treelet_count = ctl + 3, tb.tlist = top_tlist.as<uint32_t>();
+            tb.tlist_used = tb.bins_used + HL_TOP_MAX_LEVELS; // (the last per-level slot: levels stop at HL_TOP_MAX_LEVELS - 1)
+        }
+        if (resplit_top)
+        {
+            thrust::counting_iterator<uint32_t> ids(0u);
+            HL_CUDA(cub::DeviceSelect::If(top_tmp.p, top_tmp_bytes, ids, top_clusters.as<uint32_t>(), ctl, (int)(2 * n - 1), IsClusterRoot { t, C_top }, st));
+            HL_CUDA(cub::DeviceSelect::If(top_tmp.p, top_tmp_bytes, ids, top_free.as<uint32_t>(), ctl + 1, (int)(n - 1), IsUpperNode { t, C_top }, st));
+            if (two_level)
+            {
+                k_coarse_boxes<<<grid_for(k_cap, 256, cap), 256, 0, st>>>(t, top_clusters.as<uint32_t>(), ctl, C);
+                ctx->launches++;
+            }
+            uint32_t*           bar    = ctl + 4;
+            unsigned long long* trace  = top_trace_buf.p ? top_trace_buf.as<unsigned long long>() : nullptr;
+            void*               args[] = { (void*)&t, (void*)&tb, (void*)&bar, (void*)&trace };
+            HL_CUDA(cudaLaunchCooperativeKernel((const void*)k_top_build, dim3((unsigned)top_grid), dim3(256), args, 0, st));
+            ctx->launches += 5;
+            if (!two_level)
+            {
+                k_top_small<<<grid_for(k_cap / 2 + 1, 128, ctx->sm_count * 16), 128, 0, st>>>(t, tb);
+                k_top_refit<<<grid_for(n, 256, cap), 256, 0, st>>>(t, tb);
+                ctx->launches += 2;
+            }
+            if (trace)
+            {
+                std::vector<unsigned long long> h(1000);
+                std::vector<uint32_t>           hc(top_ctl_words);
+                HL_CUDA(cudaMemcpyAsync(h.data(), trace, 8000, cudaMemcpyDeviceToHost, st));
+                HL_CUDA(cudaMemcpyAsync(hc.data(), ctl, 4 * top_ctl_words, cudaMemcpyDeviceToHost, st));
+                HL_CUDA(cudaStreamSynchronize(st));
+                fprintf(stderr, "[top re-split] n %u C %u K %u small %u treelets %u grid %d: phase us:", n, C_top, hc[0], hc[6], hc[3], top_grid);
+                for (uint32_t k = 2; k < h[0] && k < 1000; k++) fprintf(stderr, " %.1f", (double)(h[k] - h[k - 1]) * 1e-3);
+                fprintf(stderr, "\n  nodes per level:");
+                for (uint32_t k = 0; k < HL_TOP_MAX_LEVELS && hc[8 + k]; k++) fprintf(stderr, " %u", hc[8 + k]);
+                fprintf(stderr, "\n");
+            }
+        }
+        else if (two_level)
+        {
+            // a tree of at most C_A primitives: ONE treelet whose only coarse subtree is the radix tree's root
+            const TopTreelet whole = { 1u, 0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu };
+            const uint32_t   zero = 0u, one = 1u;
+            HL_CUDA(cudaMemcpyAsync(top_treelets.p, &whole, sizeof(whole), cudaMemcpyHostToDevice, st));
+            HL_CUDA(cudaMemcpyAsync(top_tlist.p, &zero, 4, cudaMemcpyHostToDevice, st));
+            HL_CUDA(cudaMemcpyAsync(top_clusters.p, &zero, 4, cudaMemcpyHostToDevice, st));
+            HL_CUDA(cudaMemcpyAsync(ctl + 3, &one, 4, cudaMemcpyHostToDevice, st));
+        }
+        if (two_level)
+        {
+            k_treelets<<<ctx->sm_count * 3, HL_TREELET_THREADS, sizeof(TreeletSmem), st>>>(t, tb, C, ctl + 7);
+            ctx->launches++;
+            if (resplit_top)
+            {
+                k_top_refit_treelets<<<grid_for(k_cap, 256, cap), 256, 0, st>>>(t, tb);
+                ctx->launches++;
+            }
         }
     }
     // collapse: one persistent launch over a device-side work queue, then the leaf records in a parallel pass
@@ -563,8 +1163,11 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     HL_CUDA(cudaEventRecord(e1, st));
     HL_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, 8, cudaMemcpyDeviceToHost, st));
     HL_CUDA(cudaMemcpyAsync(&out.root, t.box, sizeof(Box), cudaMemcpyDeviceToHost, st));
+    uint32_t treelet_err = 0;
+    if (two_level) HL_CUDA(cudaMemcpyAsync(&treelet_err, top_ctl.as<uint32_t>() + 7, 4, cudaMemcpyDeviceToHost, st));
     HL_CUDA(cudaMemcpyAsync(&out.sah_cost, t.cost, 4, cudaMemcpyDeviceToHost, st));
     HL_CUDA(cudaStreamSynchronize(st));
+    if (treelet_err) throw CudaError(HL_ERR_STATE, treelet_err == 1u ? "BVH build: a treelet exceeds the shared-memory arrays" : "BVH build: treelet node ids and clusters do not add up");
     out.n_nodes = h_ctr[0], out.n_leaves = h_ctr[1], out.n_binary = 2 * n - 1;
     {
         const float a = box_half_area(out.root);
