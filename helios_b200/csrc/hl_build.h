@@ -163,14 +163,13 @@ HL_HD void sah_leaf_costs(BinaryTree& t, uint32_t node, float area)
 {
     for (int i = 0; i < 7; i++) t.cost[(size_t)node * 7 + i] = area * t.c_prim;
 }
-HL_HD void sah_node_costs(BinaryTree& t, uint32_t node, float area)
+// the recurrences for one node from its children's rows cl[1..7], cr[1..7] ([0] unused); P = primitives below the node.
+// Writes the node's row and decisions and returns the row in out[0..6].
+HL_HD void sah_node_costs_rows(BinaryTree& t, uint32_t node, float area, uint32_t P, const float* cl, const float* cr, float* out)
 {
-    float cl[8], cr[8];
     const float inf = hl_inf();
-    cl[0] = cr[0] = inf;
-    for (int i = 0; i < 7; i++) cl[i + 1] = load_f32_coherent(t.cost + (size_t)t.left[node] * 7 + i), cr[i + 1] = load_f32_coherent(t.cost + (size_t)t.right[node] * 7 + i);
-    float    D[9];
-    uint32_t K[9];
+    float       D[9];
+    uint32_t    K[9];
     for (int j = 2; j <= 8; j++)
     {
         float    best = inf;
@@ -182,7 +181,6 @@ HL_HD void sah_node_costs(BinaryTree& t, uint32_t node, float area)
         }
         D[j] = best, K[j] = kb;
     }
-    const uint32_t P       = subtree_prims(t, node);
     const float    c_leaf  = P <= HL_MAX_LEAF_PRIMS ? area * (float)P * t.c_prim : inf;
     const float    c_inner = area * HL_SAH_C_NODE + D[8];
     // (the decision must be valid whatever the costs are: with coordinates around 1e20 the areas overflow to +inf, and
@@ -191,14 +189,21 @@ HL_HD void sah_node_costs(BinaryTree& t, uint32_t node, float area)
     float          c       = leaf ? c_leaf : c_inner;
     uint32_t       d       = leaf ? 0u : 15u;
     uint32_t       packed  = d | (K[8] << 28);
-    t.cost[(size_t)node * 7] = c;
+    t.cost[(size_t)node * 7] = c, out[0] = c;
     for (int i = 2; i <= 7; i++)
     {
         if (D[i] < c) c = D[i], d = K[i];
         packed |= d << (4 * (i - 1));
-        t.cost[(size_t)node * 7 + (i - 1)] = c;
+        t.cost[(size_t)node * 7 + (i - 1)] = c, out[i - 1] = c;
     }
     t.dec[node] = packed;
+}
+HL_HD void sah_node_costs(BinaryTree& t, uint32_t node, float area)
+{
+    float cl[8], cr[8], out[7];
+    cl[0] = cr[0] = hl_inf();
+    for (int i = 0; i < 7; i++) cl[i + 1] = load_f32_coherent(t.cost + (size_t)t.left[node] * 7 + i), cr[i + 1] = load_f32_coherent(t.cost + (size_t)t.right[node] * 7 + i);
+    sah_node_costs_rows(t, node, area, subtree_prims(t, node), cl, cr, out);
 }
 
 // bottom-up fit: called once per leaf (after its box is written); the second arrival at a node continues.

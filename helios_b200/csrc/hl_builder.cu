@@ -361,11 +361,16 @@ __global__ void k_top_refit(BinaryTree t, TopBuild tb)
 // through a coarse subtree.  Everything is a function of the input: items in (cluster index, Morton) order, node ids by
 // (level, range index), ties by (axis, bin) — the tree is the same run to run.
 #ifndef HL_TREELET_PRIMS
-#define HL_TREELET_PRIMS 1024u
+#define HL_TREELET_PRIMS 512u /* 36 KB of shared memory per block: 6 treelets in flight per SM (1024 / 256 threads: 69 KB, 3 per SM — the kernel waits on its own barriers and dependent loads, so treelets in flight are what fills the SM) */
 #endif
-#define HL_TREELET_THREADS 256
+#ifndef HL_TREELET_THREADS
+#define HL_TREELET_THREADS 128
+#endif
 #define HL_TREELET_WARPS (HL_TREELET_THREADS / 32)
 #define HL_TREELET_PER_THREAD (HL_TREELET_PRIMS / HL_TREELET_THREADS)
+#define HL_TREELET_TINY 3u   /* ranges of 2..3 clusters are finished by one thread (every partition is evaluated, from registers) */
+#define HL_TREELET_EXACT 8u  /* ranges of at most this many clusters: exact SAH over all three axes by one warp, a candidate plane per lane (the rule of top_small_node); larger ones: 16 bins along the longest axis */
+#define HL_TREELET_ROWS 160u /* warp-built nodes whose children's rows are kept in shared memory (a node per > HL_TOP_SMALL clusters: ~60 in a balanced treelet); a treelet with more of them — a long chain of lopsided splits — is fitted through global memory */
 // first fit, fine clusters only: the thread of a cluster root walks its subtree in post-order (stackless: parent links) and
 // writes leaf boxes, boxes and cost tables — no arrival counters, no fences (the atomic bottom-up pass took 46 of the 80 ms of
 // a 50M-triangle build)
@@ -422,16 +427,30 @@ struct TreeletSmem
     uint32_t prims[HL_TREELET_PRIMS];                          // item primitive counts
     uint32_t node[HL_TREELET_PRIMS];                           // item = fine cluster: its binary node id
     uint32_t ids[HL_TREELET_PRIMS];                            // node ids the treelet may use; [0] becomes its root
-    uint32_t sub_root[HL_TREELET_PRIMS];                       // coarse subtrees of the treelet (sorted by cluster index): root node,
-    uint32_t sub_off[HL_TREELET_PRIMS + 1];                    //   first position in the concatenated leaf ranges
     uint16_t perm[2][HL_TREELET_PRIMS];
     uint16_t seg_start[2][HL_TREELET_PRIMS / 2 + 2], seg_cnt[2][HL_TREELET_PRIMS / 2 + 2];
     uint32_t seg_link[2][HL_TREELET_PRIMS / 2 + 2];
     uint16_t seg_left[HL_TREELET_PRIMS / 2 + 2];   // items that go left, per range of the current level
     uint16_t level_base[HL_TREELET_PRIMS + 2];     // ids[level_base[L] ...] = the nodes created at level L
-    uint16_t small_start[HL_TREELET_PRIMS / 2 + 2], small_cnt[HL_TREELET_PRIMS / 2 + 2], small_id[HL_TREELET_PRIMS / 2 + 2]; // ranges finished by one thread
-    uint32_t small_link[HL_TREELET_PRIMS / 2 + 2]; // bit 31 of small_start's companion: see small_buf
+    uint16_t small_start[HL_TREELET_PRIMS / 2 + 2], small_cnt[HL_TREELET_PRIMS / 2 + 2]; // ranges finished by one thread
+    uint32_t small_link[HL_TREELET_PRIMS / 2 + 2];
     uint8_t  small_buf[HL_TREELET_PRIMS / 2 + 2];  // which perm buffer holds the range
+    uint16_t small_parent[HL_TREELET_PRIMS / 2 + 2]; // local index (position in ids) of the warp-built node above the range
+    uint16_t seg_parent[2][HL_TREELET_PRIMS / 2 + 2];
+    // bottom-up in shared memory: the cost-table rows of the two children of every warp-built node (filled by whoever finishes
+    // the child: the scan stage for single clusters, treelet_small for small ranges, the level pass for warp-built nodes)
+    union
+    {
+        struct
+        {
+            uint32_t sub_root[HL_TREELET_PRIMS];    // coarse subtrees of the treelet (sorted by cluster index): root node,
+            uint32_t sub_off[HL_TREELET_PRIMS + 1]; //   first position in the concatenated leaf ranges (dead once the items are collected)
+        };
+        float child_row[HL_TREELET_ROWS][2][7];
+    };
+    float    node_area[HL_TREELET_ROWS];
+    uint32_t node_prims[HL_TREELET_ROWS];
+    uint16_t node_parent[HL_TREELET_ROWS]; // local index of the parent | side << 15; 0xFFFF = the treelet's root
     alignas(16) TopBin bins[HL_TREELET_WARPS][HL_TOP_BINS]; // (top_clear_bin stores 16 bytes at a time)
     uint32_t scan[HL_TREELET_WARPS + 1];
     uint32_t n_items, n_ids, n_sub;
@@ -512,87 +531,125 @@ __device__ __forceinline__ bool treelet_choose(const TopBin* bins, uint32_t lane
     }
     return best < hl_inf();
 }
-// a range of 2..HL_TOP_SMALL items, by ONE thread: the whole subtree with exact SAH splits (items sorted along each axis, every
-// position between two neighbours is a candidate; the rule of top_small_node), then its boxes / counts / cost tables bottom-up
-__device__ void treelet_small(BinaryTree& t, const TreeletSmem& S, const uint16_t* pin, uint32_t count, uint32_t link, uint32_t id0)
+// a range of 2 or 3 items, by ONE thread, from registers: for three items every partition (one item against the other two) is
+// evaluated — a superset of the sorted-sweep candidates of top_small_node.  Links the nodes, writes their boxes / counts / cost
+// tables; `up` (may be null) receives the row of the range's root.
+struct TinyItem
 {
-    uint8_t  ord[HL_TOP_SMALL];
-    uint32_t created[HL_TOP_SMALL];
-    uint32_t used = 0;
-    for (uint32_t k = 0; k < count; k++) ord[k] = (uint8_t)k;
-    uint8_t  slo[HL_TOP_SMALL], shi[HL_TOP_SMALL];
-    uint32_t slink[HL_TOP_SMALL];
-    int      sp = 0;
-    slo[0] = 0, shi[0] = (uint8_t)count, slink[0] = link, sp = 1;
-    while (sp > 0)
+    Box      b;
+    uint32_t prims, node;
+    float    row[8]; // [1..7]
+};
+__device__ __forceinline__ TinyItem tiny_load(const BinaryTree& t, const TreeletSmem& S, uint32_t it)
+{
+    TinyItem r;
+    for (int q = 0; q < 3; q++) r.b.lo[q] = S.lo[q][it], r.b.hi[q] = S.hi[q][it];
+    r.prims = S.prims[it], r.node = S.node[it];
+    r.row[0] = hl_inf();
+    const float* c = t.cost + (size_t)r.node * 7; // (k_fit_fine's row)
+    for (int i = 0; i < 7; i++) r.row[i + 1] = c[i];
+    return r;
+}
+// node `self` over children x (left) and y (right), both finished; returns the node as an item
+__device__ __forceinline__ TinyItem tiny_join(BinaryTree& t, uint32_t self, uint32_t link, const TinyItem& x, const TinyItem& y)
+{
+    TinyItem r;
+    top_link(t, link, self);
+    top_link(t, self << 1, x.node);
+    top_link(t, (self << 1) | 1u, y.node);
+    r.b = box_union(x.b, y.b);
+    const uint32_t p = x.prims + y.prims;
+    r.prims = p > HL_MAX_LEAF_PRIMS ? p : HL_MAX_LEAF_PRIMS + 1u, r.node = self;
+    t.box[self]   = r.b;
+    t.first[self] = 0u, t.last[self] = r.prims - 1u;
+    r.row[0] = hl_inf();
+    sah_node_costs_rows(t, self, box_half_area(r.b), r.prims, x.row, y.row, r.row + 1);
+    return r;
+}
+__device__ void treelet_tiny(BinaryTree& t, const TreeletSmem& S, const uint16_t* pin, uint32_t count, uint32_t link, uint32_t id0, float* up)
+{
+    const TinyItem a = tiny_load(t, S, pin[0]), b = tiny_load(t, S, pin[1]);
+    TinyItem       root;
+    if (count == 2u)
+        root = tiny_join(t, S.ids[id0], link, a, b);
+    else
     {
-        sp--;
-        const int      lo = slo[sp], hi = shi[sp];
-        const uint32_t lk = slink[sp];
-        if (hi - lo == 1)
-        {
-            top_link(t, lk, S.node[pin[ord[lo]]]);
-            continue;
-        }
-        const uint32_t self = S.ids[id0 + used];
-        created[used++]     = self;
-        top_link(t, lk, self);
-        float best = hl_inf();
-        int   bax = 2, bk = (lo + hi) / 2;
-        for (int pass = 0; pass < 4; pass++)
-        {
-            // passes 0..2 evaluate the axes; pass 3 restores the order of the winning axis (unless it was sorted last)
-            const int ax = pass < 3 ? pass : bax;
-            if (pass == 3 && bax == 2) break;
-            for (int a = lo + 1; a < hi; a++)
-            {
-                const uint8_t m  = ord[a];
-                const float   cm = S.lo[ax][pin[m]] + S.hi[ax][pin[m]];
-                int           b  = a - 1;
-                while (b >= lo && S.lo[ax][pin[ord[b]]] + S.hi[ax][pin[ord[b]]] > cm) ord[b + 1] = ord[b], b--;
-                ord[b + 1] = m;
-            }
-            if (pass == 3) break;
-            float    rarea[HL_TOP_SMALL];
-            uint32_t rprims[HL_TOP_SMALL];
-            float    alo[3], ahi[3];
-            uint32_t p = 0;
-            for (int q = 0; q < 3; q++) alo[q] = hl_inf(), ahi[q] = -hl_inf();
-            for (int k = hi - 1; k > lo; k--)
-            {
-                const uint32_t it = pin[ord[k]];
-                for (int q = 0; q < 3; q++) alo[q] = fminf(alo[q], S.lo[q][it]), ahi[q] = fmaxf(ahi[q], S.hi[q][it]);
-                p += S.prims[it];
-                rarea[k] = (ahi[0] - alo[0]) * (ahi[1] - alo[1]) + (ahi[1] - alo[1]) * (ahi[2] - alo[2]) + (ahi[2] - alo[2]) * (ahi[0] - alo[0]), rprims[k] = p;
-            }
-            for (int q = 0; q < 3; q++) alo[q] = hl_inf(), ahi[q] = -hl_inf();
-            p = 0;
-            for (int k = lo + 1; k < hi; k++)
-            {
-                // left = [lo, k), right = [k, hi)
-                const uint32_t it = pin[ord[k - 1]];
-                for (int q = 0; q < 3; q++) alo[q] = fminf(alo[q], S.lo[q][it]), ahi[q] = fmaxf(ahi[q], S.hi[q][it]);
-                p += S.prims[it];
-                const float larea = (ahi[0] - alo[0]) * (ahi[1] - alo[1]) + (ahi[1] - alo[1]) * (ahi[2] - alo[2]) + (ahi[2] - alo[2]) * (ahi[0] - alo[0]);
-                const float cost  = larea * (float)p + rarea[k] * (float)rprims[k];
-                if (cost < best) best = cost, bax = ax, bk = k;
-            }
-        }
-        slo[sp] = (uint8_t)bk, shi[sp] = (uint8_t)hi, slink[sp] = (self << 1) | 1u, sp++;
-        slo[sp] = (uint8_t)lo, shi[sp] = (uint8_t)bk, slink[sp] = self << 1, sp++;
+        const TinyItem c = tiny_load(t, S, pin[2]);
+        // item k alone against the other two
+        const float c0 = box_half_area(a.b) * (float)a.prims + box_half_area(box_union(b.b, c.b)) * (float)(b.prims + c.prims);
+        const float c1 = box_half_area(b.b) * (float)b.prims + box_half_area(box_union(a.b, c.b)) * (float)(a.prims + c.prims);
+        const float c2 = box_half_area(c.b) * (float)c.prims + box_half_area(box_union(a.b, b.b)) * (float)(a.prims + b.prims);
+        const int   k  = c0 <= c1 && c0 <= c2 ? 0 : (c1 <= c2 ? 1 : 2);
+        const TinyItem& one = k == 0 ? a : (k == 1 ? b : c);
+        const TinyItem& p0  = k == 0 ? b : a;
+        const TinyItem& p1  = k == 2 ? b : c;
+        const uint32_t  self = S.ids[id0], pair = S.ids[id0 + 1u];
+        // (the pair's link is written before the root's own: top_link only touches the child's parent entry and the parent's slot)
+        const TinyItem two = tiny_join(t, pair, (self << 1) | 1u, p0, p1);
+        root               = tiny_join(t, self, link, one, two);
     }
-    // children were created after their parents: the reverse order is bottom-up (all reads are of this thread's own writes or
-    // of the fine clusters fitted by k_fit_fine)
-    for (uint32_t k = used; k-- > 0u;)
+    if (up)
+        for (int i = 0; i < 7; i++) up[i] = root.row[i + 1];
+}
+// exact SAH split of a range of <= 32 items by one warp: lane j evaluates, per axis, the plane that puts the items before item
+// j — in (centroid, position) order — on the left; the cheapest of the 3 x (count - 1) planes wins, ties by (axis, position).
+// Returns false when no plane separates the items (never: positions break ties).  side = this lane's item goes right.
+__device__ __forceinline__ bool treelet_exact(const TreeletSmem& S, const uint16_t* pin, uint32_t cnt, uint32_t lane, bool& right, uint32_t& n_left)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const bool     in   = lane < cnt;
+    const uint32_t me   = in ? pin[lane] : 0u;
+    float          cj[3];
+    for (int a = 0; a < 3; a++) cj[a] = S.lo[a][me] + S.hi[a][me];
+    float    llo[3][3], lhi[3][3], rlo[3][3], rhi[3][3];
+    uint32_t lp[3] = { 0u, 0u, 0u }, rp[3] = { 0u, 0u, 0u }, lc[3] = { 0u, 0u, 0u };
+    for (int a = 0; a < 3; a++)
+        for (int q = 0; q < 3; q++) llo[a][q] = rlo[a][q] = hl_inf(), lhi[a][q] = rhi[a][q] = -hl_inf();
+    for (uint32_t i = 0; i < cnt; i++)
     {
-        const uint32_t node = created[k];
-        const uint32_t lc = t.left[node], rc = t.right[node];
-        const Box      b  = box_union(t.box[lc], t.box[rc]);
-        t.box[node]       = b;
-        const uint32_t p  = subtree_prims(t, lc) + subtree_prims(t, rc);
-        t.first[node] = 0u, t.last[node] = (p > HL_MAX_LEAF_PRIMS ? p : HL_MAX_LEAF_PRIMS + 1u) - 1u;
-        sah_node_costs(t, node, box_half_area(b));
+        const uint32_t it = pin[i];
+        float          lo[3], hi[3];
+        for (int q = 0; q < 3; q++) lo[q] = S.lo[q][it], hi[q] = S.hi[q][it];
+        const uint32_t pr = S.prims[it];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+        {
+            const float ci   = lo[a] + hi[a];
+            const bool  left = ci < cj[a] || (ci == cj[a] && i < lane);
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+            {
+                llo[a][q] = left ? fminf(llo[a][q], lo[q]) : llo[a][q], lhi[a][q] = left ? fmaxf(lhi[a][q], hi[q]) : lhi[a][q];
+                rlo[a][q] = left ? rlo[a][q] : fminf(rlo[a][q], lo[q]), rhi[a][q] = left ? rhi[a][q] : fmaxf(rhi[a][q], hi[q]);
+            }
+            lp[a] += left ? pr : 0u, rp[a] += left ? 0u : pr, lc[a] += left ? 1u : 0u;
+        }
     }
+    float    best = hl_inf();
+    uint32_t key  = 0xFFFFFFFFu; // axis << 8 | lane
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+        if (!in || lc[a] == 0u) continue;
+        const float la = (lhi[a][0] - llo[a][0]) * (lhi[a][1] - llo[a][1]) + (lhi[a][1] - llo[a][1]) * (lhi[a][2] - llo[a][2]) + (lhi[a][2] - llo[a][2]) * (lhi[a][0] - llo[a][0]);
+        const float ra = (rhi[a][0] - rlo[a][0]) * (rhi[a][1] - rlo[a][1]) + (rhi[a][1] - rlo[a][1]) * (rhi[a][2] - rlo[a][2]) + (rhi[a][2] - rlo[a][2]) * (rhi[a][0] - rlo[a][0]);
+        const float c  = la * (float)lp[a] + ra * (float)rp[a];
+        if (c < best) best = c, key = ((uint32_t)a << 8) | lane;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const float    ob = __shfl_xor_sync(FULL, best, d);
+        const uint32_t ok = __shfl_xor_sync(FULL, key, d);
+        if (ob < best || (ob == best && ok < key)) best = ob, key = ok;
+    }
+    if (key == 0xFFFFFFFFu) return false;
+    const uint32_t wa = key >> 8, wj = key & 0xFFu;
+    const float    mine = wa == 0u ? cj[0] : (wa == 1u ? cj[1] : cj[2]);
+    const float    cut  = __shfl_sync(FULL, mine, wj);
+    right  = in && !(mine < cut || (mine == cut && lane < wj));
+    n_left = (uint32_t)__popc(__ballot_sync(FULL, in && !right));
+    return true;
 }
 // err: set to 1 when a treelet does not fit the shared arrays (cannot happen while the primitive counts of the level loop are
 // upper bounds; checked by the host)
@@ -703,7 +760,7 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
             for (uint32_t k = 0; k < HL_TREELET_PER_THREAD; k++)
                 if (idf[k] != 0xFFFFFFFFu) S.ids[at++] = idf[k];
             for (uint32_t k = tid; k < own; k += HL_TREELET_THREADS) S.ids[k] = tb.free_nodes[rec.id_base + k];
-            if (tid == 0) S.n_ids = own + total, S.seg_start[0][0] = 0, S.seg_link[0][0] = link, S.level_base[0] = 0;
+            if (tid == 0) S.n_ids = own + total, S.seg_start[0][0] = 0, S.seg_link[0][0] = link, S.seg_parent[0][0] = 0xFFFFu, S.level_base[0] = 0;
             __syncthreads();
             // a treelet of ONE coarse subtree keeps that subtree's root as its root (the whole tree's root is node 0)
             if (own == 0u)
@@ -723,12 +780,12 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
             continue; // (uniform)
         }
         if (tid == 0) rec.root = S.ids[0];
-        // ---- top-down: one level per iteration, one warp per range; ranges of <= HL_TOP_SMALL items are set aside
+        // ---- top-down: one level per iteration, one warp per range; ranges of <= HL_TREELET_TINY items are set aside
         uint32_t nseg = 0u, nsmall = 0u, level = 0u, base = 0u; // base = ids consumed by the levels above
         uint32_t cur  = 0u;
-        if (n_items <= HL_TOP_SMALL)
+        if (n_items <= HL_TREELET_TINY)
         {
-            if (tid == 0) S.small_start[0] = 0, S.small_cnt[0] = (uint16_t)n_items, S.small_link[0] = link, S.small_buf[0] = 0;
+            if (tid == 0) S.small_start[0] = 0, S.small_cnt[0] = (uint16_t)n_items, S.small_link[0] = link, S.small_buf[0] = 0, S.small_parent[0] = 0xFFFFu;
             nsmall = 1u;
         }
         else
@@ -744,60 +801,90 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
                 const uint32_t  s0 = S.seg_start[cur][k], cnt = S.seg_cnt[cur][k];
                 const uint16_t* pin = S.perm[cur] + s0;
                 uint16_t*       pout = S.perm[cur ^ 1u] + s0;
-                // centroid bounds
+                // centroid bounds, and the node's own box and primitive count
                 uint32_t clo[3] = { HL_ORD_POS_INF, HL_ORD_POS_INF, HL_ORD_POS_INF }, chi[3] = { HL_ORD_NEG_INF, HL_ORD_NEG_INF, HL_ORD_NEG_INF };
+                uint32_t blo[3] = { HL_ORD_POS_INF, HL_ORD_POS_INF, HL_ORD_POS_INF }, bhi[3] = { HL_ORD_NEG_INF, HL_ORD_NEG_INF, HL_ORD_NEG_INF };
+                uint32_t psum = 0u;
                 for (uint32_t i = lane; i < cnt; i += 32u)
                 {
                     const uint32_t it = pin[i];
                     for (int a = 0; a < 3; a++)
                     {
-                        const uint32_t c = f2ord(0.5f * (S.lo[a][it] + S.hi[a][it]));
+                        const float    l = S.lo[a][it], h = S.hi[a][it];
+                        const uint32_t c = f2ord(0.5f * (l + h));
                         clo[a] = min(clo[a], c), chi[a] = max(chi[a], c);
+                        blo[a] = min(blo[a], f2ord(l)), bhi[a] = max(bhi[a], f2ord(h));
                     }
+                    psum += S.prims[it];
                 }
                 float cbl[3], cbh[3];
-                for (int a = 0; a < 3; a++) cbl[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, clo[a])), cbh[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, chi[a]));
-                const float e0 = cbh[0] - cbl[0], e1 = cbh[1] - cbl[1], e2 = cbh[2] - cbl[2];
-                const int   ax = e0 >= e1 && e0 >= e2 ? 0 : (e1 >= e2 ? 1 : 2); // longest axis of the centroid bounds (top_bin_axis)
-                const float al = ax == 0 ? cbl[0] : (ax == 1 ? cbl[1] : cbl[2]), ah = ax == 0 ? cbh[0] : (ax == 1 ? cbh[1] : cbh[2]);
-                TopBin*     bins = S.bins[warp];
-                if (lane < HL_TOP_BINS) top_clear_bin(bins + lane);
-                __syncwarp();
-                for (uint32_t i = lane; i < cnt; i += 32u)
+                Box   nb;
+                for (int a = 0; a < 3; a++)
                 {
-                    const uint32_t it = pin[i];
-                    const int      bi = top_bin_of(0.5f * (S.lo[ax][it] + S.hi[ax][it]), al, ah);
-                    if (bi < 0) continue;
-                    TopBin& B = bins[bi];
-                    for (int q = 0; q < 3; q++) atomicMin(&B.lo[q], f2ord(S.lo[q][it])), atomicMax(&B.hi[q], f2ord(S.hi[q][it]));
-                    atomicAdd(&B.prims, S.prims[it]), atomicAdd(&B.clusters, 1u);
+                    cbl[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, clo[a])), cbh[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, chi[a]));
+                    nb.lo[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, blo[a])), nb.hi[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, bhi[a]));
                 }
-                __syncwarp();
-                uint32_t   sbin, n_left;
-                const bool planar = treelet_choose(bins, lane, sbin, n_left);
-                __syncwarp();
-                if (!planar) n_left = cnt / 2u; // all centroids equal: first half left
-                uint32_t nl = 0u, nr = 0u;
-                for (uint32_t i0 = 0; i0 < cnt; i0 += 32u)
+                psum = __reduce_add_sync(0xFFFFFFFFu, psum);
+                uint32_t n_left = 0u;
+                if (cnt <= HL_TREELET_EXACT)
                 {
-                    const uint32_t i  = i0 + lane;
-                    const bool     in = i < cnt;
-                    uint32_t       it = 0u;
-                    bool           right = false;
-                    if (in)
-                    {
-                        it    = pin[i];
-                        right = planar ? top_bin_of(0.5f * (S.lo[ax][it] + S.hi[ax][it]), al, ah) > (int)sbin : i >= n_left;
-                    }
+                    bool       right  = false;
+                    const bool planar = treelet_exact(S, pin, cnt, lane, right, n_left);
+                    if (!planar) n_left = cnt / 2u, right = lane >= n_left; // (cannot happen for finite boxes)
+                    const bool     in = lane < cnt;
                     const uint32_t mr = __ballot_sync(0xFFFFFFFFu, in && right), ml = __ballot_sync(0xFFFFFFFFu, in && !right);
                     const uint32_t lt = (1u << lane) - 1u;
-                    if (in) pout[right ? n_left + nr + (uint32_t)__popc(mr & lt) : nl + (uint32_t)__popc(ml & lt)] = (uint16_t)it;
-                    nl += (uint32_t)__popc(ml), nr += (uint32_t)__popc(mr);
+                    if (in) pout[right ? n_left + (uint32_t)__popc(mr & lt) : (uint32_t)__popc(ml & lt)] = pin[lane];
+                }
+                else
+                {
+                    const float e0 = cbh[0] - cbl[0], e1 = cbh[1] - cbl[1], e2 = cbh[2] - cbl[2];
+                    const int   ax = e0 >= e1 && e0 >= e2 ? 0 : (e1 >= e2 ? 1 : 2); // longest axis of the centroid bounds (top_bin_axis)
+                    const float al = ax == 0 ? cbl[0] : (ax == 1 ? cbl[1] : cbl[2]), ah = ax == 0 ? cbh[0] : (ax == 1 ? cbh[1] : cbh[2]);
+                    TopBin*     bins = S.bins[warp];
+                    if (lane < HL_TOP_BINS) top_clear_bin(bins + lane);
+                    __syncwarp();
+                    for (uint32_t i = lane; i < cnt; i += 32u)
+                    {
+                        const uint32_t it = pin[i];
+                        const int      bi = top_bin_of(0.5f * (S.lo[ax][it] + S.hi[ax][it]), al, ah);
+                        if (bi < 0) continue;
+                        TopBin& B = bins[bi];
+                        for (int q = 0; q < 3; q++) atomicMin(&B.lo[q], f2ord(S.lo[q][it])), atomicMax(&B.hi[q], f2ord(S.hi[q][it]));
+                        atomicAdd(&B.prims, S.prims[it]), atomicAdd(&B.clusters, 1u);
+                    }
+                    __syncwarp();
+                    uint32_t   sbin;
+                    const bool planar = treelet_choose(bins, lane, sbin, n_left);
+                    __syncwarp();
+                    if (!planar) n_left = cnt / 2u; // all centroids equal: first half left
+                    uint32_t nl = 0u, nr = 0u;
+                    for (uint32_t i0 = 0; i0 < cnt; i0 += 32u)
+                    {
+                        const uint32_t i  = i0 + lane;
+                        const bool     in = i < cnt;
+                        uint32_t       it = 0u;
+                        bool           right = false;
+                        if (in)
+                        {
+                            it    = pin[i];
+                            right = planar ? top_bin_of(0.5f * (S.lo[ax][it] + S.hi[ax][it]), al, ah) > (int)sbin : i >= n_left;
+                        }
+                        const uint32_t mr = __ballot_sync(0xFFFFFFFFu, in && right), ml = __ballot_sync(0xFFFFFFFFu, in && !right);
+                        const uint32_t lt = (1u << lane) - 1u;
+                        if (in) pout[right ? n_left + nr + (uint32_t)__popc(mr & lt) : nl + (uint32_t)__popc(ml & lt)] = (uint16_t)it;
+                        nl += (uint32_t)__popc(ml), nr += (uint32_t)__popc(mr);
+                    }
                 }
                 if (lane == 0u)
                 {
+                    const uint32_t self = S.ids[base + k], idx = base + k;
+                    const uint32_t pf   = psum > HL_MAX_LEAF_PRIMS ? psum : HL_MAX_LEAF_PRIMS + 1u;
                     S.seg_left[k] = (uint16_t)n_left;
-                    top_link(t, S.seg_link[cur][k], S.ids[base + k]);
+                    top_link(t, S.seg_link[cur][k], self);
+                    t.box[self]   = nb;
+                    t.first[self] = 0u, t.last[self] = pf - 1u;
+                    if (idx < HL_TREELET_ROWS) S.node_area[idx] = box_half_area(nb), S.node_prims[idx] = pf, S.node_parent[idx] = (uint16_t)(S.seg_parent[cur][k] == 0xFFFFu ? 0xFFFFu : (S.seg_parent[cur][k] | ((S.seg_link[cur][k] & 1u) << 15)));
                 }
             }
             __syncthreads();
@@ -810,8 +897,8 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
                 if (k < nseg)
                 {
                     s0 = S.seg_start[cur][k], cnt = S.seg_cnt[cur][k], nl = S.seg_left[k], self = S.ids[base + k];
-                    need       = (nl > HL_TOP_SMALL ? 1u : 0u) + (cnt - nl > HL_TOP_SMALL ? 1u : 0u);
-                    need_small = (nl >= 2u && nl <= HL_TOP_SMALL ? 1u : 0u) + (cnt - nl >= 2u && cnt - nl <= HL_TOP_SMALL ? 1u : 0u);
+                    need       = (nl > HL_TREELET_TINY ? 1u : 0u) + (cnt - nl > HL_TREELET_TINY ? 1u : 0u);
+                    need_small = (nl >= 2u && nl <= HL_TREELET_TINY ? 1u : 0u) + (cnt - nl >= 2u && cnt - nl <= HL_TREELET_TINY ? 1u : 0u);
                 }
                 uint32_t tot, tot_small;
                 uint32_t at  = total_next + treelet_block_scan(need, S.scan, tot);
@@ -823,11 +910,16 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
                     {
                         const uint32_t cs = side ? s0 + nl : s0, cc = side ? cnt - nl : nl, lk = (self << 1) | side;
                         if (cc == 1u)
-                            top_link(t, lk, S.node[pnew[cs]]);
-                        else if (cc <= HL_TOP_SMALL)
-                            S.small_start[ats] = (uint16_t)cs, S.small_cnt[ats] = (uint16_t)cc, S.small_link[ats] = lk, S.small_buf[ats] = (uint8_t)(cur ^ 1u), ats++;
+                        {
+                            const uint32_t item_node = S.node[pnew[cs]];
+                            top_link(t, lk, item_node);
+                            if (base + k < HL_TREELET_ROWS)
+                                for (int i = 0; i < 7; i++) S.child_row[base + k][side][i] = t.cost[(size_t)item_node * 7 + i]; // (k_fit_fine's row)
+                        }
+                        else if (cc <= HL_TREELET_TINY)
+                            S.small_start[ats] = (uint16_t)cs, S.small_cnt[ats] = (uint16_t)cc, S.small_link[ats] = lk, S.small_buf[ats] = (uint8_t)(cur ^ 1u), S.small_parent[ats] = (uint16_t)(base + k), ats++;
                         else
-                            S.seg_start[cur ^ 1u][at] = (uint16_t)cs, S.seg_cnt[cur ^ 1u][at] = (uint16_t)cc, S.seg_link[cur ^ 1u][at] = lk, at++;
+                            S.seg_start[cur ^ 1u][at] = (uint16_t)cs, S.seg_cnt[cur ^ 1u][at] = (uint16_t)cc, S.seg_link[cur ^ 1u][at] = lk, S.seg_parent[cur ^ 1u][at] = (uint16_t)(base + k), at++;
                     }
                 }
                 total_next += tot, nsmall += tot_small;
@@ -837,7 +929,9 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
             nseg = total_next, cur ^= 1u;
             __syncthreads();
         }
-        // ---- the small ranges: ids by an exclusive scan over (count - 1), one thread per range (build + fit)
+        // ---- the small ranges: ids by an exclusive scan over (count - 1), one thread per range (build + fit).  Range k goes to
+        // lane k / warps of warp k % warps: the ranges are spread over ALL warps of the block (the threads run long, divergent
+        // instruction streams: with ranges 0..31 on warp 0 the other warps waited at the barrier below for 40 % of the kernel)
         {
             uint32_t run = base;
             for (uint32_t k0 = 0; k0 < nsmall; k0 += HL_TREELET_THREADS)
@@ -846,26 +940,54 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
                 const uint32_t need = k < nsmall ? (uint32_t)S.small_cnt[k] - 1u : 0u;
                 uint32_t       tot;
                 const uint32_t at = run + treelet_block_scan(need, S.scan, tot);
-                if (k < nsmall) treelet_small(t, S, S.perm[S.small_buf[k]] + S.small_start[k], S.small_cnt[k], S.small_link[k], at);
+                if (k < nsmall) S.seg_start[0][k] = (uint16_t)at; // (the range lists are free now: seg_start[0] holds the id offsets)
                 run += tot;
+            }
+            __syncthreads();
+            for (uint32_t k0 = 0; k0 < nsmall; k0 += HL_TREELET_THREADS)
+            {
+                const uint32_t k = k0 + lane * HL_TREELET_WARPS + warp;
+                if (k < nsmall)
+                {
+                    const uint32_t par = S.small_parent[k];
+                    float*         up  = par < HL_TREELET_ROWS ? S.child_row[par][S.small_link[k] & 1u] : nullptr;
+                    treelet_tiny(t, S, S.perm[S.small_buf[k]] + S.small_start[k], S.small_cnt[k], S.small_link[k], S.seg_start[0][k], up);
+                }
             }
         }
         __syncthreads();
-        // ---- bottom-up over the levels: box, primitive count, collapse cost table of every node the warps created
-        for (uint32_t L = level; L-- > 0u;)
+        // ---- bottom-up over the levels the warps created (boxes and counts were written on the way down): the collapse cost tables,
+        // from the children's rows in shared memory; through global memory when the treelet has more warp-built nodes than rows
+        if (base <= HL_TREELET_ROWS)
         {
-            const uint32_t b0 = S.level_base[L], b1 = S.level_base[L + 1u];
-            for (uint32_t k = b0 + tid; k < b1; k += HL_TREELET_THREADS)
+            for (uint32_t L = level; L-- > 0u;)
             {
-                const uint32_t node = S.ids[k];
-                const uint32_t lc = __ldcg(t.left + node), rc = __ldcg(t.right + node);
-                const Box      b  = box_union(load_box_coherent(&t.box[lc]), load_box_coherent(&t.box[rc]));
-                t.box[node]       = b;
-                const uint32_t p  = subtree_prims_cg(t, lc) + subtree_prims_cg(t, rc);
-                t.first[node] = 0u, t.last[node] = (p > HL_MAX_LEAF_PRIMS ? p : HL_MAX_LEAF_PRIMS + 1u) - 1u;
-                sah_node_costs(t, node, box_half_area(b));
+                const uint32_t b0 = S.level_base[L], b1 = S.level_base[L + 1u];
+                for (uint32_t k = b0 + tid; k < b1; k += HL_TREELET_THREADS)
+                {
+                    float cl[8], cr[8], out[7];
+                    cl[0] = cr[0] = hl_inf();
+                    for (int i = 0; i < 7; i++) cl[i + 1] = S.child_row[k][0][i], cr[i + 1] = S.child_row[k][1][i];
+                    sah_node_costs_rows(t, S.ids[k], S.node_area[k], S.node_prims[k], cl, cr, out);
+                    const uint32_t par = S.node_parent[k];
+                    if (par != 0xFFFFu)
+                        for (int i = 0; i < 7; i++) S.child_row[par & 0x7FFFu][par >> 15][i] = out[i];
+                }
+                __syncthreads();
             }
-            __syncthreads();
+        }
+        else
+        {
+            for (uint32_t L = level; L-- > 0u;)
+            {
+                const uint32_t b0 = S.level_base[L], b1 = S.level_base[L + 1u];
+                for (uint32_t k = b0 + tid; k < b1; k += HL_TREELET_THREADS)
+                {
+                    const uint32_t node = S.ids[k];
+                    sah_node_costs(t, node, box_half_area(load_box_coherent(&t.box[node]))); // (children's rows past the L1 as well: load_f32_coherent)
+                }
+                __syncthreads();
+            }
         }
     }
 }
@@ -980,7 +1102,9 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     const bool two_level = C != 0 && C <= 8u && n >= 2 && n > C && getenv("HL_NO_TREELETS") == nullptr;
     while (!two_level && C && tri_tree && n / C > (4u << 20)) C *= 2;
     const bool     resplit  = C != 0 && n >= 2 && n > C;
-    const uint32_t C_A      = n > (16u << 20) ? 128u : (n > (4u << 20) ? 64u : 32u); // coarse cut of the two-level re-split
+    // coarse cut of the two-level re-split; at most HL_TREELET_PRIMS / HL_TOP_SMALL, so that a node of <= HL_TOP_SMALL coarse
+    // subtrees is always a treelet (top_init_node) and the level loop never produces SMALL nodes
+    const uint32_t C_A      = std::min<uint32_t>(n > (4u << 20) ? 64u : 32u, HL_TREELET_PRIMS / HL_TOP_SMALL);
     const uint32_t C_top    = two_level ? C_A : C;                    // cluster size of the level-synchronous kernels
     const bool     resplit_top = resplit && n > C_top;                // (a tree of at most C_A primitives is one treelet)
     const uint32_t k_cap    = resplit_top ? (uint32_t)std::min<uint64_t>(n, 4ull * n / C_top + 1024) : (two_level ? 1u : 0u);
@@ -1137,7 +1261,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         }
         if (two_level)
         {
-            k_treelets<<<ctx->sm_count * 3, HL_TREELET_THREADS, sizeof(TreeletSmem), st>>>(t, tb, C, ctl + 7);
+            k_treelets<<<ctx->sm_count * 6, HL_TREELET_THREADS, sizeof(TreeletSmem), st>>>(t, tb, C, ctl + 7);
             ctx->launches++;
             if (resplit_top)
             {
