@@ -369,7 +369,7 @@ __global__ void k_top_refit(BinaryTree t, TopBuild tb)
 #define HL_TREELET_WARPS (HL_TREELET_THREADS / 32)
 #define HL_TREELET_PER_THREAD (HL_TREELET_PRIMS / HL_TREELET_THREADS)
 #define HL_TREELET_TINY 3u   /* ranges of 2..3 clusters are finished by one thread (every partition is evaluated, from registers) */
-#define HL_TREELET_EXACT 8u  /* ranges of at most this many clusters: exact SAH over all three axes by one warp, a candidate plane per lane (the rule of top_small_node); larger ones: 16 bins along the longest axis */
+#define HL_TREELET_EXACT 8u  /* ranges of at most this many clusters (<= 8: lane = 8 axis + candidate): exact SAH over all three axes by one warp, a candidate plane per lane (the rule of top_small_node); larger ones: 16 bins along the longest axis */
 #define HL_TREELET_ROWS 160u /* warp-built nodes whose children's rows are kept in shared memory (a node per > HL_TOP_SMALL clusters: ~60 in a balanced treelet); a treelet with more of them — a long chain of lopsided splits — is fitted through global memory */
 // first fit, fine clusters only: the thread of a cluster root walks its subtree in post-order (stackless: parent links) and
 // writes leaf boxes, boxes and cost tables — no arrival counters, no fences (the atomic bottom-up pass took 46 of the 80 ms of
@@ -377,9 +377,18 @@ __global__ void k_top_refit(BinaryTree t, TopBuild tb)
 __global__ void k_fit_fine(BinaryTree t, const Box* prim_boxes, const uint32_t* sorted, uint32_t C)
 {
     const uint32_t leaf0 = t.n - 1;
-    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < 2u * t.n - 1u; m += gridDim.x * blockDim.x)
+    // one thread per LEAF (its parent chain is read with neighbouring threads: coalesced; a thread per node re-read five
+    // scattered words per node to find the cluster roots — 5.8 ms at 50M triangles): the thread of a cluster's first leaf fits it
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < t.n; j += gridDim.x * blockDim.x)
     {
-        if (!top_is_cluster_root(t, m, C)) continue;
+        uint32_t m = leaf0 + j;
+        for (;;)
+        {
+            const uint32_t p = t.parent[m];
+            if (p == 0xFFFFFFFFu || subtree_prims(t, p) > C) break;
+            m = p;
+        }
+        if (subtree_first(t, m) != j) continue;
         uint32_t node = m;
         while (node < leaf0) node = t.left[node];
         for (;;)
@@ -405,7 +414,6 @@ __global__ void k_fit_fine(BinaryTree t, const Box* prim_boxes, const uint32_t* 
         }
     }
 }
-
 // boxes of the coarse subtrees' roots (what the level loop bins): union of the leaf boxes k_fit_fine wrote.  The nodes between
 // the two cuts are not fitted here — the treelets re-link them.
 __global__ void k_coarse_boxes(BinaryTree t, const uint32_t* cluster, const uint32_t* n_clusters, uint32_t C)
@@ -591,50 +599,43 @@ __device__ void treelet_tiny(BinaryTree& t, const TreeletSmem& S, const uint16_t
     if (up)
         for (int i = 0; i < 7; i++) up[i] = root.row[i + 1];
 }
-// exact SAH split of a range of <= 32 items by one warp: lane j evaluates, per axis, the plane that puts the items before item
-// j — in (centroid, position) order — on the left; the cheapest of the 3 x (count - 1) planes wins, ties by (axis, position).
-// Returns false when no plane separates the items (never: positions break ties).  side = this lane's item goes right.
+// exact SAH split of a range of <= 8 items by one warp: lane 8 a + j evaluates, along axis a, the plane that puts the items
+// before item j — in (centroid, position) order — on the left; the cheapest of the 3 x (count - 1) planes wins, ties by (axis,
+// position).  Returns false when no plane separates the items (only when no centroid compares: non-finite boxes).  right = the
+// item at position `lane` goes right.
 __device__ __forceinline__ bool treelet_exact(const TreeletSmem& S, const uint16_t* pin, uint32_t cnt, uint32_t lane, bool& right, uint32_t& n_left)
 {
     const unsigned FULL = 0xFFFFFFFFu;
-    const bool     in   = lane < cnt;
-    const uint32_t me   = in ? pin[lane] : 0u;
-    float          cj[3];
-    for (int a = 0; a < 3; a++) cj[a] = S.lo[a][me] + S.hi[a][me];
-    float    llo[3][3], lhi[3][3], rlo[3][3], rhi[3][3];
-    uint32_t lp[3] = { 0u, 0u, 0u }, rp[3] = { 0u, 0u, 0u }, lc[3] = { 0u, 0u, 0u };
-    for (int a = 0; a < 3; a++)
-        for (int q = 0; q < 3; q++) llo[a][q] = rlo[a][q] = hl_inf(), lhi[a][q] = rhi[a][q] = -hl_inf();
+    const uint32_t a = lane >> 3, j = lane & 7u;
+    const bool     cand = a < 3u && j < cnt;
+    const uint32_t ax = cand ? a : 0u, me = pin[cand ? j : 0u];
+    const float    cj = S.lo[ax][me] + S.hi[ax][me];
+    float          llo[3], lhi[3], rlo[3], rhi[3];
+    uint32_t       lp = 0u, rp = 0u, lc = 0u;
+    for (int q = 0; q < 3; q++) llo[q] = rlo[q] = hl_inf(), lhi[q] = rhi[q] = -hl_inf();
     for (uint32_t i = 0; i < cnt; i++)
     {
         const uint32_t it = pin[i];
-        float          lo[3], hi[3];
-        for (int q = 0; q < 3; q++) lo[q] = S.lo[q][it], hi[q] = S.hi[q][it];
+        const float    ci = S.lo[ax][it] + S.hi[ax][it];
+        const bool     left = ci < cj || (ci == cj && i < j);
         const uint32_t pr = S.prims[it];
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+        for (int q = 0; q < 3; q++)
         {
-            const float ci   = lo[a] + hi[a];
-            const bool  left = ci < cj[a] || (ci == cj[a] && i < lane);
-#pragma unroll
-            for (int q = 0; q < 3; q++)
-            {
-                llo[a][q] = left ? fminf(llo[a][q], lo[q]) : llo[a][q], lhi[a][q] = left ? fmaxf(lhi[a][q], hi[q]) : lhi[a][q];
-                rlo[a][q] = left ? rlo[a][q] : fminf(rlo[a][q], lo[q]), rhi[a][q] = left ? rhi[a][q] : fmaxf(rhi[a][q], hi[q]);
-            }
-            lp[a] += left ? pr : 0u, rp[a] += left ? 0u : pr, lc[a] += left ? 1u : 0u;
+            const float lo = S.lo[q][it], hi = S.hi[q][it];
+            llo[q] = left ? fminf(llo[q], lo) : llo[q], lhi[q] = left ? fmaxf(lhi[q], hi) : lhi[q];
+            rlo[q] = left ? rlo[q] : fminf(rlo[q], lo), rhi[q] = left ? rhi[q] : fmaxf(rhi[q], hi);
         }
+        lp += left ? pr : 0u, rp += left ? 0u : pr, lc += left ? 1u : 0u;
     }
     float    best = hl_inf();
-    uint32_t key  = 0xFFFFFFFFu; // axis << 8 | lane
-#pragma unroll
-    for (int a = 0; a < 3; a++)
+    uint32_t key  = 0xFFFFFFFFu; // axis << 8 | position
+    if (cand && lc != 0u)
     {
-        if (!in || lc[a] == 0u) continue;
-        const float la = (lhi[a][0] - llo[a][0]) * (lhi[a][1] - llo[a][1]) + (lhi[a][1] - llo[a][1]) * (lhi[a][2] - llo[a][2]) + (lhi[a][2] - llo[a][2]) * (lhi[a][0] - llo[a][0]);
-        const float ra = (rhi[a][0] - rlo[a][0]) * (rhi[a][1] - rlo[a][1]) + (rhi[a][1] - rlo[a][1]) * (rhi[a][2] - rlo[a][2]) + (rhi[a][2] - rlo[a][2]) * (rhi[a][0] - rlo[a][0]);
-        const float c  = la * (float)lp[a] + ra * (float)rp[a];
-        if (c < best) best = c, key = ((uint32_t)a << 8) | lane;
+        const float la = (lhi[0] - llo[0]) * (lhi[1] - llo[1]) + (lhi[1] - llo[1]) * (lhi[2] - llo[2]) + (lhi[2] - llo[2]) * (lhi[0] - llo[0]);
+        const float ra = (rhi[0] - rlo[0]) * (rhi[1] - rlo[1]) + (rhi[1] - rlo[1]) * (rhi[2] - rlo[2]) + (rhi[2] - rlo[2]) * (rhi[0] - rlo[0]);
+        const float c  = la * (float)lp + ra * (float)rp;
+        if (c < hl_inf()) best = c, key = (a << 8) | j;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
@@ -645,8 +646,9 @@ __device__ __forceinline__ bool treelet_exact(const TreeletSmem& S, const uint16
     }
     if (key == 0xFFFFFFFFu) return false;
     const uint32_t wa = key >> 8, wj = key & 0xFFu;
-    const float    mine = wa == 0u ? cj[0] : (wa == 1u ? cj[1] : cj[2]);
-    const float    cut  = __shfl_sync(FULL, mine, wj);
+    const bool     in = lane < cnt;
+    const uint32_t it = pin[in ? lane : 0u], cut_it = pin[wj];
+    const float    mine = S.lo[wa][it] + S.hi[wa][it], cut = S.lo[wa][cut_it] + S.hi[wa][cut_it];
     right  = in && !(mine < cut || (mine == cut && lane < wj));
     n_left = (uint32_t)__popc(__ballot_sync(FULL, in && !right));
     return true;
@@ -802,18 +804,17 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
                 const uint16_t* pin = S.perm[cur] + s0;
                 uint16_t*       pout = S.perm[cur ^ 1u] + s0;
                 // centroid bounds, and the node's own box and primitive count
-                uint32_t clo[3] = { HL_ORD_POS_INF, HL_ORD_POS_INF, HL_ORD_POS_INF }, chi[3] = { HL_ORD_NEG_INF, HL_ORD_NEG_INF, HL_ORD_NEG_INF };
-                uint32_t blo[3] = { HL_ORD_POS_INF, HL_ORD_POS_INF, HL_ORD_POS_INF }, bhi[3] = { HL_ORD_NEG_INF, HL_ORD_NEG_INF, HL_ORD_NEG_INF };
+                float    clo[3] = { hl_inf(), hl_inf(), hl_inf() }, chi[3] = { -hl_inf(), -hl_inf(), -hl_inf() };
+                float    blo[3] = { hl_inf(), hl_inf(), hl_inf() }, bhi[3] = { -hl_inf(), -hl_inf(), -hl_inf() };
                 uint32_t psum = 0u;
                 for (uint32_t i = lane; i < cnt; i += 32u)
                 {
                     const uint32_t it = pin[i];
                     for (int a = 0; a < 3; a++)
                     {
-                        const float    l = S.lo[a][it], h = S.hi[a][it];
-                        const uint32_t c = f2ord(0.5f * (l + h));
-                        clo[a] = min(clo[a], c), chi[a] = max(chi[a], c);
-                        blo[a] = min(blo[a], f2ord(l)), bhi[a] = max(bhi[a], f2ord(h));
+                        const float l = S.lo[a][it], h = S.hi[a][it], c = 0.5f * (l + h);
+                        clo[a] = fminf(clo[a], c), chi[a] = fmaxf(chi[a], c);
+                        blo[a] = fminf(blo[a], l), bhi[a] = fmaxf(bhi[a], h);
                     }
                     psum += S.prims[it];
                 }
@@ -821,8 +822,8 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
                 Box   nb;
                 for (int a = 0; a < 3; a++)
                 {
-                    cbl[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, clo[a])), cbh[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, chi[a]));
-                    nb.lo[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, blo[a])), nb.hi[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, bhi[a]));
+                    cbl[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, f2ord(clo[a]))), cbh[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, f2ord(chi[a])));
+                    nb.lo[a] = ord2f(__reduce_min_sync(0xFFFFFFFFu, f2ord(blo[a]))), nb.hi[a] = ord2f(__reduce_max_sync(0xFFFFFFFFu, f2ord(bhi[a])));
                 }
                 psum = __reduce_add_sync(0xFFFFFFFFu, psum);
                 uint32_t n_left = 0u;
@@ -1099,12 +1100,15 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     uint32_t   C        = ctx->sah_cluster == 0 ? 0u : (tri_tree ? ctx->sah_cluster : 1u);
     // two-level re-split (k_treelets): the fine cut stays at C whatever the size — nothing is kept per fine cluster —, the
     // level loop runs over the coarse cut C_A and stops at treelets.  HL_NO_TREELETS=1 (debug / A-B runs): the one-level re-split.
-    const bool two_level = C != 0 && C <= 8u && n >= 2 && n > C && getenv("HL_NO_TREELETS") == nullptr;
+    // Triangle trees only: an instance tree has a few thousand large, overlapping boxes — planes that cannot cut through a coarse
+    // subtree of 32 instances cost the city scene 7 % of its frame time, and its build takes 0.1 ms either way.
+    const bool two_level = tri_tree && C != 0 && C <= 8u && n >= 2 && n > C && getenv("HL_NO_TREELETS") == nullptr;
     while (!two_level && C && tri_tree && n / C > (4u << 20)) C *= 2;
     const bool     resplit  = C != 0 && n >= 2 && n > C;
     // coarse cut of the two-level re-split; at most HL_TREELET_PRIMS / HL_TOP_SMALL, so that a node of <= HL_TOP_SMALL coarse
     // subtrees is always a treelet (top_init_node) and the level loop never produces SMALL nodes
-    const uint32_t C_A      = std::min<uint32_t>(n > (4u << 20) ? 64u : 32u, HL_TREELET_PRIMS / HL_TOP_SMALL);
+    uint32_t       C_A      = std::min<uint32_t>(n > (4u << 20) ? 64u : 32u, HL_TREELET_PRIMS / HL_TOP_SMALL);
+    if (const char* e = getenv("HL_COARSE_CUT")) C_A = std::min<uint32_t>(std::max(2 * C, (uint32_t)atoi(e)), HL_TREELET_PRIMS / HL_TOP_SMALL); // (tuning runs)
     const uint32_t C_top    = two_level ? C_A : C;                    // cluster size of the level-synchronous kernels
     const bool     resplit_top = resplit && n > C_top;                // (a tree of at most C_A primitives is one treelet)
     const uint32_t k_cap    = resplit_top ? (uint32_t)std::min<uint64_t>(n, 4ull * n / C_top + 1024) : (two_level ? 1u : 0u);
@@ -1190,7 +1194,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     }
     if (two_level)
     {
-        k_fit_fine<<<grid_for(2 * n - 1, 256, cap), 256, 0, st>>>(t, d_boxes, sorted, C); // boxes + cost tables inside the fine clusters
+        k_fit_fine<<<grid_for(n, 256, cap), 256, 0, st>>>(t, d_boxes, sorted, C); // boxes + cost tables inside the fine clusters
         ctx->launches++;
     }
     else
