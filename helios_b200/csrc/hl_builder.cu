@@ -361,15 +361,19 @@ __global__ void k_top_refit(BinaryTree t, TopBuild tb)
 // through a coarse subtree.  Everything is a function of the input: items in (cluster index, Morton) order, node ids by
 // (level, range index), ties by (axis, bin) — the tree is the same run to run.
 #ifndef HL_TREELET_PRIMS
-#define HL_TREELET_PRIMS 512u /* 36 KB of shared memory per block: 6 treelets in flight per SM (1024 / 256 threads: 69 KB, 3 per SM — the kernel waits on its own barriers and dependent loads, so treelets in flight are what fills the SM) */
+#define HL_TREELET_PRIMS 512u /* 44 KB of shared memory per block of 128 threads: 5 treelets in flight per SM.  Measured (tools/tune_trace.py set "treelet"): 256 / 512 / 1024 primitives give SAH 123.7 / 122.7 / 122.5 on the 5M-triangle foliage mesh (one-level re-split: 120.6) and the same frame times within the run-to-run noise */
 #endif
 #ifndef HL_TREELET_THREADS
 #define HL_TREELET_THREADS 128
 #endif
 #define HL_TREELET_WARPS (HL_TREELET_THREADS / 32)
 #define HL_TREELET_PER_THREAD (HL_TREELET_PRIMS / HL_TREELET_THREADS)
+#ifndef HL_TREELET_TINY
 #define HL_TREELET_TINY 3u   /* ranges of 2..3 clusters are finished by one thread (every partition is evaluated, from registers) */
+#endif
+#ifndef HL_TREELET_EXACT
 #define HL_TREELET_EXACT 8u  /* ranges of at most this many clusters (<= 8: lane = 8 axis + candidate): exact SAH over all three axes by one warp, a candidate plane per lane (the rule of top_small_node); larger ones: 16 bins along the longest axis */
+#endif
 #define HL_TREELET_ROWS 160u /* warp-built nodes whose children's rows are kept in shared memory (a node per > HL_TOP_SMALL clusters: ~60 in a balanced treelet); a treelet with more of them — a long chain of lopsided splits — is fitted through global memory */
 // first fit, fine clusters only: the thread of a cluster root walks its subtree in post-order (stackless: parent links) and
 // writes leaf boxes, boxes and cost tables — no arrival counters, no fences (the atomic bottom-up pass took 46 of the 80 ms of

@@ -150,6 +150,49 @@ def test_builder_sah_cluster_never_changes_a_result(api, oracle_mod, scene):
     assert nodes[100_000] == nodes[0]  # a cut above the root leaves the radix tree alone
 
 
+@pytest.mark.parametrize("scene", ["soup", "foliage", "degenerate"])
+def test_builder_two_level_resplit(api, oracle_mod, scene, monkeypatch):
+    """The two-level re-split (hl_builder.cu k_treelets: level loop over a coarse cut, every treelet re-split by one block in
+    shared memory) against the one-level re-split (HL_NO_TREELETS=1) and the oracle: a different tree, the same hits bit for
+    bit; the same tree (wide-node count, SAH cost) on every run; and a degenerate input — every triangle twice, most of them
+    in one spot, so that whole treelets have equal centroids — still builds and still returns the oracle's hits"""
+    if scene == "soup":
+        s = scenes.triangle_soup(300_000, 480, 270)
+    elif scene == "foliage":
+        s = scenes.foliage_scene(n_clusters=3000, width=320, height=180)
+    else:
+        s = scenes.triangle_soup(40_000, 320, 180)
+        m = s.meshes[0]
+        # collapse the second half of the vertices onto one point (equal centroids, zero-extent boxes), then list every triangle twice
+        v = m.vertices.copy()
+        v["position"][len(v) // 2 :] = v["position"][len(v) // 2]
+        m.vertices = v
+        m.indices = np.concatenate([m.indices, m.indices])
+        sm = m.submeshes.copy()
+        sm["index_count"] *= 2
+        m.submeshes = sm
+    pc = s.push_constants(1)
+    ref = oracle_mod.OracleScene(s).trace_primary_ids(pc)
+    stats = []
+    for env in (None, None, "1"):
+        if env:
+            monkeypatch.setenv("HL_NO_TREELETS", env)
+        ctx = api.Context(s.width, s.height)
+        handles = ctx.load_scene(s)
+        st = ctx.mesh_build_stats(handles[-2] if scene == "foliage" else handles[0])
+        stats.append((int(st["wide_nodes"]), float(st["sah_cost"])))
+        # duplicated triangles: equal t, the tie rule picks the lower primitive id on both sides
+        check_ids(ctx.trace_primary_ids(pc), ref)
+        ctx.close()
+    monkeypatch.delenv("HL_NO_TREELETS", raising=False)
+    assert stats[0] == stats[1], f"two builds of the same input differ: {stats[0]} vs {stats[1]}"
+    if scene != "degenerate":
+        assert stats[2][0] != stats[0][0]  # the one-level re-split builds another tree
+        # (measured: +1.4 % on the terrain, +2 % on the 5M-triangle foliage mesh, +5 % on this small foliage mesh — above the
+        #  treelets a plane cannot cut through a coarse subtree)
+        assert stats[0][1] < 1.08 * stats[2][1], f"SAH cost {stats[0][1]} vs {stats[2][1]} of the one-level re-split"
+
+
 def test_terrain_sky_scene(api, oracle_mod):
     from helios_b200.sky import sky_coefficients
 

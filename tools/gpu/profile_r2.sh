@@ -10,7 +10,7 @@ ncu -i gpurun_out/${TAG}_frame.ncu-rep --page raw --csv > gpurun_out/${TAG}_fram
 # source pages (SASS + per-instruction counters) of the launches that matter: k_extend bounce 0 and 1, k_shade 0 and 1, k_connect 0, k_tail (first)
 for k in 0 1 2 3 4 12; do ncu -i gpurun_out/${TAG}_frame.ncu-rep --page source --csv --launch-skip $k --launch-count 1 2>/dev/null | cut -d, -f1-12 > gpurun_out/${TAG}_frame_source_$k.csv; done
 rm -f gpurun_out/${TAG}_frame.ncu-rep
-ncu --set full --clock-control none --import-source on -k regex:'k_fit|k_top_build|k_top_small|k_top_refit|k_collapse|k_radix_tree|k_write_leaves|k_tri_boxes' -c 9 -o gpurun_out/${TAG}_builder -f python tools/sweep_build.py --sizes 1000000 --no-oracle-above 0 > gpurun_out/${TAG}_builder.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_fit_fine|k_coarse_boxes|k_top_build|k_treelets|k_top_refit_treelets|k_collapse|k_radix_tree|k_write_leaves|k_tri_boxes' -c 10 -o gpurun_out/${TAG}_builder -f python tools/sweep_build.py --sizes 1000000 --no-oracle-above 0 > gpurun_out/${TAG}_builder.log 2>&1
 ncu -i gpurun_out/${TAG}_builder.ncu-rep --page raw --csv > gpurun_out/${TAG}_builder_raw.csv 2>/dev/null
 rm -f gpurun_out/${TAG}_builder.ncu-rep
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_builder_launches.csv python tools/sweep_build.py --sizes 1000000 --no-oracle-above 0 > /dev/null 2>&1

@@ -9,7 +9,8 @@ from helios_b200 import scenes, api, abi
 for mk in (lambda: scenes.cornell_box(64, 48),
            lambda: scenes.foliage_scene(n_clusters=60, cards_per_cluster=12, width=64, height=36, ground_grid=8, tex_size=32),
            lambda: scenes.city_scene(n_instances=30, n_meshes=3, width=64, height=36, floors=(2, 4), detail=(1, 3)),
-           lambda: scenes.terrain_scene(grid=40, n_spheres=6, sphere_level=1, width=64, height=36, textured=True)):
+           lambda: scenes.terrain_scene(grid=40, n_spheres=6, sphere_level=1, width=64, height=36, textured=True),
+           lambda: scenes.triangle_soup(30_000, 64, 36)):  # the two-level re-split with a few dozen treelets (k_treelets)
     s = mk()
     ctx = api.Context(s.width, s.height)
     ctx.load_scene(s)

@@ -44,6 +44,7 @@ VARIANT_SETS["coop"] = {
     "coop2": ["-DHL_COOP_K=2"], "coop2_mb7": ["-DHL_COOP_K=2", "-DHL_TRACE_MIN_BLOCKS=7"], "coop3_mb6": ["-DHL_COOP_K=3", "-DHL_TRACE_MIN_BLOCKS=6"],
 }
 VARIANT_SETS["fol"] = {"base": [], "tri3": ["-DHL_TRI_PER_STEP=3"], "tri4": ["-DHL_TRI_PER_STEP=4"], "tri1": ["-DHL_TRI_PER_STEP=1"], "refill4": ["-DHL_REFILL_MIN=4"], "refill16": ["-DHL_REFILL_MIN=16"]}
+VARIANT_SETS["treelet"] = {"base": [], "tiny1": ["-DHL_TREELET_TINY=1"], "exact3": ["-DHL_TREELET_EXACT=3"], "prims256": ["-DHL_TREELET_PRIMS=256"], "prims1024": ["-DHL_TREELET_PRIMS=1024"]}
 VARIANTS = VARIANT_SETS[os.environ.get("HL_TUNE_SET", "occ")]
 OUT = ROOT / "build" / "variants"
 if sys.argv[1] == "build":
