@@ -28,7 +28,7 @@ namespace hl
 #define HL_TRACE_BOUNDS __launch_bounds__(HL_TRACE_BLOCK)
 #endif
 #ifndef HL_TRACE_GRID_MULT
-#define HL_TRACE_GRID_MULT 8 /* persistent trace kernels: CTAs launched per SM */
+#define HL_TRACE_GRID_MULT 6 /* persistent trace kernels: CTAs launched per SM (7 fit; measured with four frames in flight, tools/tune_trace.py set "grid": 4 / 5 / 6 / 7 / 8 / 12 give 1.461 / 1.431 / 1.444 / 1.489 / 1.468 / 1.479 ms on configs[1] and 4.69 / 4.47 / 4.22 / 4.31 / 4.34 / 4.34 ms on configs[2]: one CTA slot per SM left to the other frames' kernels) */
 #endif
 #ifndef HL_SHADE_BLOCK
 #define HL_SHADE_BLOCK 128
