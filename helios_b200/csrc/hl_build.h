@@ -853,7 +853,7 @@ HL_HD void publish_task(CollapseTask* slot, CollapseTask t)
 // queue `next` (slots handed out by `next_count`) and returns how many it appended.
 // leaf_writer(dst_leaf_index, sorted_leaf_position) stores one leaf primitive record.
 template <class LeafWriter>
-HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, CollapseTask* next, uint32_t* next_count, LeafWriter& leaf_writer)
+HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out, CollapseTask* next, uint32_t* next_count, LeafWriter& leaf_writer, uint32_t* outstanding = nullptr)
 {
     uint32_t ch[8];
     uint32_t ch_inner = 0; // bit k: child k becomes a wide node of its own
@@ -907,12 +907,13 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
     {
         float bc = 3.0e38f;
         int   bk = -1, bs = -1;
-        for (int k = 0; k < nch; k++)
+        // (the remaining children x the free slots, both in ascending order: bit scans instead of 64 tests per round)
+        for (uint32_t km = ~child_done & ((1u << nch) - 1u); km; km &= km - 1u)
         {
-            if (child_done & (1u << k)) continue;
-            for (int s = 0; s < 8; s++)
+            const int k = hl_bfind(km & (0u - km));
+            for (uint32_t sm = ~slot_done & 0xFFu; sm; sm &= sm - 1u)
             {
-                if (slot_done & (1u << s)) continue;
+                const int   s = hl_bfind(sm & (0u - sm));
                 const float c = cost[k * 8 + s];
                 if (c < bc) bc = c, bk = k, bs = s;
             }
@@ -949,6 +950,24 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
     uint32_t first_task = hl_alloc_var(next_count, n_inner);
     if (!n_inner) w.child_base = 0u;
     if (!n_leafprims) w.leaf_base = 0u;
+    // the children's tasks first: the threads polling for them start while this one still quantises boxes and writes leaves.
+    // `outstanding` (persistent GPU launch: published - finished tasks) grows BEFORE a child can be seen, so that a child which
+    // finishes before its parent does never brings the count to zero early.
+    if (outstanding)
+    {
+        hl_alloc_var(outstanding, n_inner);
+#if defined(__CUDA_ARCH__)
+        __threadfence(); // the count is in place before any of the tasks below can be seen
+#endif
+    }
+    for (int s = 0; s < 8; s++)
+        if (slot_child[s] >= 0 && (imask & (1u << s)))
+        {
+            CollapseTask nt;
+            nt.wide = w.child_base + inner_rank, nt.bnode = ch[slot_child[s]];
+            publish_task(next + (first_task + inner_rank), nt);
+            inner_rank++;
+        }
     for (int s = 0; s < 8; s++)
     {
         if (slot_child[s] < 0)
@@ -966,10 +985,6 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
         if (imask & (1u << s))
         {
             w.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
-            CollapseTask nt;
-            nt.wide = w.child_base + inner_rank, nt.bnode = c;
-            publish_task(next + (first_task + inner_rank), nt);
-            inner_rank++;
         }
         else
         {

@@ -1037,15 +1037,14 @@ __global__ void __launch_bounds__(128) k_collapse(BinaryTree t, WideOut out, Col
         }
         if (ready)
         {
-            const uint32_t spawned = collapse_one(t, task, out, queue, ctl + 2, writer);
-            have                   = false;
-            // outstanding += spawned - 1 (summed over the lanes that finished a task together: one atomic); the update that brings
-            // it to zero ends the launch.  Every finished task was published before, so zero is only reached at the very end.
+            collapse_one(t, task, out, queue, ctl + 2, writer, ctl + 4); // (adds the tasks it publishes to ctl[4] before publishing them)
+            have = false;
+            // outstanding -= 1 per finished task (summed over the lanes that finished together: one atomic); the update that brings
+            // it to zero ends the launch: every published task was counted before it became visible, so zero means none is left.
             {
                 namespace cg = cooperative_groups;
-                const cg::coalesced_group g     = cg::coalesced_threads();
-                const uint32_t            delta = cg::reduce(g, spawned - 1u, cg::plus<uint32_t>());
-                if (g.thread_rank() == 0 && atomicAdd(ctl + 4, delta) + delta == 0u)
+                const cg::coalesced_group g = cg::coalesced_threads();
+                if (g.thread_rank() == 0 && atomicSub(ctl + 4, g.size()) == g.size())
                 {
                     __threadfence();
                     *vdone = 1u;
