@@ -60,6 +60,9 @@ def build_library(force: bool = False, verbose: bool = False, defines: list[str]
 TEST_VARIANTS = {
     # a 3-entry traversal stack: tests/test_gpu_edges.py checks that overflows are counted and hl_get_counters fails loudly
     "stack3": ["-DHL_STACK_FAST=2", "-DHL_STACK_SPILL=1"],
+    # four shared-memory cost rows per treelet: nearly every treelet of the two-level BVH re-split is fitted through global memory
+    # (the path a treelet with a long chain of lopsided splits takes): tests/test_gpu_edges.py compares the trees
+    "rows4": ["-DHL_TREELET_ROWS=4"],
 }
 
 

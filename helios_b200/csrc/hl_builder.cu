@@ -374,7 +374,9 @@ __global__ void k_top_refit(BinaryTree t, TopBuild tb)
 #ifndef HL_TREELET_EXACT
 #define HL_TREELET_EXACT 8u  /* ranges of at most this many clusters (<= 8: lane = 8 axis + candidate): exact SAH over all three axes by one warp, a candidate plane per lane (the rule of top_small_node); larger ones: 16 bins along the longest axis */
 #endif
+#ifndef HL_TREELET_ROWS
 #define HL_TREELET_ROWS 160u /* warp-built nodes whose children's rows are kept in shared memory (a node per > HL_TOP_SMALL clusters: ~60 in a balanced treelet); a treelet with more of them — a long chain of lopsided splits — is fitted through global memory */
+#endif
 // first fit, fine clusters only: the thread of a cluster root walks its subtree in post-order (stackless: parent links) and
 // writes leaf boxes, boxes and cost tables — no arrival counters, no fences (the atomic bottom-up pass took 46 of the 80 ms of
 // a 50M-triangle build)

@@ -405,3 +405,46 @@ def test_stack_overflow_fails_hl_get_counters_loudly(tmp_path):
     r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=dict(os.environ, HELIOS_B200_LIB=str(lib)), timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "status 5 True" in r.stdout and "reset ok" in r.stdout, r.stdout  # HL_ERR_LIMIT
+
+
+def test_treelet_fallback_fit_builds_the_same_tree():
+    """hl_builder.cu k_treelets keeps the cost rows of a treelet's warp-built nodes in shared memory (HL_TREELET_ROWS of them) and
+    fits a treelet that has more through global memory.  tests/_variants/libhelios_b200_rows4.so (4 rows: nearly every treelet
+    takes that path) must build the same trees — wide-node count and SAH cost — and return the same hits as the product library."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import textwrap
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    lib = root / "tests" / "_variants" / "libhelios_b200_rows4.so"
+    if not lib.exists():
+        pytest.skip("test variant not built (python __graft_entry__.py)")
+    prog = textwrap.dedent(
+        """
+        import sys, json, hashlib
+        sys.path.insert(0, %r)
+        import numpy as np
+        from helios_b200 import api, scenes
+        out = []
+        for s in (scenes.triangle_soup(120_000, 160, 90), scenes.foliage_scene(n_clusters=2000, width=160, height=90)):
+            ctx = api.Context(s.width, s.height)
+            handles = ctx.load_scene(s)
+            st = [ctx.mesh_build_stats(h) for h in handles]
+            ids = ctx.trace_primary_ids(s.push_constants(1))
+            out.append({"nodes": [int(x["wide_nodes"]) for x in st], "sah": [float(x["sah_cost"]) for x in st],
+                        "hits": hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in ids)).hexdigest()})
+            ctx.close()
+        print("RESULT " + json.dumps(out))
+        """
+        % str(root)
+    )
+    res = []
+    plain = {k: v for k, v in os.environ.items() if k != "HELIOS_B200_LIB"}
+    for env in (plain, dict(plain, HELIOS_B200_LIB=str(lib))):
+        r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:]))
+    assert res[0] == res[1], f"{res[0]} vs {res[1]}"
