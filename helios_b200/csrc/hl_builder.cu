@@ -1149,12 +1149,8 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         if (two_level)
         {
             top_treelets.alloc(sizeof(TopTreelet) * ((size_t)k_cap + 1), st), top_tlist.alloc(4ull * ((size_t)k_cap + 1), st);
-            static bool attr_set = false;
-            if (!attr_set)
-            {
-                HL_CUDA(cudaFuncSetAttribute(k_treelets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeletSmem)));
-                attr_set = true;
-            }
+            // (per device, so not cached in a static: a process may hold contexts on several GPUs)
+            HL_CUDA(cudaFuncSetAttribute(k_treelets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeletSmem)));
         }
         top_tmp_bytes = std::max(a, b);
         top_tmp.alloc(std::max<size_t>(top_tmp_bytes, 16), st);
