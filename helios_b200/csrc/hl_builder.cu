@@ -467,7 +467,7 @@ struct TreeletSmem
     uint16_t node_parent[HL_TREELET_ROWS]; // local index of the parent | side << 15; 0xFFFF = the treelet's root
     alignas(16) TopBin bins[HL_TREELET_WARPS][HL_TOP_BINS]; // (top_clear_bin stores 16 bytes at a time)
     uint32_t scan[HL_TREELET_WARPS + 1];
-    uint32_t n_items, n_ids, n_sub;
+    uint32_t n_items, n_ids, n_next;
 };
 // exclusive prefix sum over one value per thread of the block (blockDim.x == HL_TREELET_THREADS); returns the total in `total`
 __device__ __forceinline__ uint32_t treelet_block_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total)
@@ -661,18 +661,24 @@ __device__ __forceinline__ bool treelet_exact(const TreeletSmem& S, const uint16
 }
 // err: set to 1 when a treelet does not fit the shared arrays (cannot happen while the primitive counts of the level loop are
 // upper bounds; checked by the host)
-__global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, TopBuild tb, uint32_t C, uint32_t* err)
+// cursor: the next treelet to hand out (zeroed by the host): treelets hold 2 .. 512 primitives, so the blocks take them one at a
+// time instead of a fixed stride
+__global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, TopBuild tb, uint32_t C, uint32_t* err, uint32_t* cursor)
 {
     extern __shared__ __align__(16) unsigned char treelet_raw[];
     TreeletSmem&   S     = *(TreeletSmem*)treelet_raw;
     const uint32_t tid   = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t leaf0 = t.n - 1;
     const uint32_t count = *tb.treelet_count;
-    for (uint32_t ti = blockIdx.x; ti < count; ti += gridDim.x)
+    for (;;)
     {
+        __syncthreads(); // the previous treelet is finished with the shared arrays (and with n_next)
+        if (tid == 0) S.n_next = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const uint32_t ti = S.n_next;
+        if (ti >= count) break;
         TopTreelet&    rec = tb.treelet[ti];
         const uint32_t m   = rec.count, link = rec.link;
-        __syncthreads(); // the previous treelet is finished with the shared arrays
         // ---- the treelet's coarse subtrees, sorted by cluster index (they registered in arrival order)
         {
             const uint32_t* list = tb.tlist + rec.list_base;
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(HL_TREELET_THREADS) k_treelets(BinaryTree t, T
             uint32_t total;
             uint32_t at = treelet_block_scan(sizes, S.scan, total);
             for (uint32_t k = tid * per; k < min(m, tid * per + per); k++) S.sub_off[k] = at, at += subtree_prims(t, S.sub_root[k]);
-            if (tid == 0) S.sub_off[m] = total, S.n_sub = m;
+            if (tid == 0) S.sub_off[m] = total;
             __syncthreads();
         }
         const uint32_t P = S.sub_off[m];
@@ -1118,7 +1124,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     const bool     resplit_top = resplit && n > C_top;                // (a tree of at most C_A primitives is one treelet)
     const uint32_t k_cap    = resplit_top ? (uint32_t)std::min<uint64_t>(n, 4ull * n / C_top + 1024) : (two_level ? 1u : 0u);
     const uint32_t bins_cap = k_cap / (HL_TOP_SMALL + 1u) + 2u;
-    const size_t   top_ctl_words = 8 + 2 * (HL_TOP_MAX_LEVELS + 1);
+    const size_t   top_ctl_words = 8 + 2 * (HL_TOP_MAX_LEVELS + 1) + 1; // (+ the treelet cursor)
     ScratchBuf     top_crec;
     ScratchBuf     top_clusters, top_free, top_cnode, top_level[2], top_bins[2], top_list, top_small, top_ctl, top_tmp, top_trace_buf, top_treelets, top_tlist;
     size_t         top_tmp_bytes = 0;
@@ -1266,7 +1272,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
         }
         if (two_level)
         {
-            k_treelets<<<ctx->sm_count * 6, HL_TREELET_THREADS, sizeof(TreeletSmem), st>>>(t, tb, C, ctl + 7);
+            k_treelets<<<ctx->sm_count * 5, HL_TREELET_THREADS, sizeof(TreeletSmem), st>>>(t, tb, C, ctl + 7, ctl + (top_ctl_words - 1));
             ctx->launches++;
             if (resplit_top)
             {
