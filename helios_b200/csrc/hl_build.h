@@ -873,25 +873,48 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
         {
             sp--;
             const uint32_t m = sn[sp], i = ss[sp];
-            uint32_t       d = 0;
-            if (m < leaf0) d = (t.dec[m] >> (4 * ((i < 1 ? 1 : i) - 1))) & 15u;
+            uint32_t       d = 0, lm = 0, rm = 0;
+            if (m < leaf0)
+            {
+                // (decisions and links together: one round trip per binary level instead of two)
+                const uint32_t dw = t.dec[m];
+                lm = t.left[m], rm = t.right[m];
+                d  = (dw >> (4 * ((i < 1 ? 1 : i) - 1))) & 15u;
+            }
             if (m >= leaf0 || d == 0u)
                 ch[nch++] = m;
             else if (d == 15u)
                 ch_inner |= 1u << nch, ch[nch++] = m;
             else
             {
-                sn[sp] = t.right[m], ss[sp++] = i - d;
-                sn[sp] = t.left[m], ss[sp++] = d;
+                sn[sp] = rm, ss[sp++] = i - d;
+                sn[sp] = lm, ss[sp++] = d;
             }
         }
     }
     const Box nb = t.box[task.bnode];
     // octant-ordered slot assignment: greedy minimum of cost(child, slot) = (centroid_c - centroid_node) . dir(slot)
+    // the children's boxes and leaf ranges, loaded ONCE and all at the same time (unrolled: eight independent gathers in flight —
+    // the kernel waits on memory, ncu: 46 long-scoreboard stalls per issued instruction when they were loaded one per loop trip,
+    // twice)
+    Box      cb[8];
+    uint32_t cprims[8], cfirst[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; k++)
+        if (k < nch)
+        {
+            const uint32_t c = ch[k];
+            cb[k] = t.box[c];
+            const bool     lf = c >= leaf0;
+            const uint32_t f = lf ? c - leaf0 : t.first[c], l = lf ? c - leaf0 : t.last[c];
+            cfirst[k] = f, cprims[k] = l - f + 1u;
+        }
     float cx[8], cy[8], cz[8];
     for (int k = 0; k < nch; k++)
     {
-        const Box& b = t.box[ch[k]];
+        const Box& b = cb[k];
         cx[k] = (b.lo[0] + b.hi[0]) - (nb.lo[0] + nb.hi[0]);
         cy[k] = (b.lo[1] + b.hi[1]) - (nb.lo[1] + nb.hi[1]);
         cz[k] = (b.lo[2] + b.hi[2]) - (nb.lo[2] + nb.hi[2]);
@@ -936,11 +959,10 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
     for (int s = 0; s < 8; s++)
     {
         if (slot_child[s] < 0) continue;
-        const uint32_t c = ch[slot_child[s]];
         if (ch_inner & (1u << slot_child[s]))
             n_inner++, imask |= 1u << s;
         else
-            n_leafprims += subtree_prims(t, c);
+            n_leafprims += cprims[slot_child[s]];
     }
     w.imask      = (uint8_t)imask;
     // (every lane allocates, also with amount 0: the lanes of a warp that build a node together share one atomic per counter)
@@ -977,8 +999,7 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
             w.qhix[s] = w.qhiy[s] = w.qhiz[s] = 0;
             continue;
         }
-        const uint32_t c = ch[slot_child[s]];
-        const Box&     b = t.box[c];
+        const Box& b = cb[slot_child[s]];
         quantize_axis(w.px, ex, b.lo[0], b.hi[0], w.qlox[s], w.qhix[s]);
         quantize_axis(w.py, ey, b.lo[1], b.hi[1], w.qloy[s], w.qhiy[s]);
         quantize_axis(w.pz, ez, b.lo[2], b.hi[2], w.qloz[s], w.qhiz[s]);
@@ -988,7 +1009,7 @@ HL_HD uint32_t collapse_one(const BinaryTree& t, CollapseTask task, WideOut out,
         }
         else
         {
-            const uint32_t cnt = subtree_prims(t, c), f = subtree_first(t, c);
+            const uint32_t cnt = cprims[slot_child[s]], f = cfirst[slot_child[s]];
             w.meta[s]          = (uint8_t)((((1u << cnt) - 1u) << 5) | leaf_off);
             for (uint32_t k = 0; k < cnt; k++) leaf_writer(w.leaf_base + leaf_off + k, f + k);
             leaf_off += cnt;
