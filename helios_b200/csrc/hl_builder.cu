@@ -1031,9 +1031,12 @@ __global__ void __launch_bounds__(128) k_collapse(BinaryTree t, WideOut out, Col
     volatile uint32_t* vdone = ctl + 5;
     uint32_t           idx   = 0;
     bool               have  = false;
+    unsigned           nap   = 64u; // ns between two looks at an empty slot: doubles up to ~4 us (every resident thread polls: at a
+                                    // fixed 64 ns the polls alone asked more of the L2 than it delivers, and the working threads'
+                                    // loads queued behind them — ncu: 46 long-scoreboard stalls per issued instruction)
     for (;;)
     {
-        if (!have) idx = hl_alloc_var(ctl + 3, 1u), have = true; // one atomic per group of lanes that need a new queue index
+        if (!have) idx = hl_alloc_var(ctl + 3, 1u), have = true, nap = 64u; // one atomic per group of lanes that need a new queue index
         bool ready = false;
         CollapseTask task;
         task.wide = task.bnode = 0xFFFFFFFFu;
@@ -1062,7 +1065,10 @@ __global__ void __launch_bounds__(128) k_collapse(BinaryTree t, WideOut out, Col
         else if (*vdone)
             break;
         else
-            __nanosleep(64); // waiting lanes yield the issue slots to the lanes of the warp that hold a task
+        {
+            __nanosleep(nap); // waiting lanes yield the issue slots to the lanes of the warp that hold a task
+            nap = nap < 4096u ? nap * 2u : nap;
+        }
     }
 }
 
@@ -1292,7 +1298,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
     wo.nodes = big_nodes.as<WideNode>(), wo.node_counter = ctr.as<uint32_t>(), wo.leaf_counter = ctr.as<uint32_t>() + 1;
     DeferredLeafWriter deferred;
     deferred.leaf_pos = leaf_pos.as<uint32_t>();
-    k_collapse<<<cap, 128, 0, st>>>(t, wo, queue.as<CollapseTask>(), capacity, ctr.as<uint32_t>(), deferred);
+    k_collapse<<<ctx->sm_count * 10, 128, 0, st>>>(t, wo, queue.as<CollapseTask>(), capacity, ctr.as<uint32_t>(), deferred); // (48 registers: 10 blocks per SM are resident; the kernel waits on memory)
     k_write_leaves<<<grid_for(n, 256, cap), 256, 0, st>>>(make_writer(sorted, out.leaves.p), leaf_pos.as<uint32_t>(), n);
     ctx->launches += 2;
     HL_CUDA(cudaEventRecord(e1, st));
