@@ -292,10 +292,13 @@ __global__ void __launch_bounds__(256, 4) k_top_build(BinaryTree t, TopBuild tb,
             for (uint32_t i = tid; i < K; i += nthr) top_bin_cluster(t, tb, level, i);
         grid_barrier(bar);
         top_trace(trace, ntrace);
-        for (uint32_t j = warp; j < nodes; j += nwarps) top_choose_node_warp(tb, level, j, lane);
-        grid_barrier(bar);
-        top_trace(trace, ntrace);
-        for (uint32_t j = tid; j < nodes; j += nthr) top_commit_node(t, tb, level, j);
+        // CHOOSE + COMMIT of a node by the same warp (a node's commit only needs its own choice): one grid barrier less per level
+        for (uint32_t j = warp; j < nodes; j += nwarps)
+        {
+            top_choose_node_warp(tb, level, j, lane);
+            __syncwarp();
+            if (lane == 0u) top_commit_node(t, tb, level, j);
+        }
         grid_barrier(bar);
         top_trace(trace, ntrace);
         if (__ldcg(tb.level_count + level + 1u) == 0u) break; // only single / small nodes were left
@@ -1155,7 +1158,10 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
             HL_CUDA(cub::DeviceSelect::If(nullptr, b, ids, top_free.as<uint32_t>(), top_ctl.as<uint32_t>() + 1, (int)(n - 1), IsUpperNode { BinaryTree(), C_top }, st));
             int per_sm = 0;
             HL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_top_build, 256, 0));
+            // blocks: a thread per ~4 clusters of the expected cut, between one and four blocks per SM — every grid barrier costs
+            // one atomic arrival per block on one address, and the level loop of the two-level re-split is nothing but barriers
             top_grid = ctx->sm_count * std::max(1, std::min(per_sm, 4));
+            top_grid = std::max(1, std::min<int>(top_grid, std::max<int>(ctx->sm_count, (int)((k_cap + 1023u) / 1024u))));
             top_grid = std::max(1, std::min<int>(top_grid, (int)((k_cap + 255u) / 256u)));
         }
         if (two_level)
