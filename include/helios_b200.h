@@ -319,7 +319,11 @@ HL_API hl_status hl_event_elapsed_ms(hl_context ctx, int slot_begin, int slot_en
                                    of ~30; captured per frame slot, re-captured when scene tables or integrator settings change) */
 /* builder knob (applies to meshes / scene tables created afterwards; changes the tree, never a traversal result) */
 #define HL_OPT_SAH_CLUSTER 4    /* binned-SAH re-split of the LBVH above a cut: primitives per cluster below the cut
-                                   (default 2; larger = faster build, coarser refinement); 0 = plain LBVH topology */
+                                   (default 2; larger = faster build, coarser refinement); 0 = plain LBVH topology.  Triangle
+                                   meshes with 1..8 primitives per cluster are re-split in two levels (a level loop over coarse
+                                   subtrees, then one thread block per treelet of <= 512 primitives; environment variable
+                                   HL_NO_TREELETS=1: the one-level re-split, for A/B runs); larger settings and instance trees
+                                   take the one-level re-split */
 HL_API hl_status hl_set_option(hl_context ctx, int option, int64_t value);
 /* number of kernels launched by this library on this context since creation */
 HL_API hl_status hl_kernel_launches(hl_context ctx, uint64_t* out);
