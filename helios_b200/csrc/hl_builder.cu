@@ -8,10 +8,13 @@
 //   morton         24 read, 8 + 4 written                                36
 //   radix sort     8 passes x (12 read + 12 written)  (CUB, 63 key bits) 192
 //   radix_tree     ~2 x 8 key reads (cached), 24 written                 40
-//   fit            24 read (sorted box) + 2 x 24 written + 48 read + 2 x 28 cost-table rows written, 56 read   232
-//   top re-split   clusters of <= C primitives (K ~ N / C..N): 2 selects over the node ids (8), then per level
-//                  K x (24 box + 4 node id) read twice + 21 + 6 atomics per cluster still above a small node;
-//                  ~log2(K / 16) + imbalance levels; refit of the K - 1 re-linked nodes (as `fit`)       ~150 (C = 2)
+//   fit (fine)     24 read (sorted box) + 24 written + 28 cost row per leaf, the same per node inside a fine cluster        ~230
+//   re-split       two levels (k_treelets below): level loop over the coarse cut (K_A ~ N / 20 clusters: 32 B records, ~12 levels:
+//                  a few MB per level, bound by its grid barriers), then per treelet of <= 512 primitives ONE pass over its fine
+//                  clusters: ~4 links + 24 box + 28 cost row read per cluster, and per re-linked node 3 links + 24 box + 8 range +
+//                  28 cost row + 4 decisions written (all levels of the treelet run in shared memory)                            ~150
+//                  (instance trees / HL_NO_TREELETS: the one-level re-split of round 1 — clusters of <= C primitives through a
+//                  level loop of BIN / CHOOSE / COMMIT / ASSIGN passes, K x (24 box + 4 node id) read twice + ~27 atomics per level)
 //   collapse       ~48 read (boxes) + 8 decisions + 0.12 x 80 node + 48 leaf + 48 src + 2 x 8 queue   ~180
 //   total                                                              ~ 930 B / triangle
 #include "hl_internal.h"
