@@ -1166,6 +1166,7 @@ static void build_wide_device(hl_context_t* ctx, const Box* d_boxes, uint32_t n,
             top_grid = ctx->sm_count * std::max(1, std::min(per_sm, 4));
             top_grid = std::max(1, std::min<int>(top_grid, std::max<int>(ctx->sm_count, (int)((k_cap + 1023u) / 1024u))));
             top_grid = std::max(1, std::min<int>(top_grid, (int)((k_cap + 255u) / 256u)));
+            if (const char* e = getenv("HL_TOP_GRID")) top_grid = std::max(1, std::min(top_grid, atoi(e))); // (tuning runs)
         }
         if (two_level)
         {
