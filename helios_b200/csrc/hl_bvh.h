@@ -374,6 +374,9 @@ HL_HD bool instance_passthrough(const SceneView& s, uint32_t id, f3 o, f3 d)
 #ifndef HL_TRI_PER_STEP
 #define HL_TRI_PER_STEP 2
 #endif
+#ifndef HL_PREFETCH_NEXT_NODE
+#define HL_PREFETCH_NEXT_NODE 0
+#endif
 struct Trav
 {
     RayCtx          r;    // ray in the space of the tree being traversed
@@ -464,6 +467,19 @@ HL_HD void trav_step_nodes(const SceneView& s, Trav& t, TravStack& st)
     const uint32_t mask = intersect_children(t.nodes + (base + rel), t.r, t.tmin, t.best.t, cb, lb, im);
     t.ngroup.x = cb, t.ngroup.y = (mask & 0xFF000000u) | im;
     t.tgroup.x = lb, t.tgroup.y = mask & 0x00FFFFFFu;
+#if defined(__CUDA_ARCH__) && HL_PREFETCH_NEXT_NODE
+    // the node this lane visits next (the nearest child that was hit) is known now, one step — and possibly a triangle phase —
+    // before its five loads are issued: ask for its lines
+    if (t.ngroup.y > 0x00FFFFFFu)
+    {
+        const uint32_t h2 = t.ngroup.y;
+        const uint32_t s2 = (uint32_t)(hl_bfind(h2) - 24) ^ t.r.octinv;
+        const uint32_t r2 = (uint32_t)hl_popc((h2 & 0xFFu) & ~(0xFFFFFFFFu << s2));
+        const char*    pn = (const char*)(t.nodes + (cb + r2));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + 64));
+    }
+#endif
 }
 // triangle postponing (after Ylitie et al.): a lane that has a leaf group AND inner children pending may
 // put the leaf group on the stack and keep descending, so that triangle tests run when many lanes have one

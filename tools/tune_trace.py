@@ -46,6 +46,7 @@ VARIANT_SETS["coop"] = {
 VARIANT_SETS["fol"] = {"base": [], "tri3": ["-DHL_TRI_PER_STEP=3"], "tri4": ["-DHL_TRI_PER_STEP=4"], "tri1": ["-DHL_TRI_PER_STEP=1"], "refill4": ["-DHL_REFILL_MIN=4"], "refill16": ["-DHL_REFILL_MIN=16"]}
 VARIANT_SETS["treelet"] = {"base": [], "tiny1": ["-DHL_TREELET_TINY=1"], "exact3": ["-DHL_TREELET_EXACT=3"], "prims256": ["-DHL_TREELET_PRIMS=256"], "prims1024": ["-DHL_TREELET_PRIMS=1024"]}
 VARIANT_SETS["grid"] = {"g8": [], "g4": ["-DHL_TRACE_GRID_MULT=4"], "g5": ["-DHL_TRACE_GRID_MULT=5"], "g6": ["-DHL_TRACE_GRID_MULT=6"], "g7": ["-DHL_TRACE_GRID_MULT=7"], "g12": ["-DHL_TRACE_GRID_MULT=12"]}
+VARIANT_SETS["prefetch"] = {"base": [], "pf": ["-DHL_PREFETCH_NEXT_NODE=1"]}
 VARIANTS = VARIANT_SETS[os.environ.get("HL_TUNE_SET", "occ")]
 OUT = ROOT / "build" / "variants"
 if sys.argv[1] == "build":
